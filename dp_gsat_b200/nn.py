@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's model surfaces (same names, constructor arguments, forward signatures and
+state_dict keys), backed by the sm_100a kernels of libgsat_b200.so.
+
+  reference file                         -> here
+  src/models/conv_layers.py:14-34  GINConv            -> GINConv
+  src/models/gin.py:12-81          GIN                -> GIN
+  src/utils/get_model.py:7-68      get_model/Criterion/BatchSequential/MLP -> same names
+  torch_geometric InstanceNorm / global_add_pool / global_mean_pool        -> InstanceNorm / ops.global_*_pool
+  src/run_gsat.py:888-927, example/gsat.py:120-139  ExtractorMLP           -> ExtractorMLP
+
+Dense Linear / BatchNorm1d layers are (for now) PyTorch library calls; every gather / scatter / segment / sampling
+op is a kernel of this repo.  Dropout masks can be injected (``masks``) for parity tests; otherwise F.dropout.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as tnn
+import torch.nn.functional as F
+
+from . import ops
+from .index import GraphIndex, get_graph_index
+
+
+def _dropout(x, p: float, training: bool, masks=None, key: str = ''):
+    if not training or p == 0.0:
+        return x
+    if masks is None:
+        return F.dropout(x, p, True)
+    m = masks.get(key, x.shape, p).to(device=x.device, dtype=x.dtype)
+    return x * m / (1.0 - p)
+
+
+class InstanceNorm(tnn.Module):
+    """torch_geometric.nn.InstanceNorm(C) with its defaults (eps 1e-5, affine False, no running stats), applied
+    per graph over contiguous row segments.  ``batch`` may be the reference's int64 segment-id vector (then the
+    segment pointers come from the cached GraphIndex passed as ``seg``) or a prepared (seg_ptr, num_segments)."""
+
+    def __init__(self, in_channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.in_channels, self.eps = in_channels, eps
+
+    def forward(self, x, batch, seg=None):
+        if seg is None:
+            seg = segments_from_batch(batch)
+        seg_ptr, G = seg
+        return ops.segment_instance_norm(x, seg_ptr, G, self.eps)
+
+
+def segments_from_batch(batch: torch.Tensor):
+    """(seg_ptr int32 [G+1], G) from a non-decreasing int64 segment-id vector, through K0."""
+    dummy = _EMPTY_EDGES.get(batch.device)
+    if dummy is None:
+        dummy = torch.zeros((2, 0), dtype=torch.int64, device=batch.device)
+        _EMPTY_EDGES[batch.device] = dummy
+    gi = get_graph_index(dummy, batch)
+    gi.require_graph_contiguous()
+    return gi.node_ptr, gi.G
+
+
+_EMPTY_EDGES = {}
+
+
+class BatchSequential(tnn.Sequential):
+    """src/utils/get_model.py:47-54."""
+
+    def forward(self, inputs, batch, seg=None, masks=None, key: str = 'ext'):
+        li = 0
+        for module in self._modules.values():
+            if isinstance(module, InstanceNorm):
+                inputs = module(inputs, batch, seg)
+            elif isinstance(module, tnn.Dropout):
+                inputs = _dropout(inputs, module.p, self.training, masks, f'{key}.{li}')
+                li += 1
+            else:
+                inputs = module(inputs)
+        return inputs
+
+
+class MLP(BatchSequential):
+    """src/utils/get_model.py:57-68 (state_dict keys '0','4','8' as in the reference Sequential)."""
+
+    def __init__(self, channels: Sequence[int], dropout: float, bias: bool = True):
+        m = []
+        for i in range(1, len(channels)):
+            m.append(tnn.Linear(channels[i - 1], channels[i], bias))
+            if i < len(channels) - 1:
+                m.append(InstanceNorm(channels[i]))
+                m.append(tnn.ReLU())
+                m.append(tnn.Dropout(dropout))
+        super().__init__(*m)
+
+
+class Criterion(tnn.Module):
+    """src/utils/get_model.py:19-34."""
+
+    def __init__(self, num_class, multi_label):
+        super().__init__()
+        self.num_class, self.multi_label = num_class, multi_label
+
+    def forward(self, logits, targets):
+        if self.num_class == 2 and not self.multi_label:
+            return F.binary_cross_entropy_with_logits(logits, targets.float())
+        elif self.num_class > 2 and not self.multi_label:
+            return F.cross_entropy(logits, targets.long())
+        is_labeled = targets == targets
+        return F.binary_cross_entropy_with_logits(logits[is_labeled], targets[is_labeled].float())
+
+
+def get_preds(logits, multi_label):
+    """src/utils/get_model.py:37-44."""
+    if multi_label:
+        return (logits.sigmoid() > 0.5).float()
+    if logits.shape[1] > 1:
+        return logits.argmax(dim=1).float()
+    return (logits.sigmoid() > 0.5).float()
+
+
+class GINConv(tnn.Module):
+    """src/models/conv_layers.py:14-34 over torch_geometric GINConv(nn, eps=0., train_eps=False): ``eps`` is a
+    buffer, present in the state_dict."""
+
+    def __init__(self, nn: tnn.Module, eps: float = 0.0, train_eps: bool = False):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:
+            raise NotImplementedError('train_eps=True is never used by the reference (gin.py:40)')
+        self.register_buffer('eps', torch.tensor([eps]))
+
+    def forward(self, x, edge_index, edge_attr=None, edge_atten=None, size=None, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(edge_index, None, num_nodes=x.shape[0])
+        out = ops.gin_aggregate(x, edge_atten, gi, self.initial_eps)
+        return self.nn(out)
+
+
+class GIN(tnn.Module):
+    """src/models/gin.py:12-81."""
+
+    def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
+        super().__init__()
+        self.n_layers = model_config['n_layers']
+        hidden_size = model_config['hidden_size']
+        self.edge_attr_dim = edge_attr_dim
+        self.dropout_p = model_config['dropout_p']
+        self.use_edge_attr = model_config.get('use_edge_attr', True)
+        if model_config.get('atom_encoder', False):
+            self.node_encoder = AtomEncoder(emb_dim=hidden_size)
+        else:
+            self.node_encoder = tnn.Linear(x_dim, hidden_size)
+        if edge_attr_dim != 0 and self.use_edge_attr:
+            raise NotImplementedError('GINEConv (edge features in GIN) is a SURVEY §8f "next" row, not built yet')
+        self.convs = tnn.ModuleList()
+        self.relu = tnn.ReLU()
+        for _ in range(self.n_layers):
+            self.convs.append(GINConv(GIN.MLP(hidden_size, hidden_size)))
+        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
+        self.masks = None     # parity tests inject dropout masks here
+
+    @staticmethod
+    def MLP(in_channels: int, out_channels: int):
+        return tnn.Sequential(tnn.Linear(in_channels, out_channels), tnn.BatchNorm1d(out_channels),
+                              tnn.ReLU(inplace=True), tnn.Linear(out_channels, out_channels))
+
+    def pool(self, x, batch, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(_no_edges(batch.device), batch)
+        return ops.global_add_pool(x, gi)
+
+    def get_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin'):
+        gi = get_graph_index(edge_index, batch)
+        x = self.node_encoder(x)
+        for i in range(self.n_layers):
+            x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
+            x = self.relu(x)
+            x = _dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
+        return x
+
+    def forward(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin.clf'):
+        gi = get_graph_index(edge_index, batch)
+        x = self.get_emb(x, edge_index, batch, edge_attr, edge_atten, mask_key=mask_key)
+        return self.fc_out(self.pool(x, batch, gi))
+
+    def get_graph_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None):
+        return self.pool(self.get_emb(x, edge_index, batch, edge_attr, edge_atten), batch)
+
+    def get_pred_from_emb(self, emb, batch):
+        return self.fc_out(self.pool(emb, batch))
+
+
+def _no_edges(device):
+    d = _EMPTY_EDGES.get(device)
+    if d is None:
+        d = torch.zeros((2, 0), dtype=torch.int64, device=device)
+        _EMPTY_EDGES[device] = d
+    return d
+
+
+ATOM_FEATURE_DIMS = [119, 4, 12, 12, 10, 6, 6, 2, 2]
+BOND_FEATURE_DIMS = [5, 6, 2]
+
+
+class AtomEncoder(tnn.Module):
+    """ogb 1.3.2 AtomEncoder: sum of 9 embedding tables."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.atom_embedding_list = tnn.ModuleList()
+        for d in ATOM_FEATURE_DIMS:
+            emb = tnn.Embedding(d, emb_dim)
+            tnn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+
+    def forward(self, x):
+        out = 0
+        for i, emb in enumerate(self.atom_embedding_list):
+            out = out + emb(x[:, i])
+        return out
+
+
+class BondEncoder(tnn.Module):
+    """ogb 1.3.2 BondEncoder."""
+
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.bond_embedding_list = tnn.ModuleList()
+        for d in BOND_FEATURE_DIMS:
+            emb = tnn.Embedding(d, emb_dim)
+            tnn.init.xavier_uniform_(emb.weight.data)
+            self.bond_embedding_list.append(emb)
+
+    def forward(self, edge_attr):
+        out = 0
+        for i, emb in enumerate(self.bond_embedding_list):
+            out = out + emb(edge_attr[:, i])
+        return out
+
+
+class ExtractorMLP(tnn.Module):
+    """Upstream form  ExtractorMLP(hidden_size, learn_edge_att).forward(emb, edge_index, batch)
+    (example/gsat.py:120-139) and fork form  ExtractorMLP(hidden_size, shared_config, type).forward(emb, edge_index,
+    batch, type)  (src/run_gsat.py:888-927; parameters live under '<type>_feature_extractor')."""
+
+    def __init__(self, hidden_size, shared_config, type: Optional[str] = None):
+        super().__init__()
+        if isinstance(shared_config, bool):
+            shared_config = {'learn_edge_att': shared_config, 'extractor_dropout_p': 0.5}
+        self.learn_edge_att = shared_config['learn_edge_att']
+        dropout_p = shared_config['extractor_dropout_p']
+        self.kind = type
+        self._name = 'feature_extractor' if type is None else f'{type}_feature_extractor'
+        if type is not None:
+            setattr(self, f'{type}_learn_edge_att', self.learn_edge_att)
+        if self.learn_edge_att:
+            mlp = MLP([hidden_size * 2, hidden_size * 4, hidden_size, 1], dropout=dropout_p)
+        else:
+            mlp = MLP([hidden_size * 1, hidden_size * 2, hidden_size, 1], dropout=dropout_p)
+        setattr(self, self._name, mlp)
+        self.masks = None
+
+    def forward(self, emb, edge_index, batch, type: Optional[str] = None):
+        if type is not None and type != self.kind:
+            return None      # the reference falls through and returns None for an unknown type
+        mlp = getattr(self, self._name)
+        gi = get_graph_index(edge_index, batch)
+        gi.require_graph_contiguous()
+        if self.learn_edge_att:
+            f12 = ops.gather_concat(emb, gi)      # cat(emb[col], emb[row]) with col, row = edge_index
+            return mlp(f12, None, seg=(gi.edge_ptr, gi.G), masks=self.masks)
+        return mlp(emb, None, seg=(gi.node_ptr, gi.G), masks=self.masks)
+
+
+def get_model(x_dim, edge_attr_dim, num_class, multi_label, model_config, device):
+    """src/utils/get_model.py:7-16."""
+    if model_config['model_name'] == 'GIN':
+        model = GIN(x_dim, edge_attr_dim, num_class, multi_label, model_config)
+    elif model_config['model_name'] == 'PNA':
+        from .pna import PNA
+        model = PNA(x_dim, edge_attr_dim, num_class, multi_label, model_config)
+    else:
+        raise ValueError('[ERROR] Unknown model name!')
+    return model.to(device)

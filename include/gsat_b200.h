@@ -1,0 +1,163 @@
+/*
+ * gsat_b200.h -- C ABI of libgsat_b200.so, the B200 (sm_100a) implementation of GSAT's per-step
+ * stochastic-attention message-passing path.
+ *
+ * The reference (mihikamd/DP-GSAT) is pure Python: there is no FFI in it.  Each entry point below replaces the
+ * chain of PyTorch / torch_geometric / torch_scatter / torch_sparse calls at the cited reference file:line
+ * (paths relative to the reference root); the Python package dp_gsat_b200 binds them with ctypes and re-exposes
+ * the reference's own surfaces (GINConv, GIN, ExtractorMLP, GSAT.forward_pass, reorder_like, ...).
+ * INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (PyTorch);
+ *    the library never allocates, frees or retains memory, and never synchronises the host with the device
+ *  - fp32 values, int32 indices internally (N, E < 2^31); the reference's int64 edge_index is consumed once,
+ *    by gsatb_index_build
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph capturable
+ *  - return 0 on success, a negative GSATB_E* code otherwise; nothing throws across the ABI
+ *  - nullable pointers are marked [nullable]
+ *  - feature widths H, C must be multiples of 4 (128-bit vector access) unless stated
+ */
+#ifndef GSAT_B200_H
+#define GSAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSATB_VERSION 100
+
+#define GSATB_OK 0
+#define GSATB_EINVAL -1        /* null pointer / negative size / unsupported flag */
+#define GSATB_ESHAPE -2        /* unsupported width (H % 4 != 0, H too large, ...) */
+#define GSATB_EALIGN -3        /* pointer not 16-byte aligned */
+#define GSATB_EWS_TOO_SMALL -4 /* workspace smaller than gsatb_*_workspace() */
+#define GSATB_EARCH -5         /* device is not compute capability 10.x */
+#define GSATB_ENOT_SYMMETRIC -6
+#define GSATB_ELAUNCH -7       /* CUDA launch error (see cudaGetLastError) */
+
+typedef void* gsatb_stream_t; /* cudaStream_t */
+
+int gsatb_version(void);
+const char* gsatb_strerror(int code);
+/* 0 when the current device is sm_100-class, GSATB_EARCH otherwise (no fallback path exists). */
+int gsatb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K0  index builder.  Replaces, once per batch instead of every step:
+ *   torch_geometric.utils.is_undirected            src/run_gsat.py:232,242   example/gsat.py:80
+ *   torch_sparse.transpose(coalesced=False)        src/run_gsat.py:243       example/gsat.py:81
+ *   reorder_like (sort_edge_index + 2 argsorts)    src/utils/utils.py:19-25
+ *   the implicit COO->segment conversions inside MessagePassing.propagate / scatter / InstanceNorm / pooling
+ *   int(batch.max())+1 host syncs                  (PyG InstanceNorm, global_add_pool)
+ * Canonical orders are the stable ascending (dst,src) and (src,dst) orders; outputs are bit-exact against
+ * oracle/gsat_oracle.py::build_index_oracle.
+ *   flags[0] = number of rank positions whose (src,dst)/(dst,src) keys differ (0 <=> is_undirected)
+ *   flags[1] = number of duplicate directed edges
+ *   flags[2] = graph-contiguity violations (batch not sorted, edges not grouped by graph, edge crossing graphs)
+ *   flags[3] = out-of-range node / graph ids
+ * rev[e] = -1 where no reverse edge matches.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t gsatb_index_build_workspace(int64_t N, int64_t E, int64_t G);
+int gsatb_index_build(const int64_t* edge_index /* [2,E] */, const int64_t* batch /* [N] */,
+                      int64_t N, int64_t E, int64_t G,
+                      int32_t* src, int32_t* dst, int32_t* rev,
+                      int32_t* rowptr_dst /* [N+1] */, int32_t* eid_by_dst, int32_t* src_by_dst,
+                      int32_t* rowptr_src /* [N+1] */, int32_t* eid_by_src, int32_t* dst_by_src,
+                      int32_t* node_ptr /* [G+1] */, int32_t* edge_ptr /* [G+1] */,
+                      int32_t* node_graph /* [N] */, int32_t* edge_graph /* [E] */,
+                      int32_t* flags /* [4] */, void* ws, size_t ws_bytes, gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K3  attention-weighted GIN aggregation.  Replaces GINConv.forward/message up to (not including) self.nn:
+ *   src/models/conv_layers.py:14-34  (+ PyG propagate: index_select, x_j*edge_atten, scatter-add, += (1+eps) x)
+ *   out[i] = (sum over CSR row i, in order: att[eid] * x[src]) + (1+eps) * x[i]
+ * bwd:  dx[j] = (sum over CSC row j: att[eid] * g[dst]) + (1+eps) g[j] ;  datt[e] = <x[src(e)], g[dst(e)]>
+ * att [nullable] = edge_atten None (first GNN pass, run_gsat.py:191).  Deterministic: no atomics.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_gin_aggregate_fwd(const float* x, const float* att, const int32_t* rowptr_dst, const int32_t* eid_by_dst,
+                            const int32_t* src_by_dst, float eps, float* out, int64_t N, int64_t E, int H,
+                            gsatb_stream_t stream);
+int gsatb_gin_aggregate_bwd(const float* gout, const float* x, const float* att, const int32_t* rowptr_src,
+                            const int32_t* eid_by_src, const int32_t* dst_by_src, float eps, float* dx,
+                            float* datt /* [nullable] */, int64_t N, int64_t E, int H, gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K5  graph readout.  Replaces global_add_pool / global_mean_pool (src/models/gin.py:34,53, pna.py:47,62).
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_pool_fwd(const float* x, const int32_t* node_ptr, float* out, int64_t N, int64_t G, int H, int mean,
+                   gsatb_stream_t stream);
+int gsatb_pool_bwd(const float* gout, const int32_t* node_ptr, const int32_t* node_graph, float* dx, int64_t N,
+                   int64_t G, int H, int mean, gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Per-graph InstanceNorm over contiguous row segments (PyG InstanceNorm, eps=1e-5, no affine, biased variance of
+ * the centred values), the norm inside the extractor MLP: src/utils/get_model.py:47-68, src/run_gsat.py:912-915.
+ *   y = (x - mean_g) * rstd_g ; saves rstd [G,C] for backward.  Empty segments are skipped.
+ * bwd:  gx = rstd * (gy - mean_g(gy) - y * mean_g(gy*y))
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_segnorm_fwd(const float* x, const int32_t* seg_ptr, float* y, float* rstd, int64_t M, int64_t G, int C,
+                      float eps, gsatb_stream_t stream);
+int gsatb_segnorm_bwd(const float* gy, const float* y, const float* rstd, const int32_t* seg_ptr, float* gx,
+                      int64_t M, int64_t G, int C, gsatb_stream_t stream);
+
+/* Edge feature gather of the extractor: out[e] = [emb[src(e)] , emb[dst(e)]]  (cat(emb[col], emb[row]),
+ * src/run_gsat.py:912-914, example/gsat.py:133-135); bwd sums over CSC then CSR rows (deterministic, replaces the
+ * index_add_ atomics of index_select's autograd). */
+int gsatb_gather_concat_fwd(const float* emb, const int32_t* src, const int32_t* dst, float* out, int64_t E, int H,
+                            gsatb_stream_t stream);
+int gsatb_gather_concat_bwd(const float* g, const int32_t* rowptr_src, const int32_t* eid_by_src,
+                            const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N, int H,
+                            gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K2  concrete (Gumbel-sigmoid) sampling + undirected reverse-edge average + information loss.  Replaces
+ *   concrete_sample / sampling          src/run_gsat.py:866-885   example/gsat.py:94-103
+ *   (att + att[rev]) / 2                src/run_gsat.py:241-247   example/gsat.py:79-85
+ *   info loss (KL to Bernoulli(r))      src/run_gsat.py:126-132   example/gsat.py:30-31
+ * mode bits: 1 TRAINING (add logistic noise log u - log(1-u)); 2 AVERAGE (needs rev); 4 INFO_ON_EDGE_ATT (fork:
+ * loss on the averaged attention; default upstream: on att); 8 NO_INFO (skip the reduction)
+ * noise_u [nullable]: injected uniform draw in [1e-10, 1-1e-10]; when null and TRAINING, a counter-based
+ * Philox4x32-10 stream (seed, offset + e) is used and can be regenerated in backward.
+ * r_tensor [nullable]: per-edge r (fork: sigmoid(dual logits).detach()); else r_scalar.
+ * info_mean[0] = mean_e f(a_e).  The reduction is two-stage with a fixed order (deterministic).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define GSATB_MODE_TRAINING 1
+#define GSATB_MODE_AVERAGE 2
+#define GSATB_MODE_INFO_ON_EDGE_ATT 4
+#define GSATB_MODE_NO_INFO 8
+size_t gsatb_sample_workspace(int64_t E);
+int gsatb_sample_avg_info_fwd(const float* logit, const float* noise_u, const int32_t* rev, const float* r_tensor,
+                              float r_scalar, float temp, int mode, uint64_t seed, uint64_t offset, float* att,
+                              float* edge_att, float* info_mean, int64_t E, void* ws, size_t ws_bytes,
+                              gsatb_stream_t stream);
+/* g_att, g_edge_att [nullable] upstream gradients; g_info: device scalar d loss / d info_mean [nullable]. */
+int gsatb_sample_avg_info_bwd(const float* g_att, const float* g_edge_att, const float* g_info, const float* att,
+                              const float* edge_att, const int32_t* rev, const float* r_tensor, float r_scalar,
+                              float temp, int mode, float* dlogit, int64_t E, gsatb_stream_t stream);
+
+/* out[e] = v[rev[e]]  (reorder_like(transpose(ei, v), ei, v), src/utils/utils.py:19-25); C values per edge. */
+int gsatb_gather_rev(const float* v, const int32_t* rev, float* out, int64_t E, int C, gsatb_stream_t stream);
+
+/* General reorder_like: position p of the stable (row,col) order of `to` is matched with position p of the stable
+ * (row,col) order of `from` (src/utils/utils.py:20-22): map[order_to[p]] = order_from[p]; mismatch[0] counts
+ * positions whose (row,col) differ (the reference raises ValueError when any does, utils.py:23-24). */
+int gsatb_match_orders(const int32_t* order_to, const int32_t* order_from, const int32_t* src_to,
+                       const int32_t* dst_to, const int32_t* src_from, const int32_t* dst_from, int32_t* map,
+                       int32_t* mismatch, int64_t E, gsatb_stream_t stream);
+
+/* K2' node->edge lift: edge_att[e] = a[src] * a[dst]  (src/run_gsat.py:870-875); bwd is row-parallel over
+ * CSR + CSC (deterministic). */
+int gsatb_lift_fwd(const float* node_att, const int32_t* src, const int32_t* dst, float* edge_att, int64_t E,
+                   gsatb_stream_t stream);
+int gsatb_lift_bwd(const float* g_edge, const float* node_att, const int32_t* rowptr_dst, const int32_t* eid_by_dst,
+                   const int32_t* src_by_dst, const int32_t* rowptr_src, const int32_t* eid_by_src,
+                   const int32_t* dst_by_src, float* d_node, int64_t N, gsatb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSAT_B200_H */

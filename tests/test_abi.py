@@ -1,0 +1,82 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/gsat_b200.h declares; host logic
+(header parser, sharding, generators).  No compute calls: there is no GPU here."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from dp_gsat_b200._lib import LIB_PATH, parse_header
+    assert os.path.exists(LIB_PATH)
+    protos = parse_header()
+    assert len(protos) >= 20
+    cdll = ctypes.CDLL(LIB_PATH)
+    for name in protos:
+        assert hasattr(cdll, name), f'{name} declared in include/gsat_b200.h but not exported'
+    cdll.gsatb_version.restype = ctypes.c_int
+    assert cdll.gsatb_version() == 100
+    cdll.gsatb_strerror.restype = ctypes.c_char_p
+    assert b'workspace' in cdll.gsatb_strerror(-4)
+    cdll.gsatb_index_build_workspace.restype = ctypes.c_size_t
+    cdll.gsatb_index_build_workspace.argtypes = [ctypes.c_int64] * 3
+    assert cdll.gsatb_index_build_workspace(100, 1000, 4) >= 7 * 4000
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import the oracle nor run without CUDA."""
+    import dp_gsat_b200
+    pkg = os.path.join(ROOT, 'dp_gsat_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            txt = open(os.path.join(pkg, fn)).read()
+            assert 'import oracle' not in txt and 'from oracle' not in txt, fn
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            dp_gsat_b200.get_graph_index(torch.zeros((2, 3), dtype=torch.int64), torch.zeros(2, dtype=torch.int64))
+        with pytest.raises(RuntimeError):
+            dp_gsat_b200.ops.gin_aggregate(torch.zeros(2, 4), None, None, 0.0)
+
+
+def test_generators_shapes():
+    from dp_gsat_b200.data import ba2motifs_batch, molhiv_like_batch, in_degree_histogram
+    from oracle import gsat_oracle as O
+    b = ba2motifs_batch(128, seed=0)
+    assert b.num_nodes == 3200 and b.x.shape == (3200, 10) and b.y.shape == (128, 1)
+    assert b.num_edges == 64 * 50 + 64 * 52
+    idx = O.build_index_oracle(b.edge_index, b.batch)
+    assert idx['symmetric'] and idx['graph_contiguous'] and not idx['has_dup']
+    key = b.edge_index[0] * 3200 + b.edge_index[1]
+    assert bool((key[1:] > key[:-1]).all())                      # dense_to_sparse (row-major) order
+    assert float(b.edge_label.sum()) == 64 * 10 + 64 * 12
+    m = molhiv_like_batch(64, seed=0)
+    idx = O.build_index_oracle(m.edge_index, m.batch)
+    assert idx['symmetric'] and idx['graph_contiguous'] and not idx['has_dup']
+    assert m.x.dtype == torch.int64 and m.x.shape[1] == 9 and m.edge_attr.shape[1] == 3
+    assert in_degree_histogram(m).sum() == m.num_nodes
+
+
+def test_line_graph_dual_matches_definition():
+    from dp_gsat_b200.data import line_graph_dual
+    # 4-node graph of the comment at reference src/datasets/mutag_dual.py:181-193
+    prim = np.array([[1, 2], [2, 1], [1, 3], [3, 1], [2, 4], [4, 2], [1, 4], [4, 1], [2, 3], [3, 2]]) - 1
+    ds, dd, ng = line_graph_dual(prim[:, 0], prim[:, 1], np.zeros(4, dtype=np.int64))
+    deg = np.bincount(prim[:, 0], minlength=4)
+    assert ds.shape[0] == int((deg * (deg - 1)).sum())
+    assert np.array_equal(ds[0::2], dd[1::2]) and np.array_equal(dd[0::2], ds[1::2])     # mutual reverses, adjacent
+    assert all(prim[a, 0] == prim[b, 0] for a, b in zip(ds, dd))                          # share the first endpoint
+
+
+def test_shard_bounds_balance_edges():
+    from dp_gsat_b200.data import ba2motifs_batch, shard_batch
+    b = ba2motifs_batch(64, seed=3)
+    parts = [shard_batch(b, r, 4) for r in range(4)]
+    assert sum(p.num_graphs for p in parts) == 64
+    assert sum(p.num_edges for p in parts) == b.num_edges
+    assert max(p.num_edges for p in parts) - min(p.num_edges for p in parts) <= 52
+    for p in parts:
+        assert int(p.edge_index.max()) < p.num_nodes and int(p.batch.max()) == p.num_graphs - 1

@@ -1,0 +1,150 @@
+"""CPU suite, part 1: the oracle against the golden vectors generated from the reference's own function bodies
+(tests/golden/make_golden.py), the Mutagenicity topology fixture and analytic known answers."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gsat_oracle as O
+from tests.conftest import GOLDEN
+
+
+@pytest.fixture(scope='module')
+def gold():
+    return torch.load(os.path.join(GOLDEN, 'ref_functions.pt'))
+
+
+def test_reorder_like_matches_reference_body(gold):
+    for name in ('kat4', 'rand_a', 'rand_b'):
+        ei, vals, out = (gold[f'reorder_like/{name}/{k}'] for k in ('edge_index', 'values', 'out'))
+        t_idx, t_val = O.transpose(ei, vals)
+        assert torch.equal(O.reorder_like(t_idx, ei, t_val), out)
+        rev = O.reverse_edge_permutation(ei)
+        assert torch.equal(vals[rev], out)                       # reorder_like(transpose(ei,v), ei, v) == v[rev]
+        idx = O.build_index_oracle(ei, torch.zeros(int(ei.max()) + 1, dtype=torch.long))
+        assert torch.equal(idx['rev'].long(), rev) and idx['symmetric'] and not idx['has_dup']
+
+
+def test_reorder_like_raises_on_directed():
+    ei = torch.tensor([[0, 1, 2], [1, 2, 0]])
+    assert not O.is_undirected(ei)
+    with pytest.raises(ValueError):
+        O.reorder_like(torch.stack([ei[1], ei[0]]), ei, torch.arange(3.))
+
+
+def test_concrete_sample_get_r_lift_gumbel_f1_against_reference(gold):
+    lg, u = gold['concrete/logits'], gold['concrete/u']
+    assert torch.allclose(O.concrete_sample(lg, 1, True, u), gold['concrete/train'], rtol=0, atol=0)
+    assert torch.equal(O.concrete_sample(lg, 1, False), gold['concrete/eval'])
+    for e, r in gold['get_r'].tolist():
+        assert O.get_r(10, 0.1, int(e), final_r=0.5) == pytest.approx(r, abs=0)
+    for e, r in gold['get_r_init07'].tolist():
+        assert O.get_r(10, 0.1, int(e), init_r=0.9, final_r=0.7) == pytest.approx(r, abs=0)
+    assert torch.equal(O.lift_node_att_to_edge_att(gold['lift/node_att'][:4], gold['lift/edge_index']), gold['lift/out'])
+    assert torch.equal(O.gumbel_sigmoid(lg, tau=0.1, noise_u=gold['gumbel/U']), gold['gumbel/out_tau0.1'])
+    assert torch.equal(O.f1_sparsity_loss(gold['f1/p'], gold['f1/y']), gold['f1/out'])
+
+
+def test_get_r_analytic():
+    assert O.get_r(10, 0.1, 25, final_r=0.5) == pytest.approx(0.7)
+    assert O.get_r(10, 0.1, 40, final_r=0.5) == pytest.approx(0.5)
+    assert O.get_r(10, 0.1, 400, final_r=0.5) == 0.5
+
+
+def test_criterion_mlp_extractor_loss_against_reference(gold):
+    crit = O.Criterion(2, False)
+    assert torch.equal(crit(gold['criterion/logits'], gold['criterion/y']), gold['criterion/out'])
+    mlp = O.MLP([16, 32, 8, 1], dropout=0.5)
+    mlp.load_state_dict(gold['mlp/state'])           # identical state_dict keys ('0','4','8')
+    mlp.eval()
+    assert torch.allclose(mlp(gold['mlp/x'], gold['mlp/batch']), gold['mlp/out_eval'], rtol=0, atol=0)
+    ex = O.ExtractorMLP(8, True)
+    ex.load_state_dict(gold['extractor/state'])
+    ex.eval()
+    out = ex(gold['extractor/emb'], gold['extractor/edge_index'], gold['extractor/batch'])
+    assert torch.allclose(out, gold['extractor/out_eval'], rtol=0, atol=0)
+    g = O.GSAT(None, None, crit, final_r=0.7, decay_interval=10, decay_r=0.1)
+    loss, ld = g.__loss__(gold['loss/att'], gold['criterion/logits'], gold['criterion/y'], int(gold['loss/epoch']))
+    assert torch.equal(loss, gold['loss/total'])
+    assert ld['pred'] == pytest.approx(float(gold['loss/pred']), abs=0)
+    assert ld['info'] == pytest.approx(float(gold['loss/info']), abs=0)
+
+
+def test_mutag_fixture_reverse_is_xor1():
+    from dp_gsat_b200.data import load_mutag_fixture
+    src, dst, ng = load_mutag_fixture(os.path.join(GOLDEN, 'mutag_slice.npz'))
+    ei = torch.from_numpy(np.stack([src, dst]))
+    assert O.is_undirected(ei)
+    rev = O.reverse_edge_permutation(ei)
+    assert torch.equal(rev, torch.arange(ei.shape[1]) ^ 1)
+    idx = O.build_index_oracle(ei, torch.from_numpy(ng))
+    assert idx['symmetric'] and idx['graph_contiguous'] and not idx['has_dup']
+    summ = json.load(open(os.path.join(GOLDEN, 'mutag_full_summary.json')))
+    assert summ['rev_is_xor1'] and summ['is_undirected'] and summ['slice_edges'] == ei.shape[1]
+
+
+def test_analytic_known_answers():
+    torch.manual_seed(0)
+    # info loss at att == r is ~0 ; concrete sample with u = 0.5 has no noise
+    a = torch.full((10, 1), 0.7)
+    assert abs(float(O.info_loss(a, 0.7))) < 1e-5
+    lg = torch.randn(9, 1)
+    assert torch.equal(O.concrete_sample(lg, 1, True, torch.full_like(lg, 0.5)), lg.sigmoid())
+    # GINConv with att == 1 equals plain GIN aggregation
+    ei = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]])
+    x = torch.randn(3, 4)
+    conv = O.GINConv(torch.nn.Identity())
+    assert torch.allclose(conv(x, ei, edge_atten=torch.ones(4, 1)), conv(x, ei))
+    # PNA: std of a constant segment is sqrt(1e-5); empty rows give 0 for min / max / mean
+    src = torch.ones(4, 2)
+    idx = torch.tensor([0, 0, 2, 2])
+    assert torch.allclose(O.aggregate_std(src, idx, 4)[0], torch.full((2,), 1e-5).sqrt())
+    assert torch.equal(O.scatter_min(src, idx, 4)[1], torch.zeros(2))
+    assert torch.equal(O.scatter_max(src, idx, 4)[3], torch.zeros(2))
+    assert torch.equal(O.scatter_mean(src, idx, 4)[1], torch.zeros(2))
+    # InstanceNorm: per-graph zero mean / unit (biased) variance
+    xn = O.InstanceNorm(3)(torch.randn(20, 3), torch.tensor([0] * 8 + [1] * 12))
+    assert torch.allclose(xn[:8].mean(0), torch.zeros(3), atol=1e-6)
+    assert torch.allclose(xn[8:].var(0, unbiased=False), torch.ones(3), atol=1e-3)
+
+
+def test_oracle_gradcheck_fp64():
+    """fp64 gradcheck of the oracle's differentiable pieces."""
+    torch.manual_seed(0)
+    ei = torch.tensor([[0, 1, 1, 2, 2, 3, 3, 0], [1, 0, 2, 1, 3, 2, 0, 3]])
+    x = torch.randn(4, 4, dtype=torch.double, requires_grad=True)
+    att = torch.rand(8, 1, dtype=torch.double, requires_grad=True)
+    conv = O.GINConv(torch.nn.Identity()).double()
+    assert torch.autograd.gradcheck(lambda a, b: conv(a, ei, edge_atten=b), (x, att))
+    lg = torch.randn(8, 1, dtype=torch.double, requires_grad=True)
+    u = torch.rand(8, 1, dtype=torch.double).clamp(1e-3, 1 - 1e-3)
+    f = lambda l: O.info_loss(O.undirected_average(O.concrete_sample(l, 1, True, u), ei), 0.7)
+    assert torch.autograd.gradcheck(f, (lg,))
+    inorm = O.InstanceNorm(4)
+    seg = torch.tensor([0, 0, 0, 1, 1, 1, 1, 1])
+    z = torch.randn(8, 4, dtype=torch.double, requires_grad=True)
+    assert torch.autograd.gradcheck(lambda t: inorm(t, seg), (z,))
+
+
+def test_oracle_step_runs_and_is_deterministic():
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(8, seed=0)
+    cfg = {'model_name': 'GIN', 'hidden_size': 16, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    outs = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        clf = O.get_model(10, 0, 2, False, cfg)
+        ext = O.ExtractorMLP(16, {'learn_edge_att': True, 'extractor_dropout_p': 0.5})
+        ms = O.MaskSource(2)
+        clf.masks = ms
+        ext.masks = ms
+        g = O.GSAT(clf, ext, O.Criterion(2, False), learn_edge_att=True, final_r=0.5)
+        g.train()
+        u = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
+        edge_att, loss, ld, logits = g.forward_pass(b, 0, True, noise_u=u)
+        loss.backward()
+        outs.append((edge_att.detach(), loss.detach(), clf.convs[0].nn[0].weight.grad.clone()))
+    assert all(torch.equal(a, c) for a, c in zip(*outs))
+    assert outs[0][0].shape == (b.num_edges, 1) and torch.isfinite(outs[0][1])
