@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: GSAT-GIN training-step throughput in directed edges / second on the large synthetic
+BA-motif batch (BASELINE.json configs[3]: ~10 M edges, hidden 128), graph-sharded data-parallel at N GPUs.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on the host cores
+
+A step = forward_pass(training=True) (both GNN passes, extractor, sampler, reverse-average, losses) + backward +
+gradient all-reduce (N>1) + Adam step.  `value` is measured with the shard resident in HBM; `e2e` is measured through
+the public API from pinned HOST buffers (H2D of the batch + index build + step + D2H of the loss inside the timed
+region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'gsat_gin_train_step_directed_edges_per_sec'
+UNIT = 'edges/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--graphs', type=int, default=196000, help='BA-2Motifs-shaped graphs in the global batch (cfg4)')
+    ap.add_argument('--hidden', type=int, default=128)
+    ap.add_argument('--layers', type=int, default=2)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-graphs', type=int, default=0, help='0 = size automatically (~10-30 s of CPU work)')
+    return ap.parse_args()
+
+
+def model_cfg(a):
+    return ({'model_name': 'GIN', 'hidden_size': a.hidden, 'n_layers': a.layers, 'dropout_p': 0.3,
+             'use_edge_attr': False}, {'learn_edge_att': True, 'extractor_dropout_p': 0.5})
+
+
+def workload_name(a):
+    return f'cfg4 large synthetic BA-2Motifs batch: {a.graphs} graphs, GSAT-GIN hidden {a.hidden}, {a.layers} layers'
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU path (the oracle port of the reference's algorithm) -- cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(a, n_graphs, steps, warmup, threads):
+    """edges/s of the oracle's training step on `n_graphs` BA-2Motifs graphs, host cores."""
+    from oracle import gsat_oracle as O
+    from dp_gsat_b200.data import ba2motifs_batch
+    torch.set_num_threads(threads)
+    cfg, shared = model_cfg(a)
+    torch.manual_seed(0)
+    b = ba2motifs_batch(n_graphs, seed=0)
+    clf = O.get_model(b.x.shape[1], 0, 2, False, cfg)
+    ext = O.ExtractorMLP(a.hidden, shared)
+    g = O.GSAT(clf, ext, O.Criterion(2, False), learn_edge_att=True, final_r=0.5)
+    g.train()
+    opt = torch.optim.Adam(list(ext.parameters()) + list(clf.parameters()), lr=1e-3)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, loss, _, _ = g.forward_pass(b, 0, True)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return b.num_edges * len(times) / tot, b.num_edges, tot / len(times)
+
+
+def auto_cpu_sample(a, threads, budget_s):
+    """Pick a sample size whose (warmup + steps) oracle run costs about budget_s, from a small probe."""
+    rate, _, _ = cpu_oracle_rate(a, 200, 1, 1, threads)
+    return rate
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    probe_rate = auto_cpu_sample(a, threads, 0)
+    total_steps = a.steps + a.warmup
+    budget = 150.0
+    n_graphs = a.cpu_sample_graphs or int(max(200, min(20000, probe_rate * budget / total_steps / 51.0)))
+    rate, n_edges, sec = cpu_oracle_rate(a, n_graphs, a.steps, a.warmup, threads)
+    cfg = {'workload': workload_name(a), 'hidden': a.hidden, 'layers': a.layers, 'global_graphs': a.graphs,
+           'sample': f'{n_graphs} graphs / {n_edges} edges per step (bounded sample of the same generator)'}
+    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': cfg['sample'] + '; oracle/gsat_oracle.py (pure-PyTorch restatement; the '
+                             'reference cannot be imported: torch_geometric/torch_scatter/torch_sparse absent)'},
+            'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import dp_gsat_b200 as G
+    from dp_gsat_b200._lib import lib
+    from dp_gsat_b200.data import ba2motifs_batch, shard_batch
+    from dp_gsat_b200.parallel import TrainStep, broadcast_parameters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, shared = model_cfg(a)
+    full = ba2motifs_batch(a.graphs, seed=0)
+    E_global = full.num_edges
+    shard_host = shard_batch(full, rank, world).pin_memory()
+    del full
+    torch.manual_seed(0)
+    clf = G.get_model(shard_host.x.shape[1], 0, 2, False, cfg, dev)
+    ext = G.ExtractorMLP(a.hidden, shared).to(dev)
+    broadcast_parameters(clf)
+    broadcast_parameters(ext)
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5, lazy_metrics=True)
+    gsat.train()
+    step = TrainStep(gsat, lr=1e-3)
+    data = shard_host.to(dev)
+    N_loc, E_loc, H = data.num_nodes, data.num_edges, a.hidden
+
+    for _ in range(a.warmup):
+        step(data, 0)
+    barrier()
+
+    L = lib()
+    L.timer = {'gsatb_gin_aggregate_fwd': [], 'gsatb_gin_aggregate_bwd': []}
+    launches0 = L.launches
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        _, loss, _, _ = step(data, 0)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clk = clocks.stop() if rank == 0 else None
+    launches = L.launches - launches0
+    timer, L.timer = L.timer, None
+    ms_step = float(ms.item()) / a.steps
+    value = E_global / (ms_step * 1e-3)
+
+    # roofline of the dominant kernel of ours: K3 forward (gather-scale-segmented-sum), measured live above
+    fwd_ms = [s.elapsed_time(e) for s, e in timer['gsatb_gin_aggregate_fwd']]
+    bwd_ms = [s.elapsed_time(e) for s, e in timer['gsatb_gin_aggregate_bwd']]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    alg_fwd = 8.0 * N_loc * H + 8.0 * E_loc + 4.0 * N_loc
+    alg_bwd = 12.0 * N_loc * H + 16.0 * E_loc
+    avg_fwd = sum(fwd_ms) / max(len(fwd_ms), 1)
+    avg_bwd = sum(bwd_ms) / max(len(bwd_ms), 1)
+    ach = alg_fwd / (avg_fwd * 1e-3) / 1e9 if avg_fwd > 0 else 0.0
+    roofline = {'kernel': 'k_gin_aggregate_fwd (K3)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                'frac': ach / peak, 'traffic': None,
+                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback 6650 GB/s',
+                'algorithmic_bytes_per_launch': alg_fwd, 'avg_launch_ms': avg_fwd, 'launches_timed': len(fwd_ms),
+                'frac_of_nominal_8TBs': ach / 8000.0,
+                'k3_bwd': {'achieved': alg_bwd / (avg_bwd * 1e-3) / 1e9 if avg_bwd > 0 else 0.0,
+                           'algorithmic_bytes_per_launch': alg_bwd, 'avg_launch_ms': avg_bwd},
+                'share_of_step': (sum(fwd_ms) + sum(bwd_ms)) / a.steps / ms_step}
+
+    # end-to-end through the public API from pinned host buffers
+    G.clear_index_cache()
+    e2e_steps = max(1, a.e2e_steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d = shard_host.to(dev, non_blocking=True)          # H2D of this step's inputs
+        _, loss, _, _ = step(d, 0)                          # index build (K0) + step
+        loss_host = float(loss.item())                      # D2H of the step's result
+    barrier()
+    t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e = {'value': E_global / float(t_e2e.item()), 'unit': UNIT, 'h2d_bytes_per_step': shard_host.nbytes() * world,
+           'd2h_bytes_per_step': 4 * world, 'ms_per_step': float(t_e2e.item()) * 1e3, 'steps': e2e_steps,
+           'last_loss': loss_host}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        probe = auto_cpu_sample(a, threads, 0)
+        n_graphs = a.cpu_sample_graphs or int(max(200, min(8000, probe * 20.0 / 3 / 51.0)))
+        rate, n_edges, sec = cpu_oracle_rate(a, n_graphs, 2, 1, threads)
+        cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                        'sample': f'{n_graphs} graphs / {n_edges} edges per step of the same generator, 1 warm-up + 2 '
+                                  f'timed steps, {sec:.2f} s/step; oracle/gsat_oracle.py on torch CPU'}
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(a), 'global_edges': E_global, 'global_nodes': a.graphs * 25,
+                           'hidden': a.hidden, 'layers': a.layers, 'parallelism': f'graph-sharded dp{world}',
+                           'l2_policy': 'inputs larger than L2 (per-rank activations >> 126 MB)'},
+                'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': launches,
+                'clocks': clk}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)

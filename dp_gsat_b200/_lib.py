@@ -62,6 +62,8 @@ class _Lib:
             fn.restype = restype
             fn.argtypes = argtypes
         self._device_checked = False
+        self.launches = 0          # kernels launched through this library (bench.py reports the timed-region delta)
+        self.timer = None          # optional {entry name: [(start_event, end_event), ...]} filled by call()
 
     def strerror(self, code: int) -> str:
         return self.cdll.gsatb_strerror(code).decode()
@@ -76,10 +78,23 @@ class _Lib:
             raise RuntimeError(f'dp_gsat_b200: {self.strerror(rc)}')
         self._device_checked = True
 
+    # kernels launched per C-ABI call (index_build: see csrc/index_build.cu -- 5 fixed + 2 orders x (2 sorts x
+    # 3 kernels x passes + 3) + 1; counted with passes=3)
+    KERNELS_PER_CALL = {'gsatb_index_build': 5 + 2 * (2 * 3 * 3 + 3) + 1, 'gsatb_sample_avg_info_fwd': 2}
+
     def call(self, name: str, *args):
         """Call an int-returning entry point; raise on a non-zero code."""
         self.check_device()
-        rc = getattr(self.cdll, name)(*args)
+        self.launches += self.KERNELS_PER_CALL.get(name, 1)
+        t = self.timer
+        if t is not None and name in t:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()                      # on torch's current stream == the stream the kernel is launched on
+            rc = getattr(self.cdll, name)(*args)
+            e1.record()
+            t[name].append((e0, e1))
+        else:
+            rc = getattr(self.cdll, name)(*args)
         if rc != 0:
             msg = f'{name} failed: {self.strerror(rc)} (code {rc})'
             if rc in (-1, -2, -3, -6):

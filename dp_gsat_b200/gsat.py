@@ -144,6 +144,7 @@ class GSAT(tnn.Module):
         self.pred_loss_coef, self.info_loss_coef = pred_loss_coef, info_loss_coef
         self.lazy_metrics = lazy_metrics
         self.seed = seed
+        self.pred_scale = self.info_scale = 1.0   # data-parallel shard weights (G_local/G_global, E_local/E_global)
         self._step = 0
         try:
             self.device = next(self.parameters()).device
@@ -151,8 +152,8 @@ class GSAT(tnn.Module):
             self.device = torch.device('cuda')
 
     def __loss__(self, info_mean, clf_logits, clf_labels, epoch):
-        pred_loss = self.criterion(clf_logits, clf_labels) * self.pred_loss_coef
-        il = info_mean * self.info_loss_coef
+        pred_loss = self.criterion(clf_logits, clf_labels) * (self.pred_loss_coef * self.pred_scale)
+        il = info_mean * (self.info_loss_coef * self.info_scale)
         loss = pred_loss + il
         if self.lazy_metrics:
             loss_dict = {'loss': loss.detach(), 'pred': pred_loss.detach(), 'info': il.detach()}

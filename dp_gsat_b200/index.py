@@ -18,7 +18,7 @@ from ._lib import lib, ptr, stream
 class GraphIndex:
     __slots__ = ('N', 'E', 'G', 'src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src',
                  'eid_by_src', 'dst_by_src', 'node_ptr', 'edge_ptr', 'node_graph', 'edge_graph', 'flags_dev',
-                 '_flags_host', 'device')
+                 '_flags_host', 'device', '_plans')
 
     def __init__(self, edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: Optional[int] = None):
         if not edge_index.is_cuda:
@@ -54,6 +54,7 @@ class GraphIndex:
                    ptr(self.edge_ptr), ptr(self.node_graph), ptr(self.edge_graph), ptr(self.flags_dev), ptr(ws),
                    ctypes.c_size_t(ws_bytes), stream())
         self._flags_host = None
+        self._plans = None
 
     # flags are read once (one D2H of 16 bytes), not every step
     @property
@@ -76,6 +77,29 @@ class GraphIndex:
     @property
     def graph_contiguous(self) -> bool:
         return self.flags[2] == 0
+
+    def chunk_plan(self, max_rows: int, by: str = 'edge'):
+        """Graph-aligned row ranges of at most ~max_rows rows (edges or nodes) with rebased segment pointers:
+        [(r0, r1, seg_ptr_local int32 [g1-g0+1], g1-g0)].  Computed once per index (one small D2H copy)."""
+        key = (by, int(max_rows))
+        plans = getattr(self, '_plans', None)
+        if plans is None:
+            plans = self._plans = {}
+        if key not in plans:
+            self.require_graph_contiguous()
+            ptr_dev = self.edge_ptr if by == 'edge' else self.node_ptr
+            ptr_host = ptr_dev.cpu().numpy().astype('int64')
+            out, g0 = [], 0
+            G = self.G
+            while g0 < G:
+                import numpy as np
+                g1 = int(np.searchsorted(ptr_host, ptr_host[g0] + max_rows, side='right')) - 1
+                g1 = min(max(g1, g0 + 1), G)
+                r0, r1 = int(ptr_host[g0]), int(ptr_host[g1])
+                out.append((r0, r1, (ptr_dev[g0:g1 + 1] - r0).contiguous(), g1 - g0))
+                g0 = g1
+            plans[key] = out
+        return plans[key]
 
     def require_graph_contiguous(self):
         if not self.graph_contiguous:

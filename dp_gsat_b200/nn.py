@@ -257,6 +257,7 @@ class ExtractorMLP(tnn.Module):
             mlp = MLP([hidden_size * 1, hidden_size * 2, hidden_size, 1], dropout=dropout_p)
         setattr(self, self._name, mlp)
         self.masks = None
+        self.chunk_rows = 1 << 21      # rows per graph-aligned chunk (0 = never chunk)
 
     def forward(self, emb, edge_index, batch, type: Optional[str] = None):
         if type is not None and type != self.kind:
@@ -266,8 +267,20 @@ class ExtractorMLP(tnn.Module):
         gi.require_graph_contiguous()
         if self.learn_edge_att:
             f12 = ops.gather_concat(emb, gi)      # cat(emb[col], emb[row]) with col, row = edge_index
-            return mlp(f12, None, seg=(gi.edge_ptr, gi.G), masks=self.masks)
-        return mlp(emb, None, seg=(gi.node_ptr, gi.G), masks=self.masks)
+            rows, seg_all = f12, (gi.edge_ptr, gi.G)
+        else:
+            rows, seg_all = emb, (gi.node_ptr, gi.G)
+        if self.chunk_rows and rows.shape[0] > self.chunk_rows and self.masks is None:
+            # InstanceNorm is per graph, so graph-aligned row ranges are independent: run them one after the other
+            # and recompute each range in backward, which bounds the [rows, 4H] activations held at any time
+            from torch.utils.checkpoint import checkpoint
+            outs = []
+            for r0, r1, seg_ptr, ng in gi.chunk_plan(self.chunk_rows, 'edge' if self.learn_edge_att else 'node'):
+                fn = lambda t, sp=seg_ptr, n=ng: mlp(t, None, seg=(sp, n))
+                outs.append(checkpoint(fn, rows[r0:r1], use_reentrant=False) if torch.is_grad_enabled()
+                            else fn(rows[r0:r1]))
+            return torch.cat(outs, dim=0)
+        return mlp(rows, None, seg=seg_all, masks=self.masks)
 
 
 def get_model(x_dim, edge_attr_dim, num_class, multi_label, model_config, device):

@@ -624,12 +624,13 @@ class GSAT(nn.Module):
         self.final_r, self.decay_interval, self.decay_r, self.init_r = final_r, decay_interval, decay_r, init_r
         self.info_on = info_on
         self.pred_loss_coef, self.info_loss_coef = pred_loss_coef, info_loss_coef
+        self.pred_scale = self.info_scale = 1.0   # data-parallel shard weights (G_local/G_global, E_local/E_global)
 
     def __loss__(self, att, clf_logits, clf_labels, epoch, r=None):
-        pred_loss = self.criterion(clf_logits, clf_labels) * self.pred_loss_coef
+        pred_loss = self.criterion(clf_logits, clf_labels) * (self.pred_loss_coef * self.pred_scale)
         if r is None:
             r = get_r(self.decay_interval, self.decay_r, epoch, init_r=self.init_r, final_r=self.final_r)
-        il = info_loss(att, r) * self.info_loss_coef
+        il = info_loss(att, r) * (self.info_loss_coef * self.info_scale)
         loss = pred_loss + il
         return loss, {'loss': loss.item(), 'pred': pred_loss.item(), 'info': il.item()}
 
