@@ -1,0 +1,310 @@
+// Persistent, warp-specialised tcgen05 GEMM skeleton shared by every dense layer of the path (node MLPs, extractor
+// MLP, their backward dX products).  "Swap-AB" orientation:
+//
+//      D^T[out channel (TMEM lane), row (TMEM column)]  =  W[out, K] (A operand)  x  X[row, K]^T (B operand)
+//
+// so that one epilogue thread owns one output CHANNEL and walks the 128 rows (nodes / edges) of the tile in its
+// registers: per-channel reductions over rows -- BatchNorm batch statistics, per-graph InstanceNorm statistics,
+// bias gradients -- are thread-local, with no shuffles and no atomics.
+//
+//   warp 0      TMA producer: streams W in [128 x 64] bf16 K-blocks (SWIZZLE_128B) through an mbarrier ring
+//   warp 1      MMA issuer: one elected thread, tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128 N=128 K=16
+//   warp 2      TMEM allocator (256 columns = two 128-column accumulators, double-buffered across M-blocks)
+//   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+//   warps 8-15  B-operand producers: global (fp32 / bf16 / gathered rows) -> fused prologue -> bf16 -> swizzled smem
+//
+// A tile = up to 128 rows; for the extractor the tiles are graph-aligned (whole graphs per tile) so that the
+// per-graph InstanceNorm closes inside the tile.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace tcg {
+
+constexpr int TILE_ROWS = 128;
+constexpr int KBLK = 64;                      // bf16 elements per 128-byte swizzle row
+constexpr int BLK_BYTES = TILE_ROWS * 128;    // one [128 x 64] bf16 K-block = 16 KiB
+constexpr int THREADS = 512;
+constexpr int EPI_WARP0 = 4, PRO_WARP0 = 8, PRO_WARPS = 8;
+constexpr int PRO_UNROLL = 8;                 // row-chunks whose global loads one producer thread keeps in flight
+constexpr int MAX_SEG = 32;                   // graphs per tile the InstanceNorm epilogues support
+
+struct Tiling {
+    int64_t rows;               // total rows
+    int num_tiles;
+    const int32_t* tile_row;    // [num_tiles + 1] first row of each tile (nullptr: uniform 128-row tiles)
+    const int32_t* tile_seg;    // [num_tiles + 1] first graph of each tile (InstanceNorm epilogues), nullable
+    const int32_t* seg_ptr;     // [G + 1] row offsets of the graphs, nullable
+};
+
+struct Shape {
+    int K, KB;      // reduction size and its 64-blocks
+    int OUT, NMB;   // output channels and their 128-blocks
+    int NA;         // W ring stages
+    int NBUF;       // B tile buffers (2 when they fit, else 1)
+};
+
+struct SmemLayout {
+    uint32_t a_off, b_off, bar_off, misc_off, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const Shape& s) {
+    SmemLayout l;
+    l.a_off = 0;
+    l.b_off = l.a_off + (uint32_t)s.NA * BLK_BYTES;
+    l.bar_off = l.b_off + (uint32_t)s.NBUF * s.KB * BLK_BYTES;
+    l.misc_off = l.bar_off + 256;
+    l.total = l.misc_off + 1024 + 1024;   // + slack for the manual 1024-byte alignment of the base
+    return l;
+}
+
+__device__ __forceinline__ void tile_range(const Tiling& t, int tile, int64_t& r0, int& cnt) {
+    if (t.tile_row) {
+        r0 = t.tile_row[tile];
+        cnt = t.tile_row[tile + 1] - (int)r0;
+    } else {
+        r0 = (int64_t)tile * TILE_ROWS;
+        int64_t left = t.rows - r0;
+        cnt = left < TILE_ROWS ? (int)left : TILE_ROWS;
+    }
+}
+
+// The kernel.  `Op` supplies:
+//    struct Params                               (copied by value into the kernel)
+//    struct EpiState                             (per-thread state living across tiles)
+//    struct Raw; static void load8(P, grow, k, K, Raw&)              issue the global loads of 8 consecutive k of a row
+//    static void transform8(P, Raw, grow, k, K, uint32_t out[4])     fused prologue -> 8 bf16
+//    static void epi_init(P, EpiState&, ch)
+//    static void epilogue(P, EpiState&, taddr, ch, ch_valid, r0, cnt, tile, misc smem, lane/warp ids)
+//    static void epi_finish(P, EpiState&, ch, ch_valid)
+template <class Op>
+__global__ void __launch_bounds__(THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Shape sh, const typename Op::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const SmemLayout L = smem_layout(sh);
+    uint8_t* sA = smem + L.a_off;
+    uint8_t* sB = smem + L.b_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* a_full = bars;             // [NA]  (NA <= 8)
+    uint64_t* a_empty = bars + 8;        // [NA]
+    uint64_t* b_full = bars + 16;        // [2]
+    uint64_t* b_empty = bars + 18;       // [2]
+    uint64_t* acc_full = bars + 20;      // [2]
+    uint64_t* acc_empty = bars + 22;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint8_t* misc = smem + L.misc_off;   // 1 KiB scratch for the epilogue (segment tables)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_w);
+        for (int i = 0; i < sh.NA; ++i) {
+            tc::mbar_init(&a_full[i], 1);
+            tc::mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&b_full[i], PRO_WARPS * 32);
+            tc::mbar_init(&b_empty[i], 1);
+            tc::mbar_init(&acc_full[i], 1);
+            tc::mbar_init(&acc_empty[i], 128);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, 256);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: W K-blocks =====================
+        if (lane == 0) {
+            uint32_t ca = 0;
+            for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
+                for (int mb = 0; mb < sh.NMB; ++mb) {
+                    for (int kb = 0; kb < sh.KB; ++kb, ++ca) {
+                        const uint32_t s = ca % sh.NA, use = ca / sh.NA;
+                        tc::mbar_wait(&a_empty[s], (use & 1) ^ 1);
+                        tc::mbar_arrive_expect_tx(&a_full[s], BLK_BYTES);
+                        tc::tma_load_2d(sA + s * BLK_BYTES, &tmap_w, &a_full[s], kb * KBLK, mb * TILE_ROWS);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, TILE_ROWS);
+            uint32_t ca = 0, cm = 0, it = 0;
+            for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
+                tc::mbar_wait(&b_full[buf], ub & 1);
+                tc::tc_fence_after();
+                const uint32_t b_base = tc::smem_u32(sB + (size_t)buf * sh.KB * BLK_BYTES);
+                for (int mb = 0; mb < sh.NMB; ++mb, ++cm) {
+                    const uint32_t slot = cm & 1, us = cm >> 1;
+                    tc::mbar_wait(&acc_empty[slot], (us & 1) ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + slot * 128;
+                    for (int kb = 0; kb < sh.KB; ++kb, ++ca) {
+                        const uint32_t s = ca % sh.NA, use = ca / sh.NA;
+                        tc::mbar_wait(&a_full[s], use & 1);
+                        tc::tc_fence_after();
+                        const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(sA + s * BLK_BYTES));
+                        const uint64_t b_desc = tc::make_desc_k_sw128(b_base + kb * BLK_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte row
+                            tc::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
+                                            (kb | k4) != 0);
+                        tc::mma_commit(&a_empty[s]);        // ring slot free once these MMAs have read it
+                    }
+                    tc::mma_commit(&acc_full[slot]);        // accumulator complete -> epilogue
+                }
+                tc::mma_commit(&b_empty[buf]);              // B tile buffer free -> producers
+            }
+        }
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+        // ===================== epilogue =====================
+        const int q = warp - EPI_WARP0;                     // TMEM lane quarter this warp may access
+        typename Op::EpiState st;
+        uint32_t ce = 0;
+        bool first = true;
+        for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
+            int64_t r0;
+            int cnt;
+            tile_range(tl, tile, r0, cnt);
+            for (int mb = 0; mb < sh.NMB; ++mb, ++ce) {
+                const uint32_t slot = ce & 1, us = ce >> 1;
+                const int ch = mb * 128 + q * 32 + lane;
+                if (first || sh.NMB > 1) Op::epi_init(p, st, ch, ch < sh.OUT, first);
+                tc::mbar_wait(&acc_full[slot], us & 1);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
+                Op::epilogue(p, tl, st, taddr, ch, ch < sh.OUT, r0, cnt, tile, misc, q, lane);
+                tc::tc_fence_before();
+                tc::mbar_arrive(&acc_empty[slot]);
+                if (sh.NMB > 1) Op::epi_finish(p, st, ch, ch < sh.OUT, false);
+            }
+            first = false;
+        }
+        if (sh.NMB == 1) Op::epi_finish(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true);
+    } else if (warp >= PRO_WARP0) {
+        // ===================== B-operand producers =====================
+        const int pt = threadIdx.x - PRO_WARP0 * 32;        // 0..255
+        const int r_in = (pt & 31) >> 3, c_in = pt & 7, pw = pt >> 5;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x, ++it) {
+            int64_t r0;
+            int cnt;
+            tile_range(tl, tile, r0, cnt);
+            const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
+            tc::mbar_wait(&b_empty[buf], (ub & 1) ^ 1);
+            uint8_t* bt = sB + (size_t)buf * sh.KB * BLK_BYTES;
+            // work unit = (K-block, group of 4 rows): 8 lanes cover the 8 16-byte chunks of one 128-byte row.
+            // PRO_UNROLL units are loaded back to back before any is transformed, to keep HBM requests in flight.
+            const int units = sh.KB * (TILE_ROWS / 4);
+            for (int u0 = pw; u0 < units; u0 += PRO_WARPS * PRO_UNROLL) {
+                typename Op::Raw raw[PRO_UNROLL];
+#pragma unroll
+                for (int j = 0; j < PRO_UNROLL; ++j) {
+                    const int u = u0 + j * PRO_WARPS;
+                    const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
+                    const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
+                    if (u < units && row < cnt && k < sh.K) Op::load8(p, r0 + row, k, sh.K, raw[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < PRO_UNROLL; ++j) {
+                    const int u = u0 + j * PRO_WARPS;
+                    if (u < units) {
+                        const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
+                        const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
+                        uint32_t o[4] = {0u, 0u, 0u, 0u};
+                        if (row < cnt && k < sh.K) Op::transform8(p, raw[j], r0 + row, k, sh.K, o);
+                        *reinterpret_cast<uint4*>(bt + (size_t)kb * BLK_BYTES + tc::sw128_offset(row, c_in * 8)) =
+                            make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+            }
+            tc::fence_proxy_async_smem();
+            tc::mbar_arrive(&b_full[buf]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 256);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled get_encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (PFN_tmapEncodeTiled)ptr;
+    }
+    return fn;
+}
+
+// W padded bf16 [rows_pad (multiple of 128), k_pad (multiple of 64)] row-major -> [128 x 64] SWIZZLE_128B boxes
+inline int make_weight_tmap(CUtensorMap* tm, const void* w, int rows_pad, int k_pad) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn) return GSATB_ELAUNCH;
+    cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)rows_pad};
+    cuuint64_t gstride[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {KBLK, TILE_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GSATB_OK : GSATB_EINVAL;
+}
+
+inline Shape make_shape(int K, int OUT) {
+    Shape s;
+    s.K = K;
+    s.KB = (K + KBLK - 1) / KBLK;
+    s.OUT = OUT;
+    s.NMB = (OUT + 127) / 128;
+    const int budget = 227 * 1024 - 256 - 2048 - 1024;
+    s.NBUF = (2 * s.KB * BLK_BYTES + 4 * BLK_BYTES <= budget) ? 2 : 1;
+    int na = (budget - s.NBUF * s.KB * BLK_BYTES) / BLK_BYTES;
+    s.NA = na > 8 ? 8 : na;
+    return s;
+}
+
+template <class Op>
+int launch(const void* w_bf16_padded, const Tiling& tl, int K, int OUT, const typename Op::Params& p,
+           cudaStream_t st) {
+    if (tl.num_tiles <= 0) return GSATB_OK;
+    Shape sh = make_shape(K, OUT);
+    if (sh.KB > 8 || sh.NA < 2) return GSATB_ESHAPE;
+    CUtensorMap tm;
+    int rc = make_weight_tmap(&tm, w_bf16_padded, sh.NMB * 128, sh.KB * KBLK);
+    if (rc != GSATB_OK) return rc;
+    SmemLayout L = smem_layout(sh);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_tc_gemm<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return GSATB_ELAUNCH;
+        attr_set = true;
+    }
+    int grid = tl.num_tiles < GSATB_NUM_SMS ? tl.num_tiles : GSATB_NUM_SMS;
+    k_tc_gemm<Op><<<grid, THREADS, L.total, st>>>(tm, tl, sh, p);
+    if (cudaPeekAtLastError() != cudaSuccess) return GSATB_ELAUNCH;
+    return GSATB_OK;
+}
+
+}  // namespace tcg

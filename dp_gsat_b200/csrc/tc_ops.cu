@@ -1,0 +1,167 @@
+// Dense layers of the path on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), built on tc_gemm.cuh.
+//
+// Precision contract: operands are rounded to bf16 (8-bit mantissa), products are accumulated in fp32 in TMEM.
+// The parity bound for these ops is therefore the documented "bf16 MLP" tolerance (tests/test_gpu_tc.py), not the
+// rtol 1e-5 of the fp32 gather / scatter / sampler kernels.
+#include <cuda_bf16.h>
+#include "tc_gemm.cuh"
+
+namespace {
+
+using namespace tcg;
+
+__device__ __forceinline__ void load8_f32(const float* __restrict__ src, int k, int K, float v[8]) {
+    if (k + 8 <= K && ((reinterpret_cast<uintptr_t>(src + k) & 15u) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src + k + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldg(src + k + i) : 0.f;
+    }
+}
+__device__ __forceinline__ void pack8(const float v[8], uint32_t o[4]) {
+    o[0] = tc::pack_bf16(v[0], v[1]);
+    o[1] = tc::pack_bf16(v[2], v[3]);
+    o[2] = tc::pack_bf16(v[4], v[5]);
+    o[3] = tc::pack_bf16(v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// OpLinear:  out[row, ch] = act( x[row, :] . W[ch, :] + bias[ch] )          (nn.Linear; x fp32, out fp32)
+//   optional per-channel column statistics  sum(z), sum(z^2)  over all rows (BatchNorm batch stats), written as
+//   per-CTA partials [gridDim][2][OUT] and reduced in a fixed order by k_reduce_partials (deterministic).
+// ------------------------------------------------------------------------------------------------------------
+struct OpLinear {
+    struct Params {
+        const float* x;
+        int ldx;
+        const float* in_scale;   // [K] optional fused prologue  relu(x * scale + shift)  (BatchNorm + ReLU folded)
+        const float* in_shift;
+        const float* bias;       // [OUT] nullable
+        float* out;
+        int ldo;
+        int relu_out;
+        float* stat_partials;    // nullable
+        int OUT;
+    };
+    struct EpiState {
+        float s1, s2;
+    };
+    struct Raw {
+        float v[8];
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
+        load8_f32(p.x + grow * p.ldx, k, K, r.v);
+    }
+    __device__ static void transform8(const Params& p, Raw& r, int64_t, int k, int K, uint32_t o[4]) {
+        if (p.in_scale) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (k + i < K) r.v[i] = fmaxf(fmaf(r.v[i], __ldg(p.in_scale + k + i), __ldg(p.in_shift + k + i)), 0.f);
+        }
+        pack8(r.v, o);
+    }
+    __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int cnt, int, uint8_t*, int, int) {
+        const float b = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tc::tmem_ld_32x32(taddr + c * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                if (col < cnt) {
+                    float z = v[j] + b;
+                    st.s1 += z;
+                    st.s2 = fmaf(z, z, st.s2);
+                    if (p.relu_out) z = fmaxf(z, 0.f);
+                    if (ch_ok) p.out[(r0 + col) * p.ldo + ch] = z;
+                }
+            }
+        }
+    }
+    __device__ static void epi_finish(const Params& p, EpiState& st, int ch, bool ch_ok, bool) {
+        if (p.stat_partials && ch_ok) {
+            p.stat_partials[((size_t)blockIdx.x * 2 + 0) * p.OUT + ch] = st.s1;
+            p.stat_partials[((size_t)blockIdx.x * 2 + 1) * p.OUT + ch] = st.s2;
+        }
+    }
+};
+
+// fp32 [OUT, K] (or its transpose) -> zero-padded bf16 [pad128(rows), pad64(cols)]
+__global__ void k_prep_weight(const float* __restrict__ w, int OUT, int K, int transpose, __nv_bfloat16* __restrict__ wp,
+                              int rows_pad, int cols_pad) {
+    const int total = rows_pad * cols_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / cols_pad, c = i % cols_pad;
+        float v = 0.f;
+        if (!transpose) {
+            if (r < OUT && c < K) v = w[(size_t)r * K + c];
+        } else {
+            if (r < K && c < OUT) v = w[(size_t)c * K + r];
+        }
+        wp[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// out[j] = sum over parts (fixed order, fp64 accumulate) of partials[part][j]
+__global__ void k_reduce_partials(const float* __restrict__ partials, int parts, int width, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= width) return;
+    double acc = 0.0;
+    for (int q = 0; q < parts; ++q) acc += (double)partials[(size_t)q * width + j];
+    out[j] = acc;
+}
+
+inline Tiling uniform_tiling(int64_t rows) {
+    Tiling t;
+    t.rows = rows;
+    t.num_tiles = (int)((rows + TILE_ROWS - 1) / TILE_ROWS);
+    t.tile_row = nullptr;
+    t.tile_seg = nullptr;
+    t.seg_ptr = nullptr;
+    return t;
+}
+
+}  // namespace
+
+extern "C" int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpose, void* wp, gsatb_stream_t stream) {
+    if (!w || !wp || OUT <= 0 || K <= 0) return GSATB_EINVAL;
+    const int rows = transpose ? K : OUT, cols = transpose ? OUT : K;
+    const int rows_pad = (rows + 127) / 128 * 128, cols_pad = (cols + 63) / 64 * 64;
+    k_prep_weight<<<(rows_pad * cols_pad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        w, OUT, K, transpose, (__nv_bfloat16*)wp, rows_pad, cols_pad);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" size_t gsatb_tc_stat_partials_elems(int OUT) { return (size_t)GSATB_NUM_SMS * 2 * OUT; }
+
+extern "C" int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift,
+                                   const void* w_bf16, const float* bias, float* out, int ldo, int relu_out,
+                                   float* stat_partials, double* stats, int64_t rows, int K, int OUT,
+                                   gsatb_stream_t stream) {
+    if (rows < 0 || K <= 0 || OUT <= 0) return GSATB_EINVAL;
+    if (rows == 0) return GSATB_OK;
+    if (!x || !w_bf16 || !out) return GSATB_EINVAL;
+    if ((in_scale == nullptr) != (in_shift == nullptr)) return GSATB_EINVAL;
+    if (stat_partials && (OUT > 128 || !stats)) return GSATB_ESHAPE;
+    if (K > 512) return GSATB_ESHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    OpLinear::Params p{x, ldx, in_scale, in_shift, bias, out, ldo, relu_out, stat_partials, OUT};
+    Tiling tl = uniform_tiling(rows);
+    if (stat_partials)
+        cudaMemsetAsync(stat_partials, 0, gsatb_tc_stat_partials_elems(OUT) * sizeof(float), st);
+    int rc = launch<OpLinear>(w_bf16, tl, K, OUT, p, st);
+    if (rc != GSATB_OK) return rc;
+    if (stat_partials) {
+        k_reduce_partials<<<(2 * OUT + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS, 2 * OUT, stats);
+        GSATB_CHECK_LAUNCH();
+    }
+    return GSATB_OK;
+}

@@ -157,6 +157,25 @@ int gsatb_lift_bwd(const float* g_edge, const float* node_att, const int32_t* ro
                    const int32_t* src_by_dst, const int32_t* rowptr_src, const int32_t* eid_by_src,
                    const int32_t* dst_by_src, float* d_node, int64_t N, gsatb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense layers on the tensor cores (tcgen05.mma kind::f16: bf16 operands, fp32 accumulation in TMEM; weights
+ * streamed by TMA, activations staged through shared memory by producer warps with the prologue fused).
+ * Replaces the nn.Linear / BatchNorm1d / ReLU chains of src/models/gin.py:55-62 and the Linear layers of the
+ * extractor MLP (src/utils/get_model.py:57-68).  Tolerance: bf16 operand rounding (documented in the tests).
+ *
+ * gsatb_tc_prep_weight: fp32 W [OUT,K] (or its transpose) -> zero-padded bf16 [pad128(rows), pad64(cols)],
+ * the layout the TMA descriptor of every tc op expects.
+ * gsatb_tc_linear_fwd: out = act(pro(x) W^T + bias); pro(x) = relu(x*in_scale + in_shift) when in_scale is
+ * given (BatchNorm+ReLU folded into the operand load), identity otherwise; act = ReLU when relu_out.
+ * With stat_partials (OUT <= 128): stats[0:OUT] = sum_rows z, stats[OUT:2OUT] = sum_rows z^2 of the pre-activation
+ * z (BatchNorm batch statistics), reduced in a fixed order in fp64.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpose, void* w_bf16_padded, gsatb_stream_t stream);
+size_t gsatb_tc_stat_partials_elems(int OUT);
+int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, const void* w_bf16_padded,
+                        const float* bias, float* out, int ldo, int relu_out, float* stat_partials, double* stats,
+                        int64_t rows, int K, int OUT, gsatb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
