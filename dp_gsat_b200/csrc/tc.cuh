@@ -31,9 +31,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Spin with back-off: a waiting warp that keeps issuing try_wait/branch pairs steals issue slots from the working
+// warps of its SM sub-partition (measured: 3/4 of all executed instructions were barrier polls before this).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    if (mbar_try_wait(bar, parity)) return;
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+// One thread polls the mbarrier, the rest of the role group sleeps in a named hardware barrier (no issue slots).
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void group_mbar_wait(bool leader, uint64_t* bar, uint32_t parity, int bar_id, int nthreads) {
+    if (leader) mbar_wait(bar, parity);
+    named_bar_sync(bar_id, nthreads);
 }
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)

@@ -1,0 +1,336 @@
+// Extractor MLP forward on the tensor cores (reference src/run_gsat.py:909-927 + src/utils/get_model.py:57-68:
+// cat(emb[col], emb[row]) -> Linear -> InstanceNorm(batch[col]) -> ReLU -> Dropout -> Linear -> InstanceNorm -> ReLU
+// -> Dropout -> Linear(H, 1)).
+//
+// Two launches over graph-aligned tiles (whole graphs, <= 128 rows per tile, so every per-graph InstanceNorm closes
+// inside the tile's accumulator):
+//   ext_fwd1: gather emb[src] | emb[dst] straight into the swizzled B operand (the [E, 2H] concat is never
+//             materialised) -> GEMM1 on tcgen05 -> per-graph InstanceNorm in the epilogue (thread = channel, the
+//             tile's rows are its TMEM columns) -> xhat1 stored as bf16 [E, C1] (+ rstd1 [G, C1] for backward)
+//   ext_fwd2: xhat1 -> ReLU -> Dropout fused into the operand load -> GEMM2 -> InstanceNorm -> ReLU -> Dropout ->
+//             dot with w3 (+ b3) reduced across channels with a shuffle transpose -> one logit per row
+// The Linear biases in front of an InstanceNorm cancel exactly (the norm subtracts the per-graph mean), so b1 and b2
+// are not read; their gradients are exactly zero.
+#include "tc_ops_common.cuh"
+
+namespace {
+
+using namespace tcg;
+
+// Walk one accumulator row (one channel; the tile's rows are its TMEM columns) in 32-column chunks, split into
+// (chunk, graph) pieces.  Control flow is uniform across the CTA (graph boundaries are per tile, not per channel) and
+// the per-element work is a 32-wide statically unrolled, bit-mask predicated body, which keeps the code small: a
+// branchy 32x unroll made the first version of this epilogue instruction-cache bound (ncu: stall_no_inst).
+//   piece(c, v, mask, s)   columns j of chunk c with bit j of mask set belong to graph s
+//   seg_end(s)             graph s is complete
+//   chunk_begin(c) / chunk_end(c)
+template <class Piece, class SegEnd, class ChunkBegin, class ChunkEnd>
+__device__ __forceinline__ void for_pieces(uint32_t taddr, const int* bnd, int nseg, Piece piece, SegEnd seg_end,
+                                           ChunkBegin chunk_begin, ChunkEnd chunk_end) {
+    const int cnt = bnd[nseg];
+    int s = 0;
+    while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+#pragma unroll 1
+    for (int c = 0; c * 32 < cnt; ++c) {
+        float v[32];
+        tc::tmem_ld_32x32(taddr + c * 32, v);
+        tc::tmem_ld_wait();
+        chunk_begin(c);
+        const int cbeg = c * 32, cend = min(cbeg + 32, cnt);
+#pragma unroll 1
+        while (s < nseg && bnd[s] < cend) {
+            const int lo = max(bnd[s], cbeg) - cbeg, hi = min(bnd[s + 1], cend) - cbeg;
+            const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            piece(c, v, m, s);
+            if (bnd[s + 1] <= cend) {
+                seg_end(s);
+                ++s;
+                while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+            } else {
+                break;
+            }
+        }
+        chunk_end(c);
+    }
+}
+
+// Per-graph InstanceNorm (biased variance of the centred values, as PyG computes it) of one accumulator row.
+// emit(c, j, col, xhat) is called for every valid column; seg_rstd(s, rstd) once per non-empty graph.
+template <class Emit, class SegRstd, class ChunkBegin, class ChunkEnd>
+__device__ __forceinline__ void instance_norm_rows(uint32_t taddr, const int* bnd, int nseg, float eps, Emit emit,
+                                                   SegRstd seg_rstd, ChunkBegin chunk_begin, ChunkEnd chunk_end) {
+    float mean[MAX_SEG], rs[MAX_SEG];
+    auto nop_c = [](int) {};
+    {
+        float acc = 0.f;
+        for_pieces(taddr, bnd, nseg,
+                   [&](int, const float* v, uint32_t m, int) {
+                       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                       for (int j = 0; j < 32; j += 4) {
+                           s0 += ((m >> j) & 1u) ? v[j] : 0.f;
+                           s1 += ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
+                           s2 += ((m >> (j + 2)) & 1u) ? v[j + 2] : 0.f;
+                           s3 += ((m >> (j + 3)) & 1u) ? v[j + 3] : 0.f;
+                       }
+                       acc += (s0 + s1) + (s2 + s3);
+                   },
+                   [&](int s) {
+                       mean[s] = acc / (float)(bnd[s + 1] - bnd[s]);
+                       acc = 0.f;
+                   },
+                   nop_c, nop_c);
+    }
+    {
+        float acc = 0.f;
+        for_pieces(taddr, bnd, nseg,
+                   [&](int, const float* v, uint32_t m, int s) {
+                       const float mu = mean[s];
+                       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                       for (int j = 0; j < 32; j += 4) {
+                           const float d0 = ((m >> j) & 1u) ? v[j] - mu : 0.f;
+                           const float d1 = ((m >> (j + 1)) & 1u) ? v[j + 1] - mu : 0.f;
+                           const float d2 = ((m >> (j + 2)) & 1u) ? v[j + 2] - mu : 0.f;
+                           const float d3 = ((m >> (j + 3)) & 1u) ? v[j + 3] - mu : 0.f;
+                           s0 = fmaf(d0, d0, s0);
+                           s1 = fmaf(d1, d1, s1);
+                           s2 = fmaf(d2, d2, s2);
+                           s3 = fmaf(d3, d3, s3);
+                       }
+                       acc += (s0 + s1) + (s2 + s3);
+                   },
+                   [&](int s) {
+                       const float r = 1.f / sqrtf(acc / (float)(bnd[s + 1] - bnd[s]) + eps);
+                       rs[s] = r;
+                       seg_rstd(s, r);
+                       acc = 0.f;
+                   },
+                   nop_c, nop_c);
+    }
+    for_pieces(taddr, bnd, nseg,
+               [&](int c, const float* v, uint32_t m, int s) {
+                   const float mu = mean[s], r = rs[s];
+                   // emit() must be branch-free: compute unconditionally, predicate only stores on `in`
+#pragma unroll
+                   for (int j = 0; j < 32; ++j) emit(c, j, c * 32 + j, ((m >> j) & 1u) != 0, (v[j] - mu) * r);
+               },
+               [](int) {}, chunk_begin, chunk_end);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct OpExtFwd1 {
+    struct Params {
+        const float* emb;       // [N, H]
+        const int32_t* src;     // [E] nullable: node mode (rows are nodes, K = H)
+        const int32_t* dst;
+        int H;
+        uint16_t* xhat;         // bf16 bits [rows, C]
+        float* rstd;            // [G, C]
+        int C;
+        float eps;
+    };
+    struct EpiState {};
+    struct Raw {
+        float v[8];
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
+        if (p.src) {
+            const int node = k < p.H ? __ldg(p.src + grow) : __ldg(p.dst + grow);
+            load8_f32(p.emb + (int64_t)node * p.H, k < p.H ? k : k - p.H, p.H, r.v);
+        } else {
+            load8_f32(p.emb + grow * p.H, k, K, r.v);
+        }
+    }
+    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) { pack8(r.v, o); }
+    __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane) {
+        const int* bnd;
+        int g0;
+        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
+        uint16_t* dst = p.xhat + r0 * p.C + ch;
+        instance_norm_rows(
+            taddr, bnd, nseg, p.eps,
+            [&](int, int, int col, bool in, float xh) {
+                const uint16_t bits = float_to_bf16_bits(xh);
+                if (in && ch_ok) dst[(int64_t)col * p.C] = bits;
+            },
+            [&](int s, float r) {
+                if (ch_ok) p.rstd[(int64_t)(g0 + s) * p.C + ch] = r;
+            },
+            [](int) {}, [](int) {});
+    }
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+};
+
+// ------------------------------------------------------------------------------------------------------------
+struct OpExtFwd2 {
+    struct Params {
+        const uint16_t* xhat1;   // bf16 bits [rows, C1]
+        int C1;
+        Dropout drop1;
+        const float* w3;         // [H]
+        const float* b3;         // [1] nullable
+        uint16_t* xhat2;         // bf16 bits [rows, H]
+        float* rstd2;            // [G, H]
+        Dropout drop2;
+        float* logit;            // [rows]
+        int H;
+        float eps;
+    };
+    struct EpiState {
+        uint32_t par;
+    };
+    struct Raw {
+        uint4 q;
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
+        r.q = __ldg(reinterpret_cast<const uint4*>(p.xhat1 + grow * p.C1 + k));
+    }
+    __device__ static void transform8(const Params& p, Raw& r, int64_t grow, int k, int, uint32_t o[4]) {
+        float v[8];
+        unpack8(r.q, v);
+        uint32_t keep = 0xFFu;
+        if (p.drop1.enabled) {
+            if (p.drop1.mask) {                      // injected keep mask: 8 bytes of the row (C1 % 8 == 0)
+                const uint2 mb = __ldg(reinterpret_cast<const uint2*>(p.drop1.mask + grow * p.C1 + k));
+                keep = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    keep |= ((((i < 4 ? mb.x : mb.y) >> (8 * (i & 3))) & 0xFFu) != 0u ? 1u : 0u) << i;
+            } else {
+                keep = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    keep |= (hash_keep(p.drop1, (uint32_t)grow, hash_ch_term(p.drop1, k + i)) ? 1u : 0u) << i;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? fmaxf(v[i], 0.f) * p.drop1.scale : 0.f;
+        pack8(v, o);
+    }
+    __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool first) {
+        if (first) st.par = 0;
+    }
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int cnt, int tile, uint8_t* misc, int q, int lane) {
+        const int* bnd;
+        int g0;
+        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
+        float* red = reinterpret_cast<float*>(misc + 1024) + st.par * 512;   // [4 warps][128 columns]
+        for (int c = (cnt + 31) / 32; c < 4; ++c) red[q * 128 + c * 32 + lane] = 0.f;   // chunks the norm skips
+        const float w3 = ch_ok ? __ldg(p.w3 + ch) : 0.f;
+        uint16_t* dst = p.xhat2 + r0 * p.H + ch;
+        const bool use_mask = p.drop2.enabled && p.drop2.mask != nullptr;
+        const uint32_t hash_ch = hash_ch_term(p.drop2, ch);
+        float a[32];
+        instance_norm_rows(
+            taddr, bnd, nseg, p.eps,
+            [&](int, int j, int col, bool in, float xh) {
+                const uint16_t bits = float_to_bf16_bits(xh);
+                if (in && ch_ok) dst[(int64_t)col * p.H] = bits;
+                float h = fmaxf(xh, 0.f);
+                const bool keep = use_mask ? (in && ch_ok ? __ldg(p.drop2.mask + (r0 + col) * p.H + ch) != 0 : false)
+                                           : hash_keep(p.drop2, (uint32_t)(r0 + col), hash_ch);
+                h = (!p.drop2.enabled || keep) ? h * p.drop2.scale : 0.f;
+                a[j] = (in && ch_ok) ? h * w3 : a[j];
+            },
+            [&](int s, float r) {
+                if (ch_ok) p.rstd2[(int64_t)(g0 + s) * p.H + ch] = r;
+            },
+            [&](int) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = 0.f;
+            },
+            [&](int c) {
+                // transpose-reduce: lane l ends with the sum over the warp's 32 channels of column c*32 + l
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const bool upper = (lane & off) != 0;
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const float send = upper ? a[i] : a[i + off];
+                        const float keep = upper ? a[i + off] : a[i];
+                        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                red[q * 128 + c * 32 + lane] = a[0];
+            });
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int col = q * 32 + lane;
+        if (col < cnt)
+            p.logit[r0 + col] = red[col] + red[128 + col] + red[256 + col] + red[384 + col] + (p.b3 ? __ldg(p.b3) : 0.f);
+        st.par ^= 1u;
+    }
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+};
+
+inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
+    Dropout d;
+    d.mask = mask;
+    d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
+    d.enabled = training && pdrop > 0.f;
+    d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
+    double t = (double)pdrop * 16777216.0;
+    d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
+    return d;
+}
+
+}  // namespace
+
+// Host-side greedy packing of consecutive graphs into tiles of <= max_rows rows and <= max_seg graphs.
+// seg_ptr_host is the HOST copy of edge_ptr / node_ptr ([G+1]).  tile_row / tile_seg need room for G+1 entries.
+extern "C" int gsatb_tile_plan_host(const int32_t* seg_ptr_host, int64_t G, int max_rows, int max_seg,
+                                    int32_t* tile_row, int32_t* tile_seg, int32_t* num_tiles) {
+    if (!seg_ptr_host || !tile_row || !tile_seg || !num_tiles || G < 0) return GSATB_EINVAL;
+    if (max_rows > tcg::TILE_ROWS || max_seg > tcg::MAX_SEG) return GSATB_ESHAPE;
+    int32_t nt = 0;
+    int64_t g = 0;
+    while (g < G) {
+        const int32_t r0 = seg_ptr_host[g];
+        int64_t g1 = g;
+        while (g1 < G && (g1 - g) < max_seg && seg_ptr_host[g1 + 1] - r0 <= max_rows) ++g1;
+        if (g1 == g) return GSATB_ESHAPE;      // a single graph does not fit one tile
+        tile_row[nt] = r0;
+        tile_seg[nt] = (int32_t)g;
+        ++nt;
+        g = g1;
+    }
+    tile_row[nt] = G > 0 ? seg_ptr_host[G] : 0;
+    tile_seg[nt] = (int32_t)G;
+    *num_tiles = nt;
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int32_t* dst, const void* w1_bf16,
+                                 const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
+                                 int num_tiles, void* xhat1, float* rstd1, int64_t rows, int H, int C1, float eps,
+                                 gsatb_stream_t stream) {
+    if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
+    if (rows == 0 || num_tiles == 0) return GSATB_OK;
+    if (!emb || !w1_bf16 || !tile_row || !tile_seg || !seg_ptr || !xhat1 || !rstd1) return GSATB_EINVAL;
+    if ((src == nullptr) != (dst == nullptr)) return GSATB_EINVAL;
+    if (H % 8 != 0) return GSATB_ESHAPE;
+    const int K = src ? 2 * H : H;
+    if (K > 512) return GSATB_ESHAPE;
+    OpExtFwd1::Params p{emb, src, dst, H, (uint16_t*)xhat1, rstd1, C1, eps};
+    Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
+    return launch<OpExtFwd1>(w1_bf16, tl, K, C1, p, (cudaStream_t)stream);
+}
+
+extern "C" int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16, const float* w3, const float* b3,
+                                 const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
+                                 const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
+                                 int num_tiles, void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H,
+                                 float eps, gsatb_stream_t stream) {
+    if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
+    if (rows == 0 || num_tiles == 0) return GSATB_OK;
+    if (!xhat1 || !w2_bf16 || !w3 || !tile_row || !tile_seg || !seg_ptr || !xhat2 || !rstd2 || !logit)
+        return GSATB_EINVAL;
+    if (C1 % 8 != 0 || C1 > 512 || H > 128) return GSATB_ESHAPE;
+    OpExtFwd2::Params p{(const uint16_t*)xhat1, C1, make_dropout(mask1, seed * 2 + 1, pdrop, training), w3, b3,
+                        (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps};
+    Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
+    return launch<OpExtFwd2>(w2_bf16, tl, C1, H, p, (cudaStream_t)stream);
+}

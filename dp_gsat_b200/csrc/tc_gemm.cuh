@@ -29,6 +29,7 @@ constexpr int THREADS = 512;
 constexpr int EPI_WARP0 = 4, PRO_WARP0 = 8, PRO_WARPS = 8;
 constexpr int PRO_UNROLL = 8;                 // row-chunks whose global loads one producer thread keeps in flight
 constexpr int MAX_SEG = 32;                   // graphs per tile the InstanceNorm epilogues support
+constexpr int MISC_BYTES = 8192;             // epilogue scratch: segment tables (4 warps) + cross-warp reductions
 
 struct Tiling {
     int64_t rows;               // total rows
@@ -36,6 +37,7 @@ struct Tiling {
     const int32_t* tile_row;    // [num_tiles + 1] first row of each tile (nullptr: uniform 128-row tiles)
     const int32_t* tile_seg;    // [num_tiles + 1] first graph of each tile (InstanceNorm epilogues), nullable
     const int32_t* seg_ptr;     // [G + 1] row offsets of the graphs, nullable
+    long long* dbg;             // optional per-CTA cycle counters [gridDim][16] (gsatb_tc_set_profile_buffer)
 };
 
 struct Shape {
@@ -55,7 +57,7 @@ __host__ __device__ inline SmemLayout smem_layout(const Shape& s) {
     l.b_off = l.a_off + (uint32_t)s.NA * BLK_BYTES;
     l.bar_off = l.b_off + (uint32_t)s.NBUF * s.KB * BLK_BYTES;
     l.misc_off = l.bar_off + 256;
-    l.total = l.misc_off + 1024 + 1024;   // + slack for the manual 1024-byte alignment of the base
+    l.total = l.misc_off + MISC_BYTES + 1024;   // + slack for the manual 1024-byte alignment of the base
     return l;
 }
 
@@ -141,19 +143,26 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_bf16(128, TILE_ROWS);
             uint32_t ca = 0, cm = 0, it = 0;
+            long long w_b = 0, w_acc = 0, w_a = 0, t_all = clock64(), t0;
             for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
+                t0 = clock64();
                 tc::mbar_wait(&b_full[buf], ub & 1);
+                w_b += clock64() - t0;
                 tc::tc_fence_after();
                 const uint32_t b_base = tc::smem_u32(sB + (size_t)buf * sh.KB * BLK_BYTES);
                 for (int mb = 0; mb < sh.NMB; ++mb, ++cm) {
                     const uint32_t slot = cm & 1, us = cm >> 1;
+                    t0 = clock64();
                     tc::mbar_wait(&acc_empty[slot], (us & 1) ^ 1);
+                    w_acc += clock64() - t0;
                     tc::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + slot * 128;
                     for (int kb = 0; kb < sh.KB; ++kb, ++ca) {
                         const uint32_t s = ca % sh.NA, use = ca / sh.NA;
+                        t0 = clock64();
                         tc::mbar_wait(&a_full[s], use & 1);
+                        w_a += clock64() - t0;
                         tc::tc_fence_after();
                         const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(sA + s * BLK_BYTES));
                         const uint64_t b_desc = tc::make_desc_k_sw128(b_base + kb * BLK_BYTES);
@@ -167,6 +176,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
                 }
                 tc::mma_commit(&b_empty[buf]);              // B tile buffer free -> producers
             }
+            if (tl.dbg) {
+                long long* d = tl.dbg + (size_t)blockIdx.x * 16;
+                d[0] = clock64() - t_all;
+                d[1] = w_b;
+                d[2] = w_acc;
+                d[3] = w_a;
+            }
         }
     } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
         // ===================== epilogue =====================
@@ -174,6 +190,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
         typename Op::EpiState st;
         uint32_t ce = 0;
         bool first = true;
+        long long w_full = 0, t_epi = 0, t0;
         for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
             int64_t r0;
             int cnt;
@@ -182,10 +199,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
                 const uint32_t slot = ce & 1, us = ce >> 1;
                 const int ch = mb * 128 + q * 32 + lane;
                 if (first || sh.NMB > 1) Op::epi_init(p, st, ch, ch < sh.OUT, first);
-                tc::mbar_wait(&acc_full[slot], us & 1);
+                t0 = clock64();
+                tc::group_mbar_wait(q == 0 && lane == 0, &acc_full[slot], us & 1, 3, 128);
+                w_full += clock64() - t0;
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
+                t0 = clock64();
                 Op::epilogue(p, tl, st, taddr, ch, ch < sh.OUT, r0, cnt, tile, misc, q, lane);
+                t_epi += clock64() - t0;
                 tc::tc_fence_before();
                 tc::mbar_arrive(&acc_empty[slot]);
                 if (sh.NMB > 1) Op::epi_finish(p, st, ch, ch < sh.OUT, false);
@@ -193,6 +214,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
             first = false;
         }
         if (sh.NMB == 1) Op::epi_finish(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true);
+        if (tl.dbg && q == 0 && lane == 0) {
+            long long* d = tl.dbg + (size_t)blockIdx.x * 16;
+            d[4] = w_full;
+            d[5] = t_epi;
+        }
     } else if (warp >= PRO_WARP0) {
         // ===================== B-operand producers =====================
         const int pt = threadIdx.x - PRO_WARP0 * 32;        // 0..255
@@ -203,35 +229,48 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
             int cnt;
             tile_range(tl, tile, r0, cnt);
             const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
-            tc::mbar_wait(&b_empty[buf], (ub & 1) ^ 1);
+            long long t0 = clock64();
+            tc::group_mbar_wait(pt == 0, &b_empty[buf], (ub & 1) ^ 1, 2, PRO_WARPS * 32);
+            long long t1 = clock64();
             uint8_t* bt = sB + (size_t)buf * sh.KB * BLK_BYTES;
             // work unit = (K-block, group of 4 rows): 8 lanes cover the 8 16-byte chunks of one 128-byte row.
             // PRO_UNROLL units are loaded back to back before any is transformed, to keep HBM requests in flight.
             const int units = sh.KB * (TILE_ROWS / 4);
+            // units (= KB * 32) is a multiple of PRO_WARPS * PRO_UNROLL when KB is even; the kb == KB guard covers
+            // odd KB.  Loads are unconditional on clamped coordinates (K % 8 == 0, so an 8-chunk is wholly in or
+            // out) and invalid chunks are zeroed by a select: no branches, so ptxas keeps all loads in flight.
             for (int u0 = pw; u0 < units; u0 += PRO_WARPS * PRO_UNROLL) {
                 typename Op::Raw raw[PRO_UNROLL];
 #pragma unroll
                 for (int j = 0; j < PRO_UNROLL; ++j) {
-                    const int u = u0 + j * PRO_WARPS;
+                    const int u = min(u0 + j * PRO_WARPS, units - 1);
                     const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
                     const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
-                    if (u < units && row < cnt && k < sh.K) Op::load8(p, r0 + row, k, sh.K, raw[j]);
+                    const bool ok = row < cnt && k < sh.K;
+                    Op::load8(p, r0 + (ok ? row : 0), ok ? k : 0, sh.K, raw[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < PRO_UNROLL; ++j) {
-                    const int u = u0 + j * PRO_WARPS;
-                    if (u < units) {
-                        const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
-                        const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
-                        uint32_t o[4] = {0u, 0u, 0u, 0u};
-                        if (row < cnt && k < sh.K) Op::transform8(p, raw[j], r0 + row, k, sh.K, o);
+                    const int uj = u0 + j * PRO_WARPS;
+                    const int u = min(uj, units - 1);
+                    const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
+                    const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
+                    const bool ok = row < cnt && k < sh.K;
+                    uint32_t o[4];
+                    Op::transform8(p, raw[j], r0 + (ok ? row : 0), ok ? k : 0, sh.K, o);
+                    if (uj < units)
                         *reinterpret_cast<uint4*>(bt + (size_t)kb * BLK_BYTES + tc::sw128_offset(row, c_in * 8)) =
-                            make_uint4(o[0], o[1], o[2], o[3]);
-                    }
+                            ok ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
                 }
             }
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&b_full[buf]);
+            if (tl.dbg && pt == 0) {
+                long long* d = tl.dbg + (size_t)blockIdx.x * 16;
+                d[6] += t1 - t0;
+                d[7] += clock64() - t1;
+                d[8] += 1;
+            }
         }
     }
     tc::tc_fence_before();
@@ -278,17 +317,24 @@ inline Shape make_shape(int K, int OUT) {
     s.KB = (K + KBLK - 1) / KBLK;
     s.OUT = OUT;
     s.NMB = (OUT + 127) / 128;
-    const int budget = 227 * 1024 - 256 - 2048 - 1024;
+    const int budget = 227 * 1024 - 256 - MISC_BYTES - 1024 - 1024;
     s.NBUF = (2 * s.KB * BLK_BYTES + 4 * BLK_BYTES <= budget) ? 2 : 1;
     int na = (budget - s.NBUF * s.KB * BLK_BYTES) / BLK_BYTES;
     s.NA = na > 8 ? 8 : na;
     return s;
 }
 
+inline long long*& profile_buffer() {
+    static long long* buf = nullptr;
+    return buf;
+}
+
 template <class Op>
-int launch(const void* w_bf16_padded, const Tiling& tl, int K, int OUT, const typename Op::Params& p,
+int launch(const void* w_bf16_padded, const Tiling& tl_in, int K, int OUT, const typename Op::Params& p,
            cudaStream_t st) {
-    if (tl.num_tiles <= 0) return GSATB_OK;
+    if (tl_in.num_tiles <= 0) return GSATB_OK;
+    Tiling tl = tl_in;
+    tl.dbg = profile_buffer();
     Shape sh = make_shape(K, OUT);
     if (sh.KB > 8 || sh.NA < 2) return GSATB_ESHAPE;
     CUtensorMap tm;

@@ -3,30 +3,11 @@
 // Precision contract: operands are rounded to bf16 (8-bit mantissa), products are accumulated in fp32 in TMEM.
 // The parity bound for these ops is therefore the documented "bf16 MLP" tolerance (tests/test_gpu_tc.py), not the
 // rtol 1e-5 of the fp32 gather / scatter / sampler kernels.
-#include <cuda_bf16.h>
-#include "tc_gemm.cuh"
+#include "tc_ops_common.cuh"
 
 namespace {
 
 using namespace tcg;
-
-__device__ __forceinline__ void load8_f32(const float* __restrict__ src, int k, int K, float v[8]) {
-    if (k + 8 <= K && ((reinterpret_cast<uintptr_t>(src + k) & 15u) == 0)) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + k));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(src + k + 4));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (k + i < K) ? __ldg(src + k + i) : 0.f;
-    }
-}
-__device__ __forceinline__ void pack8(const float v[8], uint32_t o[4]) {
-    o[0] = tc::pack_bf16(v[0], v[1]);
-    o[1] = tc::pack_bf16(v[2], v[3]);
-    o[2] = tc::pack_bf16(v[4], v[5]);
-    o[3] = tc::pack_bf16(v[6], v[7]);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // OpLinear:  out[row, ch] = act( x[row, :] . W[ch, :] + bias[ch] )          (nn.Linear; x fp32, out fp32)
@@ -57,33 +38,48 @@ struct OpLinear {
     }
     __device__ static void transform8(const Params& p, Raw& r, int64_t, int k, int K, uint32_t o[4]) {
         if (p.in_scale) {
+            float sc[8], sf[8];
+            load8_f32(p.in_scale, k, K, sc);
+            load8_f32(p.in_shift, k, K, sf);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (k + i < K) r.v[i] = fmaxf(fmaf(r.v[i], __ldg(p.in_scale + k + i), __ldg(p.in_shift + k + i)), 0.f);
+            for (int i = 0; i < 8; ++i) r.v[i] = fmaxf(fmaf(r.v[i], sc[i], sf[i]), 0.f);
         }
         pack8(r.v, o);
     }
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
+    // Straight-line code: every column is computed unconditionally and only the store is predicated, so the 32
+    // columns of a chunk are independent instruction streams the scheduler can interleave (a per-column branch
+    // left the single epilogue warp of each sub-partition latency-bound at ~100 cycles per column).
     __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
                                     int64_t r0, int cnt, int, uint8_t*, int, int) {
         const float b = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
+        float* o = p.out + r0 * p.ldo + ch;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             float v[32];
             tc::tmem_ld_32x32(taddr + c * 32, v);
             tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = c * 32 + j;
-                if (col < cnt) {
-                    float z = v[j] + b;
-                    st.s1 += z;
-                    st.s2 = fmaf(z, z, st.s2);
-                    if (p.relu_out) z = fmaxf(z, 0.f);
-                    if (ch_ok) p.out[(r0 + col) * p.ldo + ch] = z;
+            for (int j = 0; j < 32; j += 2) {
+                const int c0 = c * 32 + j, c1 = c0 + 1;
+                const bool ok0 = c0 < cnt, ok1 = c1 < cnt;
+                float z0 = v[j] + b, z1 = v[j + 1] + b;
+                const float y0 = ok0 ? z0 : 0.f, y1 = ok1 ? z1 : 0.f;
+                s1a += y0;
+                s1b += y1;
+                s2a = fmaf(y0, y0, s2a);
+                s2b = fmaf(y1, y1, s2b);
+                if (p.relu_out) {
+                    z0 = fmaxf(z0, 0.f);
+                    z1 = fmaxf(z1, 0.f);
                 }
+                if (ok0 && ch_ok) o[(int64_t)c0 * p.ldo] = z0;
+                if (ok1 && ch_ok) o[(int64_t)c1 * p.ldo] = z1;
             }
         }
+        st.s1 += s1a + s1b;
+        st.s2 += s2a + s2b;
     }
     __device__ static void epi_finish(const Params& p, EpiState& st, int ch, bool ch_ok, bool) {
         if (p.stat_partials && ch_ok) {
@@ -118,16 +114,6 @@ __global__ void k_reduce_partials(const float* __restrict__ partials, int parts,
     out[j] = acc;
 }
 
-inline Tiling uniform_tiling(int64_t rows) {
-    Tiling t;
-    t.rows = rows;
-    t.num_tiles = (int)((rows + TILE_ROWS - 1) / TILE_ROWS);
-    t.tile_row = nullptr;
-    t.tile_seg = nullptr;
-    t.seg_ptr = nullptr;
-    return t;
-}
-
 }  // namespace
 
 extern "C" int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpose, void* wp, gsatb_stream_t stream) {
@@ -137,6 +123,14 @@ extern "C" int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpos
     k_prep_weight<<<(rows_pad * cols_pad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         w, OUT, K, transpose, (__nv_bfloat16*)wp, rows_pad, cols_pad);
     GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+// Development aid: per-CTA cycle counters of the skeleton's roles ([148][16] int64, zeroed by the caller):
+// 0 MMA-thread total, 1 wait B full, 2 wait accumulator free, 3 wait W block, 4 epilogue wait, 5 epilogue work,
+// 6 producer wait, 7 producer fill, 8 tiles.  Pass NULL to switch it off.
+extern "C" int gsatb_tc_set_profile_buffer(void* buf) {
+    tcg::profile_buffer() = (long long*)buf;
     return GSATB_OK;
 }
 
@@ -151,7 +145,9 @@ extern "C" int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scal
     if (!x || !w_bf16 || !out) return GSATB_EINVAL;
     if ((in_scale == nullptr) != (in_shift == nullptr)) return GSATB_EINVAL;
     if (stat_partials && (OUT > 128 || !stats)) return GSATB_ESHAPE;
-    if (K > 512) return GSATB_ESHAPE;
+    if (K > 512 || K % 8 != 0 || ldx % 4 != 0) return GSATB_ESHAPE;
+    if (!gsatb_aligned16(x) || (in_scale && (!gsatb_aligned16(in_scale) || !gsatb_aligned16(in_shift))))
+        return GSATB_EALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     OpLinear::Params p{x, ldx, in_scale, in_shift, bias, out, ldo, relu_out, stat_partials, OUT};
     Tiling tl = uniform_tiling(rows);

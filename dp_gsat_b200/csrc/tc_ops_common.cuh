@@ -1,0 +1,95 @@
+// Helpers shared by the tensor-core ops (operand packing, dropout hash, segment tables, uniform tiling).
+#pragma once
+#include <cuda_bf16.h>
+#include "tc_gemm.cuh"
+
+namespace tcg {
+
+// 8 consecutive floats of a row.  Contract of the tensor-core ops: K % 8 == 0, row stride % 4 == 0 and 16-byte
+// aligned bases, so the chunk is two aligned 128-bit loads with no tail (checked at the C entry points).
+__device__ __forceinline__ void load8_f32(const float* __restrict__ src, int k, int, float v[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + k));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + k + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void pack8(const float v[8], uint32_t o[4]) {
+    o[0] = tc::pack_bf16(v[0], v[1]);
+    o[1] = tc::pack_bf16(v[2], v[3]);
+    o[2] = tc::pack_bf16(v[4], v[5]);
+    o[3] = tc::pack_bf16(v[6], v[7]);
+}
+// 8 bf16 (one 16-byte load) -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4& q, float v[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+    __nv_bfloat16 h = __float2bfloat16_rn(f);
+    return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// Dropout keep decision for element `idx` of a tensor: counter-based (regenerable in backward), 24-bit threshold.
+// mask (uint8, 1 = keep) overrides the hash when given (parity tests inject masks).
+struct Dropout {
+    const uint8_t* mask;   // nullable
+    uint32_t seed;
+    uint32_t thr24;        // drop when (hash >> 8) < thr24 ;  thr24 = p * 2^24
+    float scale;           // 1 / (1 - p)   (1 when disabled)
+    int enabled;
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+// element (row, ch) of a [rows, C] tensor; the hash needs no 64-bit arithmetic (rows < 2^31, ch < 2^16)
+// ch_term = ch * 0x7FEB352D + seed (hoisted by callers that walk rows of one channel)
+__device__ __forceinline__ bool hash_keep(const Dropout& d, uint32_t row, uint32_t ch_term) {
+    uint32_t h = row * 0x9E3779B1u + ch_term;
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    return (h >> 8) >= d.thr24;
+}
+__device__ __forceinline__ uint32_t hash_ch_term(const Dropout& d, int ch) { return (uint32_t)ch * 0x7FEB352Du + d.seed; }
+__device__ __forceinline__ bool dropout_keep(const Dropout& d, int64_t row, int ch, int C) {
+    if (!d.enabled) return true;
+    if (d.mask) return __ldg(d.mask + row * C + ch) != 0;
+    return hash_keep(d, (uint32_t)row, hash_ch_term(d, ch));
+}
+
+inline Tiling uniform_tiling(int64_t rows) {
+    Tiling t;
+    t.rows = rows;
+    t.num_tiles = (int)((rows + TILE_ROWS - 1) / TILE_ROWS);
+    t.tile_row = nullptr;
+    t.tile_seg = nullptr;
+    t.seg_ptr = nullptr;
+    t.dbg = nullptr;
+    return t;
+}
+
+// Per-warp copy of the tile's graph boundaries (local row offsets) in the epilogue scratch: bnd[0..nseg]
+__device__ __forceinline__ int load_segments(const Tiling& tl, int tile, int64_t r0, uint8_t* misc, int q, int lane,
+                                             const int*& bnd, int& g0) {
+    int* mine = reinterpret_cast<int*>(misc) + q * (MAX_SEG + 2);
+    g0 = __ldg(tl.tile_seg + tile);
+    const int nseg = __ldg(tl.tile_seg + tile + 1) - g0;
+    __syncwarp();
+    for (int s = lane; s <= nseg; s += 32) mine[s] = __ldg(tl.seg_ptr + g0 + s) - (int)r0;
+    __syncwarp();
+    bnd = mine;
+    return nseg;
+}
+
+}  // namespace tcg

@@ -101,6 +101,31 @@ class GraphIndex:
             plans[key] = out
         return plans[key]
 
+    def tile_plan(self, by: str = 'edge'):
+        """Graph-aligned tiles (<= 128 rows, <= 32 graphs) for the fused tensor-core extractor kernels:
+        (tile_row int32 [T+1], tile_seg int32 [T+1], T) on the device, or None when some graph exceeds one tile.
+        Built once per index from a host copy of the segment pointers (gsatb_tile_plan_host)."""
+        key = ('tiles', by)
+        plans = self._plans
+        if plans is None:
+            plans = self._plans = {}
+        if key not in plans:
+            self.require_graph_contiguous()
+            ptr_dev = self.edge_ptr if by == 'edge' else self.node_ptr
+            host = ptr_dev.cpu().contiguous()
+            tr = torch.empty(self.G + 1, dtype=torch.int32)
+            ts = torch.empty(self.G + 1, dtype=torch.int32)
+            nt = ctypes.c_int32(0)
+            rc = lib().cdll.gsatb_tile_plan_host(ctypes.c_void_p(host.data_ptr()), self.G, 128, 32,
+                                                 ctypes.c_void_p(tr.data_ptr()), ctypes.c_void_p(ts.data_ptr()),
+                                                 ctypes.byref(nt))
+            if rc != 0:
+                plans[key] = None
+            else:
+                T = int(nt.value)
+                plans[key] = (tr[:T + 1].to(self.device), ts[:T + 1].to(self.device), T)
+        return plans[key]
+
     def require_graph_contiguous(self):
         if not self.graph_contiguous:
             raise ValueError('batch must be non-decreasing and edges grouped by graph (PyG Batch collate order); '

@@ -172,9 +172,36 @@ int gsatb_lift_bwd(const float* g_edge, const float* node_att, const int32_t* ro
  * ---------------------------------------------------------------------------------------------------------- */
 int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpose, void* w_bf16_padded, gsatb_stream_t stream);
 size_t gsatb_tc_stat_partials_elems(int OUT);
+/* Development aid: device buffer [148][16] int64 (zeroed by the caller) that the tensor-core kernels fill with
+ * per-role cycle counters (see csrc/tc_ops.cu); NULL switches it off (the default). */
+int gsatb_tc_set_profile_buffer(void* buf);
 int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, const void* w_bf16_padded,
                         const float* bias, float* out, int ldo, int relu_out, float* stat_partials, double* stats,
                         int64_t rows, int K, int OUT, gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * K1  extractor MLP forward, fused on the tensor cores.  Replaces ExtractorMLP.forward (src/run_gsat.py:909-927,
+ * example/gsat.py:131-139) and the MLP/InstanceNorm stack of src/utils/get_model.py:47-68.
+ * Tiles are graph-aligned: gsatb_tile_plan_host packs consecutive graphs into tiles of <= 128 rows / <= 32 graphs
+ * from the HOST copy of edge_ptr (node_ptr in node mode); it returns GSATB_ESHAPE when one graph alone exceeds a
+ * tile (the caller then uses the unfused segnorm path).
+ *   ext_fwd1: rows = edges: B operand = [emb[src] | emb[dst]] gathered on the fly (src == NULL: node mode, B =
+ *             emb rows); xhat1 = InstanceNorm(B W1^T) stored as bf16 [rows, C1]; rstd1 [G, C1]
+ *   ext_fwd2: logit = (Dropout(ReLU(InstanceNorm(Dropout(ReLU(xhat1)) W2^T))) . w3) + b3; also xhat2 bf16 [rows, H]
+ *             and rstd2 [G, H] for backward.  mask1 [rows, C1] / mask2 [rows, H] (uint8 keep masks) are optional
+ *             injected dropout masks; otherwise a counter hash of (seed, element index) decides, and backward can
+ *             regenerate it.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_tile_plan_host(const int32_t* seg_ptr_host, int64_t G, int max_rows, int max_seg, int32_t* tile_row,
+                         int32_t* tile_seg, int32_t* num_tiles);
+int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int32_t* dst, const void* w1_bf16_padded,
+                      const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles,
+                      void* xhat1, float* rstd1, int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
+int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16_padded, const float* w3, const float* b3,
+                      const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
+                      const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles,
+                      void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H, float eps,
+                      gsatb_stream_t stream);
 
 #ifdef __cplusplus
 }
