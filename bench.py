@@ -37,6 +37,8 @@ def parse():
     ap.add_argument('--hidden', type=int, default=128)
     ap.add_argument('--layers', type=int, default=2)
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
+                    help='bf16: tcgen05 MLPs (bf16 operands, fp32 accumulate); fp32: strict library-sgemm path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-graphs', type=int, default=0, help='0 = size automatically (~10-30 s of CPU work)')
     return ap.parse_args()
@@ -186,6 +188,7 @@ def run_b200(a):
     ext = G.ExtractorMLP(a.hidden, shared).to(dev)
     broadcast_parameters(clf)
     broadcast_parameters(ext)
+    clf.precision = ext.precision = a.precision
     gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5, lazy_metrics=True)
     gsat.train()
     step = TrainStep(gsat, lr=1e-3)
@@ -270,8 +273,8 @@ def run_b200(a):
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': workload_name(a), 'global_edges': E_global, 'global_nodes': a.graphs * 25,
+                'dtype': 'bf16' if a.precision == 'bf16' else 'f32', 'data': 'synthetic',
+                'config': {'workload': workload_name(a), 'precision': a.precision + (' tensor-core MLP operands, fp32 accumulate / gather / scatter / sampler' if a.precision == 'bf16' else ''), 'global_edges': E_global, 'global_nodes': a.graphs * 25,
                            'hidden': a.hidden, 'layers': a.layers, 'parallelism': f'graph-sharded dp{world}',
                            'l2_policy': 'inputs larger than L2 (per-rank activations >> 126 MB)'},
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': launches,

@@ -1,0 +1,353 @@
+// Extractor MLP backward (autograd of reference src/utils/get_model.py:57-68 inside src/run_gsat.py:909-927).
+//
+//   head  (SIMT, thread = channel, CTA = graph): dlogit -> through w3, Dropout2, ReLU2 and InstanceNorm2 -> dz2 (bf16),
+//         plus per-graph partials of d w3
+//   bwd1  (tcgen05): dh1 = dz2 W2 (A operand = W2^T), epilogue = Dropout1 / ReLU1 masks + InstanceNorm1 backward
+//         (per-graph sums are thread-local, as in the forward) -> dz1 (bf16)
+//   bwd0  (tcgen05): d f12 = dz1 W1 (A operand = W1^T) -> fp32 [rows, Kin]; the scatter back to the nodes is the
+//         deterministic gsatb_gather_concat_bwd
+//   h1 / f12 are re-materialised in bf16 by two elementwise kernels for the weight-gradient GEMMs (dW2 = dz2^T h1,
+//   dW1 = dz1^T f12), which are plain library GEMMs issued by the Python side.
+// Dropout masks are regenerated from the same counter hash (or read from the injected mask tensors).
+#include "tc_ops_common.cuh"
+
+namespace {
+
+using namespace tcg;
+
+// ---- head -------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_ext_bwd_head(const float* __restrict__ dlogit, const uint16_t* __restrict__ xhat2, const float* __restrict__ rstd2,
+               const float* __restrict__ w3, const int32_t* __restrict__ seg_ptr, Dropout drop2,
+               uint16_t* __restrict__ dz2, float* __restrict__ dw3_part, int H) {
+    const int g = blockIdx.x;
+    const int ch = blockIdx.y * 128 + threadIdx.x;
+    if (ch >= H) return;
+    const int b0 = __ldg(seg_ptr + g), b1 = __ldg(seg_ptr + g + 1);
+    const int n = b1 - b0;
+    if (n <= 0) {
+        dw3_part[(int64_t)g * H + ch] = 0.f;
+        return;
+    }
+    const float w = __ldg(w3 + ch);
+    const uint32_t cht = hash_ch_term(drop2, ch);
+    const bool use_mask = drop2.enabled && drop2.mask != nullptr;
+    float s1 = 0.f, s2 = 0.f, dw = 0.f;
+    for (int r = b0; r < b1; ++r) {
+        const float x = bf16_bits_to_float(__ldg(xhat2 + (int64_t)r * H + ch));
+        const bool keep = !drop2.enabled || (use_mask ? __ldg(drop2.mask + (int64_t)r * H + ch) != 0
+                                                       : hash_keep(drop2, (uint32_t)r, cht));
+        const float dl = __ldg(dlogit + r);
+        const float gate = (x > 0.f && keep) ? drop2.scale : 0.f;
+        const float dxh = dl * w * gate;
+        s1 += dxh;
+        s2 = fmaf(dxh, x, s2);
+        dw = fmaf(dl, x * gate, dw);
+    }
+    const float inv_n = 1.f / (float)n;
+    const float m1 = s1 * inv_n, m2 = s2 * inv_n, rs = __ldg(rstd2 + (int64_t)g * H + ch);
+    for (int r = b0; r < b1; ++r) {
+        const float x = bf16_bits_to_float(__ldg(xhat2 + (int64_t)r * H + ch));
+        const bool keep = !drop2.enabled || (use_mask ? __ldg(drop2.mask + (int64_t)r * H + ch) != 0
+                                                       : hash_keep(drop2, (uint32_t)r, cht));
+        const float dxh = __ldg(dlogit + r) * w * ((x > 0.f && keep) ? drop2.scale : 0.f);
+        dz2[(int64_t)r * H + ch] = float_to_bf16_bits(rs * (dxh - m1 - x * m2));
+    }
+    dw3_part[(int64_t)g * H + ch] = dw;
+}
+
+// ---- shared pieces walker (same structure as the forward InstanceNorm) ---------------------------------------------
+template <class Piece, class SegEnd>
+__device__ __forceinline__ void for_pieces_bwd(uint32_t taddr, const int* bnd, int nseg, Piece piece, SegEnd seg_end) {
+    const int cnt = bnd[nseg];
+    int s = 0;
+    while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+#pragma unroll 1
+    for (int c = 0; c * 32 < cnt; ++c) {
+        float v[32];
+        tc::tmem_ld_32x32(taddr + c * 32, v);
+        tc::tmem_ld_wait();
+        const int cbeg = c * 32, cend = min(cbeg + 32, cnt);
+#pragma unroll 1
+        while (s < nseg && bnd[s] < cend) {
+            const int lo = max(bnd[s], cbeg) - cbeg, hi = min(bnd[s + 1], cend) - cbeg;
+            const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            piece(c, v, m, s);
+            if (bnd[s + 1] <= cend) {
+                seg_end(s);
+                ++s;
+                while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+            } else {
+                break;
+            }
+        }
+    }
+}
+
+// ---- bwd1: dh1 = dz2 W2, then masks + InstanceNorm1 backward -> dz1 ---------------------------------------------
+struct OpExtBwd1 {
+    struct Params {
+        const uint16_t* dz2;     // bf16 [rows, H]   (B operand rows)
+        int H;
+        const uint16_t* xhat1;   // bf16 [rows, C1]
+        const float* rstd1;      // [G, C1]
+        Dropout drop1;
+        uint16_t* dz1;           // bf16 [rows, C1]
+        int C1;
+    };
+    struct EpiState {};
+    struct Raw {
+        uint4 q;
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
+        r.q = __ldg(reinterpret_cast<const uint4*>(p.dz2 + grow * p.H + k));
+    }
+    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
+        o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
+    }
+    __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
+    // Per chunk of 32 columns the xhat1 values are fetched FIRST (32 independent loads in flight per thread) and the
+    // gated gradient e = dh1 * keep * scale * (xhat1 > 0) overwrites the accumulator registers; only then are the
+    // (chunk, graph) pieces reduced / emitted.  (The first version loaded inside the per-column expression and the
+    // loads serialised: 147 k cycles per 128-column block.)
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane) {
+        const int* bnd;
+        int g0;
+        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
+        const int cnt = bnd[nseg];
+        const int chc = ch_ok ? ch : 0;
+        const uint16_t* xs = p.xhat1 + r0 * p.C1 + chc;
+        uint16_t* dst = p.dz1 + r0 * p.C1 + chc;
+        const bool use_mask = p.drop1.enabled && p.drop1.mask != nullptr;
+        const uint8_t* mk = use_mask ? p.drop1.mask + r0 * p.C1 + chc : nullptr;
+        const uint32_t cht = hash_ch_term(p.drop1, chc);
+        const uint32_t row0 = (uint32_t)r0;
+        float m1[MAX_SEG], m2[MAX_SEG];
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            int s = 0;
+            while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+            float a1 = 0.f, a2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c * 32 < cnt; ++c) {
+                float v[32], xv[32];
+                tc::tmem_ld_32x32(taddr + c * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = min(c * 32 + j, cnt - 1);
+                    xv[j] = bf16_bits_to_float(__ldg(xs + (int64_t)col * p.C1));
+                }
+                uint32_t keep = 0xffffffffu;
+                if (p.drop1.enabled) {
+                    keep = 0u;
+                    if (use_mask) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            keep |= (__ldg(mk + (int64_t)min(c * 32 + j, cnt - 1) * p.C1) != 0 ? 1u : 0u) << j;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            keep |= (hash_keep(p.drop1, row0 + (uint32_t)(c * 32 + j), cht) ? 1u : 0u) << j;
+                    }
+                }
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    v[j] = (xv[j] > 0.f && ((keep >> j) & 1u)) ? v[j] * p.drop1.scale : 0.f;   // v := gated gradient e
+                const int cbeg = c * 32, cend = min(cbeg + 32, cnt);
+#pragma unroll 1
+                while (s < nseg && bnd[s] < cend) {
+                    const int lo = max(bnd[s], cbeg) - cbeg, hi = min(bnd[s + 1], cend) - cbeg;
+                    const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                    if (pass == 0) {
+                        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float e0 = ((m >> j) & 1u) ? v[j] : 0.f, e1 = ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
+                            s1a += e0;
+                            s1b += e1;
+                            s2a = fmaf(e0, xv[j], s2a);
+                            s2b = fmaf(e1, xv[j + 1], s2b);
+                        }
+                        a1 += s1a + s1b;
+                        a2 += s2a + s2b;
+                    } else {
+                        const float mu1 = m1[s], mu2 = m2[s];
+                        const float rs = ch_ok ? __ldg(p.rstd1 + (int64_t)(g0 + s) * p.C1 + ch) : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const uint16_t bits = float_to_bf16_bits(rs * (v[j] - mu1 - xv[j] * mu2));
+                            if (((m >> j) & 1u) && ch_ok) dst[(int64_t)(cbeg + j) * p.C1] = bits;
+                        }
+                    }
+                    if (bnd[s + 1] <= cend) {
+                        if (pass == 0) {
+                            const float inv_n = 1.f / (float)(bnd[s + 1] - bnd[s]);
+                            m1[s] = a1 * inv_n;
+                            m2[s] = a2 * inv_n;
+                            a1 = a2 = 0.f;
+                        }
+                        ++s;
+                        while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
+                    } else {
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+};
+
+// ---- bwd0: out = x_bf16 W^T (fp32 out), used for d f12 = dz1 W1 ------------------------------------------------------
+struct OpLinearBf16In {
+    struct Params {
+        const uint16_t* x;   // bf16 [rows, K]
+        int ldx;
+        float* out;          // fp32 [rows, OUT]
+        int ldo;
+    };
+    struct EpiState {};
+    struct Raw {
+        uint4 q;
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
+        r.q = __ldg(reinterpret_cast<const uint4*>(p.x + grow * p.ldx + k));
+    }
+    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
+        o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
+    }
+    __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int cnt, int, uint8_t*, int, int) {
+        float* o = p.out + r0 * p.ldo + ch;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            if (c * 32 >= cnt) break;
+            float v[32];
+            tc::tmem_ld_32x32(taddr + c * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                if (col < cnt && ch_ok) o[(int64_t)col * p.ldo] = v[j];
+            }
+        }
+    }
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+};
+
+// ---- re-materialisation for the weight-gradient GEMMs ----------------------------------------------------------------
+__global__ void k_ext_make_h1(const uint16_t* __restrict__ xhat1, Dropout drop1, uint16_t* __restrict__ h1,
+                              int64_t rows, int C1) {
+    const int64_t chunks = rows * (C1 / 8);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / (C1 / 8);
+        const int k = (int)(i - row * (C1 / 8)) * 8;
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(xhat1 + row * C1 + k));
+        float v[8];
+        unpack8(q, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            v[j] = (v[j] > 0.f && dropout_keep(drop1, row, k + j, C1)) ? v[j] * drop1.scale : 0.f;
+        uint32_t o[4];
+        pack8(v, o);
+        *reinterpret_cast<uint4*>(h1 + row * C1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void k_ext_make_f12(const float* __restrict__ emb, const int32_t* __restrict__ src,
+                               const int32_t* __restrict__ dst, uint16_t* __restrict__ f12, int64_t rows, int H) {
+    const int K = src ? 2 * H : H;
+    const int64_t chunks = rows * (K / 8);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / (K / 8);
+        const int k = (int)(i - row * (K / 8)) * 8;
+        const int64_t node = src ? (k < H ? __ldg(src + row) : __ldg(dst + row)) : row;
+        float v[8];
+        load8_f32(emb + node * H, (src && k >= H) ? k - H : k, H, v);
+        uint32_t o[4];
+        pack8(v, o);
+        *reinterpret_cast<uint4*>(f12 + row * K + k) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+inline Dropout make_dropout_b(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
+    Dropout d;
+    d.mask = mask;
+    d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
+    d.enabled = training && pdrop > 0.f;
+    d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
+    double t = (double)pdrop * 16777216.0;
+    d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
+    return d;
+}
+
+}  // namespace
+
+extern "C" int gsatb_tc_ext_bwd_head(const float* dlogit, const void* xhat2, const float* rstd2, const float* w3,
+                                     const int32_t* seg_ptr, const uint8_t* mask2, uint64_t seed, float pdrop,
+                                     int training, void* dz2, float* dw3_part, int64_t rows, int64_t G, int H,
+                                     gsatb_stream_t stream) {
+    if (rows < 0 || G < 0 || H <= 0) return GSATB_EINVAL;
+    if (rows == 0 || G == 0) return GSATB_OK;
+    if (!dlogit || !xhat2 || !rstd2 || !w3 || !seg_ptr || !dz2 || !dw3_part) return GSATB_EINVAL;
+    dim3 grid((unsigned)G, (unsigned)((H + 127) / 128));
+    k_ext_bwd_head<<<grid, 128, 0, (cudaStream_t)stream>>>(dlogit, (const uint16_t*)xhat2, rstd2, w3, seg_ptr,
+                                                          make_dropout_b(mask2, seed * 2 + 2, pdrop, training),
+                                                          (uint16_t*)dz2, dw3_part, H);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_tc_ext_bwd1(const void* dz2, const void* w2t_bf16, const void* xhat1, const float* rstd1,
+                                 const uint8_t* mask1, uint64_t seed, float pdrop, int training,
+                                 const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
+                                 int num_tiles, void* dz1, int64_t rows, int H, int C1, gsatb_stream_t stream) {
+    if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
+    if (rows == 0 || num_tiles == 0) return GSATB_OK;
+    if (!dz2 || !w2t_bf16 || !xhat1 || !rstd1 || !tile_row || !tile_seg || !seg_ptr || !dz1) return GSATB_EINVAL;
+    if (H % 8 != 0 || H > 512) return GSATB_ESHAPE;
+    OpExtBwd1::Params p{(const uint16_t*)dz2, H, (const uint16_t*)xhat1, rstd1,
+                        make_dropout_b(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)dz1, C1};
+    Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
+    return launch<OpExtBwd1>(w2t_bf16, tl, H, C1, p, (cudaStream_t)stream);
+}
+
+extern "C" int gsatb_tc_linear_bf16in_fwd(const void* x_bf16, int ldx, const void* w_bf16, float* out, int ldo,
+                                          int64_t rows, int K, int OUT, gsatb_stream_t stream) {
+    if (rows < 0 || K <= 0 || OUT <= 0) return GSATB_EINVAL;
+    if (rows == 0) return GSATB_OK;
+    if (!x_bf16 || !w_bf16 || !out) return GSATB_EINVAL;
+    if (K > 512 || K % 8 != 0 || ldx % 8 != 0) return GSATB_ESHAPE;
+    OpLinearBf16In::Params p{(const uint16_t*)x_bf16, ldx, out, ldo};
+    Tiling tl = uniform_tiling(rows);
+    return launch<OpLinearBf16In>(w_bf16, tl, K, OUT, p, (cudaStream_t)stream);
+}
+
+extern "C" int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed, float pdrop, int training,
+                                    void* h1, int64_t rows, int C1, gsatb_stream_t stream) {
+    if (rows < 0 || C1 <= 0 || C1 % 8 != 0) return GSATB_EINVAL;
+    if (rows == 0) return GSATB_OK;
+    if (!xhat1 || !h1) return GSATB_EINVAL;
+    int64_t blocks = (rows * (C1 / 8) + 255) / 256;
+    if (blocks > (int64_t)GSATB_NUM_SMS * 32) blocks = (int64_t)GSATB_NUM_SMS * 32;
+    k_ext_make_h1<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)xhat1, make_dropout_b(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)h1, rows, C1);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* dst, void* f12, int64_t rows,
+                                     int H, gsatb_stream_t stream) {
+    if (rows < 0 || H <= 0 || H % 8 != 0) return GSATB_EINVAL;
+    if (rows == 0) return GSATB_OK;
+    if (!emb || !f12 || ((src == nullptr) != (dst == nullptr))) return GSATB_EINVAL;
+    const int K = src ? 2 * H : H;
+    int64_t blocks = (rows * (K / 8) + 255) / 256;
+    if (blocks > (int64_t)GSATB_NUM_SMS * 32) blocks = (int64_t)GSATB_NUM_SMS * 32;
+    k_ext_make_f12<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(emb, src, dst, (uint16_t*)f12, rows, H);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}

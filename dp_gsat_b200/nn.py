@@ -157,6 +157,7 @@ class GIN(tnn.Module):
             self.convs.append(GINConv(GIN.MLP(hidden_size, hidden_size)))
         self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
         self.masks = None     # parity tests inject dropout masks here
+        self.precision = 'fp32'   # 'bf16': node MLPs on tcgen05 (tc.gin_mlp_relu); 'fp32': strict library path
 
     @staticmethod
     def MLP(in_channels: int, out_channels: int):
@@ -170,9 +171,16 @@ class GIN(tnn.Module):
     def get_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin'):
         gi = get_graph_index(edge_index, batch)
         x = self.node_encoder(x)
+        fused = self.precision == 'bf16' and x.shape[1] % 8 == 0 and x.shape[1] <= 128
         for i in range(self.n_layers):
-            x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
-            x = self.relu(x)
+            if fused:
+                # K3 aggregation, then the node MLP + ReLU on the tensor cores (tc.gin_mlp_relu)
+                from . import tc
+                agg = ops.gin_aggregate(x, edge_atten, gi, self.convs[i].initial_eps)
+                x = tc.gin_mlp_relu(agg, self.convs[i].nn, self.training)
+            else:
+                x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
+                x = self.relu(x)
             x = _dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
         return x
 
@@ -258,6 +266,10 @@ class ExtractorMLP(tnn.Module):
         setattr(self, self._name, mlp)
         self.masks = None
         self.chunk_rows = 1 << 21      # rows per graph-aligned chunk (0 = never chunk)
+        self.precision = 'fp32'        # 'fp32': strict path (library sgemm + segment-norm kernels, rtol 1e-5 parity);
+        #                                'bf16': fused tcgen05 kernels (tc.fused_extractor), documented bf16 tolerance
+        self.seed = 0
+        self._calls = 0
 
     def forward(self, emb, edge_index, batch, type: Optional[str] = None):
         if type is not None and type != self.kind:
@@ -265,6 +277,22 @@ class ExtractorMLP(tnn.Module):
         mlp = getattr(self, self._name)
         gi = get_graph_index(edge_index, batch)
         gi.require_graph_contiguous()
+        if self.precision == 'bf16' and emb.shape[1] % 8 == 0 and emb.shape[1] <= 128 \
+                and gi.tile_plan('edge' if self.learn_edge_att else 'node') is not None:
+            # fused tensor-core path (tcgen05, bf16 operands): K1 of the design.  Falls through to the fp32 path when
+            # a graph exceeds one 128-row tile or the width is unsupported -- same math, different precision mode.
+            from . import tc
+            lin = [m for m in mlp if isinstance(m, tnn.Linear)]
+            p = next(m.p for m in mlp if isinstance(m, tnn.Dropout))
+            rows_n = gi.E if self.learn_edge_att else gi.N
+            m1 = m2 = None
+            if self.masks is not None and self.training and p > 0:
+                m1 = self.masks.get('ext.0', (rows_n, lin[0].weight.shape[0]), p).to(device=emb.device, dtype=torch.uint8)
+                m2 = self.masks.get('ext.1', (rows_n, lin[1].weight.shape[0]), p).to(device=emb.device, dtype=torch.uint8)
+            self._calls += 1
+            return tc.fused_extractor(emb, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
+                                      lin[2].bias, gi, edge_mode=self.learn_edge_att, pdrop=p, training=self.training,
+                                      seed=self.seed * 1000003 + self._calls, mask1=m1, mask2=m2)
         if self.learn_edge_att:
             f12 = ops.gather_concat(emb, gi)      # cat(emb[col], emb[row]) with col, row = edge_index
             rows, seg_all = f12, (gi.edge_ptr, gi.G)

@@ -76,3 +76,153 @@ def extractor_forward(emb: torch.Tensor, gi: GraphIndex, w1: torch.Tensor, w2: t
            ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T,
            ptr(xhat2), ptr(rstd2), ptr(logit), rows, C1, H, ctypes.c_float(eps), stream())
     return logit, dict(xhat1=xhat1, rstd1=rstd1, xhat2=xhat2, rstd2=rstd2, plan=plan)
+
+
+class _FusedExtractor(torch.autograd.Function):
+    """Extractor MLP (Linear -> InstanceNorm -> ReLU -> Dropout, twice, then Linear(H, 1)) as five tensor-core /
+    segment kernels forward and backward.  Parameter gradients: dW2 = dz2^T h1 and dW1 = dz1^T f12 are plain
+    library GEMMs on the re-materialised bf16 operands; b1 / b2 sit in front of an InstanceNorm and get exact zeros."""
+
+    @staticmethod
+    def forward(ctx, emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps):
+        res = extractor_forward(emb, gi, w1, w2, w3, b3, edge_mode=edge_mode, pdrop=pdrop, training=training,
+                                seed=seed, mask1=mask1, mask2=mask2, eps=eps)
+        if res is None:
+            raise ValueError('a graph exceeds one 128-row tile; use the fp32 extractor path for this batch')
+        logit, saved = res
+        ctx.saved = saved
+        ctx.cfg = (gi, edge_mode, float(pdrop), bool(training), int(seed), mask1, mask2)
+        ctx.save_for_backward(emb, w1, w2, w3)
+        ctx.has_b = (b1 is not None, b2 is not None, b3 is not None)
+        return logit
+
+    @staticmethod
+    def backward(ctx, dlogit):
+        emb, w1, w2, w3 = ctx.saved_tensors
+        gi, edge_mode, pdrop, training, seed, mask1, mask2 = ctx.cfg
+        sv = ctx.saved
+        tile_row, tile_seg, T = sv['plan']
+        L = lib()
+        dev = emb.device
+        N, H = emb.shape
+        C1 = w1.shape[0]
+        Kin = w1.shape[1]
+        rows = gi.E if edge_mode else gi.N
+        seg_ptr = gi.edge_ptr if edge_mode else gi.node_ptr
+        dlogit = dlogit.contiguous().view(-1).float()
+        w3f = w3.detach().reshape(-1).contiguous()
+        dz2 = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
+        dw3_part = torch.empty((gi.G, H), dtype=torch.float32, device=dev)
+        L.call('gsatb_tc_ext_bwd_head', ptr(dlogit), ptr(sv['xhat2']), ptr(sv['rstd2']), ptr(w3f), ptr(seg_ptr),
+               ptr(mask2), ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(dz2), ptr(dw3_part), rows,
+               gi.G, H, stream())
+        dz1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
+        w2t = prep_weight(w2, transpose=True)         # [C1, H]: A operand of dh1 = dz2 W2
+        L.call('gsatb_tc_ext_bwd1', ptr(dz2), ptr(w2t), ptr(sv['xhat1']), ptr(sv['rstd1']), ptr(mask1),
+               ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr),
+               T, ptr(dz1), rows, H, C1, stream())
+        # weight gradients (library GEMMs, fp32 accumulate) on re-materialised bf16 operands
+        h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
+        L.call('gsatb_tc_ext_make_h1', ptr(sv['xhat1']), ptr(mask1), ctypes.c_uint64(seed), ctypes.c_float(pdrop),
+               int(training), ptr(h1), rows, C1, stream())
+        dW2 = _mm_f32(dz2.t(), h1)
+        del h1
+        f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
+        L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None,
+               ptr(gi.dst) if edge_mode else None, ptr(f12), rows, H, stream())
+        dW1 = _mm_f32(dz1.t(), f12)
+        del f12
+        # input gradient: d f12 = dz1 W1, then the deterministic scatter back to the nodes
+        w1t = prep_weight(w1, transpose=True)         # [Kin, C1]
+        df = torch.empty((rows, Kin), dtype=torch.float32, device=dev)
+        L.call('gsatb_tc_linear_bf16in_fwd', ptr(dz1), C1, ptr(w1t), ptr(df), Kin, rows, C1, Kin, stream())
+        if edge_mode:
+            demb = torch.empty((N, H), dtype=torch.float32, device=dev)
+            L.call('gsatb_gather_concat_bwd', ptr(df), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst),
+                   ptr(gi.eid_by_dst), ptr(demb), N, H, stream())
+        else:
+            demb = df
+        dw3 = dw3_part.sum(0).view_as(w3)
+        db3 = dlogit.sum().view(1) if ctx.has_b[2] else None
+        db1 = torch.zeros(C1, device=dev) if ctx.has_b[0] else None
+        db2 = torch.zeros(H, device=dev) if ctx.has_b[1] else None
+        return (demb, dW1, db1, dW2, db2, dw3, db3, None, None, None, None, None, None, None, None)
+
+
+def _mm_f32(a_bf16: torch.Tensor, b_bf16: torch.Tensor) -> torch.Tensor:
+    """Plain library GEMM (cuBLAS) of bf16 operands with an fp32 result."""
+    try:
+        return torch.mm(a_bf16, b_bf16, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a_bf16, b_bf16).float()
+
+
+def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: float, training: bool, seed: int,
+                    mask1=None, mask2=None, eps: float = 1e-5):
+    return _FusedExtractor.apply(emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps)
+
+
+class _GinMlpFused(torch.autograd.Function):
+    """GIN node MLP  relu(Linear2(relu(BatchNorm1d(Linear1(x)))))  (reference src/models/gin.py:55-62 + the ReLU of
+    :50) with both Linears on tcgen05: Linear1's epilogue accumulates the BatchNorm batch statistics per channel
+    (thread-local, deterministic), BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU into its
+    epilogue.  Backward: dX products on tcgen05, weight gradients as plain library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps):
+        x = x.contiguous()
+        N, K = x.shape
+        H = w1.shape[0]
+        w1p, w2p = prep_weight(w1), prep_weight(w2)
+        if training:
+            z1, stats = linear(x, w1p, b1, H, want_stats=True)
+            mean64 = stats[:H] / N
+            var64 = (stats[H:] / N - mean64 * mean64).clamp_min(0.0)
+            mean, var = mean64.float(), var64.float()
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var * (N / max(N - 1, 1)), alpha=momentum)
+                nbt.add_(1)
+        else:
+            z1 = linear(x, w1p, b1, H)
+            mean, var = running_mean, running_var
+        rstd = torch.rsqrt(var + eps)
+        scale = (gamma * rstd).contiguous()
+        shift = (beta - mean * scale).contiguous()
+        h = linear(z1, w2p, b2, w2.shape[0], in_scale=scale, in_shift=shift, relu_out=True)
+        ctx.save_for_backward(x, z1, h, w1, w2, gamma, mean, rstd, scale, shift)
+        ctx.training = training
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, z1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        N = x.shape[0]
+        H = w1.shape[0]
+        d2 = dh * (h > 0)
+        db2 = d2.sum(0)
+        a1 = torch.relu(torch.addcmul(shift, z1, scale))
+        dW2 = _mm_f32(d2.bfloat16().t(), a1.bfloat16())
+        da1 = linear(d2, prep_weight(w2, transpose=True), None, H)
+        g = da1 * (a1 > 0)
+        del a1, da1, d2
+        xhat = (z1 - mean) * rstd
+        dbeta = g.sum(0)
+        dgamma = (g * xhat).sum(0)
+        if ctx.training:
+            dz1 = (gamma * rstd) * (g - dbeta / N - xhat * (dgamma / N))
+        else:
+            dz1 = g * (gamma * rstd)
+        del g, xhat
+        db1 = dz1.sum(0)
+        dW1 = _mm_f32(dz1.bfloat16().t(), x.bfloat16())
+        dx = linear(dz1, prep_weight(w1, transpose=True), None, x.shape[1]) if ctx.needs_input_grad[0] else None
+        return dx, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None
+
+
+def gin_mlp_relu(x, seq, training: bool):
+    """``relu(seq(x))`` for seq = GIN.MLP(...) = Sequential(Linear, BatchNorm1d, ReLU, Linear)."""
+    lin1, bn, _, lin2 = seq[0], seq[1], seq[2], seq[3]
+    return _GinMlpFused.apply(x, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight, lin2.bias, bn.running_mean,
+                              bn.running_var, bn.num_batches_tracked, training and bn.training,
+                              bn.momentum if bn.momentum is not None else 0.1, bn.eps)

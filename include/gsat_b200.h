@@ -203,6 +203,31 @@ int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16_padded, const float
                       void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H, float eps,
                       gsatb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K1 backward (autograd of the extractor MLP).  seg_ptr / tiles as in the forward; seed, pdrop, training and the
+ * optional injected masks must equal the forward call's so that the dropout masks are regenerated identically.
+ *   ext_bwd_head : dlogit [rows] -> dz2 bf16 [rows,H] (through w3, Dropout2, ReLU2, InstanceNorm2);
+ *                  dw3_part [G,H] per-graph partial sums of d w3 (summed by the caller)
+ *   ext_bwd1     : dh1 = dz2 W2 on tcgen05 (w2t = gsatb_tc_prep_weight(W2, transpose=1)), epilogue = Dropout1 /
+ *                  ReLU1 masks + InstanceNorm1 backward -> dz1 bf16 [rows,C1]
+ *   linear_bf16in: out fp32 [rows,OUT] = x_bf16 [rows,K] W^T   (d f12 = dz1 W1 with w = prep(W1, transpose=1))
+ *   make_h1/f12  : bf16 re-materialisation of Dropout(ReLU(xhat1)) and of the gathered input rows, the right-hand
+ *                  operands of the weight-gradient GEMMs dW2 = dz2^T h1, dW1 = dz1^T f12 (plain library GEMMs)
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_tc_ext_bwd_head(const float* dlogit, const void* xhat2, const float* rstd2, const float* w3,
+                          const int32_t* seg_ptr, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
+                          void* dz2, float* dw3_part, int64_t rows, int64_t G, int H, gsatb_stream_t stream);
+int gsatb_tc_ext_bwd1(const void* dz2, const void* w2t_bf16_padded, const void* xhat1, const float* rstd1,
+                      const uint8_t* mask1, uint64_t seed, float pdrop, int training, const int32_t* tile_row,
+                      const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles, void* dz1, int64_t rows, int H,
+                      int C1, gsatb_stream_t stream);
+int gsatb_tc_linear_bf16in_fwd(const void* x_bf16, int ldx, const void* w_bf16_padded, float* out, int ldo,
+                               int64_t rows, int K, int OUT, gsatb_stream_t stream);
+int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed, float pdrop, int training, void* h1,
+                         int64_t rows, int C1, gsatb_stream_t stream);
+int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* dst, void* f12, int64_t rows, int H,
+                          gsatb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
