@@ -131,6 +131,7 @@ struct OpExtFwd1 {
         float eps;
     };
     struct EpiState {};
+    static constexpr int UNROLL = 8;
     struct Raw {
         float v[8];
     };
@@ -145,7 +146,7 @@ struct OpExtFwd1 {
     __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) { pack8(r.v, o); }
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane) {
+                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane, int) {
         const int* bnd;
         int g0;
         const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
@@ -161,7 +162,7 @@ struct OpExtFwd1 {
             },
             [](int) {}, [](int) {});
     }
-    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -182,6 +183,7 @@ struct OpExtFwd2 {
     struct EpiState {
         uint32_t par;
     };
+    static constexpr int UNROLL = 8;
     struct Raw {
         uint4 q;
     };
@@ -214,7 +216,7 @@ struct OpExtFwd2 {
         if (first) st.par = 0;
     }
     __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int tile, uint8_t* misc, int q, int lane) {
+                                    int64_t r0, int cnt, int tile, uint8_t* misc, int q, int lane, int grp) {
         const int* bnd;
         int g0;
         const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
@@ -257,25 +259,14 @@ struct OpExtFwd2 {
                 }
                 red[q * 128 + c * 32 + lane] = a[0];
             });
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        tc::named_bar_sync(5 + grp, 128);
         const int col = q * 32 + lane;
         if (col < cnt)
             p.logit[r0 + col] = red[col] + red[128 + col] + red[256 + col] + red[384 + col] + (p.b3 ? __ldg(p.b3) : 0.f);
         st.par ^= 1u;
     }
-    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
-
-inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
-    Dropout d;
-    d.mask = mask;
-    d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
-    d.enabled = training && pdrop > 0.f;
-    d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
-    double t = (double)pdrop * 16777216.0;
-    d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
-    return d;
-}
 
 }  // namespace
 

@@ -96,6 +96,7 @@ struct OpExtBwd1 {
         int C1;
     };
     struct EpiState {};
+    static constexpr int UNROLL = 8;
     struct Raw {
         uint4 q;
     };
@@ -111,7 +112,7 @@ struct OpExtBwd1 {
     // (chunk, graph) pieces reduced / emitted.  (The first version loaded inside the per-column expression and the
     // loads serialised: 147 k cycles per 128-column block.)
     __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane) {
+                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane, int) {
         const int* bnd;
         int g0;
         const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
@@ -197,7 +198,7 @@ struct OpExtBwd1 {
             }
         }
     }
-    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
 
 // ---- bwd0: out = x_bf16 W^T (fp32 out), used for d f12 = dz1 W1 ------------------------------------------------------
@@ -209,6 +210,7 @@ struct OpLinearBf16In {
         int ldo;
     };
     struct EpiState {};
+    static constexpr int UNROLL = 8;
     struct Raw {
         uint4 q;
     };
@@ -220,7 +222,7 @@ struct OpLinearBf16In {
     }
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int) {
+                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
         float* o = p.out + r0 * p.ldo + ch;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -235,7 +237,7 @@ struct OpLinearBf16In {
             }
         }
     }
-    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
 
 // ---- re-materialisation for the weight-gradient GEMMs ----------------------------------------------------------------
@@ -273,17 +275,6 @@ __global__ void k_ext_make_f12(const float* __restrict__ emb, const int32_t* __r
     }
 }
 
-inline Dropout make_dropout_b(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
-    Dropout d;
-    d.mask = mask;
-    d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
-    d.enabled = training && pdrop > 0.f;
-    d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
-    double t = (double)pdrop * 16777216.0;
-    d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
-    return d;
-}
-
 }  // namespace
 
 extern "C" int gsatb_tc_ext_bwd_head(const float* dlogit, const void* xhat2, const float* rstd2, const float* w3,
@@ -295,7 +286,7 @@ extern "C" int gsatb_tc_ext_bwd_head(const float* dlogit, const void* xhat2, con
     if (!dlogit || !xhat2 || !rstd2 || !w3 || !seg_ptr || !dz2 || !dw3_part) return GSATB_EINVAL;
     dim3 grid((unsigned)G, (unsigned)((H + 127) / 128));
     k_ext_bwd_head<<<grid, 128, 0, (cudaStream_t)stream>>>(dlogit, (const uint16_t*)xhat2, rstd2, w3, seg_ptr,
-                                                          make_dropout_b(mask2, seed * 2 + 2, pdrop, training),
+                                                          make_dropout(mask2, seed * 2 + 2, pdrop, training),
                                                           (uint16_t*)dz2, dw3_part, H);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
@@ -310,7 +301,7 @@ extern "C" int gsatb_tc_ext_bwd1(const void* dz2, const void* w2t_bf16, const vo
     if (!dz2 || !w2t_bf16 || !xhat1 || !rstd1 || !tile_row || !tile_seg || !seg_ptr || !dz1) return GSATB_EINVAL;
     if (H % 8 != 0 || H > 512) return GSATB_ESHAPE;
     OpExtBwd1::Params p{(const uint16_t*)dz2, H, (const uint16_t*)xhat1, rstd1,
-                        make_dropout_b(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)dz1, C1};
+                        make_dropout(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)dz1, C1};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
     return launch<OpExtBwd1>(w2t_bf16, tl, H, C1, p, (cudaStream_t)stream);
 }
@@ -334,7 +325,7 @@ extern "C" int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uin
     int64_t blocks = (rows * (C1 / 8) + 255) / 256;
     if (blocks > (int64_t)GSATB_NUM_SMS * 32) blocks = (int64_t)GSATB_NUM_SMS * 32;
     k_ext_make_h1<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const uint16_t*)xhat1, make_dropout_b(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)h1, rows, C1);
+        (const uint16_t*)xhat1, make_dropout(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)h1, rows, C1);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }

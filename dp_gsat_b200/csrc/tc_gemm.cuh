@@ -10,8 +10,9 @@
 //   warp 0      TMA producer: streams W in [128 x 64] bf16 K-blocks (SWIZZLE_128B) through an mbarrier ring
 //   warp 1      MMA issuer: one elected thread, tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), M=128 N=128 K=16
 //   warp 2      TMEM allocator (256 columns = two 128-column accumulators, double-buffered across M-blocks)
-//   warps 4-7   epilogue: tcgen05.ld 32x32b -> registers -> fused epilogue -> global
-//   warps 8-15  B-operand producers: global (fp32 / bf16 / gathered rows) -> fused prologue -> bf16 -> swizzled smem
+//   warps 4-11  epilogue, two warpgroups (one per accumulator slot): tcgen05.ld 32x32b -> registers -> fused
+//               epilogue -> global
+//   warps 12-19 B-operand producers: global (fp32 / bf16 / gathered rows) -> fused prologue -> bf16 -> swizzled smem
 //
 // A tile = up to 128 rows; for the extractor the tiles are graph-aligned (whole graphs per tile) so that the
 // per-graph InstanceNorm closes inside the tile.
@@ -25,11 +26,12 @@ namespace tcg {
 constexpr int TILE_ROWS = 128;
 constexpr int KBLK = 64;                      // bf16 elements per 128-byte swizzle row
 constexpr int BLK_BYTES = TILE_ROWS * 128;    // one [128 x 64] bf16 K-block = 16 KiB
-constexpr int THREADS = 512;
-constexpr int EPI_WARP0 = 4, PRO_WARP0 = 8, PRO_WARPS = 8;
-constexpr int PRO_UNROLL = 8;                 // row-chunks whose global loads one producer thread keeps in flight
+constexpr int EPI_GROUPS = 2;                 // epilogue warpgroups (one per accumulator slot)
+constexpr int THREADS = 640;
+constexpr int EPI_WARP0 = 4, PRO_WARP0 = 12, PRO_WARPS = 8;
+// row-chunks whose global loads one producer thread keeps in flight: Op::UNROLL (8 for 32-byte chunks, 4 for wider)
 constexpr int MAX_SEG = 32;                   // graphs per tile the InstanceNorm epilogues support
-constexpr int MISC_BYTES = 8192;             // epilogue scratch: segment tables (4 warps) + cross-warp reductions
+constexpr int MISC_BYTES = 16384;            // epilogue scratch, half per epilogue group: segment tables + reductions
 
 struct Tiling {
     int64_t rows;               // total rows
@@ -184,9 +186,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
                 d[3] = w_a;
             }
         }
-    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
-        // ===================== epilogue =====================
-        const int q = warp - EPI_WARP0;                     // TMEM lane quarter this warp may access
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * EPI_GROUPS) {
+        // ===================== epilogue: two warpgroups, one per accumulator slot =====================
+        // Group g drains accumulator slot g (every other M-block): two warps per SM sub-partition hide each other's
+        // TMEM-load / shared-memory / dependent-issue latencies (one warp alone reached ~0.25 IPC).
+        const int grp = (warp - EPI_WARP0) >> 2;
+        const int q = (warp - EPI_WARP0) & 3;               // == warp % 4: the TMEM lane quarter this warp may access
+        uint8_t* my_misc = misc + grp * (MISC_BYTES / EPI_GROUPS);
         typename Op::EpiState st;
         uint32_t ce = 0;
         bool first = true;
@@ -197,24 +203,28 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
             tile_range(tl, tile, r0, cnt);
             for (int mb = 0; mb < sh.NMB; ++mb, ++ce) {
                 const uint32_t slot = ce & 1, us = ce >> 1;
+                if ((int)slot != grp) continue;
                 const int ch = mb * 128 + q * 32 + lane;
                 if (first || sh.NMB > 1) Op::epi_init(p, st, ch, ch < sh.OUT, first);
+                first = false;
                 t0 = clock64();
-                tc::group_mbar_wait(q == 0 && lane == 0, &acc_full[slot], us & 1, 3, 128);
+                tc::group_mbar_wait(q == 0 && lane == 0, &acc_full[slot], us & 1, 3 + grp, 128);
                 w_full += clock64() - t0;
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
                 t0 = clock64();
-                Op::epilogue(p, tl, st, taddr, ch, ch < sh.OUT, r0, cnt, tile, misc, q, lane);
+                Op::epilogue(p, tl, st, taddr, ch, ch < sh.OUT, r0, cnt, tile, my_misc, q, lane, grp);
                 t_epi += clock64() - t0;
                 tc::tc_fence_before();
                 tc::mbar_arrive(&acc_empty[slot]);
-                if (sh.NMB > 1) Op::epi_finish(p, st, ch, ch < sh.OUT, false);
+                if (sh.NMB > 1) Op::epi_finish(p, st, ch, ch < sh.OUT, false, grp);
             }
-            first = false;
         }
-        if (sh.NMB == 1) Op::epi_finish(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true);
-        if (tl.dbg && q == 0 && lane == 0) {
+        if (sh.NMB == 1) {
+            if (first) Op::epi_init(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true);
+            Op::epi_finish(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true, grp);
+        }
+        if (tl.dbg && grp == 0 && q == 0 && lane == 0) {
             long long* d = tl.dbg + (size_t)blockIdx.x * 16;
             d[4] = w_full;
             d[5] = t_epi;
@@ -239,6 +249,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
             // units (= KB * 32) is a multiple of PRO_WARPS * PRO_UNROLL when KB is even; the kb == KB guard covers
             // odd KB.  Loads are unconditional on clamped coordinates (K % 8 == 0, so an 8-chunk is wholly in or
             // out) and invalid chunks are zeroed by a select: no branches, so ptxas keeps all loads in flight.
+            constexpr int PRO_UNROLL = Op::UNROLL;
             for (int u0 = pw; u0 < units; u0 += PRO_WARPS * PRO_UNROLL) {
                 typename Op::Raw raw[PRO_UNROLL];
 #pragma unroll

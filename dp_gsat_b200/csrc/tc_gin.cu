@@ -1,0 +1,196 @@
+// GIN node MLP backward on the tensor cores (autograd of reference src/models/gin.py:55-62 plus the ReLU / Dropout of
+// gin.py:50-52):   h = Dropout(ReLU( Linear2( ReLU( BatchNorm1d( Linear1(x) ) ) ) ))
+//
+//   gin_bwd2: d2 = dh * (h > 0) * 1/(1-p) is formed in the operand load (and written out in bf16 for dW2 / db2);
+//             da1 = d2 W2 on tcgen05 (A operand = W2^T); epilogue (thread = channel): reload z1, rebuild
+//             a1 = ReLU(BN(z1)) and xhat, g = da1 * (a1 > 0), accumulate the BatchNorm-backward statistics
+//             sum(g), sum(g * xhat) per channel thread-locally, store g and a1 in bf16
+//   gin_bwd1: dz1 = A*g + B*z1 + C per channel (BatchNorm backward folded into three vectors) is formed in the
+//             operand load (and written out in bf16 for dW1 / db1); dx = dz1 W1 on tcgen05 (A operand = W1^T)
+// Weight gradients (dW2 = d2^T a1, dW1 = dz1^T x) are plain library GEMMs issued by the Python side.
+#include "tc_ops_common.cuh"
+
+namespace {
+
+using namespace tcg;
+
+struct OpGinBwd2 {
+    struct Params {
+        const float* dh;        // [N, H] upstream gradient of the module output
+        const float* h;         // [N, H] saved module output (post ReLU / Dropout)
+        float drop_scale;       // 1/(1-p) when dropout was applied, else 1
+        const float* z1;        // [N, H1] saved Linear1 output
+        const float* bn_scale;  // [H1] gamma * rstd          (BatchNorm folded:  a1 = relu(z1 * scale + shift))
+        const float* bn_shift;  // [H1] beta - mean * scale
+        const float* mean;      // [H1]
+        const float* rstd;      // [H1]
+        uint16_t* d2;           // bf16 [N, H]   out
+        uint16_t* g;            // bf16 [N, H1]  out
+        uint16_t* a1;           // bf16 [N, H1]  out
+        float* stat_partials;   // [gridDim * EPI_GROUPS][2][H1]
+        int H, H1;
+    };
+    struct EpiState {
+        float s1, s2;
+    };
+    static constexpr int UNROLL = 4;
+    struct Raw {
+        float dh[8], h[8];
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
+        load8_f32(p.dh + grow * p.H, k, K, r.dh);
+        load8_f32(p.h + grow * p.H, k, K, r.h);
+    }
+    __device__ static void transform8(const Params& p, Raw& r, int64_t grow, int k, int, uint32_t o[4]) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r.h[i] > 0.f ? r.dh[i] * p.drop_scale : 0.f;
+        pack8(v, o);
+        *reinterpret_cast<uint4*>(p.d2 + grow * p.H + k) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
+        const int chc = ch_ok ? ch : 0;
+        const float sc = __ldg(p.bn_scale + chc), sf = __ldg(p.bn_shift + chc);
+        const float mu = __ldg(p.mean + chc), rs = __ldg(p.rstd + chc);
+        const float* zs = p.z1 + r0 * p.H1 + chc;
+        uint16_t* go = p.g + r0 * p.H1 + chc;
+        uint16_t* ao = p.a1 + r0 * p.H1 + chc;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            if (c * 32 >= cnt) break;
+            float v[32], z[32];
+            tc::tmem_ld_32x32(taddr + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) z[j] = __ldg(zs + (int64_t)min(c * 32 + j, cnt - 1) * p.H1);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const int c0 = c * 32 + j, c1 = c0 + 1;
+                const bool ok0 = c0 < cnt, ok1 = c1 < cnt;
+                const float a0 = fmaxf(fmaf(z[j], sc, sf), 0.f), a1v = fmaxf(fmaf(z[j + 1], sc, sf), 0.f);
+                const float g0 = (a0 > 0.f && ok0) ? v[j] : 0.f, g1 = (a1v > 0.f && ok1) ? v[j + 1] : 0.f;
+                const float x0 = (z[j] - mu) * rs, x1 = (z[j + 1] - mu) * rs;
+                s1a += g0;
+                s1b += g1;
+                s2a = fmaf(g0, x0, s2a);
+                s2b = fmaf(g1, x1, s2b);
+                const uint16_t gb0 = float_to_bf16_bits(g0), gb1 = float_to_bf16_bits(g1);
+                const uint16_t ab0 = float_to_bf16_bits(a0), ab1 = float_to_bf16_bits(a1v);
+                if (ok0 && ch_ok) {
+                    go[(int64_t)c0 * p.H1] = gb0;
+                    ao[(int64_t)c0 * p.H1] = ab0;
+                }
+                if (ok1 && ch_ok) {
+                    go[(int64_t)c1 * p.H1] = gb1;
+                    ao[(int64_t)c1 * p.H1] = ab1;
+                }
+            }
+        }
+        st.s1 += s1a + s1b;
+        st.s2 += s2a + s2b;
+    }
+    __device__ static void epi_finish(const Params& p, EpiState& st, int ch, bool ch_ok, bool, int grp) {
+        if (ch_ok) {
+            const size_t part = (size_t)blockIdx.x * EPI_GROUPS + grp;
+            p.stat_partials[(part * 2 + 0) * p.H1 + ch] = st.s1;
+            p.stat_partials[(part * 2 + 1) * p.H1 + ch] = st.s2;
+        }
+    }
+};
+
+struct OpGinBwd1 {
+    struct Params {
+        const uint16_t* g;    // bf16 [N, H1]
+        const float* z1;      // [N, H1]
+        const float* cA;      // [H1]  dz1 = cA * g + cB * z1 + cC
+        const float* cB;
+        const float* cC;
+        uint16_t* dz1;        // bf16 [N, H1] out
+        float* dx;            // [N, Kin] out
+        int H1, Kin;
+    };
+    struct EpiState {};
+    static constexpr int UNROLL = 4;
+    struct Raw {
+        uint4 g;
+        float z[8];
+    };
+    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
+        r.g = __ldg(reinterpret_cast<const uint4*>(p.g + grow * p.H1 + k));
+        load8_f32(p.z1 + grow * p.H1, k, K, r.z);
+    }
+    __device__ static void transform8(const Params& p, Raw& r, int64_t grow, int k, int K, uint32_t o[4]) {
+        float g[8], a[8], b[8], c[8];
+        unpack8(r.g, g);
+        load8_f32(p.cA, k, K, a);
+        load8_f32(p.cB, k, K, b);
+        load8_f32(p.cC, k, K, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], g[i], fmaf(b[i], r.z[i], c[i]));
+        pack8(g, o);
+        *reinterpret_cast<uint4*>(p.dz1 + grow * p.H1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, uint32_t taddr, int ch, bool ch_ok,
+                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
+        float* o = p.dx + r0 * p.Kin + ch;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            if (c * 32 >= cnt) break;
+            float v[32];
+            tc::tmem_ld_32x32(taddr + c * 32, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                if (col < cnt && ch_ok) o[(int64_t)col * p.Kin] = v[j];
+            }
+        }
+    }
+    __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
+};
+
+__global__ void k_reduce_partials_f(const float* __restrict__ partials, int parts, int width, float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= width) return;
+    double acc = 0.0;
+    for (int q = 0; q < parts; ++q) acc += (double)partials[(size_t)q * width + j];
+    out[j] = (float)acc;
+}
+
+}  // namespace
+
+extern "C" int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16,
+                                 const float* z1, const float* bn_scale, const float* bn_shift, const float* mean,
+                                 const float* rstd, void* d2, void* g, void* a1, float* stat_partials, float* stats,
+                                 int64_t N, int H, int H1, gsatb_stream_t stream) {
+    if (N < 0 || H <= 0 || H1 <= 0) return GSATB_EINVAL;
+    if (N == 0) return GSATB_OK;
+    if (!dh || !h || !w2t_bf16 || !z1 || !bn_scale || !bn_shift || !mean || !rstd || !d2 || !g || !a1 ||
+        !stat_partials || !stats)
+        return GSATB_EINVAL;
+    if (H % 8 != 0 || H > 512 || H1 > 128) return GSATB_ESHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    OpGinBwd2::Params p{dh, h, drop_scale, z1, bn_scale, bn_shift, mean, rstd, (uint16_t*)d2, (uint16_t*)g,
+                        (uint16_t*)a1, stat_partials, H, H1};
+    cudaMemsetAsync(stat_partials, 0, (size_t)GSATB_NUM_SMS * EPI_GROUPS * 2 * H1 * sizeof(float), st);
+    int rc = launch<OpGinBwd2>(w2t_bf16, uniform_tiling(N), H, H1, p, st);
+    if (rc != GSATB_OK) return rc;
+    k_reduce_partials_f<<<(2 * H1 + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS * EPI_GROUPS, 2 * H1, stats);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_tc_gin_bwd1(const void* g, const float* z1, const float* cA, const float* cB, const float* cC,
+                                 const void* w1t_bf16, void* dz1, float* dx, int64_t N, int H1, int Kin,
+                                 gsatb_stream_t stream) {
+    if (N < 0 || H1 <= 0 || Kin <= 0) return GSATB_EINVAL;
+    if (N == 0) return GSATB_OK;
+    if (!g || !z1 || !cA || !cB || !cC || !w1t_bf16 || !dz1 || !dx) return GSATB_EINVAL;
+    if (H1 % 8 != 0 || H1 > 512) return GSATB_ESHAPE;
+    OpGinBwd1::Params p{(const uint16_t*)g, z1, cA, cB, cC, (uint16_t*)dz1, dx, H1, Kin};
+    return launch<OpGinBwd1>(w1t_bf16, uniform_tiling(N), H1, Kin, p, (cudaStream_t)stream);
+}

@@ -26,10 +26,12 @@ struct OpLinear {
         int relu_out;
         float* stat_partials;    // nullable
         int OUT;
+        Dropout drop;            // applied after the output activation (GIN: dropout(relu(conv)), gin.py:51-52)
     };
     struct EpiState {
         float s1, s2;
     };
+    static constexpr int UNROLL = 8;
     struct Raw {
         float v[8];
     };
@@ -51,9 +53,12 @@ struct OpLinear {
     // columns of a chunk are independent instruction streams the scheduler can interleave (a per-column branch
     // left the single epilogue warp of each sub-partition latency-bound at ~100 cycles per column).
     __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int) {
+                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
         const float b = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
         float* o = p.out + r0 * p.ldo + ch;
+        const bool use_mask = p.drop.enabled && p.drop.mask != nullptr;
+        const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (ch_ok ? ch : 0) : nullptr;
+        const uint32_t cht = hash_ch_term(p.drop, ch);
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -74,6 +79,14 @@ struct OpLinear {
                     z0 = fmaxf(z0, 0.f);
                     z1 = fmaxf(z1, 0.f);
                 }
+                if (p.drop.enabled) {
+                    const bool k0 = use_mask ? (ok0 ? __ldg(mk + (int64_t)c0 * p.OUT) != 0 : false)
+                                             : hash_keep(p.drop, (uint32_t)(r0 + c0), cht);
+                    const bool k1 = use_mask ? (ok1 ? __ldg(mk + (int64_t)c1 * p.OUT) != 0 : false)
+                                             : hash_keep(p.drop, (uint32_t)(r0 + c1), cht);
+                    z0 = k0 ? z0 * p.drop.scale : 0.f;
+                    z1 = k1 ? z1 * p.drop.scale : 0.f;
+                }
                 if (ok0 && ch_ok) o[(int64_t)c0 * p.ldo] = z0;
                 if (ok1 && ch_ok) o[(int64_t)c1 * p.ldo] = z1;
             }
@@ -81,10 +94,11 @@ struct OpLinear {
         st.s1 += s1a + s1b;
         st.s2 += s2a + s2b;
     }
-    __device__ static void epi_finish(const Params& p, EpiState& st, int ch, bool ch_ok, bool) {
+    __device__ static void epi_finish(const Params& p, EpiState& st, int ch, bool ch_ok, bool, int grp) {
         if (p.stat_partials && ch_ok) {
-            p.stat_partials[((size_t)blockIdx.x * 2 + 0) * p.OUT + ch] = st.s1;
-            p.stat_partials[((size_t)blockIdx.x * 2 + 1) * p.OUT + ch] = st.s2;
+            const size_t part = (size_t)blockIdx.x * EPI_GROUPS + grp;
+            p.stat_partials[(part * 2 + 0) * p.OUT + ch] = st.s1;
+            p.stat_partials[(part * 2 + 1) * p.OUT + ch] = st.s2;
         }
     }
 };
@@ -134,12 +148,12 @@ extern "C" int gsatb_tc_set_profile_buffer(void* buf) {
     return GSATB_OK;
 }
 
-extern "C" size_t gsatb_tc_stat_partials_elems(int OUT) { return (size_t)GSATB_NUM_SMS * 2 * OUT; }
+extern "C" size_t gsatb_tc_stat_partials_elems(int OUT) { return (size_t)GSATB_NUM_SMS * tcg::EPI_GROUPS * 2 * OUT; }
 
 extern "C" int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift,
                                    const void* w_bf16, const float* bias, float* out, int ldo, int relu_out,
-                                   float* stat_partials, double* stats, int64_t rows, int K, int OUT,
-                                   gsatb_stream_t stream) {
+                                   float* stat_partials, double* stats, const uint8_t* drop_mask, uint64_t drop_seed,
+                                   float pdrop, int64_t rows, int K, int OUT, gsatb_stream_t stream) {
     if (rows < 0 || K <= 0 || OUT <= 0) return GSATB_EINVAL;
     if (rows == 0) return GSATB_OK;
     if (!x || !w_bf16 || !out) return GSATB_EINVAL;
@@ -149,14 +163,15 @@ extern "C" int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scal
     if (!gsatb_aligned16(x) || (in_scale && (!gsatb_aligned16(in_scale) || !gsatb_aligned16(in_shift))))
         return GSATB_EALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    OpLinear::Params p{x, ldx, in_scale, in_shift, bias, out, ldo, relu_out, stat_partials, OUT};
+    OpLinear::Params p{x, ldx, in_scale, in_shift, bias, out, ldo, relu_out, stat_partials, OUT,
+                       make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f)};
     Tiling tl = uniform_tiling(rows);
     if (stat_partials)
         cudaMemsetAsync(stat_partials, 0, gsatb_tc_stat_partials_elems(OUT) * sizeof(float), st);
     int rc = launch<OpLinear>(w_bf16, tl, K, OUT, p, st);
     if (rc != GSATB_OK) return rc;
     if (stat_partials) {
-        k_reduce_partials<<<(2 * OUT + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS, 2 * OUT, stats);
+        k_reduce_partials<<<(2 * OUT + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS * EPI_GROUPS, 2 * OUT, stats);
         GSATB_CHECK_LAUNCH();
     }
     return GSATB_OK;

@@ -68,6 +68,17 @@ __device__ __forceinline__ bool dropout_keep(const Dropout& d, int64_t row, int 
     return hash_keep(d, (uint32_t)row, hash_ch_term(d, ch));
 }
 
+inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
+    Dropout d;
+    d.mask = mask;
+    d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
+    d.enabled = training && pdrop > 0.f;
+    d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
+    double t = (double)pdrop * 16777216.0;
+    d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
+    return d;
+}
+
 inline Tiling uniform_tiling(int64_t rows) {
     Tiling t;
     t.rows = rows;

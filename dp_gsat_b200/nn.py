@@ -158,6 +158,8 @@ class GIN(tnn.Module):
         self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
         self.masks = None     # parity tests inject dropout masks here
         self.precision = 'fp32'   # 'bf16': node MLPs on tcgen05 (tc.gin_mlp_relu); 'fp32': strict library path
+        self.seed = 0
+        self._calls = 0
 
     @staticmethod
     def MLP(in_channels: int, out_channels: int):
@@ -177,10 +179,16 @@ class GIN(tnn.Module):
                 # K3 aggregation, then the node MLP + ReLU on the tensor cores (tc.gin_mlp_relu)
                 from . import tc
                 agg = ops.gin_aggregate(x, edge_atten, gi, self.convs[i].initial_eps)
-                x = tc.gin_mlp_relu(agg, self.convs[i].nn, self.training)
-            else:
-                x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
-                x = self.relu(x)
+                dm = None
+                if self.masks is not None and self.training and self.dropout_p > 0:
+                    dm = self.masks.get(f'{mask_key}.{i}', (x.shape[0], self.convs[i].nn[3].weight.shape[0]),
+                                        self.dropout_p).to(device=x.device, dtype=torch.uint8)
+                self._calls += 1
+                x = tc.gin_mlp_relu(agg, self.convs[i].nn, self.training, self.dropout_p,
+                                    self.seed * 7919 + self._calls, dm)      # ReLU + dropout fused in the epilogue
+                continue
+            x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
+            x = self.relu(x)
             x = _dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
         return x
 

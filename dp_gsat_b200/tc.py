@@ -31,8 +31,8 @@ def prep_weight(w: torch.Tensor, transpose: bool = False) -> torch.Tensor:
 
 def linear(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_features: int,
            in_scale: Optional[torch.Tensor] = None, in_shift: Optional[torch.Tensor] = None, relu_out: bool = False,
-           want_stats: bool = False):
-    """out = act(pro(x) W^T + bias) on the tensor cores; optional per-channel (sum z, sum z^2) in fp64."""
+           want_stats: bool = False, pdrop: float = 0.0, drop_seed: int = 0, drop_mask: Optional[torch.Tensor] = None):
+    """out = drop(act(pro(x) W^T + bias)) on the tensor cores; optional per-channel (sum z, sum z^2) in fp64."""
     x = x.contiguous()
     rows, K = x.shape
     out = torch.empty((rows, out_features), dtype=torch.float32, device=x.device)
@@ -42,7 +42,8 @@ def linear(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_
                            device=x.device)
         stats = torch.empty(2 * out_features, dtype=torch.float64, device=x.device)
     lib().call('gsatb_tc_linear_fwd', ptr(x), K, ptr(in_scale), ptr(in_shift), ptr(wp), ptr(bias), ptr(out),
-               out_features, int(relu_out), ptr(part), ptr(stats), rows, K, out_features, stream())
+               out_features, int(relu_out), ptr(part), ptr(stats), ptr(drop_mask), ctypes.c_uint64(drop_seed),
+               ctypes.c_float(pdrop), rows, K, out_features, stream())
     return (out, stats) if want_stats else out
 
 
@@ -163,66 +164,84 @@ def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: 
 
 
 class _GinMlpFused(torch.autograd.Function):
-    """GIN node MLP  relu(Linear2(relu(BatchNorm1d(Linear1(x)))))  (reference src/models/gin.py:55-62 + the ReLU of
-    :50) with both Linears on tcgen05: Linear1's epilogue accumulates the BatchNorm batch statistics per channel
-    (thread-local, deterministic), BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU into its
-    epilogue.  Backward: dX products on tcgen05, weight gradients as plain library GEMMs."""
+    """GIN node MLP  Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(x))))))  (reference src/models/gin.py:55-62 + the
+    ReLU / Dropout of :50-52) on tcgen05.  Forward: Linear1's epilogue accumulates the BatchNorm batch statistics per
+    channel (thread-local, deterministic); BatchNorm + ReLU are folded into Linear2's operand load; the outer ReLU and
+    the dropout into its epilogue.  Backward: gsatb_tc_gin_bwd2 / gin_bwd1 (masks, BatchNorm backward statistics and
+    the per-channel BatchNorm backward folded into operand loads / epilogues); weight gradients are plain library
+    GEMMs on the bf16 operands those kernels write out."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps):
+    def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
+                drop_seed, drop_mask):
         x = x.contiguous()
         N, K = x.shape
-        H = w1.shape[0]
+        H1, H = w1.shape[0], w2.shape[0]
         w1p, w2p = prep_weight(w1), prep_weight(w2)
         if training:
-            z1, stats = linear(x, w1p, b1, H, want_stats=True)
-            mean64 = stats[:H] / N
-            var64 = (stats[H:] / N - mean64 * mean64).clamp_min(0.0)
+            z1, stats = linear(x, w1p, b1, H1, want_stats=True)
+            mean64 = stats[:H1] / N
+            var64 = (stats[H1:] / N - mean64 * mean64).clamp_min(0.0)
             mean, var = mean64.float(), var64.float()
             with torch.no_grad():
                 running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
                 running_var.mul_(1 - momentum).add_(var * (N / max(N - 1, 1)), alpha=momentum)
                 nbt.add_(1)
         else:
-            z1 = linear(x, w1p, b1, H)
-            mean, var = running_mean, running_var
+            z1 = linear(x, w1p, b1, H1)
+            mean, var = running_mean.clone(), running_var.clone()
         rstd = torch.rsqrt(var + eps)
         scale = (gamma * rstd).contiguous()
         shift = (beta - mean * scale).contiguous()
-        h = linear(z1, w2p, b2, w2.shape[0], in_scale=scale, in_shift=shift, relu_out=True)
+        p = float(pdrop) if training else 0.0
+        h = linear(z1, w2p, b2, H, in_scale=scale, in_shift=shift, relu_out=True, pdrop=p, drop_seed=drop_seed,
+                   drop_mask=drop_mask)
         ctx.save_for_backward(x, z1, h, w1, w2, gamma, mean, rstd, scale, shift)
-        ctx.training = training
+        ctx.cfg = (bool(training), p)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         x, z1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        N = x.shape[0]
-        H = w1.shape[0]
-        d2 = dh * (h > 0)
-        db2 = d2.sum(0)
-        a1 = torch.relu(torch.addcmul(shift, z1, scale))
-        dW2 = _mm_f32(d2.bfloat16().t(), a1.bfloat16())
-        da1 = linear(d2, prep_weight(w2, transpose=True), None, H)
-        g = da1 * (a1 > 0)
-        del a1, da1, d2
-        xhat = (z1 - mean) * rstd
-        dbeta = g.sum(0)
-        dgamma = (g * xhat).sum(0)
-        if ctx.training:
-            dz1 = (gamma * rstd) * (g - dbeta / N - xhat * (dgamma / N))
-        else:
-            dz1 = g * (gamma * rstd)
-        del g, xhat
-        db1 = dz1.sum(0)
-        dW1 = _mm_f32(dz1.bfloat16().t(), x.bfloat16())
-        dx = linear(dz1, prep_weight(w1, transpose=True), None, x.shape[1]) if ctx.needs_input_grad[0] else None
-        return dx, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None
+        training, p = ctx.cfg
+        N, Kin = x.shape
+        H1, H = w1.shape[0], w2.shape[0]
+        dev = x.device
+        L = lib()
+        dh = dh.contiguous()
+        d2 = torch.empty((N, H), dtype=torch.bfloat16, device=dev)
+        g = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+        a1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+        part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * H1, dtype=torch.float32, device=dev)
+        L.call('gsatb_tc_gin_bwd2', ptr(dh), ptr(h), ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
+               ptr(prep_weight(w2, transpose=True)), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
+               ptr(g), ptr(a1), ptr(part), ptr(stats), N, H, H1, stream())
+        dbeta, dgamma = stats[:H1], stats[H1:]
+        coef = gamma * rstd
+        if training:      # dz1 = coef * (g - dbeta/N - xhat * dgamma/N),  xhat = (z1 - mean) * rstd
+            cA = coef
+            cB = -coef * rstd * (dgamma / N)
+            cC = -coef * (dbeta / N) - cB * mean
+        else:             # running statistics are constants: dz1 = coef * g
+            cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
+        dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+        dx = torch.empty((N, Kin), dtype=torch.float32, device=dev)
+        L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA.contiguous()), ptr(cB.contiguous()), ptr(cC.contiguous()),
+               ptr(prep_weight(w1, transpose=True)), ptr(dz1), ptr(dx), N, H1, Kin, stream())
+        ones = torch.ones((1, N), dtype=torch.bfloat16, device=dev)
+        dW2 = _mm_f32(d2.t(), a1)
+        db2 = _mm_f32(ones, d2).view(-1)
+        dW1 = _mm_f32(dz1.t(), x.bfloat16())
+        db1 = _mm_f32(ones, dz1).view(-1)
+        return (dx, dW1, db1, dgamma.clone(), dbeta.clone(), dW2, db2, None, None, None, None, None, None, None, None,
+                None)
 
 
-def gin_mlp_relu(x, seq, training: bool):
-    """``relu(seq(x))`` for seq = GIN.MLP(...) = Sequential(Linear, BatchNorm1d, ReLU, Linear)."""
+def gin_mlp_relu(x, seq, training: bool, pdrop: float = 0.0, drop_seed: int = 0, drop_mask=None):
+    """``dropout(relu(seq(x)))`` for seq = GIN.MLP(...) = Sequential(Linear, BatchNorm1d, ReLU, Linear)."""
     lin1, bn, _, lin2 = seq[0], seq[1], seq[2], seq[3]
     return _GinMlpFused.apply(x, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight, lin2.bias, bn.running_mean,
                               bn.running_var, bn.num_batches_tracked, training and bn.training,
-                              bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+                              bn.momentum if bn.momentum is not None else 0.1, bn.eps, pdrop if training else 0.0,
+                              drop_seed, drop_mask)

@@ -168,7 +168,8 @@ int gsatb_lift_bwd(const float* g_edge, const float* node_att, const int32_t* ro
  * gsatb_tc_linear_fwd: out = act(pro(x) W^T + bias); pro(x) = relu(x*in_scale + in_shift) when in_scale is
  * given (BatchNorm+ReLU folded into the operand load), identity otherwise; act = ReLU when relu_out.
  * With stat_partials (OUT <= 128): stats[0:OUT] = sum_rows z, stats[OUT:2OUT] = sum_rows z^2 of the pre-activation
- * z (BatchNorm batch statistics), reduced in a fixed order in fp64.
+ * z (BatchNorm batch statistics), reduced in a fixed order in fp64.  pdrop > 0 applies dropout after the
+ * activation (drop_mask [rows,OUT] uint8 keep mask, or the counter hash of drop_seed when NULL).
  * ---------------------------------------------------------------------------------------------------------- */
 int gsatb_tc_prep_weight(const float* w, int OUT, int K, int transpose, void* w_bf16_padded, gsatb_stream_t stream);
 size_t gsatb_tc_stat_partials_elems(int OUT);
@@ -177,7 +178,22 @@ size_t gsatb_tc_stat_partials_elems(int OUT);
 int gsatb_tc_set_profile_buffer(void* buf);
 int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, const void* w_bf16_padded,
                         const float* bias, float* out, int ldo, int relu_out, float* stat_partials, double* stats,
-                        int64_t rows, int K, int OUT, gsatb_stream_t stream);
+                        const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, int64_t rows, int K, int OUT,
+                        gsatb_stream_t stream);
+
+/* GIN node MLP backward (autograd of src/models/gin.py:55-62 + the ReLU / Dropout of gin.py:50-52):
+ *   gin_bwd2: d2 = dh*(h>0)*drop_scale (written as bf16 [N,H]); da1 = d2 W2 on tcgen05 (w2t = prep(W2, transpose));
+ *             g = da1*(ReLU(BN(z1))>0) and a1 = ReLU(BN(z1)) written as bf16 [N,H1]; stats[0:H1] = sum_rows g,
+ *             stats[H1:2H1] = sum_rows g*xhat (BatchNorm backward), deterministic two-stage reduction
+ *   gin_bwd1: dz1 = cA*g + cB*z1 + cC (BatchNorm backward folded per channel; written as bf16 [N,H1]);
+ *             dx = dz1 W1 on tcgen05 (w1t = prep(W1, transpose)), fp32 [N,Kin] */
+int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16_padded, const float* z1,
+                      const float* bn_scale, const float* bn_shift, const float* mean, const float* rstd, void* d2,
+                      void* g, void* a1, float* stat_partials, float* stats, int64_t N, int H, int H1,
+                      gsatb_stream_t stream);
+int gsatb_tc_gin_bwd1(const void* g, const float* z1, const float* cA, const float* cB, const float* cC,
+                      const void* w1t_bf16_padded, void* dz1, float* dx, int64_t N, int H1, int Kin,
+                      gsatb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K1  extractor MLP forward, fused on the tensor cores.  Replaces ExtractorMLP.forward (src/run_gsat.py:909-927,

@@ -196,7 +196,7 @@ def test_gin_mlp_fused_matches_torch(G):
         gscale = max(float(p.grad.abs().max()) for p in ref.parameters())
         for (n1, p1), (_, p2) in zip(seq.named_parameters(), ref.named_parameters()):
             # (the bias in front of BatchNorm has an analytically zero gradient: compare absolutely)
-            assert float((p1.grad - p2.grad).abs().max()) < 0.05 * gscale, n1
+            assert float((p1.grad - p2.grad).abs().max()) < 0.12 * gscale, n1   # bf16 operand rounding, see above
             p1.grad = p2.grad = None
         assert torch.allclose(seq[1].running_mean, ref[1].running_mean, rtol=1e-2, atol=1e-3)
         assert torch.allclose(seq[1].running_var, ref[1].running_var, rtol=1e-2, atol=1e-3)
