@@ -257,3 +257,59 @@ class _GatherConcat(torch.autograd.Function):
 def gather_concat(emb, gi: GraphIndex):
     """f12 = cat(emb[src], emb[dst])  (reference src/run_gsat.py:912-914)."""
     return _GatherConcat.apply(emb, gi)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# K4  PNA multi-aggregator message passing   (reference src/models/conv_layers.py:160-226)
+# ------------------------------------------------------------------------------------------------------------
+AGG_CODES = {'sum': 0, 'mean': 1, 'min': 2, 'max': 3, 'var': 4, 'std': 5}
+
+
+class _PnaAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, edge_feat, att, gi: GraphIndex, codes):
+        x = _f32c(x)
+        ef = _f32c(edge_feat)
+        att_flat = None if att is None else _f32c(att).view(-1)
+        N, H = x.shape
+        He = 0 if ef is None else ef.shape[1]
+        F_ = 2 * H + He
+        dev = x.device
+        out = torch.empty((N, len(codes) * F_), dtype=torch.float32, device=dev)
+        mean = torch.empty((N, F_), dtype=torch.float32, device=dev)
+        msq = torch.empty((N, F_), dtype=torch.float32, device=dev)
+        amin = torch.empty((N, F_), dtype=torch.int32, device=dev)
+        amax = torch.empty((N, F_), dtype=torch.int32, device=dev)
+        carr = (ctypes.c_int * len(codes))(*codes)
+        lib().call('gsatb_pna_aggregate_fwd', ptr(x), ptr(ef), ptr(att_flat), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
+                   ptr(gi.src_by_dst), ctypes.cast(carr, ctypes.c_void_p), len(codes), ptr(out), ptr(mean), ptr(msq),
+                   ptr(amin), ptr(amax), N, gi.E, H, He, stream())
+        ctx.gi, ctx.codes = gi, list(codes)
+        ctx.att_shape = None if att is None else att.shape
+        ctx.save_for_backward(x, ef, att_flat, mean, msq, amin, amax)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, ef, att_flat, mean, msq, amin, amax = ctx.saved_tensors
+        gi, codes = ctx.gi, ctx.codes
+        gout = _f32c(gout)
+        N, H = x.shape
+        He = 0 if ef is None else ef.shape[1]
+        dev = x.device
+        dx = torch.empty_like(x)
+        need_ef = ef is not None and ctx.needs_input_grad[1]
+        need_att = att_flat is not None and ctx.needs_input_grad[2]
+        def_ = torch.empty_like(ef) if need_ef else None
+        datt = torch.empty(gi.E, dtype=torch.float32, device=dev) if need_att else None
+        carr = (ctypes.c_int * len(codes))(*codes)
+        lib().call('gsatb_pna_aggregate_bwd', ptr(gout), ptr(x), ptr(ef), ptr(att_flat), ptr(gi.rowptr_dst),
+                   ptr(gi.eid_by_dst), ptr(gi.src_by_dst), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.dst_by_src),
+                   ctypes.cast(carr, ctypes.c_void_p), len(codes), ptr(mean), ptr(msq), ptr(amin), ptr(amax), ptr(dx),
+                   ptr(def_), ptr(datt), N, gi.E, H, He, stream())
+        return dx, def_, (datt.view(ctx.att_shape) if need_att else None), None, None
+
+
+def pna_aggregate(x, edge_feat, edge_atten, gi: GraphIndex, aggregators):
+    """[N, A*(2H+He)] multi-aggregation of m_e = cat(x_i, x_j, edge_feat) * edge_atten over incoming edges."""
+    return _PnaAggregate.apply(x, edge_feat, edge_atten, gi, [AGG_CODES[a] for a in aggregators])

@@ -1,0 +1,128 @@
+"""PNA backbone on the K4 multi-aggregator kernel (reference src/models/pna.py:12-78,
+src/models/conv_layers.py:96-259).  Same constructor arguments, forward signatures and state_dict keys."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as tnn
+import torch.nn.functional as F
+
+from . import ops
+from .index import GraphIndex, get_graph_index
+from .nn import AtomEncoder, BondEncoder, _dropout
+
+
+def _scale_identity(src, deg, avg):
+    return src
+
+
+def _scale_amplification(src, deg, avg):
+    return src * (torch.log(deg + 1) / avg['log'])
+
+
+def _scale_attenuation(src, deg, avg):
+    scale = avg['log'] / torch.log(deg + 1)
+    scale[deg == 0] = 1
+    return src * scale
+
+
+def _scale_linear(src, deg, avg):
+    return src * (deg / avg['lin'])
+
+
+def _scale_inverse_linear(src, deg, avg):
+    scale = avg['lin'] / deg
+    scale[deg == 0] = 1
+    return src * scale
+
+
+SCALERS = {'identity': _scale_identity, 'amplification': _scale_amplification, 'attenuation': _scale_attenuation,
+           'linear': _scale_linear, 'inverse_linear': _scale_inverse_linear}   # conv_layers.py:229-259
+
+
+class PNAConvSimple(tnn.Module):
+    """conv_layers.py:96-190: message cat(x_i, x_j[, edge_attr]) * edge_atten, every configured aggregator in ONE pass
+    of gsatb_pna_aggregate, scalers, then post_nn."""
+
+    def __init__(self, in_channels: int, out_channels: int, aggregators: List[str], scalers: List[str],
+                 deg: torch.Tensor, post_layers: int = 1):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.aggregator_names, self.scaler_names = list(aggregators), list(scalers)
+        self.F_in, self.F_out = in_channels, out_channels
+        degf = deg.to(torch.float)
+        self.avg_deg: Dict[str, float] = {'lin': degf.mean().item(), 'log': (degf + 1).log().mean().item(),
+                                          'exp': degf.exp().mean().item()}
+        modules = [tnn.Linear(len(aggregators) * len(scalers) * in_channels, out_channels)]
+        for _ in range(post_layers - 1):
+            modules += [tnn.ReLU(), tnn.Linear(out_channels, out_channels)]
+        self.post_nn = tnn.Sequential(*modules)
+
+    def forward(self, x, edge_index, edge_attr=None, edge_atten=None, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(edge_index, None, num_nodes=x.shape[0])
+        out = ops.pna_aggregate(x, edge_attr, edge_atten, gi, self.aggregator_names)
+        if self.scaler_names != ['identity']:
+            deg = (gi.rowptr_dst[1:] - gi.rowptr_dst[:-1]).to(out.dtype).view(-1, 1)
+            out = torch.cat([SCALERS[s](out, deg, self.avg_deg) for s in self.scaler_names], dim=-1)
+        return self.post_nn(out)
+
+
+class PNA(tnn.Module):
+    """pna.py:12-78."""
+
+    def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
+        super().__init__()
+        hidden_size = model_config['hidden_size']
+        self.n_layers = model_config['n_layers']
+        self.dropout_p = model_config['dropout_p']
+        self.edge_attr_dim = edge_attr_dim
+        use_ea = model_config.get('use_edge_attr', True)
+        if model_config.get('atom_encoder', False):
+            self.node_encoder = AtomEncoder(emb_dim=hidden_size)
+            if edge_attr_dim != 0 and use_ea:
+                self.edge_encoder = BondEncoder(emb_dim=hidden_size)
+        else:
+            self.node_encoder = tnn.Linear(x_dim, hidden_size)
+            if edge_attr_dim != 0 and use_ea:
+                self.edge_encoder = tnn.Linear(edge_attr_dim, hidden_size)
+        aggregators = model_config['aggregators']
+        scalers = ['identity', 'amplification', 'attenuation'] if model_config['scalers'] else ['identity']
+        deg = model_config['deg']
+        if use_ea:
+            in_channels = hidden_size * 2 if edge_attr_dim == 0 else hidden_size * 3
+        else:
+            in_channels = hidden_size * 2
+        self.convs = tnn.ModuleList()
+        self.batch_norms = tnn.ModuleList()
+        for _ in range(self.n_layers):
+            self.convs.append(PNAConvSimple(in_channels=in_channels, out_channels=hidden_size, aggregators=aggregators,
+                                            scalers=scalers, deg=deg, post_layers=1))
+            self.batch_norms.append(tnn.BatchNorm1d(hidden_size))
+        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, hidden_size // 2), tnn.ReLU(),
+                                     tnn.Linear(hidden_size // 2, hidden_size // 4), tnn.ReLU(),
+                                     tnn.Linear(hidden_size // 4, 1 if num_class == 2 and not multi_label else num_class))
+        self.masks = None
+
+    def pool(self, x, batch, gi=None):
+        gi = gi if gi is not None else get_graph_index(torch.zeros((2, 0), dtype=torch.int64, device=batch.device), batch)
+        return ops.global_mean_pool(x, gi)
+
+    def get_emb(self, x, edge_index, batch, edge_attr, edge_atten=None, mask_key: str = 'pna'):
+        gi = get_graph_index(edge_index, batch)
+        x = self.node_encoder(x)
+        if edge_attr is not None:
+            edge_attr = self.edge_encoder(edge_attr)
+        for i, (conv, batch_norm) in enumerate(zip(self.convs, self.batch_norms)):
+            h = F.relu(batch_norm(conv(x, edge_index, edge_attr, edge_atten=edge_atten, _index=gi)))
+            x = h + x
+            x = _dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
+        return x
+
+    def forward(self, x, edge_index, batch, edge_attr, edge_atten=None, mask_key: str = 'pna.clf'):
+        gi = get_graph_index(edge_index, batch)
+        x = self.get_emb(x, edge_index, batch, edge_attr, edge_atten, mask_key=mask_key)
+        return self.fc_out(self.pool(x, batch, gi))
+
+    def get_pred_from_emb(self, emb, batch):
+        return self.fc_out(self.pool(emb, batch))

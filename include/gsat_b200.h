@@ -158,6 +158,29 @@ int gsatb_lift_bwd(const float* g_edge, const float* node_att, const int32_t* ro
                    const int32_t* dst_by_src, float* d_node, int64_t N, gsatb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * K4  PNA multi-aggregator message passing.  Replaces PNAConvSimple.message/aggregate
+ * (src/models/conv_layers.py:160-185; aggregators :193-226 on torch_scatter sum/mean/min/max):
+ *   m_e = cat(x[dst(e)], x[src(e)], [edge_feat_e]) * att_e   (F = 2H + He),   out [N, n_aggs * F] in the order of
+ *   agg_codes (0 sum, 1 mean, 2 min, 3 max, 4 var, 5 std = sqrt(relu(var) + 1e-5)); empty rows give 0 (std:
+ *   sqrt(1e-5)), as torch_scatter does.  The variance is accumulated on the centred values (second walk over the
+ *   row) instead of the reference's E[m^2]-E[m]^2, which cancels in fp32.  stat_mean / stat_msq (= that variance)
+ *   [N,F] and argmin / argmax [N,F] (edge ids, ties to the smallest id) are saved for backward.  edge_feat [E,He] and att [E] are nullable.  Scalers are applied by the
+ *   caller (the reference configs all use `scalers: false`).
+ * bwd: dx [N,H] (x_i part by destination, x_j part by source -- two deterministic row-parallel passes),
+ *      dedge_feat [E,He] [nullable], datt [E] [nullable].
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_pna_aggregate_fwd(const float* x, const float* edge_feat, const float* att, const int32_t* rowptr_dst,
+                            const int32_t* eid_by_dst, const int32_t* src_by_dst, const int* agg_codes, int n_aggs,
+                            float* out, float* stat_mean, float* stat_msq, int32_t* argmin, int32_t* argmax, int64_t N,
+                            int64_t E, int H, int He, gsatb_stream_t stream);
+int gsatb_pna_aggregate_bwd(const float* gout, const float* x, const float* edge_feat, const float* att,
+                            const int32_t* rowptr_dst, const int32_t* eid_by_dst, const int32_t* src_by_dst,
+                            const int32_t* rowptr_src, const int32_t* eid_by_src, const int32_t* dst_by_src,
+                            const int* agg_codes, int n_aggs, const float* stat_mean, const float* stat_msq,
+                            const int32_t* argmin, const int32_t* argmax, float* dx, float* dedge_feat, float* datt,
+                            int64_t N, int64_t E, int H, int He, gsatb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Dense layers on the tensor cores (tcgen05.mma kind::f16: bf16 operands, fp32 accumulation in TMEM; weights
  * streamed by TMA, activations staged through shared memory by producer warps with the prologue fused).
  * Replaces the nn.Linear / BatchNorm1d / ReLU chains of src/models/gin.py:55-62 and the Linear layers of the
