@@ -18,195 +18,382 @@
 namespace {
 
 constexpr int AGG_THREADS = 256;
+constexpr int AGG_WORKERS = 8;                        // gather warps of a K3 CTA
+constexpr int K3_THREADS = (AGG_WORKERS + 1) * 32;    // + one stager warp
+constexpr int AGG_TILE = 64;      // destination rows per CTA tile
+constexpr int AGG_EMAX = 1024;    // edges of a tile staged in shared memory (denser tiles take the slow path)
 
-template <int LPR, int NV, bool HAS_ATT>
-__global__ void __launch_bounds__(AGG_THREADS)
-k_gin_aggregate_fwd(const float4* __restrict__ x, const float* __restrict__ att, const int32_t* __restrict__ rowptr,
-                    const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr, float self_scale,
-                    float4* __restrict__ out, int64_t N, int HV) {
-    constexpr int ROWS_PER_WARP = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR;            // which row of the warp
-    const int sl = lane % LPR;             // lane inside the row
-    const unsigned submask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-    const int64_t warp_global = (blockIdx.x * (int64_t)(AGG_THREADS / 32)) + (threadIdx.x >> 5);
-    const int64_t warps_total = (int64_t)gridDim.x * (AGG_THREADS / 32);
+// Both K3 kernels are persistent: a CTA walks tiles of AGG_TILE consecutive CSR rows.
+//
+// Warp 8 (the "stager") runs ONE TILE AHEAD.  It fetches the next tile's row pointers and its (neighbour, edge id,
+// attention) slices -- a chain of three dependent but fully coalesced, batched global loads -- and writes them to
+// the other half of a double buffer in shared memory as a FLAT ENTRY LIST: the edges of each row in CSR order,
+// followed by one "self" entry (neighbour = the row itself, weight = 1 + eps).  So the GIN self term is just the
+// last term of the row's sum (same order and same fused multiply-add as "out = scatter(...); out += (1+eps)*x").
+//
+// The eight worker warps then walk contiguous slices of that list: U entries are gathered back to back (U x 512 B
+// in flight per warp at H = 128) and consumed in order; a row boundary is one compare + one 128-bit store.  There
+// are no per-row predicated slots, no dependent index loads and ~40 instructions per row on the critical path (the
+// first version chased rowptr -> nbr/eid -> att -> x serially per warp: 46 % / 51 % of the measured HBM peak,
+// latency bound; a row-per-sub-warp rewrite with 4 predicated slots per row was issue bound at ~250 instructions
+// per row -- ncu, profiles/r1_k3_*.txt).
+struct AggTile {
+    int rp[AGG_TILE + 1];              // raw row pointers of the tile
+    int staged;
+    int nbr[AGG_EMAX + AGG_TILE];      // entry list: neighbour row
+    int eid[AGG_EMAX + AGG_TILE];      //             edge id (-1 for the self entry)
+    int row[AGG_EMAX + AGG_TILE];      //             global row of the entry (backward: x[row] for d att)
+    float att[AGG_EMAX + AGG_TILE];    //             weight
+};
 
-    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < N; row0 += warps_total * ROWS_PER_WARP) {
-        const int64_t row = row0 + sub;
-        const bool live = row < N;
-        int beg = 0, end = 0;
-        if (live) {
-            beg = __ldg(rowptr + row);
-            end = __ldg(rowptr + row + 1);
+// executed by ONE warp
+template <bool HAS_ATT, bool NEED_EID>
+__device__ __forceinline__ void agg_stage(AggTile& t, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid,
+                                          const int32_t* __restrict__ nbr, const float* __restrict__ att, int64_t t0,
+                                          int nr, float self_scale, int lane) {
+    constexpr int RP_PER_LANE = (AGG_TILE + 1 + 31) / 32;
+    int rp[RP_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < RP_PER_LANE; ++k) {
+        const int i = lane + k * 32;
+        rp[k] = i <= nr ? __ldg(rowptr + t0 + i) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < RP_PER_LANE; ++k) {
+        const int i = lane + k * 32;
+        if (i <= nr) t.rp[i] = rp[k];
+    }
+    __syncwarp();
+    const int e0 = t.rp[0], ne = t.rp[nr] - e0;
+    const bool staged = ne <= AGG_EMAX;
+    if (lane == 0) t.staged = staged ? 1 : 0;
+    if (!staged) return;
+    for (int r = lane; r < nr; r += 32) {             // self entries close each row
+        const int slot = t.rp[r + 1] - e0 + r;
+        t.nbr[slot] = (int)(t0 + r);
+        t.att[slot] = self_scale;
+        if (NEED_EID) {
+            t.eid[slot] = -1;
+            t.row[slot] = (int)(t0 + r);
         }
-        float4 acc[NV];
+    }
+    constexpr int U = 8;
+    for (int base = 0; base < ne; base += 32 * U) {
+        int nb[U], ed[U];
+        float av[U];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        for (int p0 = beg; p0 < end; p0 += LPR) {
-            // one coalesced fetch of up to LPR (neighbour, attention) pairs for this row
-            int my_n = 0;
-            float my_a = 1.f;
-            if (p0 + sl < end) {
-                my_n = __ldg(nbr + p0 + sl);
-                if (HAS_ATT) my_a = __ldg(att + __ldg(eid + p0 + sl));
-            }
-            const int cnt = min(LPR, end - p0);
-            for (int q0 = 0; q0 < cnt; q0 += 4) {
-                int n[4];
-                float a[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    n[u] = __shfl_sync(submask, my_n, sub * LPR + ((q0 + u) % LPR));
-                    a[u] = __shfl_sync(submask, my_a, sub * LPR + ((q0 + u) % LPR));
-                }
-                float4 g[4][NV];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (q0 + u < cnt) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int c = sl + v * LPR;
-                            if (c < HV) g[u][v] = ldg_f4(x + (int64_t)n[u] * HV + c);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (q0 + u < cnt) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int c = sl + v * LPR;
-                            if (c < HV) {
-                                if (HAS_ATT) fma4(acc[v], a[u], g[u][v]);
-                                else {
-                                    acc[v].x += g[u][v].x;
-                                    acc[v].y += g[u][v].y;
-                                    acc[v].z += g[u][v].z;
-                                    acc[v].w += g[u][v].w;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+        for (int k = 0; k < U; ++k) {
+            const int i = base + lane + k * 32;
+            const bool ok = i < ne;
+            nb[k] = ok ? __ldg(nbr + e0 + i) : 0;
+            ed[k] = (ok && (HAS_ATT || NEED_EID)) ? __ldg(eid + e0 + i) : 0;
         }
-        if (live) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const int c = sl + v * LPR;
-                if (c < HV) {
-                    float4 xs = ldg_stream_f4(x + row * HV + c);
-                    float4 o;
-                    o.x = acc[v].x + self_scale * xs.x;   // reference: out = scatter(...); out += (1+eps) * x
-                    o.y = acc[v].y + self_scale * xs.y;
-                    o.z = acc[v].z + self_scale * xs.z;
-                    o.w = acc[v].w + self_scale * xs.w;
-                    out[row * HV + c] = o;
+        for (int k = 0; k < U; ++k) av[k] = (HAS_ATT && base + lane + k * 32 < ne) ? __ldg(att + ed[k]) : 1.f;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = base + lane + k * 32;
+            if (i < ne) {
+                int lo = 0, hi = nr;                  // row of edge i: largest r with rp[r] <= e0 + i
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (t.rp[mid] <= e0 + i) lo = mid;
+                    else hi = mid;
                 }
+                const int slot = i + lo;
+                t.nbr[slot] = nb[k];
+                if (NEED_EID) {
+                    t.eid[slot] = ed[k];
+                    t.row[slot] = (int)(t0 + lo);
+                }
+                t.att[slot] = av[k];
             }
         }
     }
 }
 
+// slow path for one row of a tile that is too dense to stage (reads its slices from global memory)
+template <int LPR, int NV, bool HAS_ATT>
+__device__ __forceinline__ void agg_row_slow(const float4* __restrict__ x, const float* __restrict__ att,
+                                             const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr, int beg,
+                                             int end, int sl, int HV, float4 (&acc)[NV]) {
+    for (int p = beg; p < end; ++p) {
+        const int n = __ldg(nbr + p);
+        const float a = HAS_ATT ? __ldg(att + __ldg(eid + p)) : 1.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int c = sl + v * LPR;
+            if (c < HV) fma4(acc[v], a, ldg_f4(x + (int64_t)n * HV + c));
+        }
+    }
+}
+
+template <int LPR, int NV, bool HAS_ATT>
+__global__ void __launch_bounds__(K3_THREADS, 3)
+k_gin_aggregate_fwd(const float4* __restrict__ x, const float* __restrict__ att, const int32_t* __restrict__ rowptr,
+                    const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr, float self_scale,
+                    float4* __restrict__ out, int64_t N, int HV) {
+    constexpr int RPW = 32 / LPR;                      // sub-warps (rows side by side) per warp
+    constexpr int UNITS = AGG_WORKERS * RPW;           // sub-warps per CTA
+    constexpr int U = (NV == 1) ? 8 : (NV == 2 ? 4 : 2);   // entries in flight per sub-warp
+    __shared__ AggTile tiles[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, sl = lane % LPR;
+    const int64_t ntiles = (N + AGG_TILE - 1) / AGG_TILE;
+    if (warp == AGG_WORKERS && (int64_t)blockIdx.x < ntiles)
+        agg_stage<HAS_ATT, false>(tiles[0], rowptr, eid, nbr, att, (int64_t)blockIdx.x * AGG_TILE,
+                                  (int)min((int64_t)AGG_TILE, N - (int64_t)blockIdx.x * AGG_TILE), self_scale, lane);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        __syncthreads();       // tile `it` is staged; every worker has left tile it-1 (its buffer may be refilled)
+        const int64_t t0 = tile * AGG_TILE;
+        const int nr = (int)min((int64_t)AGG_TILE, N - t0);
+        if (warp == AGG_WORKERS) {
+            const int64_t nt = tile + gridDim.x;
+            if (nt < ntiles)
+                agg_stage<HAS_ATT, false>(tiles[(it + 1) & 1], rowptr, eid, nbr, att, nt * AGG_TILE,
+                                          (int)min((int64_t)AGG_TILE, N - nt * AGG_TILE), self_scale, lane);
+            continue;
+        }
+        const AggTile& t = tiles[it & 1];
+        const int e0 = t.rp[0];
+        const int per = (nr + UNITS - 1) / UNITS;
+        const int ra = min(nr, (warp * RPW + sub) * per), rb = min(nr, ra + per);     // this sub-warp's rows
+        if (!t.staged) {
+            for (int r = ra; r < rb; ++r) {
+                float4 acc[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                agg_row_slow<LPR, NV, HAS_ATT>(x, att, eid, nbr, t.rp[r], t.rp[r + 1], sl, HV, acc);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int c = sl + v * LPR;
+                    if (c < HV) {
+                        fma4(acc[v], self_scale, ldg_stream_f4(x + (t0 + r) * HV + c));
+                        out[(t0 + r) * HV + c] = acc[v];
+                    }
+                }
+            }
+            continue;
+        }
+        int r = ra;
+        int q = ra < nr ? t.rp[ra] - e0 + ra : 0;                         // first entry of this sub-warp
+        const int qend = ra < rb ? t.rp[rb] - e0 + rb : q;               // one past its last entry
+        int rend = ra < rb ? t.rp[ra + 1] - e0 + ra + 1 : 0;             // one past the current row's self entry
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        while (q < qend) {
+            float a[U];
+            float4 g[U][NV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int qq = min(q + u, qend - 1);                      // clamped: loads stay unconditional
+                a[u] = t.att[qq];
+                const float4* src = x + (int64_t)t.nbr[qq] * HV + sl;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) g[u][v] = (v * LPR + sl < HV) ? ldg_f4(src + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (q + u < qend) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) fma4(acc[v], a[u], g[u][v]);
+                    if (q + u + 1 == rend) {                              // the self entry just closed row r
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            if (v * LPR + sl < HV) out[(t0 + r) * HV + v * LPR + sl] = acc[v];
+                            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        ++r;
+                        rend = t.rp[min(r + 1, nr)] - e0 + r + 1;
+                    }
+                }
+            }
+            q += U;
+        }
+    }
+}
+
+// transpose-reduce of U per-lane partial sums over the LPR lanes of a sub-warp: afterwards lane (sl % U) ... every
+// lane l < U of the sub-warp holds the full sum of value l (9 shuffles for U = 8 over 32 lanes instead of 40).
+template <int LPR, int U>
+__device__ __forceinline__ float subwarp_transpose_reduce(float (&v)[U], int sl, unsigned mask) {
+    // fold the value index into the lane index while halving the number of live values
+    int live = U;
+#pragma unroll
+    for (int off = LPR / 2; off >= 1; off >>= 1) {
+        if (live > 1) {
+            const bool upper = (sl & off) != 0;
+            const int half = live / 2;
+#pragma unroll
+            for (int i = 0; i < U / 2; ++i) {
+                if (i < half) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(mask, send, off);
+                }
+            }
+            live = half;
+        } else {
+            v[0] += __shfl_xor_sync(mask, v[0], off);
+        }
+    }
+    return v[0];
+}
+
 // backward over CSC rows (edges grouped by source j): dx[j] = sum att_e g[dst_e] + (1+eps) g[j];
 // datt[e] = <x[j], g[dst_e]>
 template <int LPR, int NV, bool HAS_ATT, bool WANT_DATT>
-__global__ void __launch_bounds__(AGG_THREADS)
+__global__ void __launch_bounds__(K3_THREADS, 3)
 k_gin_aggregate_bwd(const float4* __restrict__ g, const float4* __restrict__ x, const float* __restrict__ att,
                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ eid,
                     const int32_t* __restrict__ nbr, float self_scale, float4* __restrict__ dx,
                     float* __restrict__ datt, int64_t N, int HV) {
-    constexpr int ROWS_PER_WARP = 32 / LPR;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPR;
-    const int sl = lane % LPR;
+    constexpr int RPW = 32 / LPR;
+    constexpr int UNITS = AGG_WORKERS * RPW;
+    // with d att every entry also fetches x[its own row] (L1 hits: consecutive entries share the row)
+    constexpr int U = WANT_DATT ? ((NV == 1) ? 4 : (NV == 2 ? 2 : 1)) : ((NV == 1) ? 8 : (NV == 2 ? 4 : 2));
+    __shared__ AggTile tiles[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, sl = lane % LPR;
     const unsigned submask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
-    const int64_t warp_global = (blockIdx.x * (int64_t)(AGG_THREADS / 32)) + (threadIdx.x >> 5);
-    const int64_t warps_total = (int64_t)gridDim.x * (AGG_THREADS / 32);
-
-    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < N; row0 += warps_total * ROWS_PER_WARP) {
-        const int64_t row = row0 + sub;
-        const bool live = row < N;
-        int beg = 0, end = 0;
-        if (live) {
-            beg = __ldg(rowptr + row);
-            end = __ldg(rowptr + row + 1);
+    const int64_t ntiles = (N + AGG_TILE - 1) / AGG_TILE;
+    if (warp == AGG_WORKERS && (int64_t)blockIdx.x < ntiles)
+        agg_stage<HAS_ATT, WANT_DATT>(tiles[0], rowptr, eid, nbr, att, (int64_t)blockIdx.x * AGG_TILE,
+                                      (int)min((int64_t)AGG_TILE, N - (int64_t)blockIdx.x * AGG_TILE), self_scale, lane);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        __syncthreads();
+        const int64_t t0 = tile * AGG_TILE;
+        const int nr = (int)min((int64_t)AGG_TILE, N - t0);
+        if (warp == AGG_WORKERS) {
+            const int64_t nt = tile + gridDim.x;
+            if (nt < ntiles)
+                agg_stage<HAS_ATT, WANT_DATT>(tiles[(it + 1) & 1], rowptr, eid, nbr, att, nt * AGG_TILE,
+                                              (int)min((int64_t)AGG_TILE, N - nt * AGG_TILE), self_scale, lane);
+            continue;
         }
-        float4 acc[NV], xr[NV];
+        const AggTile& t = tiles[it & 1];
+        const int e0 = t.rp[0];
+        const int per = (nr + UNITS - 1) / UNITS;
+        const int ra = min(nr, (warp * RPW + sub) * per), rb = min(nr, ra + per);
+        if (!t.staged) {
+            for (int r = ra; r < rb; ++r) {
+                float4 acc[NV], xr[NV];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            xr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int c = sl + v * LPR;
-            if (WANT_DATT && live && c < HV && end > beg) xr[v] = ldg_stream_f4(x + row * HV + c);
-        }
-        for (int p0 = beg; p0 < end; p0 += LPR) {
-            int my_n = 0, my_e = 0;
-            float my_a = 1.f;
-            if (p0 + sl < end) {
-                my_n = __ldg(nbr + p0 + sl);
-                if (HAS_ATT || WANT_DATT) my_e = __ldg(eid + p0 + sl);
-                if (HAS_ATT) my_a = __ldg(att + my_e);
-            }
-            const int cnt = min(LPR, end - p0);
-            float my_dot = 0.f;   // lane q keeps the dot product of edge p0+q
-            for (int q0 = 0; q0 < cnt; q0 += 4) {
-                int n[4];
-                float a[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    n[u] = __shfl_sync(submask, my_n, sub * LPR + ((q0 + u) % LPR));
-                    a[u] = __shfl_sync(submask, my_a, sub * LPR + ((q0 + u) % LPR));
+                for (int v = 0; v < NV; ++v) {
+                    acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c = sl + v * LPR;
+                    xr[v] = (WANT_DATT && c < HV) ? ldg_stream_f4(x + (t0 + r) * HV + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                float4 gg[4][NV];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (q0 + u < cnt) {
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int c = sl + v * LPR;
-                            if (c < HV) gg[u][v] = ldg_f4(g + (int64_t)n[u] * HV + c);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int p = t.rp[r]; p < t.rp[r + 1]; ++p) {
+                    const int n = __ldg(nbr + p);
+                    const int e = (HAS_ATT || WANT_DATT) ? __ldg(eid + p) : 0;
+                    const float a = HAS_ATT ? __ldg(att + e) : 1.f;
                     float part = 0.f;
-                    if (q0 + u < cnt) {
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int c = sl + v * LPR;
-                            if (c < HV) {
-                                fma4(acc[v], a[u], gg[u][v]);
-                                if (WANT_DATT) part += dot4(xr[v], gg[u][v]);
-                            }
+                    for (int v = 0; v < NV; ++v) {
+                        const int c = sl + v * LPR;
+                        if (c < HV) {
+                            const float4 gg = ldg_f4(g + (int64_t)n * HV + c);
+                            fma4(acc[v], a, gg);
+                            if (WANT_DATT) part += dot4(xr[v], gg);
                         }
                     }
                     if (WANT_DATT) {
 #pragma unroll
                         for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(submask, part, o);
-                        if (sl == ((q0 + u) % LPR)) my_dot = part;
+                        if (sl == 0) datt[e] = part;
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const int c = sl + v * LPR;
+                    if (c < HV) {
+                        fma4(acc[v], self_scale, ldg_stream_f4(g + (t0 + r) * HV + c));
+                        dx[(t0 + r) * HV + c] = acc[v];
                     }
                 }
             }
-            if (WANT_DATT && p0 + sl < end) datt[my_e] = my_dot;
+            continue;
         }
-        if (live) {
+        int r = ra;
+        int q = ra < nr ? t.rp[ra] - e0 + ra : 0;
+        const int qend = ra < rb ? t.rp[rb] - e0 + rb : q;
+        int rend = ra < rb ? t.rp[ra + 1] - e0 + ra + 1 : 0;
+        float4 acc[NV];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const int c = sl + v * LPR;
-                if (c < HV) {
-                    float4 gs = ldg_stream_f4(g + row * HV + c);
-                    float4 o;
-                    o.x = acc[v].x + self_scale * gs.x;
-                    o.y = acc[v].y + self_scale * gs.y;
-                    o.z = acc[v].z + self_scale * gs.z;
-                    o.w = acc[v].w + self_scale * gs.w;
-                    dx[row * HV + c] = o;
+        for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        while (q < qend) {
+            float a[U];
+            float4 gg[U][NV], xx[U][NV];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int qq = min(q + u, qend - 1);
+                a[u] = t.att[qq];
+                const float4* src = g + (int64_t)t.nbr[qq] * HV + sl;
+                const float4* xsrc = WANT_DATT ? x + (int64_t)t.row[qq] * HV + sl : nullptr;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const bool cok = v * LPR + sl < HV;
+                    gg[u][v] = cok ? ldg_f4(src + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (WANT_DATT) xx[u][v] = cok ? ldg_f4(xsrc + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
+            float part[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                part[u] = 0.f;
+                if (q + u < qend) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        fma4(acc[v], a[u], gg[u][v]);
+                        if (WANT_DATT) part[u] += dot4(xx[u][v], gg[u][v]);
+                    }
+                    if (q + u + 1 == rend) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            if (v * LPR + sl < HV) dx[(t0 + r) * HV + v * LPR + sl] = acc[v];
+                            acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        ++r;
+                        rend = t.rp[min(r + 1, nr)] - e0 + r + 1;
+                    }
+                }
+            }
+            if (WANT_DATT) {
+                // lane l < U of the sub-warp ends with the dot product of entry q + l; self entries carry eid -1
+                if (LPR >= U) {
+                    const float d = subwarp_transpose_reduce<LPR, U>(part, sl, submask);
+                    // after the fold, value index = bits of sl selected by the first log2(U) offsets (LPR/2, LPR/4, ...)
+                    int idx = 0;
+                    {
+                        int live = U;
+                        for (int off = LPR / 2; off >= 1 && live > 1; off >>= 1) {
+                            live >>= 1;
+                            if (sl & off) idx += live;
+                        }
+                    }
+                    constexpr int LOWMASK = (LPR / U) - 1;      // lanes whose remaining (low) bits are zero own a value
+                    if ((sl & LOWMASK) == 0 && q + idx < qend) {
+                        const int e = t.eid[q + idx];
+                        if (e >= 0) datt[e] = d;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float d = part[u];
+#pragma unroll
+                        for (int o = LPR / 2; o > 0; o >>= 1) d += __shfl_xor_sync(submask, d, o);
+                        if (sl == 0 && q + u < qend) {
+                            const int e = t.eid[q + u];
+                            if (e >= 0) datt[e] = d;
+                        }
+                    }
+                }
+            }
+            q += U;
         }
     }
 }
@@ -226,14 +413,23 @@ inline unsigned agg_grid(int64_t N, int lpr) {
     return (unsigned)blocks;
 }
 
+// K3 kernels are persistent: `per_sm` resident CTAs per SM, each walking tiles with a grid stride
+inline unsigned agg_tile_grid(int64_t N, int per_sm) {
+    int64_t blocks = (N + AGG_TILE - 1) / AGG_TILE;
+    const int64_t cap = (int64_t)GSATB_NUM_SMS * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
 template <bool HAS_ATT>
 int launch_fwd(const float* x, const float* att, const int32_t* rowptr, const int32_t* eid, const int32_t* nbr,
                float self_scale, float* out, int64_t N, int HV, cudaStream_t st) {
     const int lpr = pick_lpr(HV);
     const int nv = (HV + lpr - 1) / lpr;
-    const unsigned grid = agg_grid(N, lpr);
+    const unsigned grid = agg_tile_grid(N, 3);
 #define FWD_CASE(L, V)                                                                                       \
-    k_gin_aggregate_fwd<L, V, HAS_ATT><<<grid, AGG_THREADS, 0, st>>>((const float4*)x, att, rowptr, eid, nbr, \
+    k_gin_aggregate_fwd<L, V, HAS_ATT><<<grid, K3_THREADS, 0, st>>>((const float4*)x, att, rowptr, eid, nbr, \
                                                                      self_scale, (float4*)out, N, HV)
     if (nv == 1) {
         switch (lpr) {
@@ -257,9 +453,9 @@ int launch_bwd(const float* g, const float* x, const float* att, const int32_t* 
                const int32_t* nbr, float self_scale, float* dx, float* datt, int64_t N, int HV, cudaStream_t st) {
     const int lpr = pick_lpr(HV);
     const int nv = (HV + lpr - 1) / lpr;
-    const unsigned grid = agg_grid(N, lpr);
+    const unsigned grid = agg_tile_grid(N, 3);
 #define BWD_CASE(L, V)                                                                                  \
-    k_gin_aggregate_bwd<L, V, HAS_ATT, WANT_DATT><<<grid, AGG_THREADS, 0, st>>>(                         \
+    k_gin_aggregate_bwd<L, V, HAS_ATT, WANT_DATT><<<grid, K3_THREADS, 0, st>>>(                         \
         (const float4*)g, (const float4*)x, att, rowptr, eid, nbr, self_scale, (float4*)dx, datt, N, HV)
     if (nv == 1) {
         switch (lpr) {

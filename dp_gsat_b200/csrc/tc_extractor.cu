@@ -144,23 +144,34 @@ struct OpExtFwd1 {
         }
     }
     __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) { pack8(r.v, o); }
+    // staging: two buffers of 32 rows x 128 channels bf16 (16 KiB per group); the emit pass of the InstanceNorm fills
+    // one 32-row chunk, the group stores it as whole rows while the channel threads fill the other buffer.
+    static constexpr int STAGE_BYTES = 16384;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
-    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane, int) {
+    __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, const EpiCtx& cx) {
         const int* bnd;
         int g0;
-        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
-        uint16_t* dst = p.xhat + r0 * p.C + ch;
+        const int nseg = load_segments(tl, cx, bnd, g0);
+        const int nchunks = (cx.cnt + 31) >> 5;
+        if (nchunks == 0) epi_release_acc(cx);
+        uint16_t* st16 = reinterpret_cast<uint16_t*>(cx.stage) + cx.gtid;
         instance_norm_rows(
-            taddr, bnd, nseg, p.eps,
-            [&](int, int, int col, bool in, float xh) {
+            cx.taddr, bnd, nseg, p.eps,
+            [&](int c, int j, int, bool in, float xh) {
                 const uint16_t bits = float_to_bf16_bits(xh);
-                if (in && ch_ok) dst[(int64_t)col * p.C] = bits;
+                if (in) st16[((c & 1) * 32 + j) * 128] = bits;
             },
             [&](int s, float r) {
-                if (ch_ok) p.rstd[(int64_t)(g0 + s) * p.C + ch] = r;
+                if (cx.ch_ok) p.rstd[(int64_t)(g0 + s) * p.C + cx.ch] = r;
             },
-            [](int) {}, [](int) {});
+            [&](int c) {
+                if (c == nchunks - 1) epi_release_acc(cx);     // last read of the accumulator has completed
+            },
+            [&](int c) {
+                epi_sync(cx);
+                stage_store<2>(cx, cx.stage + (c & 1) * 8192, p.xhat + cx.r0 * p.C, p.C, c * 32, min(32, cx.cnt - c * 32));
+            });
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
@@ -212,26 +223,32 @@ struct OpExtFwd2 {
         for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? fmaxf(v[i], 0.f) * p.drop1.scale : 0.f;
         pack8(v, o);
     }
+    static constexpr int STAGE_BYTES = 16384;      // as OpExtFwd1: two 32-row bf16 chunk buffers for xhat2
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool first) {
         if (first) st.par = 0;
     }
-    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int tile, uint8_t* misc, int q, int lane, int grp) {
+    __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState& st, const EpiCtx& cx) {
         const int* bnd;
         int g0;
-        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
-        float* red = reinterpret_cast<float*>(misc + 1024) + st.par * 512;   // [4 warps][128 columns]
-        for (int c = (cnt + 31) / 32; c < 4; ++c) red[q * 128 + c * 32 + lane] = 0.f;   // chunks the norm skips
+        const int nseg = load_segments(tl, cx, bnd, g0);
+        const int cnt = cx.cnt, ch = cx.ch, q = cx.q, lane = cx.lane;
+        const bool ch_ok = cx.ch_ok;
+        const int64_t r0 = cx.r0;
+        const int nchunks = (cnt + 31) >> 5;
+        if (nchunks == 0) epi_release_acc(cx);
+        float* red = reinterpret_cast<float*>(cx.misc + 1024) + st.par * 512;   // [4 warps][128 columns]
+        for (int c = nchunks; c < 4; ++c) red[q * 128 + c * 32 + lane] = 0.f;   // chunks the norm skips
         const float w3 = ch_ok ? __ldg(p.w3 + ch) : 0.f;
-        uint16_t* dst = p.xhat2 + r0 * p.H + ch;
+        uint16_t* st16 = reinterpret_cast<uint16_t*>(cx.stage) + cx.gtid;
         const bool use_mask = p.drop2.enabled && p.drop2.mask != nullptr;
         const uint32_t hash_ch = hash_ch_term(p.drop2, ch);
         float a[32];
         instance_norm_rows(
-            taddr, bnd, nseg, p.eps,
-            [&](int, int j, int col, bool in, float xh) {
+            cx.taddr, bnd, nseg, p.eps,
+            [&](int c, int j, int col, bool in, float xh) {
                 const uint16_t bits = float_to_bf16_bits(xh);
-                if (in && ch_ok) dst[(int64_t)col * p.H] = bits;
+                if (in) st16[((c & 1) * 32 + j) * 128] = bits;
                 float h = fmaxf(xh, 0.f);
                 const bool keep = use_mask ? (in && ch_ok ? __ldg(p.drop2.mask + (r0 + col) * p.H + ch) != 0 : false)
                                            : hash_keep(p.drop2, (uint32_t)(r0 + col), hash_ch);
@@ -241,7 +258,8 @@ struct OpExtFwd2 {
             [&](int s, float r) {
                 if (ch_ok) p.rstd2[(int64_t)(g0 + s) * p.H + ch] = r;
             },
-            [&](int) {
+            [&](int c) {
+                if (c == nchunks - 1) epi_release_acc(cx);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = 0.f;
             },
@@ -258,8 +276,10 @@ struct OpExtFwd2 {
                     }
                 }
                 red[q * 128 + c * 32 + lane] = a[0];
+                epi_sync(cx);
+                stage_store<2>(cx, cx.stage + (c & 1) * 8192, p.xhat2 + r0 * p.H, p.H, c * 32, min(32, cnt - c * 32));
             });
-        tc::named_bar_sync(5 + grp, 128);
+        epi_sync(cx);
         const int col = q * 32 + lane;
         if (col < cnt)
             p.logit[r0 + col] = red[col] + red[128 + col] + red[256 + col] + red[384 + col] + (p.b3 ? __ldg(p.b3) : 0.f);

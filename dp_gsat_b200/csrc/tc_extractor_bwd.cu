@@ -106,56 +106,84 @@ struct OpExtBwd1 {
     __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
         o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
     }
+    // staging: the tile's [rows][128 channels] block of xhat1 (bf16, 32 KiB) is fetched with cp.async BEFORE the
+    // accumulator is awaited; pass 0 forms the gated gradient e = dh1 * keep * scale * (xhat1 > 0) and its per-graph
+    // sums (thread-local: thread = channel), remembering the gates as bits; pass 1 overwrites each xhat1 value in
+    // place by dz1 = rstd * (e - mean(e) - xhat1 * mean(e * xhat1)), and the group stores the block as whole rows.
+    static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
-    // Per chunk of 32 columns the xhat1 values are fetched FIRST (32 independent loads in flight per thread) and the
-    // gated gradient e = dh1 * keep * scale * (xhat1 > 0) overwrites the accumulator registers; only then are the
-    // (chunk, graph) pieces reduced / emitted.  (The first version loaded inside the per-column expression and the
-    // loads serialised: 147 k cycles per 128-column block.)
-    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int, int tile, uint8_t* misc, int q, int lane, int) {
+    __device__ static void epi_prefetch(const Params& p, const Tiling&, const EpiCtx& cx) {
+        epi_sync(cx);      // the previous block's copy-out has finished reading the buffer
+        stage_load_async<2>(cx, cx.stage, p.xhat1 + cx.r0 * p.C1, p.C1, 0, cx.cnt);
+        cp_async_commit();
+    }
+    __device__ static void epilogue(const Params& p, const Tiling& tl, EpiState&, const EpiCtx& cx) {
         const int* bnd;
         int g0;
-        const int nseg = load_segments(tl, tile, r0, misc, q, lane, bnd, g0);
+        const int nseg = load_segments(tl, cx, bnd, g0);
         const int cnt = bnd[nseg];
+        const int ch = cx.ch;
+        const bool ch_ok = cx.ch_ok;
         const int chc = ch_ok ? ch : 0;
-        const uint16_t* xs = p.xhat1 + r0 * p.C1 + chc;
-        uint16_t* dst = p.dz1 + r0 * p.C1 + chc;
+        const int64_t r0 = cx.r0;
         const bool use_mask = p.drop1.enabled && p.drop1.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop1.mask + r0 * p.C1 + chc : nullptr;
         const uint32_t cht = hash_ch_term(p.drop1, chc);
         const uint32_t row0 = (uint32_t)r0;
+        uint16_t* xs = reinterpret_cast<uint16_t*>(cx.stage) + cx.gtid;      // [row][128]
         float m1[MAX_SEG], m2[MAX_SEG];
+        uint32_t gate[4];
+        cp_async_wait<0>();
+        epi_sync(cx);          // xhat1 block visible to every channel thread
+        const int nchunks = (cnt + 31) >> 5;
+        if (nchunks == 0) epi_release_acc(cx);
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             int s = 0;
             while (s < nseg && bnd[s + 1] == bnd[s]) ++s;
             float a1 = 0.f, a2 = 0.f;
 #pragma unroll 1
-            for (int c = 0; c * 32 < cnt; ++c) {
+            for (int c = 0; c < nchunks; ++c) {
                 float v[32], xv[32];
-                tc::tmem_ld_32x32(taddr + c * 32, v);
+                tc::tmem_ld_32x32(cx.taddr + c * 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int col = min(c * 32 + j, cnt - 1);
-                    xv[j] = bf16_bits_to_float(__ldg(xs + (int64_t)col * p.C1));
+                for (int j = 0; j < 32; ++j) xv[j] = bf16_bits_to_float(xs[(c * 32 + j) * 128]);
+                if ((c + 1) * 32 > cnt) {      // rows past the tile end hold stale shared memory (possibly NaN bits)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) xv[j] = (c * 32 + j < cnt) ? xv[j] : 0.f;
                 }
-                uint32_t keep = 0xffffffffu;
-                if (p.drop1.enabled) {
-                    keep = 0u;
-                    if (use_mask) {
+                uint32_t gt;
+                if (pass == 0) {
+                    uint32_t keep = 0xffffffffu;
+                    if (p.drop1.enabled) {
+                        keep = 0u;
+                        if (use_mask) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            keep |= (__ldg(mk + (int64_t)min(c * 32 + j, cnt - 1) * p.C1) != 0 ? 1u : 0u) << j;
-                    } else {
+                            for (int j = 0; j < 32; ++j)
+                                keep |= (__ldg(mk + (int64_t)min(c * 32 + j, cnt - 1) * p.C1) != 0 ? 1u : 0u) << j;
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            keep |= (hash_keep(p.drop1, row0 + (uint32_t)(c * 32 + j), cht) ? 1u : 0u) << j;
+                            for (int j = 0; j < 32; ++j)
+                                keep |= (hash_keep(p.drop1, row0 + (uint32_t)(c * 32 + j), cht) ? 1u : 0u) << j;
+                        }
                     }
+                    gt = 0u;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) gt |= (xv[j] > 0.f ? 1u : 0u) << j;
+                    gt &= keep;
+                    // rows past the tile end hold stale shared memory: never gate them in
+                    if ((c + 1) * 32 > cnt) gt &= (1u << (cnt - c * 32)) - 1u;
+                    if (c == 0) gate[0] = gt;
+                    else if (c == 1) gate[1] = gt;
+                    else if (c == 2) gate[2] = gt;
+                    else gate[3] = gt;
+                } else {
+                    gt = c == 0 ? gate[0] : (c == 1 ? gate[1] : (c == 2 ? gate[2] : gate[3]));
                 }
                 tc::tmem_ld_wait();
+                if (pass == 1 && c == nchunks - 1) epi_release_acc(cx);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    v[j] = (xv[j] > 0.f && ((keep >> j) & 1u)) ? v[j] * p.drop1.scale : 0.f;   // v := gated gradient e
+                for (int j = 0; j < 32; ++j) v[j] = ((gt >> j) & 1u) ? v[j] * p.drop1.scale : 0.f;   // gated gradient e
                 const int cbeg = c * 32, cend = min(cbeg + 32, cnt);
 #pragma unroll 1
                 while (s < nseg && bnd[s] < cend) {
@@ -179,7 +207,7 @@ struct OpExtBwd1 {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const uint16_t bits = float_to_bf16_bits(rs * (v[j] - mu1 - xv[j] * mu2));
-                            if (((m >> j) & 1u) && ch_ok) dst[(int64_t)(cbeg + j) * p.C1] = bits;
+                            if ((m >> j) & 1u) xs[(cbeg + j) * 128] = bits;
                         }
                     }
                     if (bnd[s + 1] <= cend) {
@@ -197,6 +225,8 @@ struct OpExtBwd1 {
                 }
             }
         }
+        epi_sync(cx);          // dz1 block complete in the staging buffer
+        stage_store<2>(cx, cx.stage, p.dz1 + r0 * p.C1, p.C1, 0, cnt);
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
@@ -220,22 +250,11 @@ struct OpLinearBf16In {
     __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
         o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
     }
+    static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
-    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
-        float* o = p.out + r0 * p.ldo + ch;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            if (c * 32 >= cnt) break;
-            float v[32];
-            tc::tmem_ld_32x32(taddr + c * 32, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = c * 32 + j;
-                if (col < cnt && ch_ok) o[(int64_t)col * p.ldo] = v[j];
-            }
-        }
+    __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, const EpiCtx& cx) {
+        epi_emit_f32(cx, p.out, p.ldo, [](int, float acc) { return acc; });
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };

@@ -31,7 +31,8 @@ constexpr int THREADS = 640;
 constexpr int EPI_WARP0 = 4, PRO_WARP0 = 12, PRO_WARPS = 8;
 // row-chunks whose global loads one producer thread keeps in flight: Op::UNROLL (8 for 32-byte chunks, 4 for wider)
 constexpr int MAX_SEG = 32;                   // graphs per tile the InstanceNorm epilogues support
-constexpr int MISC_BYTES = 16384;            // epilogue scratch, half per epilogue group: segment tables + reductions
+constexpr int MISC_BYTES = 12288;             // epilogue scratch, half per epilogue group: segment tables + reductions
+constexpr int EPI_BAR0 = 5;                   // named barriers EPI_BAR0 + grp: epilogue-group syncs around the staging buffer
 
 struct Tiling {
     int64_t rows;               // total rows
@@ -46,21 +47,110 @@ struct Shape {
     int K, KB;      // reduction size and its 64-blocks
     int OUT, NMB;   // output channels and their 128-blocks
     int NA;         // W ring stages
-    int NBUF;       // B tile buffers (2 when they fit, else 1)
+    int NBUF;       // B buffers (2 when they fit, else 1)
+    int KBC;        // K-blocks per B buffer: KB (whole tile) or, for NMB == 1 only, a K-chunk of the tile
+    int NCH;        // K-chunks per tile = ceil(KB / KBC)
+    int STAGE;      // bytes of epilogue staging buffer per epilogue group (Op::STAGE_BYTES)
 };
 
 struct SmemLayout {
-    uint32_t a_off, b_off, bar_off, misc_off, total;
+    uint32_t a_off, b_off, stage_off, bar_off, misc_off, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const Shape& s) {
     SmemLayout l;
     l.a_off = 0;
     l.b_off = l.a_off + (uint32_t)s.NA * BLK_BYTES;
-    l.bar_off = l.b_off + (uint32_t)s.NBUF * s.KB * BLK_BYTES;
+    l.stage_off = l.b_off + (uint32_t)s.NBUF * s.KBC * BLK_BYTES;
+    l.bar_off = l.stage_off + (uint32_t)EPI_GROUPS * s.STAGE;
     l.misc_off = l.bar_off + 256;
     l.total = l.misc_off + MISC_BYTES + 1024;   // + slack for the manual 1024-byte alignment of the base
     return l;
+}
+
+// ---- epilogue context + staging helpers -----------------------------------------------------------------------
+// An epilogue thread owns one output CHANNEL (TMEM lane) and sees the tile's rows as TMEM columns, while every
+// tensor in global memory is row-major [rows, channels].  Touching global memory straight from that layout means
+// 2- or 4-byte accesses at a row stride: 64-128 bytes per warp instruction and one L1 transaction each, which left
+// these kernels 3-12x off their HBM roofline (ncu, round 1).  Instead each epilogue group (128 threads = 128
+// channels) owns a staging buffer in shared memory laid out [row][128 channels]; channel threads read / write it
+// at 2-4 bytes (conflict-free: a warp covers 64-128 contiguous bytes) and the group moves it to / from global
+// memory with 16-byte cp.async loads and 16-byte coalesced stores.
+struct EpiCtx {
+    uint32_t taddr;      // TMEM address of this warp's lane quarter of the accumulator
+    int ch, ch0, nch;    // this thread's channel, first channel of the block, valid channels in the block (<= 128)
+    bool ch_ok;
+    int64_t r0;          // first global row of the tile
+    int cnt, tile;       // rows in the tile, tile index
+    uint8_t* misc;       // MISC_BYTES / EPI_GROUPS bytes of scratch of this group
+    uint8_t* stage;      // Shape::STAGE bytes of staging buffer of this group
+    int q, lane, grp, gtid;   // warp quarter, lane, epilogue group, thread index inside the group (== ch - ch0)
+    uint64_t* acc_empty;
+};
+__device__ __forceinline__ void epi_sync(const EpiCtx& c) { tc::named_bar_sync(EPI_BAR0 + c.grp, 128); }
+// Every Op::epilogue calls this exactly once, as soon as it has read the accumulator for the last time.
+__device__ __forceinline__ void epi_release_acc(const EpiCtx& c) {
+    tc::tc_fence_before();
+    tc::mbar_arrive(c.acc_empty);
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Asynchronously copy rows [row_lo, row_lo + nrows) x channels [ch0, ch0 + nch) of the row-major tensor `g`
+// (element size ES, leading dimension ld elements; g points at element (row 0 of the TILE, channel 0)) into `buf`
+// laid out [row - row_lo][128 channels].  Caller: cp_async_commit / cp_async_wait + epi_sync before reading.
+template <int ES>
+__device__ __forceinline__ void stage_load_async(const EpiCtx& c, uint8_t* buf, const void* g, int ld, int row_lo,
+                                                 int nrows) {
+    constexpr int CPR = 128 * ES / 16, EPC = 16 / ES;     // 16-byte chunks per staged row, elements per chunk
+    const uint8_t* gb = reinterpret_cast<const uint8_t*>(g) + ((int64_t)row_lo * ld + c.ch0) * ES;
+    const bool vec = ((reinterpret_cast<uintptr_t>(gb) | (uintptr_t)((int64_t)ld * ES)) & 15u) == 0 && (c.nch % EPC) == 0;
+    if (vec) {
+        const int total = nrows * CPR;
+#pragma unroll 4
+        for (int i = c.gtid; i < total; i += 128) {
+            const int row = i / CPR, k = i % CPR;
+            if (k * EPC < c.nch) cp_async16(buf + row * (128 * ES) + k * 16, gb + (int64_t)row * ld * ES + k * 16);
+        }
+    } else {                                              // unaligned shapes: element-wise, synchronous
+        for (int i = c.gtid; i < nrows * 128; i += 128) {
+            const int row = i >> 7, k = i & 127;
+            if (k < c.nch) {
+                if (ES == 2) reinterpret_cast<uint16_t*>(buf)[i] = reinterpret_cast<const uint16_t*>(gb)[(int64_t)row * ld + k];
+                else reinterpret_cast<uint32_t*>(buf)[i] = reinterpret_cast<const uint32_t*>(gb)[(int64_t)row * ld + k];
+            }
+        }
+    }
+}
+// Copy `buf` ([row - row_lo][128 channels]) to rows [row_lo, row_lo + nrows) x channels [ch0, ch0 + nch) of `g`
+// with 16-byte coalesced stores.  Caller: epi_sync between the channel threads' writes to buf and this call.
+template <int ES>
+__device__ __forceinline__ void stage_store(const EpiCtx& c, const uint8_t* buf, void* g, int ld, int row_lo, int nrows) {
+    constexpr int CPR = 128 * ES / 16, EPC = 16 / ES;
+    uint8_t* gb = reinterpret_cast<uint8_t*>(g) + ((int64_t)row_lo * ld + c.ch0) * ES;
+    const bool vec = ((reinterpret_cast<uintptr_t>(gb) | (uintptr_t)((int64_t)ld * ES)) & 15u) == 0 && (c.nch % EPC) == 0;
+    if (vec) {
+        const int total = nrows * CPR;
+#pragma unroll 4
+        for (int i = c.gtid; i < total; i += 128) {
+            const int row = i / CPR, k = i % CPR;
+            if (k * EPC < c.nch)
+                *reinterpret_cast<uint4*>(gb + (int64_t)row * ld * ES + k * 16) =
+                    *reinterpret_cast<const uint4*>(buf + row * (128 * ES) + k * 16);
+        }
+    } else {
+        for (int i = c.gtid; i < nrows * 128; i += 128) {
+            const int row = i >> 7, k = i & 127;
+            if (k < c.nch) {
+                if (ES == 2) reinterpret_cast<uint16_t*>(gb)[(int64_t)row * ld + k] = reinterpret_cast<const uint16_t*>(buf)[i];
+                else reinterpret_cast<uint32_t*>(gb)[(int64_t)row * ld + k] = reinterpret_cast<const uint32_t*>(buf)[i];
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ void tile_range(const Tiling& t, int tile, int64_t& r0, int& cnt) {
@@ -77,11 +167,13 @@ __device__ __forceinline__ void tile_range(const Tiling& t, int tile, int64_t& r
 // The kernel.  `Op` supplies:
 //    struct Params                               (copied by value into the kernel)
 //    struct EpiState                             (per-thread state living across tiles)
+//    static constexpr int STAGE_BYTES            epilogue staging buffer per epilogue group
 //    struct Raw; static void load8(P, grow, k, K, Raw&)              issue the global loads of 8 consecutive k of a row
 //    static void transform8(P, Raw, grow, k, K, uint32_t out[4])     fused prologue -> 8 bf16
-//    static void epi_init(P, EpiState&, ch)
-//    static void epilogue(P, EpiState&, taddr, ch, ch_valid, r0, cnt, tile, misc smem, lane/warp ids)
-//    static void epi_finish(P, EpiState&, ch, ch_valid)
+//    static void epi_init(P, EpiState&, ch, ch_ok, first)
+//    static void epi_prefetch(P, Tiling, EpiCtx)   called BEFORE the accumulator is awaited (async loads into stage)
+//    static void epilogue(P, Tiling, EpiState&, EpiCtx)   must call epi_release_acc(ctx) exactly once
+//    static void epi_finish(P, EpiState&, ch, ch_ok, last, grp)
 template <class Op>
 __global__ void __launch_bounds__(THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Shape sh, const typename Op::Params p) {
@@ -98,7 +190,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
     uint64_t* acc_full = bars + 20;      // [2]
     uint64_t* acc_empty = bars + 22;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    uint8_t* misc = smem + L.misc_off;   // 1 KiB scratch for the epilogue (segment tables)
+    uint8_t* misc = smem + L.misc_off;   // epilogue scratch (segment tables, cross-warp reductions)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -142,41 +234,57 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // B buffers hold K-chunks of KBC blocks.  NCH == 1: one buffer per tile, re-used by all NMB channel blocks.
+        // NCH > 1 (NMB == 1 only): the tile's single accumulator is built chunk by chunk, so a K = 512 operand tile
+        // never has to sit in shared memory whole and the producers run ahead of the MMAs.
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc_bf16(128, TILE_ROWS);
             uint32_t ca = 0, cm = 0, it = 0;
             long long w_b = 0, w_acc = 0, w_a = 0, t_all = clock64(), t0;
-            for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
-                t0 = clock64();
-                tc::mbar_wait(&b_full[buf], ub & 1);
-                w_b += clock64() - t0;
-                tc::tc_fence_after();
-                const uint32_t b_base = tc::smem_u32(sB + (size_t)buf * sh.KB * BLK_BYTES);
-                for (int mb = 0; mb < sh.NMB; ++mb, ++cm) {
-                    const uint32_t slot = cm & 1, us = cm >> 1;
-                    t0 = clock64();
-                    tc::mbar_wait(&acc_empty[slot], (us & 1) ^ 1);
-                    w_acc += clock64() - t0;
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + slot * 128;
-                    for (int kb = 0; kb < sh.KB; ++kb, ++ca) {
-                        const uint32_t s = ca % sh.NA, use = ca / sh.NA;
+            // order of B buffers: NCH == 1: one per tile (shared by the NMB channel blocks); NCH > 1: (mb, chunk) --
+            // the producers re-stage the tile's K-chunks for every channel block (second read comes from L2).
+            const int reps = sh.NCH > 1 ? sh.NMB : 1, mbs_per_rep = sh.NCH > 1 ? 1 : sh.NMB;
+            for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
+                for (int rep = 0; rep < reps; ++rep) {
+                    for (int chk = 0; chk < sh.NCH; ++chk, ++it) {
+                        const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
                         t0 = clock64();
-                        tc::mbar_wait(&a_full[s], use & 1);
-                        w_a += clock64() - t0;
+                        tc::mbar_wait(&b_full[buf], ub & 1);
+                        w_b += clock64() - t0;
                         tc::tc_fence_after();
-                        const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(sA + s * BLK_BYTES));
-                        const uint64_t b_desc = tc::make_desc_k_sw128(b_base + kb * BLK_BYTES);
+                        const uint32_t b_base = tc::smem_u32(sB + (size_t)buf * sh.KBC * BLK_BYTES);
+                        const int kb0 = chk * sh.KBC, kb1 = min(sh.KB, kb0 + sh.KBC);
+                        for (int m = 0; m < mbs_per_rep; ++m) {
+                            const uint32_t slot = cm & 1, us = cm >> 1;
+                            if (chk == 0) {
+                                t0 = clock64();
+                                tc::mbar_wait(&acc_empty[slot], (us & 1) ^ 1);
+                                w_acc += clock64() - t0;
+                                tc::tc_fence_after();
+                            }
+                            const uint32_t d_tmem = tmem_base + slot * 128;
+                            for (int kb = kb0; kb < kb1; ++kb, ++ca) {
+                                const uint32_t s = ca % sh.NA, use = ca / sh.NA;
+                                t0 = clock64();
+                                tc::mbar_wait(&a_full[s], use & 1);
+                                w_a += clock64() - t0;
+                                tc::tc_fence_after();
+                                const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(sA + s * BLK_BYTES));
+                                const uint64_t b_desc = tc::make_desc_k_sw128(b_base + (kb - kb0) * BLK_BYTES);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte row
-                            tc::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc,
-                                            (kb | k4) != 0);
-                        tc::mma_commit(&a_empty[s]);        // ring slot free once these MMAs have read it
+                                for (int k4 = 0; k4 < 4; ++k4)      // 4 x (K = 16 bf16 = 32 bytes) inside the 128-byte row
+                                    tc::mma_bf16_ss(d_tmem, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2),
+                                                    idesc, (kb | k4) != 0);
+                                tc::mma_commit(&a_empty[s]);        // ring slot free once these MMAs have read it
+                            }
+                            if (chk == sh.NCH - 1) {
+                                tc::mma_commit(&acc_full[slot]);    // accumulator complete -> epilogue
+                                ++cm;
+                            }
+                        }
+                        tc::mma_commit(&b_empty[buf]);              // B buffer free -> producers
                     }
-                    tc::mma_commit(&acc_full[slot]);        // accumulator complete -> epilogue
                 }
-                tc::mma_commit(&b_empty[buf]);              // B tile buffer free -> producers
             }
             if (tl.dbg) {
                 long long* d = tl.dbg + (size_t)blockIdx.x * 16;
@@ -192,37 +300,45 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
         // TMEM-load / shared-memory / dependent-issue latencies (one warp alone reached ~0.25 IPC).
         const int grp = (warp - EPI_WARP0) >> 2;
         const int q = (warp - EPI_WARP0) & 3;               // == warp % 4: the TMEM lane quarter this warp may access
-        uint8_t* my_misc = misc + grp * (MISC_BYTES / EPI_GROUPS);
         typename Op::EpiState st;
+        EpiCtx cx;
+        cx.misc = misc + grp * (MISC_BYTES / EPI_GROUPS);
+        cx.stage = smem + L.stage_off + (size_t)grp * sh.STAGE;
+        cx.q = q;
+        cx.lane = lane;
+        cx.grp = grp;
+        cx.gtid = q * 32 + lane;
         uint32_t ce = 0;
         bool first = true;
         long long w_full = 0, t_epi = 0, t0;
         for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
-            int64_t r0;
-            int cnt;
-            tile_range(tl, tile, r0, cnt);
+            tile_range(tl, tile, cx.r0, cx.cnt);
+            cx.tile = tile;
             for (int mb = 0; mb < sh.NMB; ++mb, ++ce) {
                 const uint32_t slot = ce & 1, us = ce >> 1;
                 if ((int)slot != grp) continue;
-                const int ch = mb * 128 + q * 32 + lane;
-                if (first || sh.NMB > 1) Op::epi_init(p, st, ch, ch < sh.OUT, first);
+                cx.ch0 = mb * 128;
+                cx.ch = cx.ch0 + cx.gtid;
+                cx.ch_ok = cx.ch < sh.OUT;
+                cx.nch = min(128, sh.OUT - cx.ch0);
+                cx.acc_empty = &acc_empty[slot];
+                if (first || sh.NMB > 1) Op::epi_init(p, st, cx.ch, cx.ch_ok, first);
                 first = false;
+                Op::epi_prefetch(p, tl, cx);
                 t0 = clock64();
                 tc::group_mbar_wait(q == 0 && lane == 0, &acc_full[slot], us & 1, 3 + grp, 128);
                 w_full += clock64() - t0;
                 tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
+                cx.taddr = tmem_base + slot * 128 + ((uint32_t)(q * 32) << 16);
                 t0 = clock64();
-                Op::epilogue(p, tl, st, taddr, ch, ch < sh.OUT, r0, cnt, tile, my_misc, q, lane, grp);
+                Op::epilogue(p, tl, st, cx);
                 t_epi += clock64() - t0;
-                tc::tc_fence_before();
-                tc::mbar_arrive(&acc_empty[slot]);
-                if (sh.NMB > 1) Op::epi_finish(p, st, ch, ch < sh.OUT, false, grp);
+                if (sh.NMB > 1) Op::epi_finish(p, st, cx.ch, cx.ch_ok, false, grp);
             }
         }
         if (sh.NMB == 1) {
-            if (first) Op::epi_init(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true);
-            Op::epi_finish(p, st, q * 32 + lane, q * 32 + lane < sh.OUT, true, grp);
+            if (first) Op::epi_init(p, st, cx.gtid, cx.gtid < sh.OUT, true);
+            Op::epi_finish(p, st, cx.gtid, cx.gtid < sh.OUT, true, grp);
         }
         if (tl.dbg && grp == 0 && q == 0 && lane == 0) {
             long long* d = tl.dbg + (size_t)blockIdx.x * 16;
@@ -234,53 +350,57 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const Tiling tl, const Sha
         const int pt = threadIdx.x - PRO_WARP0 * 32;        // 0..255
         const int r_in = (pt & 31) >> 3, c_in = pt & 7, pw = pt >> 5;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < tl.num_tiles; tile += gridDim.x) {
             int64_t r0;
             int cnt;
             tile_range(tl, tile, r0, cnt);
-            const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
-            long long t0 = clock64();
-            tc::group_mbar_wait(pt == 0, &b_empty[buf], (ub & 1) ^ 1, 2, PRO_WARPS * 32);
-            long long t1 = clock64();
-            uint8_t* bt = sB + (size_t)buf * sh.KB * BLK_BYTES;
-            // work unit = (K-block, group of 4 rows): 8 lanes cover the 8 16-byte chunks of one 128-byte row.
-            // PRO_UNROLL units are loaded back to back before any is transformed, to keep HBM requests in flight.
-            const int units = sh.KB * (TILE_ROWS / 4);
-            // units (= KB * 32) is a multiple of PRO_WARPS * PRO_UNROLL when KB is even; the kb == KB guard covers
-            // odd KB.  Loads are unconditional on clamped coordinates (K % 8 == 0, so an 8-chunk is wholly in or
-            // out) and invalid chunks are zeroed by a select: no branches, so ptxas keeps all loads in flight.
-            constexpr int PRO_UNROLL = Op::UNROLL;
-            for (int u0 = pw; u0 < units; u0 += PRO_WARPS * PRO_UNROLL) {
-                typename Op::Raw raw[PRO_UNROLL];
+            const int nstage = sh.NCH > 1 ? sh.NMB * sh.NCH : 1;      // see the MMA issuer for the buffer order
+            for (int sgi = 0; sgi < nstage; ++sgi, ++it) {
+                const int chk = sgi % sh.NCH;
+                const uint32_t buf = it % sh.NBUF, ub = it / sh.NBUF;
+                long long t0 = clock64();
+                tc::group_mbar_wait(pt == 0, &b_empty[buf], (ub & 1) ^ 1, 2, PRO_WARPS * 32);
+                long long t1 = clock64();
+                uint8_t* bt = sB + (size_t)buf * sh.KBC * BLK_BYTES;
+                const int kb0 = chk * sh.KBC, nkb = min(sh.KB, kb0 + sh.KBC) - kb0;
+                // work unit = (K-block, group of 4 rows): 8 lanes cover the 8 16-byte chunks of one 128-byte row.
+                // PRO_UNROLL units are loaded back to back before any is transformed, to keep HBM requests in
+                // flight.  Loads are unconditional on clamped coordinates (K % 8 == 0, so an 8-chunk is wholly in or
+                // out) and invalid chunks are zeroed by a select: no branches, so ptxas keeps all loads in flight.
+                const int units = nkb * (TILE_ROWS / 4);
+                constexpr int PRO_UNROLL = Op::UNROLL;
+                for (int u0 = pw; u0 < units; u0 += PRO_WARPS * PRO_UNROLL) {
+                    typename Op::Raw raw[PRO_UNROLL];
 #pragma unroll
-                for (int j = 0; j < PRO_UNROLL; ++j) {
-                    const int u = min(u0 + j * PRO_WARPS, units - 1);
-                    const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
-                    const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
-                    const bool ok = row < cnt && k < sh.K;
-                    Op::load8(p, r0 + (ok ? row : 0), ok ? k : 0, sh.K, raw[j]);
-                }
+                    for (int j = 0; j < PRO_UNROLL; ++j) {
+                        const int u = min(u0 + j * PRO_WARPS, units - 1);
+                        const int kbl = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
+                        const int row = rg * 4 + r_in, k = (kb0 + kbl) * KBLK + c_in * 8;
+                        const bool ok = row < cnt && k < sh.K;
+                        Op::load8(p, r0 + (ok ? row : 0), ok ? k : 0, sh.K, raw[j]);
+                    }
 #pragma unroll
-                for (int j = 0; j < PRO_UNROLL; ++j) {
-                    const int uj = u0 + j * PRO_WARPS;
-                    const int u = min(uj, units - 1);
-                    const int kb = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
-                    const int row = rg * 4 + r_in, k = kb * KBLK + c_in * 8;
-                    const bool ok = row < cnt && k < sh.K;
-                    uint32_t o[4];
-                    Op::transform8(p, raw[j], r0 + (ok ? row : 0), ok ? k : 0, sh.K, o);
-                    if (uj < units)
-                        *reinterpret_cast<uint4*>(bt + (size_t)kb * BLK_BYTES + tc::sw128_offset(row, c_in * 8)) =
-                            ok ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int j = 0; j < PRO_UNROLL; ++j) {
+                        const int uj = u0 + j * PRO_WARPS;
+                        const int u = min(uj, units - 1);
+                        const int kbl = u / (TILE_ROWS / 4), rg = u % (TILE_ROWS / 4);
+                        const int row = rg * 4 + r_in, k = (kb0 + kbl) * KBLK + c_in * 8;
+                        const bool ok = row < cnt && k < sh.K;
+                        uint32_t o[4];
+                        Op::transform8(p, raw[j], r0 + (ok ? row : 0), ok ? k : 0, sh.K, o);
+                        if (uj < units)
+                            *reinterpret_cast<uint4*>(bt + (size_t)kbl * BLK_BYTES + tc::sw128_offset(row, c_in * 8)) =
+                                ok ? make_uint4(o[0], o[1], o[2], o[3]) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
-            }
-            tc::fence_proxy_async_smem();
-            tc::mbar_arrive(&b_full[buf]);
-            if (tl.dbg && pt == 0) {
-                long long* d = tl.dbg + (size_t)blockIdx.x * 16;
-                d[6] += t1 - t0;
-                d[7] += clock64() - t1;
-                d[8] += 1;
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&b_full[buf]);
+                if (tl.dbg && pt == 0) {
+                    long long* d = tl.dbg + (size_t)blockIdx.x * 16;
+                    d[6] += t1 - t0;
+                    d[7] += clock64() - t1;
+                    d[8] += 1;
+                }
             }
         }
     }
@@ -322,15 +442,26 @@ inline int make_weight_tmap(CUtensorMap* tm, const void* w, int rows_pad, int k_
     return r == CUDA_SUCCESS ? GSATB_OK : GSATB_EINVAL;
 }
 
-inline Shape make_shape(int K, int OUT) {
+inline Shape make_shape(int K, int OUT, int stage_bytes) {
     Shape s;
     s.K = K;
     s.KB = (K + KBLK - 1) / KBLK;
     s.OUT = OUT;
     s.NMB = (OUT + 127) / 128;
-    const int budget = 227 * 1024 - 256 - MISC_BYTES - 1024 - 1024;
-    s.NBUF = (2 * s.KB * BLK_BYTES + 4 * BLK_BYTES <= budget) ? 2 : 1;
-    int na = (budget - s.NBUF * s.KB * BLK_BYTES) / BLK_BYTES;
+    s.STAGE = stage_bytes;
+    const int budget = (227 * 1024 - 256 - MISC_BYTES - 1024 - 1024 - EPI_GROUPS * stage_bytes) / BLK_BYTES;   // 16 KiB blocks
+    s.KBC = s.KB;
+    s.NBUF = 2;
+    if (2 * s.KB + 3 > budget) {
+        if (s.KB > 2) {                        // chunk the K dimension: double-buffered half (or smaller) tiles
+            s.KBC = (s.KB + 1) / 2;
+            while (s.KBC > 1 && 2 * s.KBC + 3 > budget) s.KBC = (s.KBC + 1) / 2;
+        } else {
+            s.NBUF = 1;
+        }
+    }
+    s.NCH = (s.KB + s.KBC - 1) / s.KBC;
+    int na = budget - s.NBUF * s.KBC;
     s.NA = na > 8 ? 8 : na;
     return s;
 }
@@ -346,7 +477,7 @@ int launch(const void* w_bf16_padded, const Tiling& tl_in, int K, int OUT, const
     if (tl_in.num_tiles <= 0) return GSATB_OK;
     Tiling tl = tl_in;
     tl.dbg = profile_buffer();
-    Shape sh = make_shape(K, OUT);
+    Shape sh = make_shape(K, OUT, Op::STAGE_BYTES);
     if (sh.KB > 8 || sh.NA < 2) return GSATB_ESHAPE;
     CUtensorMap tm;
     int rc = make_weight_tmap(&tm, w_bf16_padded, sh.NMB * 128, sh.KB * KBLK);

@@ -48,46 +48,88 @@ struct OpGinBwd2 {
         pack8(v, o);
         *reinterpret_cast<uint4*>(p.d2 + grow * p.H + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    // staging: two buffers of 32 rows x 128 channels x 4 bytes.  z1 (fp32) is prefetched chunk by chunk with
+    // cp.async; the channel thread replaces each z1 word IN PLACE by the packed pair (g bf16 | a1 bf16 << 16), and
+    // the group then splits the words into the two bf16 output tensors with 16-byte stores.
+    static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
-    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
-        const int chc = ch_ok ? ch : 0;
+    __device__ static void epi_prefetch(const Params& p, const Tiling&, const EpiCtx& cx) {
+        epi_sync(cx);      // the previous block's copy-out has finished reading the buffers
+        if (cx.cnt > 0) stage_load_async<4>(cx, cx.stage, p.z1 + cx.r0 * p.H1, p.H1, 0, min(32, cx.cnt));
+        cp_async_commit();
+    }
+    __device__ static void store_split(const Params& p, const EpiCtx& cx, const uint32_t* buf, int row_lo, int nrows) {
+        uint16_t* gg = p.g + (cx.r0 + row_lo) * p.H1 + cx.ch0;
+        uint16_t* ga = p.a1 + (cx.r0 + row_lo) * p.H1 + cx.ch0;
+        const bool vec = (p.H1 % 8) == 0 && (cx.nch % 8) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(gg) | reinterpret_cast<uintptr_t>(ga)) & 15u) == 0;
+        if (vec) {
+            for (int i = cx.gtid; i < nrows * 16; i += 128) {
+                const int row = i >> 4, k = (i & 15) * 8;
+                if (k < cx.nch) {
+                    const uint4 w0 = *reinterpret_cast<const uint4*>(buf + row * 128 + k);
+                    const uint4 w1 = *reinterpret_cast<const uint4*>(buf + row * 128 + k + 4);
+                    uint4 og, oa;
+                    og.x = __byte_perm(w0.x, w0.y, 0x5410); oa.x = __byte_perm(w0.x, w0.y, 0x7632);
+                    og.y = __byte_perm(w0.z, w0.w, 0x5410); oa.y = __byte_perm(w0.z, w0.w, 0x7632);
+                    og.z = __byte_perm(w1.x, w1.y, 0x5410); oa.z = __byte_perm(w1.x, w1.y, 0x7632);
+                    og.w = __byte_perm(w1.z, w1.w, 0x5410); oa.w = __byte_perm(w1.z, w1.w, 0x7632);
+                    *reinterpret_cast<uint4*>(gg + (int64_t)row * p.H1 + k) = og;
+                    *reinterpret_cast<uint4*>(ga + (int64_t)row * p.H1 + k) = oa;
+                }
+            }
+        } else {
+            for (int i = cx.gtid; i < nrows * 128; i += 128) {
+                const int row = i >> 7, k = i & 127;
+                if (k < cx.nch) {
+                    gg[(int64_t)row * p.H1 + k] = (uint16_t)(buf[i] & 0xFFFFu);
+                    ga[(int64_t)row * p.H1 + k] = (uint16_t)(buf[i] >> 16);
+                }
+            }
+        }
+    }
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, const EpiCtx& cx) {
+        const int cnt = cx.cnt;
+        const int chc = cx.ch_ok ? cx.ch : 0;
         const float sc = __ldg(p.bn_scale + chc), sf = __ldg(p.bn_shift + chc);
         const float mu = __ldg(p.mean + chc), rs = __ldg(p.rstd + chc);
-        const float* zs = p.z1 + r0 * p.H1 + chc;
-        uint16_t* go = p.g + r0 * p.H1 + chc;
-        uint16_t* ao = p.a1 + r0 * p.H1 + chc;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+        const int nchunks = (cnt + 31) >> 5;
+        if (nchunks == 0) {
+            cp_async_wait<0>();
+            epi_release_acc(cx);
+        }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            if (c * 32 >= cnt) break;
-            float v[32], z[32];
-            tc::tmem_ld_32x32(taddr + c * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = __ldg(zs + (int64_t)min(c * 32 + j, cnt - 1) * p.H1);
+        for (int c = 0; c < nchunks; ++c) {
+            cp_async_wait<0>();
+            epi_sync(cx);      // chunk c of z1 is visible; chunk c-1 has been copied out by every thread
+            if (c + 1 < nchunks) {
+                stage_load_async<4>(cx, cx.stage + ((c + 1) & 1) * 16384, p.z1 + cx.r0 * p.H1, p.H1, (c + 1) * 32,
+                                    min(32, cnt - (c + 1) * 32));
+                cp_async_commit();
+            }
+            float v[32];
+            tc::tmem_ld_32x32(cx.taddr + c * 32, v);
             tc::tmem_ld_wait();
+            if (c == nchunks - 1) epi_release_acc(cx);
+            uint32_t* buf = reinterpret_cast<uint32_t*>(cx.stage + (c & 1) * 16384);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-                const int c0 = c * 32 + j, c1 = c0 + 1;
-                const bool ok0 = c0 < cnt, ok1 = c1 < cnt;
-                const float a0 = fmaxf(fmaf(z[j], sc, sf), 0.f), a1v = fmaxf(fmaf(z[j + 1], sc, sf), 0.f);
+                const bool ok0 = c * 32 + j < cnt && cx.ch_ok, ok1 = c * 32 + j + 1 < cnt && cx.ch_ok;
+                const float z0 = ok0 ? __uint_as_float(buf[j * 128 + cx.gtid]) : 0.f;
+                const float z1 = ok1 ? __uint_as_float(buf[(j + 1) * 128 + cx.gtid]) : 0.f;
+                const float a0 = fmaxf(fmaf(z0, sc, sf), 0.f), a1v = fmaxf(fmaf(z1, sc, sf), 0.f);
                 const float g0 = (a0 > 0.f && ok0) ? v[j] : 0.f, g1 = (a1v > 0.f && ok1) ? v[j + 1] : 0.f;
-                const float x0 = (z[j] - mu) * rs, x1 = (z[j + 1] - mu) * rs;
+                const float x0 = (z0 - mu) * rs, x1 = (z1 - mu) * rs;
                 s1a += g0;
                 s1b += g1;
                 s2a = fmaf(g0, x0, s2a);
                 s2b = fmaf(g1, x1, s2b);
-                const uint16_t gb0 = float_to_bf16_bits(g0), gb1 = float_to_bf16_bits(g1);
-                const uint16_t ab0 = float_to_bf16_bits(a0), ab1 = float_to_bf16_bits(a1v);
-                if (ok0 && ch_ok) {
-                    go[(int64_t)c0 * p.H1] = gb0;
-                    ao[(int64_t)c0 * p.H1] = ab0;
-                }
-                if (ok1 && ch_ok) {
-                    go[(int64_t)c1 * p.H1] = gb1;
-                    ao[(int64_t)c1 * p.H1] = ab1;
-                }
+                buf[j * 128 + cx.gtid] = (uint32_t)float_to_bf16_bits(g0) | ((uint32_t)float_to_bf16_bits(a0) << 16);
+                buf[(j + 1) * 128 + cx.gtid] = (uint32_t)float_to_bf16_bits(g1) | ((uint32_t)float_to_bf16_bits(a1v) << 16);
             }
+            epi_sync(cx);
+            store_split(p, cx, buf, c * 32, min(32, cnt - c * 32));
         }
         st.s1 += s1a + s1b;
         st.s2 += s2a + s2b;
@@ -133,22 +175,11 @@ struct OpGinBwd1 {
         pack8(g, o);
         *reinterpret_cast<uint4*>(p.dz1 + grow * p.H1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
-    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
-        float* o = p.dx + r0 * p.Kin + ch;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            if (c * 32 >= cnt) break;
-            float v[32];
-            tc::tmem_ld_32x32(taddr + c * 32, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = c * 32 + j;
-                if (col < cnt && ch_ok) o[(int64_t)col * p.Kin] = v[j];
-            }
-        }
+    __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, const EpiCtx& cx) {
+        epi_emit_f32(cx, p.dx, p.Kin, [](int, float acc) { return acc; });
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };

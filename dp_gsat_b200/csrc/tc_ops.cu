@@ -48,49 +48,40 @@ struct OpLinear {
         }
         pack8(r.v, o);
     }
+    static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
-    // Straight-line code: every column is computed unconditionally and only the store is predicated, so the 32
-    // columns of a chunk are independent instruction streams the scheduler can interleave (a per-column branch
-    // left the single epilogue warp of each sub-partition latency-bound at ~100 cycles per column).
-    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, uint32_t taddr, int ch, bool ch_ok,
-                                    int64_t r0, int cnt, int, uint8_t*, int, int, int) {
+    __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
+    // Straight-line code: every column is computed unconditionally (the 32 columns of a chunk are independent
+    // instruction streams the scheduler can interleave) and written to the staging buffer; the group then stores the
+    // chunk to global memory as whole rows.
+    __device__ static void epilogue(const Params& p, const Tiling&, EpiState& st, const EpiCtx& cx) {
+        const int ch = cx.ch, cnt = cx.cnt;
+        const bool ch_ok = cx.ch_ok;
+        const int64_t r0 = cx.r0;
         const float b = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
-        float* o = p.out + r0 * p.ldo + ch;
         const bool use_mask = p.drop.enabled && p.drop.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (ch_ok ? ch : 0) : nullptr;
         const uint32_t cht = hash_ch_term(p.drop, ch);
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tc::tmem_ld_32x32(taddr + c * 32, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const int c0 = c * 32 + j, c1 = c0 + 1;
-                const bool ok0 = c0 < cnt, ok1 = c1 < cnt;
-                float z0 = v[j] + b, z1 = v[j + 1] + b;
-                const float y0 = ok0 ? z0 : 0.f, y1 = ok1 ? z1 : 0.f;
-                s1a += y0;
-                s1b += y1;
-                s2a = fmaf(y0, y0, s2a);
-                s2b = fmaf(y1, y1, s2b);
-                if (p.relu_out) {
-                    z0 = fmaxf(z0, 0.f);
-                    z1 = fmaxf(z1, 0.f);
-                }
-                if (p.drop.enabled) {
-                    const bool k0 = use_mask ? (ok0 ? __ldg(mk + (int64_t)c0 * p.OUT) != 0 : false)
-                                             : hash_keep(p.drop, (uint32_t)(r0 + c0), cht);
-                    const bool k1 = use_mask ? (ok1 ? __ldg(mk + (int64_t)c1 * p.OUT) != 0 : false)
-                                             : hash_keep(p.drop, (uint32_t)(r0 + c1), cht);
-                    z0 = k0 ? z0 * p.drop.scale : 0.f;
-                    z1 = k1 ? z1 * p.drop.scale : 0.f;
-                }
-                if (ok0 && ch_ok) o[(int64_t)c0 * p.ldo] = z0;
-                if (ok1 && ch_ok) o[(int64_t)c1 * p.ldo] = z1;
+        epi_emit_f32(cx, p.out, p.ldo, [&](int col, float acc) {
+            const bool ok = col < cnt;
+            float z = acc + b;
+            const float y = ok ? z : 0.f;
+            if (col & 1) {
+                s1b += y;
+                s2b = fmaf(y, y, s2b);
+            } else {
+                s1a += y;
+                s2a = fmaf(y, y, s2a);
             }
-        }
+            if (p.relu_out) z = fmaxf(z, 0.f);
+            if (p.drop.enabled) {
+                const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false)
+                                        : hash_keep(p.drop, (uint32_t)(r0 + col), cht);
+                z = k ? z * p.drop.scale : 0.f;
+            }
+            return z;
+        });
         st.s1 += s1a + s1b;
         st.s2 += s2a + s2b;
     }

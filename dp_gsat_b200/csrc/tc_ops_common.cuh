@@ -90,6 +90,26 @@ inline Tiling uniform_tiling(int64_t rows) {
     return t;
 }
 
+// Stream one accumulator block out as fp32 rows through the group's staging buffer (two 32-row x 128-channel
+// fp32 buffers = 32 KiB): f(col, acc) is the value of element (row r0 + col, this thread's channel).
+template <class F>
+__device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int ld, F f) {
+    const int nchunks = (cx.cnt + 31) >> 5;
+    if (nchunks == 0) epi_release_acc(cx);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        float v[32];
+        tc::tmem_ld_32x32(cx.taddr + c * 32, v);
+        tc::tmem_ld_wait();
+        if (c == nchunks - 1) epi_release_acc(cx);
+        float* buf = reinterpret_cast<float*>(cx.stage) + (c & 1) * (32 * 128);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) buf[j * 128 + cx.gtid] = f(c * 32 + j, v[j]);
+        epi_sync(cx);      // chunk c staged; also orders chunk c-1's copy-out before chunk c+1 re-uses its buffer
+        stage_store<4>(cx, reinterpret_cast<const uint8_t*>(buf), out + cx.r0 * ld, ld, c * 32, min(32, cx.cnt - c * 32));
+    }
+}
+
 // Per-warp copy of the tile's graph boundaries (local row offsets) in the epilogue scratch: bnd[0..nseg]
 __device__ __forceinline__ int load_segments(const Tiling& tl, int tile, int64_t r0, uint8_t* misc, int q, int lane,
                                              const int*& bnd, int& g0) {
@@ -101,6 +121,10 @@ __device__ __forceinline__ int load_segments(const Tiling& tl, int tile, int64_t
     __syncwarp();
     bnd = mine;
     return nseg;
+}
+
+__device__ __forceinline__ int load_segments(const Tiling& tl, const EpiCtx& cx, const int*& bnd, int& g0) {
+    return load_segments(tl, cx.tile, cx.r0, cx.misc, cx.q, cx.lane, bnd, g0);
 }
 
 }  // namespace tcg

@@ -82,3 +82,33 @@ for name, fn in (('ext_fwd2 (eval, no dropout)', k2_nodrop), ('linear 128x128 on
     tiles = max(d[8].item(), 1)
     print(f'{name}: {e0.elapsed_time(e1):.3f} ms, tiles/CTA {tiles:.0f}; cycles per tile: ' +
           ', '.join(f'{n}={d[i].item() / tiles:.0f}' for i, n in enumerate(names[:8])))
+
+
+dz2 = (torch.randn(gi.E, H, device=dev) / 10).bfloat16()
+dz1 = torch.empty(gi.E, C1, dtype=torch.bfloat16, device=dev)
+w2t = tc.prep_weight(w2, transpose=True)
+w1t = tc.prep_weight(w1, transpose=True)
+df = torch.empty(gi.E, 2 * H, device=dev)
+
+
+def kbwd1():
+    L.call('gsatb_tc_ext_bwd1', ptr(dz2), ptr(w2t), ptr(xhat1), ptr(rstd1), None, ctypes.c_uint64(1), ctypes.c_float(0.5), 1,
+           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(dz1), gi.E, H, C1, stream())
+
+
+def kbf16in():
+    L.call('gsatb_tc_linear_bf16in_fwd', ptr(dz1), C1, ptr(w1t), ptr(df), 2 * H, gi.E, C1, 2 * H, stream())
+
+
+for name, fn in (('ext_bwd1', kbwd1), ('linear_bf16in 512->256', kbf16in)):
+    for _ in range(2):
+        fn()
+    dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    L.cdll.gsatb_tc_set_profile_buffer(ctypes.c_void_p(dbg.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    L.cdll.gsatb_tc_set_profile_buffer(None)
+    d = dbg.double().mean(0).cpu()
+    tiles = max(d[8].item(), 1)
+    print(f'{name}: {e0.elapsed_time(e1):.3f} ms, B-buffers/CTA {tiles:.0f}; cycles per B buffer: ' +
+          ', '.join(f'{n}={d[i].item() / tiles:.0f}' for i, n in enumerate(names[:8])))
