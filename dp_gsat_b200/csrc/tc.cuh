@@ -31,11 +31,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Spin with back-off: a waiting warp that keeps issuing try_wait/branch pairs steals issue slots from the working
-// warps of its SM sub-partition (measured: 3/4 of all executed instructions were barrier polls before this).
+// try_wait with a suspend-time hint: the hardware parks the thread (no issue slots) until the phase completes or the
+// hint expires.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// A waiting warp that keeps issuing try_wait / branch pairs steals issue slots from the working warps of its SM
+// sub-partition (ncu, round 1: the three control threads' polls were 25 % of all instructions issued by the
+// issue-bound extractor-backward kernel), so: one cheap probe, then long parked waits.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+    while (!mbar_try_wait_hint(bar, parity, 200000u)) {
+    }
 }
 // One thread polls the mbarrier, the rest of the role group sleeps in a named hardware barrier (no issue slots).
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -48,6 +63,12 @@ __device__ __forceinline__ void group_mbar_wait(bool leader, uint64_t* bar, uint
 
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- per-warpgroup register budget (all four warps of a warpgroup execute the same instruction) ----------------
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- TMA ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {

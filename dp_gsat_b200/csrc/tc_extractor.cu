@@ -54,57 +54,49 @@ __device__ __forceinline__ void for_pieces(uint32_t taddr, const int* bnd, int n
     }
 }
 
-// Per-graph InstanceNorm (biased variance of the centred values, as PyG computes it) of one accumulator row.
-// emit(c, j, col, xhat) is called for every valid column; seg_rstd(s, rstd) once per non-empty graph.
+// Per-graph InstanceNorm of one accumulator row (one channel).  PyG computes the biased variance of the centred values
+// in two sweeps; here ONE sweep accumulates the sums of d = x - K and d^2 around a shift K that is close to the mean
+// (the previous graph's mean of the same channel; the tile's first element for the first graph), so that
+// var = E[d^2] - E[d]^2 does not cancel, and a second sweep emits.  The accumulator is read twice instead of three
+// times (the epilogue is issue bound).
+// emit(c, j, col, in, xhat) is called for every column; seg_rstd(s, rstd) once per non-empty graph.
 template <class Emit, class SegRstd, class ChunkBegin, class ChunkEnd>
 __device__ __forceinline__ void instance_norm_rows(uint32_t taddr, const int* bnd, int nseg, float eps, Emit emit,
                                                    SegRstd seg_rstd, ChunkBegin chunk_begin, ChunkEnd chunk_end) {
     float mean[MAX_SEG], rs[MAX_SEG];
     auto nop_c = [](int) {};
     {
-        float acc = 0.f;
+        float a1 = 0.f, a2 = 0.f, K = 0.f;
+        bool have_k = false;
         for_pieces(taddr, bnd, nseg,
                    [&](int, const float* v, uint32_t m, int) {
-                       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                       for (int j = 0; j < 32; j += 4) {
-                           s0 += ((m >> j) & 1u) ? v[j] : 0.f;
-                           s1 += ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
-                           s2 += ((m >> (j + 2)) & 1u) ? v[j + 2] : 0.f;
-                           s3 += ((m >> (j + 3)) & 1u) ? v[j + 3] : 0.f;
+                       if (!have_k) {      // first piece of the tile starts at column 0 of chunk 0
+                           K = v[0];
+                           have_k = true;
                        }
-                       acc += (s0 + s1) + (s2 + s3);
+                       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                       for (int j = 0; j < 32; j += 2) {
+                           const float d0 = ((m >> j) & 1u) ? v[j] - K : 0.f;
+                           const float d1 = ((m >> (j + 1)) & 1u) ? v[j + 1] - K : 0.f;
+                           s0 += d0;
+                           s1 += d1;
+                           q0 = fmaf(d0, d0, q0);
+                           q1 = fmaf(d1, d1, q1);
+                       }
+                       a1 += s0 + s1;
+                       a2 += q0 + q1;
                    },
                    [&](int s) {
-                       mean[s] = acc / (float)(bnd[s + 1] - bnd[s]);
-                       acc = 0.f;
-                   },
-                   nop_c, nop_c);
-    }
-    {
-        float acc = 0.f;
-        for_pieces(taddr, bnd, nseg,
-                   [&](int, const float* v, uint32_t m, int s) {
-                       const float mu = mean[s];
-                       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                       for (int j = 0; j < 32; j += 4) {
-                           const float d0 = ((m >> j) & 1u) ? v[j] - mu : 0.f;
-                           const float d1 = ((m >> (j + 1)) & 1u) ? v[j + 1] - mu : 0.f;
-                           const float d2 = ((m >> (j + 2)) & 1u) ? v[j + 2] - mu : 0.f;
-                           const float d3 = ((m >> (j + 3)) & 1u) ? v[j + 3] - mu : 0.f;
-                           s0 = fmaf(d0, d0, s0);
-                           s1 = fmaf(d1, d1, s1);
-                           s2 = fmaf(d2, d2, s2);
-                           s3 = fmaf(d3, d3, s3);
-                       }
-                       acc += (s0 + s1) + (s2 + s3);
-                   },
-                   [&](int s) {
-                       const float r = 1.f / sqrtf(acc / (float)(bnd[s + 1] - bnd[s]) + eps);
+                       const float inv_n = 1.f / (float)(bnd[s + 1] - bnd[s]);
+                       const float md = a1 * inv_n;
+                       const float var = fmaxf(a2 * inv_n - md * md, 0.f);
+                       const float r = 1.f / sqrtf(var + eps);
+                       mean[s] = K + md;
                        rs[s] = r;
                        seg_rstd(s, r);
-                       acc = 0.f;
+                       K = K + md;      // shift of the next graph
+                       a1 = a2 = 0.f;
                    },
                    nop_c, nop_c);
     }
@@ -146,6 +138,7 @@ struct OpExtFwd1 {
     __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) { pack8(r.v, o); }
     // staging: two buffers of 32 rows x 128 channels bf16 (16 KiB per group); the emit pass of the InstanceNorm fills
     // one 32-row chunk, the group stores it as whole rows while the channel threads fill the other buffer.
+    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 16384;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
@@ -190,6 +183,7 @@ struct OpExtFwd2 {
         float* logit;            // [rows]
         int H;
         float eps;
+        uint16_t* h1_out;        // bf16 [rows, C1] nullable: the operand rows as fed to GEMM2
     };
     struct EpiState {
         uint32_t par;
@@ -222,7 +216,9 @@ struct OpExtFwd2 {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? fmaxf(v[i], 0.f) * p.drop1.scale : 0.f;
         pack8(v, o);
+        if (p.h1_out) *reinterpret_cast<uint4*>(p.h1_out + grow * p.C1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 16384;      // as OpExtFwd1: two 32-row bf16 chunk buffers for xhat2
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool first) {
         if (first) st.par = 0;
@@ -333,15 +329,16 @@ extern "C" int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int
 extern "C" int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16, const float* w3, const float* b3,
                                  const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
                                  const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
-                                 int num_tiles, void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H,
-                                 float eps, gsatb_stream_t stream) {
+                                 int num_tiles, void* xhat2, float* rstd2, float* logit, void* h1_out, int64_t rows,
+                                 int C1, int H, float eps, gsatb_stream_t stream) {
     if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || num_tiles == 0) return GSATB_OK;
     if (!xhat1 || !w2_bf16 || !w3 || !tile_row || !tile_seg || !seg_ptr || !xhat2 || !rstd2 || !logit)
         return GSATB_EINVAL;
     if (C1 % 8 != 0 || C1 > 512 || H > 128) return GSATB_ESHAPE;
     OpExtFwd2::Params p{(const uint16_t*)xhat1, C1, make_dropout(mask1, seed * 2 + 1, pdrop, training), w3, b3,
-                        (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps};
+                        (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps,
+                        (uint16_t*)h1_out};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
     return launch<OpExtFwd2>(w2_bf16, tl, C1, H, p, (cudaStream_t)stream);
 }

@@ -87,8 +87,6 @@ __device__ __forceinline__ void for_pieces_bwd(uint32_t taddr, const int* bnd, i
 // ---- bwd1: dh1 = dz2 W2, then masks + InstanceNorm1 backward -> dz1 ---------------------------------------------
 struct OpExtBwd1 {
     struct Params {
-        const uint16_t* dz2;     // bf16 [rows, H]   (B operand rows)
-        int H;
         const uint16_t* xhat1;   // bf16 [rows, C1]
         const float* rstd1;      // [G, C1]
         Dropout drop1;
@@ -96,16 +94,7 @@ struct OpExtBwd1 {
         int C1;
     };
     struct EpiState {};
-    static constexpr int UNROLL = 8;
-    struct Raw {
-        uint4 q;
-    };
-    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
-        r.q = __ldg(reinterpret_cast<const uint4*>(p.dz2 + grow * p.H + k));
-    }
-    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
-        o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
-    }
+    static constexpr bool TMA_B = true;      // B operand = dz2, bf16 [rows, H] as it lies in memory
     // staging: the tile's [rows][128 channels] block of xhat1 (bf16, 32 KiB) is fetched with cp.async BEFORE the
     // accumulator is awaited; pass 0 forms the gated gradient e = dh1 * keep * scale * (xhat1 > 0) and its per-graph
     // sums (thread-local: thread = channel), remembering the gates as bits; pass 1 overwrites each xhat1 value in
@@ -182,18 +171,19 @@ struct OpExtBwd1 {
                 }
                 tc::tmem_ld_wait();
                 if (pass == 1 && c == nchunks - 1) epi_release_acc(cx);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((gt >> j) & 1u) ? v[j] * p.drop1.scale : 0.f;   // gated gradient e
+                // e = gate * scale * v is never formed: the sums run over gv = gate ? v : 0 and the dropout scale is
+                // folded into the per-graph constants (pass 0: m = scale * sum / n; pass 1: dz1 = A gv + C xhat + B)
                 const int cbeg = c * 32, cend = min(cbeg + 32, cnt);
 #pragma unroll 1
                 while (s < nseg && bnd[s] < cend) {
                     const int lo = max(bnd[s], cbeg) - cbeg, hi = min(bnd[s + 1], cend) - cbeg;
                     const uint32_t m = (hi - lo >= 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+                    const uint32_t gm = gt & m;
                     if (pass == 0) {
                         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float e0 = ((m >> j) & 1u) ? v[j] : 0.f, e1 = ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
+                            const float e0 = ((gm >> j) & 1u) ? v[j] : 0.f, e1 = ((gm >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
                             s1a += e0;
                             s1b += e1;
                             s2a = fmaf(e0, xv[j], s2a);
@@ -202,19 +192,20 @@ struct OpExtBwd1 {
                         a1 += s1a + s1b;
                         a2 += s2a + s2b;
                     } else {
-                        const float mu1 = m1[s], mu2 = m2[s];
                         const float rs = ch_ok ? __ldg(p.rstd1 + (int64_t)(g0 + s) * p.C1 + ch) : 0.f;
+                        const float cA = rs * p.drop1.scale, cB = -rs * m1[s], cC = -rs * m2[s];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const uint16_t bits = float_to_bf16_bits(rs * (v[j] - mu1 - xv[j] * mu2));
+                            const float gv = ((gm >> j) & 1u) ? v[j] : 0.f;
+                            const uint16_t bits = float_to_bf16_bits(fmaf(cA, gv, fmaf(cC, xv[j], cB)));
                             if ((m >> j) & 1u) xs[(cbeg + j) * 128] = bits;
                         }
                     }
                     if (bnd[s + 1] <= cend) {
                         if (pass == 0) {
-                            const float inv_n = 1.f / (float)(bnd[s + 1] - bnd[s]);
-                            m1[s] = a1 * inv_n;
-                            m2[s] = a2 * inv_n;
+                            const float sn = p.drop1.scale / (float)(bnd[s + 1] - bnd[s]);
+                            m1[s] = a1 * sn;
+                            m2[s] = a2 * sn;
                             a1 = a2 = 0.f;
                         }
                         ++s;
@@ -234,27 +225,16 @@ struct OpExtBwd1 {
 // ---- bwd0: out = x_bf16 W^T (fp32 out), used for d f12 = dz1 W1 ------------------------------------------------------
 struct OpLinearBf16In {
     struct Params {
-        const uint16_t* x;   // bf16 [rows, K]
-        int ldx;
         float* out;          // fp32 [rows, OUT]
         int ldo;
     };
     struct EpiState {};
-    static constexpr int UNROLL = 8;
-    struct Raw {
-        uint4 q;
-    };
-    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
-        r.q = __ldg(reinterpret_cast<const uint4*>(p.x + grow * p.ldx + k));
-    }
-    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) {
-        o[0] = r.q.x; o[1] = r.q.y; o[2] = r.q.z; o[3] = r.q.w;
-    }
-    static constexpr int STAGE_BYTES = 32768;
+    static constexpr bool TMA_B = true;      // B operand = x, bf16 [rows, K] as it lies in memory
+    static constexpr int STAGE_BYTES = 16384;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
     __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, const EpiCtx& cx) {
-        epi_emit_f32(cx, p.out, p.ldo, [](int, float acc) { return acc; });
+        epi_emit_f32<16>(cx, p.out, p.ldo, [](int, float acc) { return acc; });
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };
@@ -319,10 +299,10 @@ extern "C" int gsatb_tc_ext_bwd1(const void* dz2, const void* w2t_bf16, const vo
     if (rows == 0 || num_tiles == 0) return GSATB_OK;
     if (!dz2 || !w2t_bf16 || !xhat1 || !rstd1 || !tile_row || !tile_seg || !seg_ptr || !dz1) return GSATB_EINVAL;
     if (H % 8 != 0 || H > 512) return GSATB_ESHAPE;
-    OpExtBwd1::Params p{(const uint16_t*)dz2, H, (const uint16_t*)xhat1, rstd1,
-                        make_dropout(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)dz1, C1};
+    OpExtBwd1::Params p{(const uint16_t*)xhat1, rstd1, make_dropout(mask1, seed * 2 + 1, pdrop, training),
+                        (uint16_t*)dz1, C1};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
-    return launch<OpExtBwd1>(w2t_bf16, tl, H, C1, p, (cudaStream_t)stream);
+    return launch<OpExtBwd1>(w2t_bf16, tl, H, C1, p, (cudaStream_t)stream, dz2, H);
 }
 
 extern "C" int gsatb_tc_linear_bf16in_fwd(const void* x_bf16, int ldx, const void* w_bf16, float* out, int ldo,
@@ -331,9 +311,9 @@ extern "C" int gsatb_tc_linear_bf16in_fwd(const void* x_bf16, int ldx, const voi
     if (rows == 0) return GSATB_OK;
     if (!x_bf16 || !w_bf16 || !out) return GSATB_EINVAL;
     if (K > 512 || K % 8 != 0 || ldx % 8 != 0) return GSATB_ESHAPE;
-    OpLinearBf16In::Params p{(const uint16_t*)x_bf16, ldx, out, ldo};
+    OpLinearBf16In::Params p{out, ldo};
     Tiling tl = uniform_tiling(rows);
-    return launch<OpLinearBf16In>(w_bf16, tl, K, OUT, p, (cudaStream_t)stream);
+    return launch<OpLinearBf16In>(w_bf16, tl, K, OUT, p, (cudaStream_t)stream, x_bf16, ldx);
 }
 
 extern "C" int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed, float pdrop, int training,

@@ -51,6 +51,7 @@ struct OpGinBwd2 {
     // staging: two buffers of 32 rows x 128 channels x 4 bytes.  z1 (fp32) is prefetched chunk by chunk with
     // cp.async; the channel thread replaces each z1 word IN PLACE by the packed pair (g bf16 | a1 bf16 << 16), and
     // the group then splits the words into the two bf16 output tensors with 16-byte stores.
+    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
     __device__ static void epi_prefetch(const Params& p, const Tiling&, const EpiCtx& cx) {
@@ -175,11 +176,12 @@ struct OpGinBwd1 {
         pack8(g, o);
         *reinterpret_cast<uint4*>(p.dz1 + grow * p.H1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
+    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
     __device__ static void epilogue(const Params& p, const Tiling&, EpiState&, const EpiCtx& cx) {
-        epi_emit_f32(cx, p.dx, p.Kin, [](int, float acc) { return acc; });
+        epi_emit_f32<32>(cx, p.dx, p.Kin, [](int, float acc) { return acc; });
     }
     __device__ static void epi_finish(const Params&, EpiState&, int, bool, bool, int) {}
 };

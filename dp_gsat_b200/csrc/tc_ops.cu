@@ -48,6 +48,7 @@ struct OpLinear {
         }
         pack8(r.v, o);
     }
+    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 32768;
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
     __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
@@ -63,7 +64,7 @@ struct OpLinear {
         const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (ch_ok ? ch : 0) : nullptr;
         const uint32_t cht = hash_ch_term(p.drop, ch);
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-        epi_emit_f32(cx, p.out, p.ldo, [&](int col, float acc) {
+        epi_emit_f32<32>(cx, p.out, p.ldo, [&](int col, float acc) {
             const bool ok = col < cnt;
             float z = acc + b;
             const float y = ok ? z : 0.f;

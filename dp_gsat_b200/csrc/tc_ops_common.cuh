@@ -90,10 +90,12 @@ inline Tiling uniform_tiling(int64_t rows) {
     return t;
 }
 
-// Stream one accumulator block out as fp32 rows through the group's staging buffer (two 32-row x 128-channel
-// fp32 buffers = 32 KiB): f(col, acc) is the value of element (row r0 + col, this thread's channel).
-template <class F>
+// Stream one accumulator block out as fp32 rows through the group's staging buffer: two buffers of RB rows x 128
+// channels x 4 bytes (RB = 32: 32 KiB per group, RB = 16: 16 KiB).  f(col, acc) is the value of element
+// (row r0 + col, this thread's channel); it is called for every column of a chunk that has at least one valid row.
+template <int RB, class F>
 __device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int ld, F f) {
+    constexpr int HALVES = 32 / RB;
     const int nchunks = (cx.cnt + 31) >> 5;
     if (nchunks == 0) epi_release_acc(cx);
 #pragma unroll 1
@@ -102,11 +104,17 @@ __device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int l
         tc::tmem_ld_32x32(cx.taddr + c * 32, v);
         tc::tmem_ld_wait();
         if (c == nchunks - 1) epi_release_acc(cx);
-        float* buf = reinterpret_cast<float*>(cx.stage) + (c & 1) * (32 * 128);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) buf[j * 128 + cx.gtid] = f(c * 32 + j, v[j]);
-        epi_sync(cx);      // chunk c staged; also orders chunk c-1's copy-out before chunk c+1 re-uses its buffer
-        stage_store<4>(cx, reinterpret_cast<const uint8_t*>(buf), out + cx.r0 * ld, ld, c * 32, min(32, cx.cnt - c * 32));
+        for (int h = 0; h < HALVES; ++h) {
+            const int lo = c * 32 + h * RB, n = min(RB, cx.cnt - lo);
+            if (n > 0) {       // uniform across the group
+                float* buf = reinterpret_cast<float*>(cx.stage) + (HALVES == 1 ? (c & 1) : h) * (RB * 128);
+#pragma unroll
+                for (int j = 0; j < RB; ++j) buf[j * 128 + cx.gtid] = f(lo + j, v[h * RB + j]);
+                epi_sync(cx);  // buffer staged; also orders the previous copy-out of the OTHER buffer before its re-use
+                stage_store<4>(cx, reinterpret_cast<const uint8_t*>(buf), out + cx.r0 * ld, ld, lo, n);
+            }
+        }
     }
 }
 

@@ -162,6 +162,13 @@ class GSAT(tnn.Module):
         return loss, loss_dict
 
     def forward_pass(self, data, epoch, training, noise_u: Optional[torch.Tensor] = None, r=None):
+        self.clf._enc_scope = {}          # the two GNN passes of this step share node_encoder(x) (nn._encode_once)
+        try:
+            return self._forward_pass(data, epoch, training, noise_u, r)
+        finally:
+            self.clf._enc_scope = None
+
+    def _forward_pass(self, data, epoch, training, noise_u, r):
         gi = get_graph_index(data.edge_index, data.batch, getattr(data, 'num_graphs', None) or None)
         emb = self.clf.get_emb(data.x, data.edge_index, batch=data.batch, edge_attr=data.edge_attr)
         att_log_logits = self.extractor(emb, data.edge_index, data.batch)

@@ -172,7 +172,7 @@ class GIN(tnn.Module):
 
     def get_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin'):
         gi = get_graph_index(edge_index, batch)
-        x = self.node_encoder(x)
+        x = _encode_once(self, x)
         fused = self.precision == 'bf16' and x.shape[1] % 8 == 0 and x.shape[1] <= 128
         for i in range(self.n_layers):
             if fused:
@@ -202,6 +202,20 @@ class GIN(tnn.Module):
 
     def get_pred_from_emb(self, emb, batch):
         return self.fc_out(self.pool(emb, batch))
+
+
+def _encode_once(model, x):
+    """node_encoder(x), shared between the two GNN passes of ONE GSAT.forward_pass (get_emb, then clf: same input,
+    same weights, no dropout in front of it -- example/gsat.py:75,86), so the encoder GEMM and its weight-gradient
+    GEMM run once per step instead of twice.  GSAT.forward_pass opens / closes the scope (``_enc_scope``); outside
+    of it every call encodes afresh."""
+    scope = getattr(model, '_enc_scope', None)
+    if scope is None:
+        return model.node_encoder(x)
+    key = (x.data_ptr(), tuple(x.shape), x._version, torch.is_grad_enabled())
+    if scope.get('key') != key:
+        scope['key'], scope['out'] = key, model.node_encoder(x)
+    return scope['out']
 
 
 def _no_edges(device):

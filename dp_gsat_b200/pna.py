@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .index import GraphIndex, get_graph_index
-from .nn import AtomEncoder, BondEncoder, _dropout
+from .nn import AtomEncoder, BondEncoder, _dropout, _encode_once
 
 
 def _scale_identity(src, deg, avg):
@@ -110,7 +110,7 @@ class PNA(tnn.Module):
 
     def get_emb(self, x, edge_index, batch, edge_attr, edge_atten=None, mask_key: str = 'pna'):
         gi = get_graph_index(edge_index, batch)
-        x = self.node_encoder(x)
+        x = _encode_once(self, x)
         if edge_attr is not None:
             edge_attr = self.edge_encoder(edge_attr)
         for i, (conv, batch_norm) in enumerate(zip(self.convs, self.batch_norms)):

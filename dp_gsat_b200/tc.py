@@ -49,7 +49,8 @@ def linear(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_
 
 def extractor_forward(emb: torch.Tensor, gi: GraphIndex, w1: torch.Tensor, w2: torch.Tensor, w3: torch.Tensor,
                       b3: Optional[torch.Tensor], *, edge_mode: bool, pdrop: float, training: bool, seed: int,
-                      mask1: Optional[torch.Tensor] = None, mask2: Optional[torch.Tensor] = None, eps: float = 1e-5):
+                      mask1: Optional[torch.Tensor] = None, mask2: Optional[torch.Tensor] = None, eps: float = 1e-5,
+                      keep_h1: bool = False):
     """Fused forward of the extractor MLP.  Returns (logit [rows, 1], saved) or None when the batch cannot be tiled
     (a graph with more than 128 rows)."""
     plan = gi.tile_plan('edge' if edge_mode else 'node')
@@ -68,6 +69,8 @@ def extractor_forward(emb: torch.Tensor, gi: GraphIndex, w1: torch.Tensor, w2: t
     xhat2 = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
     rstd2 = torch.empty((gi.G, H), dtype=torch.float32, device=dev)
     logit = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+    # Dropout(ReLU(xhat1)) as fed to GEMM2, written by the operand producers for the weight gradient dW2 = dz2^T h1
+    h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev) if keep_h1 else None
     L = lib()
     L.call('gsatb_tc_ext_fwd1', ptr(emb), ptr(gi.src) if edge_mode else None, ptr(gi.dst) if edge_mode else None,
            ptr(w1p), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T, ptr(xhat1), ptr(rstd1), rows, H, C1,
@@ -75,8 +78,8 @@ def extractor_forward(emb: torch.Tensor, gi: GraphIndex, w1: torch.Tensor, w2: t
     w3f = w3.detach().reshape(-1).contiguous()
     L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), ptr(mask1), ptr(mask2),
            ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T,
-           ptr(xhat2), ptr(rstd2), ptr(logit), rows, C1, H, ctypes.c_float(eps), stream())
-    return logit, dict(xhat1=xhat1, rstd1=rstd1, xhat2=xhat2, rstd2=rstd2, plan=plan)
+           ptr(xhat2), ptr(rstd2), ptr(logit), ptr(h1), rows, C1, H, ctypes.c_float(eps), stream())
+    return logit, dict(xhat1=xhat1, rstd1=rstd1, xhat2=xhat2, rstd2=rstd2, plan=plan, h1=h1)
 
 
 class _FusedExtractor(torch.autograd.Function):
@@ -87,7 +90,8 @@ class _FusedExtractor(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps):
         res = extractor_forward(emb, gi, w1, w2, w3, b3, edge_mode=edge_mode, pdrop=pdrop, training=training,
-                                seed=seed, mask1=mask1, mask2=mask2, eps=eps)
+                                seed=seed, mask1=mask1, mask2=mask2, eps=eps,
+                                keep_h1=bool(ctx.needs_input_grad[3]))
         if res is None:
             raise ValueError('a graph exceeds one 128-row tile; use the fp32 extractor path for this batch')
         logit, saved = res
@@ -123,11 +127,14 @@ class _FusedExtractor(torch.autograd.Function):
                ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr),
                T, ptr(dz1), rows, H, C1, stream())
         # weight gradients (library GEMMs, fp32 accumulate) on re-materialised bf16 operands
-        h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
-        L.call('gsatb_tc_ext_make_h1', ptr(sv['xhat1']), ptr(mask1), ctypes.c_uint64(seed), ctypes.c_float(pdrop),
-               int(training), ptr(h1), rows, C1, stream())
+        h1 = sv.get('h1')
+        if h1 is None:
+            h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
+            L.call('gsatb_tc_ext_make_h1', ptr(sv['xhat1']), ptr(mask1), ctypes.c_uint64(seed), ctypes.c_float(pdrop),
+                   int(training), ptr(h1), rows, C1, stream())
         dW2 = _mm_f32(dz2.t(), h1)
         del h1
+        sv['h1'] = None
         f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
         L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None,
                ptr(gi.dst) if edge_mode else None, ptr(f12), rows, H, stream())

@@ -229,7 +229,8 @@ int gsatb_tc_gin_bwd1(const void* g, const float* z1, const float* cA, const flo
  *   ext_fwd2: logit = (Dropout(ReLU(InstanceNorm(Dropout(ReLU(xhat1)) W2^T))) . w3) + b3; also xhat2 bf16 [rows, H]
  *             and rstd2 [G, H] for backward.  mask1 [rows, C1] / mask2 [rows, H] (uint8 keep masks) are optional
  *             injected dropout masks; otherwise a counter hash of (seed, element index) decides, and backward can
- *             regenerate it.
+ *             regenerate it.  h1_out [nullable]: bf16 [rows, C1] copy of Dropout(ReLU(xhat1)) as fed to GEMM2, kept
+ *             for the weight gradient dW2 = dz2^T h1 (saves the re-materialisation pass gsatb_tc_ext_make_h1).
  * ---------------------------------------------------------------------------------------------------------- */
 int gsatb_tile_plan_host(const int32_t* seg_ptr_host, int64_t G, int max_rows, int max_seg, int32_t* tile_row,
                          int32_t* tile_seg, int32_t* num_tiles);
@@ -239,7 +240,7 @@ int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int32_t* dst, 
 int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16_padded, const float* w3, const float* b3,
                       const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
                       const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles,
-                      void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H, float eps,
+                      void* xhat2, float* rstd2, float* logit, void* h1_out, int64_t rows, int C1, int H, float eps,
                       gsatb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------

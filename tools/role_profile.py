@@ -39,7 +39,7 @@ def k1():
 
 def k2():
     L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), None, None, ctypes.c_uint64(1), ctypes.c_float(0.5), 1,
-           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), gi.E, C1, H, ctypes.c_float(1e-5), stream())
+           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), None, gi.E, C1, H, ctypes.c_float(1e-5), stream())
 
 
 for name, fn in (('ext_fwd1', k1), ('ext_fwd2', k2)):
@@ -58,7 +58,7 @@ for name, fn in (('ext_fwd1', k1), ('ext_fwd2', k2)):
 
 def k2_nodrop():
     L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), None, None, ctypes.c_uint64(1), ctypes.c_float(0.5), 0,
-           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), gi.E, C1, H, ctypes.c_float(1e-5), stream())
+           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), None, gi.E, C1, H, ctypes.c_float(1e-5), stream())
 
 
 xl = torch.randn(gi.E, 128, device=dev)
