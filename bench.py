@@ -157,6 +157,81 @@ def run_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# roofline: algorithmic bytes / flops per launch of every kernel of ours (DESIGN.md "Kernels"), live CUDA-event times
+# ---------------------------------------------------------------------------------------------------------------
+def kernel_models(N, E, G, H):
+    """{C-ABI entry[:variant]: (algorithmic bytes per launch, flops per launch)} for the GSAT-GIN step at hidden H
+    (extractor widths 2H -> 4H -> H -> 1).  Bytes = every distinct input element read once + every output element
+    written once; the bf16 intermediates a kernel reads / writes are part of ITS contract."""
+    C1 = 4 * H
+    return {
+        'gsatb_gin_aggregate_fwd:att': (8.0 * N * H + 8.0 * E + 4.0 * N, 2.0 * E * H),
+        'gsatb_gin_aggregate_fwd:noatt': (8.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
+        'gsatb_gin_aggregate_bwd:att': (12.0 * N * H + 16.0 * E, 4.0 * E * H),
+        'gsatb_gin_aggregate_bwd:noatt': (8.0 * N * H + 8.0 * E, 1.0 * E * H),
+        'gsatb_tc_linear_fwd': (8.0 * N * H, 2.0 * N * H * H),
+        'gsatb_tc_gin_bwd2': (N * (4.0 * H + 4 * H + 4 * H + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
+        'gsatb_tc_gin_bwd1': (N * (2.0 * H + 4 * H + 2 * H + 4 * H), 2.0 * N * H * H),
+        'gsatb_tc_ext_fwd1': (4.0 * N * H + 8.0 * E + 2.0 * E * C1, 2.0 * E * 2 * H * C1),
+        'gsatb_tc_ext_fwd2': (2.0 * E * C1 + 2.0 * E * C1 + 2.0 * E * H + 4.0 * E, 2.0 * E * C1 * H),
+        'gsatb_tc_ext_bwd_head': (4.0 * E + 2.0 * E * H + 2.0 * E * H, 8.0 * E * H),
+        'gsatb_tc_ext_bwd1': (2.0 * E * H + 2.0 * E * C1 + 2.0 * E * C1, 2.0 * E * H * C1),
+        'gsatb_tc_linear_bf16in_fwd': (2.0 * E * C1 + 4.0 * E * 2 * H, 2.0 * E * C1 * 2 * H),
+        'gsatb_tc_ext_make_f12': (4.0 * N * H + 8.0 * E + 2.0 * E * 2 * H, 0.0),
+        'gsatb_tc_ext_make_h1': (4.0 * E * C1, 0.0),
+        'gsatb_gather_concat_bwd': (4.0 * E * 2 * H + 8.0 * E + 4.0 * N * H, 2.0 * E * H),
+        'gsatb_sample_avg_info_fwd': (20.0 * E, 0.0),
+        'gsatb_sample_avg_info_bwd': (20.0 * E, 0.0),
+        'gsatb_pool_fwd': (4.0 * N * H + 4.0 * G * H, 1.0 * N * H),
+        'gsatb_pool_bwd': (4.0 * N * H + 4.0 * G * H + 4.0 * N, 0.0),
+    }
+
+
+def build_roofline(timer, N, E, G, H, steps, ms_step):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    tc = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1400.0)))    # timed inside a long step
+    models = kernel_models(N, E, G, H)
+    rows = []
+    for name, evs in timer.items():
+        by_tag = {}
+        for e0, e1, tag in evs:
+            by_tag.setdefault(tag or '', []).append(e0.elapsed_time(e1))
+        for tag, ms in by_tag.items():
+            key = name + (':' + tag if tag else '')
+            tot = sum(ms)
+            row = {'kernel': key, 'launches_per_step': len(ms) / steps, 'avg_launch_ms': tot / len(ms),
+                   'share_of_step': tot / steps / ms_step}
+            if key in models:
+                nbytes, flops = models[key]
+                t_hbm, t_tc = nbytes / (hbm * 1e9), flops / (tc * 1e12)
+                sec = row['avg_launch_ms'] * 1e-3
+                if t_tc > t_hbm:
+                    row.update(bound='tensor', achieved=flops / sec / 1e12, peak=tc, unit='TFLOP/s')
+                else:
+                    row.update(bound='hbm', achieved=nbytes / sec / 1e9, peak=hbm, unit='GB/s')
+                row['frac'] = row['achieved'] / row['peak']
+                row['algorithmic_bytes_per_launch'], row['flops_per_launch'] = nbytes, flops
+            rows.append(row)
+    rows.sort(key=lambda r: -r['share_of_step'])
+    modelled = [r for r in rows if 'frac' in r]
+    top = dict(modelled[0]) if modelled else {'kernel': None, 'bound': 'hbm', 'achieved': 0.0, 'peak': hbm,
+                                              'unit': 'GB/s', 'frac': 0.0}
+    top['traffic'] = None          # dram__bytes per launch from the ncu --set full capture: see profiles/
+    top['peak_source'] = ('measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)' if peaks
+                          else 'fallback 6650 GB/s / 1400 TFLOP/s')
+    top['frac_of_nominal_8TBs'] = top['achieved'] / 8000.0 if top.get('unit') == 'GB/s' else None
+    top['dominant_by'] = 'largest share of the timed step among our kernels (CUDA events around every C-ABI call)'
+    top['kernels'] = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()} for r in rows[:16]]
+    top['ours_share_of_step'] = sum(r['share_of_step'] for r in rows)
+    return top
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------------
 def run_b200(a):
@@ -200,7 +275,9 @@ def run_b200(a):
     barrier()
 
     L = lib()
-    L.timer = {'gsatb_gin_aggregate_fwd': [], 'gsatb_gin_aggregate_bwd': []}
+    L.timer, L.timer_all = {}, True          # CUDA events around every C-ABI call of the timed region (rank-local)
+    L.timer_tag = lambda name, args: ('att' if args[1] is not None else 'noatt') if name == 'gsatb_gin_aggregate_fwd' \
+        else (('att' if args[2] is not None else 'noatt') if name == 'gsatb_gin_aggregate_bwd' else '')
     launches0 = L.launches
     clocks = Clocks(local)
     if rank == 0:
@@ -217,32 +294,10 @@ def run_b200(a):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clk = clocks.stop() if rank == 0 else None
     launches = L.launches - launches0
-    timer, L.timer = L.timer, None
+    timer, L.timer, L.timer_all, L.timer_tag = L.timer, None, False, None
     ms_step = float(ms.item()) / a.steps
     value = E_global / (ms_step * 1e-3)
-
-    # roofline of the dominant kernel of ours: K3 forward (gather-scale-segmented-sum), measured live above
-    fwd_ms = [s.elapsed_time(e) for s, e in timer['gsatb_gin_aggregate_fwd']]
-    bwd_ms = [s.elapsed_time(e) for s, e in timer['gsatb_gin_aggregate_bwd']]
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    alg_fwd = 8.0 * N_loc * H + 8.0 * E_loc + 4.0 * N_loc
-    alg_bwd = 12.0 * N_loc * H + 16.0 * E_loc
-    avg_fwd = sum(fwd_ms) / max(len(fwd_ms), 1)
-    avg_bwd = sum(bwd_ms) / max(len(bwd_ms), 1)
-    ach = alg_fwd / (avg_fwd * 1e-3) / 1e9 if avg_fwd > 0 else 0.0
-    roofline = {'kernel': 'k_gin_aggregate_fwd (K3)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                'frac': ach / peak, 'traffic': None,
-                'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback 6650 GB/s',
-                'algorithmic_bytes_per_launch': alg_fwd, 'avg_launch_ms': avg_fwd, 'launches_timed': len(fwd_ms),
-                'frac_of_nominal_8TBs': ach / 8000.0,
-                'k3_bwd': {'achieved': alg_bwd / (avg_bwd * 1e-3) / 1e9 if avg_bwd > 0 else 0.0,
-                           'algorithmic_bytes_per_launch': alg_bwd, 'avg_launch_ms': avg_bwd},
-                'share_of_step': (sum(fwd_ms) + sum(bwd_ms)) / a.steps / ms_step}
+    roofline = build_roofline(timer, N_loc, E_loc, data.num_graphs, H, a.steps, ms_step)
 
     # end-to-end through the public API from pinned host buffers
     G.clear_index_cache()

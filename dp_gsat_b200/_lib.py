@@ -63,7 +63,9 @@ class _Lib:
             fn.argtypes = argtypes
         self._device_checked = False
         self.launches = 0          # kernels launched through this library (bench.py reports the timed-region delta)
-        self.timer = None          # optional {entry name: [(start_event, end_event), ...]} filled by call()
+        self.timer = None          # optional {entry name: [(start_event, end_event, tag), ...]} filled by call()
+        self.timer_all = False     # time every entry point, not only the names already in `timer`
+        self.timer_tag = None      # optional fn(name, args) -> tag stored with each timed call (bench.py: shapes)
 
     def strerror(self, code: int) -> str:
         return self.cdll.gsatb_strerror(code).decode()
@@ -87,12 +89,12 @@ class _Lib:
         self.check_device()
         self.launches += self.KERNELS_PER_CALL.get(name, 1)
         t = self.timer
-        if t is not None and name in t:
+        if t is not None and (name in t or self.timer_all):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()                      # on torch's current stream == the stream the kernel is launched on
             rc = getattr(self.cdll, name)(*args)
             e1.record()
-            t[name].append((e0, e1))
+            t.setdefault(name, []).append((e0, e1, self.timer_tag(name, args) if self.timer_tag else None))
         else:
             rc = getattr(self.cdll, name)(*args)
         if rc != 0:
