@@ -221,7 +221,15 @@ def build_roofline(timer, N, E, G, H, steps, ms_step):
     modelled = [r for r in rows if 'frac' in r]
     top = dict(modelled[0]) if modelled else {'kernel': None, 'bound': 'hbm', 'achieved': 0.0, 'peak': hbm,
                                               'unit': 'GB/s', 'frac': 0.0}
-    top['traffic'] = None          # dram__bytes per launch from the ncu --set full capture: see profiles/
+    # dram__bytes_read + write per launch from the committed ncu --set full captures (same shapes), where one exists
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
+    except Exception:
+        pass
+    for r in rows:
+        r['traffic'] = traffic.get(r['kernel']) if (N, E, H) == (4900000, 9996000, 128) else None
+    top['traffic'] = traffic.get(top.get('kernel')) if (N, E, H) == (4900000, 9996000, 128) else None
     top['peak_source'] = ('measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)' if peaks
                           else 'fallback 6650 GB/s / 1400 TFLOP/s')
     top['frac_of_nominal_8TBs'] = top['achieved'] / 8000.0 if top.get('unit') == 'GB/s' else None
