@@ -62,10 +62,19 @@ class _Lib:
             fn.restype = restype
             fn.argtypes = argtypes
         self._device_checked = False
+        self._step_counter = None
         self.launches = 0          # kernels launched through this library (bench.py reports the timed-region delta)
         self.timer = None          # optional {entry name: [(start_event, end_event, tag), ...]} filled by call()
         self.timer_all = False     # time every entry point, not only the names already in `timer`
         self.timer_tag = None      # optional fn(name, args) -> tag stored with each timed call (bench.py: shapes)
+
+    def step_counter(self, device=None):
+        """The process-wide device step counter (int64 [1]) registered with gsatb_set_step_counter; created on first
+        use and never freed, so the pointer the library holds cannot dangle."""
+        if self._step_counter is None:
+            self._step_counter = torch.zeros(1, dtype=torch.int64, device=device or 'cuda')
+            self.cdll.gsatb_set_step_counter(ctypes.c_void_p(self._step_counter.data_ptr()))
+        return self._step_counter
 
     def strerror(self, code: int) -> str:
         return self.cdll.gsatb_strerror(code).decode()

@@ -24,3 +24,13 @@ extern "C" int gsatb_check_device(void) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return GSATB_EARCH;
     return major == 10 ? GSATB_OK : GSATB_EARCH;
 }
+
+const unsigned long long*& gsatb_step_counter_ref() {
+    static const unsigned long long* ptr = nullptr;
+    return ptr;
+}
+
+extern "C" int gsatb_set_step_counter(const uint64_t* dev_counter) {
+    gsatb_step_counter_ref() = reinterpret_cast<const unsigned long long*>(dev_counter);
+    return GSATB_OK;
+}

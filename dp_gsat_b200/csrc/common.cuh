@@ -12,6 +12,11 @@
         if (e__ != cudaSuccess) return GSATB_ELAUNCH;          \
     } while (0)
 
+// Optional device-resident step counter (gsatb_set_step_counter): added to every counter-based random stream (dropout
+// hashes, the sampler's Philox offset) INSIDE the kernels, so that a CUDA graph of a whole training step draws fresh
+// randomness on every replay although its kernel arguments are frozen.  Host-side accessor, defined in api.cu.
+const unsigned long long*& gsatb_step_counter_ref();
+
 static inline bool gsatb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // 128-bit streaming load through the read-only path without L1 allocation (data touched once).

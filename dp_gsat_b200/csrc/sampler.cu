@@ -44,8 +44,10 @@ __device__ __forceinline__ float info_df(float a, float r) {
 __global__ void __launch_bounds__(SMP_THREADS)
 k_sample_fwd(const float* __restrict__ logit, const float* __restrict__ noise_u, const int32_t* __restrict__ rev,
              const float* __restrict__ r_tensor, float r_scalar, float inv_temp, int mode, uint64_t seed,
-             uint64_t offset, float* __restrict__ att, float* __restrict__ edge_att, float* __restrict__ partial,
-             int64_t E) {
+             uint64_t offset_in, const unsigned long long* __restrict__ step, float* __restrict__ att,
+             float* __restrict__ edge_att, float* __restrict__ partial, int64_t E) {
+    // the optional device step counter selects a fresh 2^32-wide window of the Philox stream on every graph replay
+    const uint64_t offset = offset_in + (step ? ((uint64_t)__ldg(step) << 32) : 0ull);
     const bool training = mode & GSATB_MODE_TRAINING, average = mode & GSATB_MODE_AVERAGE;
     const bool on_edge = mode & GSATB_MODE_INFO_ON_EDGE_ATT, want_info = !(mode & GSATB_MODE_NO_INFO);
     float local = 0.f;
@@ -213,7 +215,7 @@ extern "C" int gsatb_sample_avg_info_fwd(const float* logit, const float* noise_
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = sample_blocks(E);
     k_sample_fwd<<<blocks, SMP_THREADS, 0, st>>>(logit, noise_u, rev, r_tensor, r_scalar, 1.f / temp, mode, seed,
-                                                 offset, att, edge_att, (float*)ws, E);
+                                                 offset, gsatb_step_counter_ref(), att, edge_att, (float*)ws, E);
     if (want_info) k_final_mean<<<1, 1024, 0, st>>>((const float*)ws, blocks, 1.f / (float)E, info_mean);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;

@@ -42,6 +42,7 @@ struct Dropout {
     uint32_t thr24;        // drop when (hash >> 8) < thr24 ;  thr24 = p * 2^24
     float scale;           // 1 / (1 - p)   (1 when disabled)
     int enabled;
+    const unsigned long long* step;   // nullable device step counter folded into the seed (gsatb_set_step_counter)
 };
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16;
@@ -61,7 +62,10 @@ __device__ __forceinline__ bool hash_keep(const Dropout& d, uint32_t row, uint32
     h *= 0xC2B2AE35u;
     return (h >> 8) >= d.thr24;
 }
-__device__ __forceinline__ uint32_t hash_ch_term(const Dropout& d, int ch) { return (uint32_t)ch * 0x7FEB352Du + d.seed; }
+__device__ __forceinline__ uint32_t hash_ch_term(const Dropout& d, int ch) {
+    const uint32_t step = d.step ? (uint32_t)__ldg(d.step) * 0x9E3779B1u : 0u;
+    return (uint32_t)ch * 0x7FEB352Du + d.seed + step;
+}
 __device__ __forceinline__ bool dropout_keep(const Dropout& d, int64_t row, int ch, int C) {
     if (!d.enabled) return true;
     if (d.mask) return __ldg(d.mask + row * C + ch) != 0;
@@ -76,6 +80,7 @@ inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int
     d.scale = d.enabled ? 1.f / (1.f - pdrop) : 1.f;
     double t = (double)pdrop * 16777216.0;
     d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
+    d.step = gsatb_step_counter_ref();
     return d;
 }
 

@@ -150,6 +150,9 @@ class GSAT(tnn.Module):
             self.device = next(self.parameters()).device
         except StopIteration:
             self.device = torch.device('cuda')
+        # device-resident step counter (gsatb_set_step_counter): bumped once per training step ON THE DEVICE, so a
+        # CUDA graph of the step (parallel.TrainStep.enable_cuda_graph) draws fresh noise / dropout on every replay
+        self.step_counter = lib().step_counter(self.device) if self.device.type == 'cuda' else None
 
     def __loss__(self, info_mean, clf_logits, clf_labels, epoch):
         pred_loss = self.criterion(clf_logits, clf_labels) * (self.pred_loss_coef * self.pred_scale)
@@ -163,6 +166,8 @@ class GSAT(tnn.Module):
 
     def forward_pass(self, data, epoch, training, noise_u: Optional[torch.Tensor] = None, r=None):
         self.clf._enc_scope = {}          # the two GNN passes of this step share node_encoder(x) (nn._encode_once)
+        if self.step_counter is not None and training:
+            self.step_counter.add_(1)
         try:
             return self._forward_pass(data, epoch, training, noise_u, r)
         finally:

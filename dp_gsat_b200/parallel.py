@@ -65,8 +65,14 @@ class TrainStep:
         self.bucket = FlatGradBucket(params)
         if fused_adam is None:
             fused_adam = self.bucket.flat.is_cuda
-        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused_adam)
+        # capturable: the step count lives on the device, so the optimizer step can sit inside a CUDA graph
+        self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused_adam,
+                                          capturable=bool(fused_adam))
         self._counts = {}
+        self.graph = None            # torch.cuda.CUDAGraph of one whole step (enable_cuda_graph)
+        self._graph_key = None
+        self._graph_out = None
+        self.launches_per_step = None
 
     def set_shard_weights(self, data):
         key = (int(data.edge_index.shape[1]), int(data.batch.numel()), int(data.y.shape[0]))
@@ -79,7 +85,50 @@ class TrainStep:
             self._counts[key] = (n_att / max(eg, 1), n_g / max(gg, 1))
         self.gsat.info_scale, self.gsat.pred_scale = self._counts[key]
 
+    @staticmethod
+    def _key(data, epoch):
+        return (data.x.data_ptr(), data.edge_index.data_ptr(), data.batch.data_ptr(), data.y.data_ptr(),
+                tuple(data.edge_index.shape), int(epoch))
+
+    def enable_cuda_graph(self, data, epoch: int, warmup: int = 3):
+        """Capture forward_pass + backward + gradient all-reduce + Adam.step on ``data`` (which must stay resident at
+        the same addresses: the reference's loaders replay identical batches every epoch) into ONE CUDA graph, so a
+        step costs one launch on the host instead of several hundred.  Fresh noise / dropout per replay comes from the
+        device step counter (gsat.step_counter).  Falls back to eager steps for any other batch / epoch / injected
+        noise.  Returns True when the graph is in place."""
+        from ._lib import lib
+        self.set_shard_weights(data)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up on a side stream, as graph capture requires
+            for _ in range(warmup):
+                self._eager(data, epoch, None)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        n0 = lib().launches
+        try:
+            with torch.cuda.graph(graph):
+                out = self._eager(data, epoch, None)
+        except Exception as exc:      # e.g. an op that cannot be captured on this build: stay on the eager path
+            import warnings
+            warnings.warn(f'CUDA graph capture of the training step failed ({exc!r}); using eager steps')
+            torch.cuda.synchronize()
+            return False
+        self.launches_per_step = lib().launches - n0
+        self.graph, self._graph_key, self._graph_out = graph, self._key(data, epoch), out
+        return True
+
+    def disable_cuda_graph(self):
+        self.graph = self._graph_key = self._graph_out = None
+
     def __call__(self, data, epoch: int, noise_u=None):
+        if self.graph is not None and noise_u is None and self._key(data, epoch) == self._graph_key:
+            self.graph.replay()
+            return self._graph_out
+        return self._eager(data, epoch, noise_u)
+
+    def _eager(self, data, epoch: int, noise_u=None):
         self.set_shard_weights(data)
         edge_att, loss, loss_dict, clf_logits = self.gsat.forward_pass(data, epoch, True, noise_u=noise_u)
         self.bucket.zero()

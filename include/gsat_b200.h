@@ -45,6 +45,13 @@ int gsatb_version(void);
 const char* gsatb_strerror(int code);
 /* 0 when the current device is sm_100-class, GSATB_EARCH otherwise (no fallback path exists). */
 int gsatb_check_device(void);
+/* Optional DEVICE-resident step counter (uint64, owned by the caller, NULL switches it off).  Every counter-based
+ * random stream of the library -- the dropout hashes of the tensor-core ops and the sampler's Philox offset -- adds
+ * its current value inside the kernel, so that a CUDA graph that captured a whole training step (kernel arguments
+ * frozen) still draws fresh randomness on each replay: the caller increments the counter once per step (in-graph).
+ * Forward and backward of one step read the same value.  This and gsatb_tc_set_profile_buffer are the only pieces
+ * of process-level state in the library. */
+int gsatb_set_step_counter(const uint64_t* dev_counter);
 
 /* ------------------------------------------------------------------------------------------------------------
  * K0  index builder.  Replaces, once per batch instead of every step:

@@ -531,3 +531,38 @@ def test_gsat_pna_step_parity(G, use_edge_attr, learn_edge_att):
         errs_o.append(eo)
     med = lambda v: sorted(v)[len(v) // 2]
     assert med(errs_g) <= 3 * med(errs_o) + 1e-4, (med(errs_g), med(errs_o))
+
+
+def test_cuda_graph_training_step(G):
+    """parallel.TrainStep.enable_cuda_graph: the whole step (forward_pass + backward + Adam) replays as one CUDA graph;
+    every replay advances the device step counter, draws fresh noise / dropout and updates the parameters."""
+    from dp_gsat_b200.data import ba2motifs_batch
+    from dp_gsat_b200.parallel import TrainStep
+    b = ba2motifs_batch(64, seed=5).to('cuda')
+    cfg = {'model_name': 'GIN', 'hidden_size': 64, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    shared = {'learn_edge_att': True, 'extractor_dropout_p': 0.5}
+    torch.manual_seed(0)
+    clf, ext = G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(64, shared).cuda()
+    clf.precision = ext.precision = 'bf16'
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5, lazy_metrics=True)
+    gsat.train()
+    step = TrainStep(gsat, lr=1e-3)
+    assert step.enable_cuda_graph(b, 0, warmup=2)
+    c0 = int(gsat.step_counter.item())
+    w0 = clf.convs[0].nn[0].weight.detach().clone()
+    losses, atts = [], []
+    for _ in range(3):
+        edge_att, loss, _, _ = step(b, 0)
+        torch.cuda.synchronize()
+        losses.append(float(loss))
+        atts.append(edge_att.detach().clone())
+    assert int(gsat.step_counter.item()) == c0 + 3
+    assert all(np.isfinite(l) for l in losses)
+    assert not torch.equal(atts[0], atts[1]) and not torch.equal(atts[1], atts[2])      # fresh concrete noise per replay
+    assert not torch.equal(w0, clf.convs[0].nn[0].weight)                               # Adam stepped inside the graph
+    # averaged attention stays symmetric under replay: edge_att[e] == edge_att[rev[e]]
+    gi = G.get_graph_index(b.edge_index, b.batch, b.num_graphs)
+    assert torch.equal(atts[2].view(-1), atts[2].view(-1)[gi.rev.long()])
+    step.disable_cuda_graph()
+    _, loss_e, _, _ = step(b, 0)                                                       # eager path still works afterwards
+    assert np.isfinite(float(loss_e))
