@@ -172,9 +172,14 @@ def kernel_models(N, E, G, H):
         'gsatb_gin_aggregate_fwd:noatt': (8.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
         'gsatb_gin_aggregate_bwd:att': (12.0 * N * H + 16.0 * E, 4.0 * E * H),
         'gsatb_gin_aggregate_bwd:noatt': (8.0 * N * H + 8.0 * E, 1.0 * E * H),
+        'gsatb_gin_aggregate_fwd_bf16:att': (6.0 * N * H + 8.0 * E + 4.0 * N, 2.0 * E * H),
+        'gsatb_gin_aggregate_fwd_bf16:noatt': (6.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
+        'gsatb_tc_linear_bf16_fwd:bf16': (4.0 * N * H, 2.0 * N * H * H),              # bf16 agg in, bf16 z1 out
+        'gsatb_tc_linear_bf16_fwd:fp32': (6.0 * N * H, 2.0 * N * H * H),              # bf16 a1 in, fp32 h out
+        'gsatb_bn_relu_bf16': (4.0 * N * H, 0.0),
         'gsatb_tc_linear_fwd': (8.0 * N * H, 2.0 * N * H * H),
-        'gsatb_tc_gin_bwd2': (N * (4.0 * H + 4 * H + 4 * H + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
-        'gsatb_tc_gin_bwd1': (N * (2.0 * H + 4 * H + 2 * H + 4 * H), 2.0 * N * H * H),
+        'gsatb_tc_gin_bwd2': (N * (4.0 * H + 4 * H + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
+        'gsatb_tc_gin_bwd1': (N * (2.0 * H + 2 * H + 2 * H + 4 * H), 2.0 * N * H * H),
         'gsatb_tc_ext_fwd1': (4.0 * N * H + 8.0 * E + 2.0 * E * C1, 2.0 * E * 2 * H * C1),
         'gsatb_tc_ext_fwd2': (2.0 * E * C1 + 2.0 * E * C1 + 2.0 * E * H + 4.0 * E, 2.0 * E * C1 * H),
         'gsatb_tc_ext_bwd_head': (4.0 * E + 2.0 * E * H + 2.0 * E * H, 8.0 * E * H),
@@ -317,8 +322,15 @@ def run_b200(a):
         step.disable_cuda_graph()
         torch.cuda.empty_cache()
     L.timer, L.timer_all = {}, True          # CUDA events around every C-ABI call of the timed region (rank-local)
-    L.timer_tag = lambda name, args: ('att' if args[1] is not None else 'noatt') if name == 'gsatb_gin_aggregate_fwd' \
-        else (('att' if args[2] is not None else 'noatt') if name == 'gsatb_gin_aggregate_bwd' else '')
+    def tag(name, args):           # variants of one entry point that have different algorithmic bytes
+        if name in ('gsatb_gin_aggregate_fwd', 'gsatb_gin_aggregate_fwd_bf16'):
+            return 'att' if args[1] is not None else 'noatt'
+        if name == 'gsatb_gin_aggregate_bwd':
+            return 'att' if args[2] is not None else 'noatt'
+        if name == 'gsatb_tc_linear_bf16_fwd':
+            return 'bf16' if args[5] else 'fp32'
+        return ''
+    L.timer_tag = tag
     launches0 = L.launches
     clocks = Clocks(local)
     if rank == 0:

@@ -13,6 +13,7 @@
 // GSAT datasets.
 //
 // HBM bound.  Algorithmic bytes / launch: fwd 8NH + 8E + 4N, bwd 12NH + 16E.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace {
@@ -128,11 +129,23 @@ __device__ __forceinline__ void agg_row_slow(const float4* __restrict__ x, const
     }
 }
 
-template <int LPR, int NV, bool HAS_ATT>
+// one float4 of a row, as fp32 or rounded to bf16 (the tensor-core node MLP consumes bf16 operands: writing them here
+// saves a quarter of the kernel's traffic and the separate cast pass)
+template <bool OUT_BF16>
+__device__ __forceinline__ void store_row4(void* out, int64_t idx, const float4& v) {
+    if (OUT_BF16) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(out)[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    } else {
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+
+template <int LPR, int NV, bool HAS_ATT, bool OUT_BF16>
 __global__ void __launch_bounds__(K3_THREADS, 3)
 k_gin_aggregate_fwd(const float4* __restrict__ x, const float* __restrict__ att, const int32_t* __restrict__ rowptr,
                     const int32_t* __restrict__ eid, const int32_t* __restrict__ nbr, float self_scale,
-                    float4* __restrict__ out, int64_t N, int HV) {
+                    void* __restrict__ out, int64_t N, int HV) {
     constexpr int RPW = 32 / LPR;                      // sub-warps (rows side by side) per warp
     constexpr int UNITS = AGG_WORKERS * RPW;           // sub-warps per CTA
     constexpr int U = (NV == 1) ? 8 : (NV == 2 ? 4 : 2);   // entries in flight per sub-warp
@@ -170,7 +183,7 @@ k_gin_aggregate_fwd(const float4* __restrict__ x, const float* __restrict__ att,
                     const int c = sl + v * LPR;
                     if (c < HV) {
                         fma4(acc[v], self_scale, ldg_stream_f4(x + (t0 + r) * HV + c));
-                        out[(t0 + r) * HV + c] = acc[v];
+                        store_row4<OUT_BF16>(out, (t0 + r) * HV + c, acc[v]);
                     }
                 }
             }
@@ -202,7 +215,7 @@ k_gin_aggregate_fwd(const float4* __restrict__ x, const float* __restrict__ att,
                     if (q + u + 1 == rend) {                              // the self entry just closed row r
 #pragma unroll
                         for (int v = 0; v < NV; ++v) {
-                            if (v * LPR + sl < HV) out[(t0 + r) * HV + v * LPR + sl] = acc[v];
+                            if (v * LPR + sl < HV) store_row4<OUT_BF16>(out, (t0 + r) * HV + v * LPR + sl, acc[v]);
                             acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                         ++r;
@@ -422,15 +435,15 @@ inline unsigned agg_tile_grid(int64_t N, int per_sm) {
     return (unsigned)blocks;
 }
 
-template <bool HAS_ATT>
+template <bool HAS_ATT, bool OUT_BF16>
 int launch_fwd(const float* x, const float* att, const int32_t* rowptr, const int32_t* eid, const int32_t* nbr,
-               float self_scale, float* out, int64_t N, int HV, cudaStream_t st) {
+               float self_scale, void* out, int64_t N, int HV, cudaStream_t st) {
     const int lpr = pick_lpr(HV);
     const int nv = (HV + lpr - 1) / lpr;
     const unsigned grid = agg_tile_grid(N, 3);
 #define FWD_CASE(L, V)                                                                                       \
-    k_gin_aggregate_fwd<L, V, HAS_ATT><<<grid, K3_THREADS, 0, st>>>((const float4*)x, att, rowptr, eid, nbr, \
-                                                                     self_scale, (float4*)out, N, HV)
+    k_gin_aggregate_fwd<L, V, HAS_ATT, OUT_BF16><<<grid, K3_THREADS, 0, st>>>((const float4*)x, att, rowptr, eid, nbr, \
+                                                                               self_scale, out, N, HV)
     if (nv == 1) {
         switch (lpr) {
             case 1: FWD_CASE(1, 1); break;
@@ -539,8 +552,24 @@ extern "C" int gsatb_gin_aggregate_fwd(const float* x, const float* att, const i
     if (H % 4 != 0 || H > 512) return GSATB_ESHAPE;
     if (!gsatb_aligned16(x) || !gsatb_aligned16(out)) return GSATB_EALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = att ? launch_fwd<true>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out, N, H / 4, st)
-                 : launch_fwd<false>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out, N, H / 4, st);
+    int rc = att ? launch_fwd<true, false>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out, N, H / 4, st)
+                 : launch_fwd<false, false>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out, N, H / 4, st);
+    if (rc != GSATB_OK) return rc;
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_gin_aggregate_fwd_bf16(const float* x, const float* att, const int32_t* rowptr_dst,
+                                            const int32_t* eid_by_dst, const int32_t* src_by_dst, float eps,
+                                            void* out_bf16, int64_t N, int64_t E, int H, gsatb_stream_t stream) {
+    if (N < 0 || E < 0 || H <= 0) return GSATB_EINVAL;
+    if (N == 0) return GSATB_OK;
+    if (!x || !out_bf16 || !rowptr_dst || (E > 0 && (!src_by_dst || (att && !eid_by_dst)))) return GSATB_EINVAL;
+    if (H % 4 != 0 || H > 512) return GSATB_ESHAPE;
+    if (!gsatb_aligned16(x) || (reinterpret_cast<uintptr_t>(out_bf16) & 7u) != 0) return GSATB_EALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = att ? launch_fwd<true, true>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out_bf16, N, H / 4, st)
+                 : launch_fwd<false, true>(x, att, rowptr_dst, eid_by_dst, src_by_dst, 1.f + eps, out_bf16, N, H / 4, st);
     if (rc != GSATB_OK) return rc;
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;

@@ -19,14 +19,14 @@ struct OpGinBwd2 {
         const float* dh;        // [N, H] upstream gradient of the module output
         const float* h;         // [N, H] saved module output (post ReLU / Dropout)
         float drop_scale;       // 1/(1-p) when dropout was applied, else 1
-        const float* z1;        // [N, H1] saved Linear1 output
+        const uint16_t* z1;     // bf16 [N, H1] saved Linear1 output
         const float* bn_scale;  // [H1] gamma * rstd          (BatchNorm folded:  a1 = relu(z1 * scale + shift))
         const float* bn_shift;  // [H1] beta - mean * scale
         const float* mean;      // [H1]
         const float* rstd;      // [H1]
         uint16_t* d2;           // bf16 [N, H]   out
         uint16_t* g;            // bf16 [N, H1]  out
-        uint16_t* a1;           // bf16 [N, H1]  out
+        uint16_t* a1;           // bf16 [N, H1]  out, nullable (the forward already keeps a1 for dW2)
         float* stat_partials;   // [gridDim * EPI_GROUPS][2][H1]
         int H, H1;
     };
@@ -48,22 +48,22 @@ struct OpGinBwd2 {
         pack8(v, o);
         *reinterpret_cast<uint4*>(p.d2 + grow * p.H + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    // staging: two buffers of 32 rows x 128 channels x 4 bytes.  z1 (fp32) is prefetched chunk by chunk with
-    // cp.async; the channel thread replaces each z1 word IN PLACE by the packed pair (g bf16 | a1 bf16 << 16), and
-    // the group then splits the words into the two bf16 output tensors with 16-byte stores.
+    // staging per group: two 32-row chunk buffers of bf16 z1 (cp.async prefetch, 2 x 8 KiB) and two of packed
+    // (g bf16 | a1 bf16 << 16) words (2 x 16 KiB) that the group splits into the two bf16 output tensors with
+    // 16-byte stores.
     static constexpr bool TMA_B = false;
-    static constexpr int STAGE_BYTES = 32768;
+    static constexpr int STAGE_BYTES = 49152;
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool) { st.s1 = st.s2 = 0.f; }
     __device__ static void epi_prefetch(const Params& p, const Tiling&, const EpiCtx& cx) {
         epi_sync(cx);      // the previous block's copy-out has finished reading the buffers
-        if (cx.cnt > 0) stage_load_async<4>(cx, cx.stage, p.z1 + cx.r0 * p.H1, p.H1, 0, min(32, cx.cnt));
+        if (cx.cnt > 0) stage_load_async<2>(cx, cx.stage + 32768, p.z1 + cx.r0 * p.H1, p.H1, 0, min(32, cx.cnt));
         cp_async_commit();
     }
     __device__ static void store_split(const Params& p, const EpiCtx& cx, const uint32_t* buf, int row_lo, int nrows) {
         uint16_t* gg = p.g + (cx.r0 + row_lo) * p.H1 + cx.ch0;
         uint16_t* ga = p.a1 + (cx.r0 + row_lo) * p.H1 + cx.ch0;
         const bool vec = (p.H1 % 8) == 0 && (cx.nch % 8) == 0 &&
-                         ((reinterpret_cast<uintptr_t>(gg) | reinterpret_cast<uintptr_t>(ga)) & 15u) == 0;
+                         ((reinterpret_cast<uintptr_t>(gg) | (p.a1 ? reinterpret_cast<uintptr_t>(ga) : 0)) & 15u) == 0;
         if (vec) {
             for (int i = cx.gtid; i < nrows * 16; i += 128) {
                 const int row = i >> 4, k = (i & 15) * 8;
@@ -76,7 +76,7 @@ struct OpGinBwd2 {
                     og.z = __byte_perm(w1.x, w1.y, 0x5410); oa.z = __byte_perm(w1.x, w1.y, 0x7632);
                     og.w = __byte_perm(w1.z, w1.w, 0x5410); oa.w = __byte_perm(w1.z, w1.w, 0x7632);
                     *reinterpret_cast<uint4*>(gg + (int64_t)row * p.H1 + k) = og;
-                    *reinterpret_cast<uint4*>(ga + (int64_t)row * p.H1 + k) = oa;
+                    if (p.a1) *reinterpret_cast<uint4*>(ga + (int64_t)row * p.H1 + k) = oa;
                 }
             }
         } else {
@@ -84,7 +84,7 @@ struct OpGinBwd2 {
                 const int row = i >> 7, k = i & 127;
                 if (k < cx.nch) {
                     gg[(int64_t)row * p.H1 + k] = (uint16_t)(buf[i] & 0xFFFFu);
-                    ga[(int64_t)row * p.H1 + k] = (uint16_t)(buf[i] >> 16);
+                    if (p.a1) ga[(int64_t)row * p.H1 + k] = (uint16_t)(buf[i] >> 16);
                 }
             }
         }
@@ -105,7 +105,7 @@ struct OpGinBwd2 {
             cp_async_wait<0>();
             epi_sync(cx);      // chunk c of z1 is visible; chunk c-1 has been copied out by every thread
             if (c + 1 < nchunks) {
-                stage_load_async<4>(cx, cx.stage + ((c + 1) & 1) * 16384, p.z1 + cx.r0 * p.H1, p.H1, (c + 1) * 32,
+                stage_load_async<2>(cx, cx.stage + 32768 + ((c + 1) & 1) * 8192, p.z1 + cx.r0 * p.H1, p.H1, (c + 1) * 32,
                                     min(32, cnt - (c + 1) * 32));
                 cp_async_commit();
             }
@@ -113,12 +113,13 @@ struct OpGinBwd2 {
             tc::tmem_ld_32x32(cx.taddr + c * 32, v);
             tc::tmem_ld_wait();
             if (c == nchunks - 1) epi_release_acc(cx);
+            const uint16_t* zb = reinterpret_cast<const uint16_t*>(cx.stage + 32768 + (c & 1) * 8192);
             uint32_t* buf = reinterpret_cast<uint32_t*>(cx.stage + (c & 1) * 16384);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const bool ok0 = c * 32 + j < cnt && cx.ch_ok, ok1 = c * 32 + j + 1 < cnt && cx.ch_ok;
-                const float z0 = ok0 ? __uint_as_float(buf[j * 128 + cx.gtid]) : 0.f;
-                const float z1 = ok1 ? __uint_as_float(buf[(j + 1) * 128 + cx.gtid]) : 0.f;
+                const float z0 = ok0 ? bf16_bits_to_float(zb[j * 128 + cx.gtid]) : 0.f;
+                const float z1 = ok1 ? bf16_bits_to_float(zb[(j + 1) * 128 + cx.gtid]) : 0.f;
                 const float a0 = fmaxf(fmaf(z0, sc, sf), 0.f), a1v = fmaxf(fmaf(z1, sc, sf), 0.f);
                 const float g0 = (a0 > 0.f && ok0) ? v[j] : 0.f, g1 = (a1v > 0.f && ok1) ? v[j + 1] : 0.f;
                 const float x0 = (z0 - mu) * rs, x1 = (z1 - mu) * rs;
@@ -147,7 +148,7 @@ struct OpGinBwd2 {
 struct OpGinBwd1 {
     struct Params {
         const uint16_t* g;    // bf16 [N, H1]
-        const float* z1;      // [N, H1]
+        const uint16_t* z1;   // bf16 [N, H1]
         const float* cA;      // [H1]  dz1 = cA * g + cB * z1 + cC
         const float* cB;
         const float* cC;
@@ -156,23 +157,23 @@ struct OpGinBwd1 {
         int H1, Kin;
     };
     struct EpiState {};
-    static constexpr int UNROLL = 4;
+    static constexpr int UNROLL = 8;
     struct Raw {
-        uint4 g;
-        float z[8];
+        uint4 g, z;
     };
-    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
+    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
         r.g = __ldg(reinterpret_cast<const uint4*>(p.g + grow * p.H1 + k));
-        load8_f32(p.z1 + grow * p.H1, k, K, r.z);
+        r.z = __ldg(reinterpret_cast<const uint4*>(p.z1 + grow * p.H1 + k));
     }
     __device__ static void transform8(const Params& p, Raw& r, int64_t grow, int k, int K, uint32_t o[4]) {
-        float g[8], a[8], b[8], c[8];
+        float g[8], z[8], a[8], b[8], c[8];
         unpack8(r.g, g);
+        unpack8(r.z, z);
         load8_f32(p.cA, k, K, a);
         load8_f32(p.cB, k, K, b);
         load8_f32(p.cC, k, K, c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], g[i], fmaf(b[i], r.z[i], c[i]));
+        for (int i = 0; i < 8; ++i) g[i] = fmaf(a[i], g[i], fmaf(b[i], z[i], c[i]));
         pack8(g, o);
         *reinterpret_cast<uint4*>(p.dz1 + grow * p.H1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -197,17 +198,17 @@ __global__ void k_reduce_partials_f(const float* __restrict__ partials, int part
 }  // namespace
 
 extern "C" int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16,
-                                 const float* z1, const float* bn_scale, const float* bn_shift, const float* mean,
+                                 const void* z1, const float* bn_scale, const float* bn_shift, const float* mean,
                                  const float* rstd, void* d2, void* g, void* a1, float* stat_partials, float* stats,
                                  int64_t N, int H, int H1, gsatb_stream_t stream) {
     if (N < 0 || H <= 0 || H1 <= 0) return GSATB_EINVAL;
     if (N == 0) return GSATB_OK;
-    if (!dh || !h || !w2t_bf16 || !z1 || !bn_scale || !bn_shift || !mean || !rstd || !d2 || !g || !a1 ||
+    if (!dh || !h || !w2t_bf16 || !z1 || !bn_scale || !bn_shift || !mean || !rstd || !d2 || !g ||
         !stat_partials || !stats)
         return GSATB_EINVAL;
     if (H % 8 != 0 || H > 512 || H1 > 128) return GSATB_ESHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    OpGinBwd2::Params p{dh, h, drop_scale, z1, bn_scale, bn_shift, mean, rstd, (uint16_t*)d2, (uint16_t*)g,
+    OpGinBwd2::Params p{dh, h, drop_scale, (const uint16_t*)z1, bn_scale, bn_shift, mean, rstd, (uint16_t*)d2, (uint16_t*)g,
                         (uint16_t*)a1, stat_partials, H, H1};
     cudaMemsetAsync(stat_partials, 0, (size_t)GSATB_NUM_SMS * EPI_GROUPS * 2 * H1 * sizeof(float), st);
     int rc = launch<OpGinBwd2>(w2t_bf16, uniform_tiling(N), H, H1, p, st);
@@ -217,13 +218,13 @@ extern "C" int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_sca
     return GSATB_OK;
 }
 
-extern "C" int gsatb_tc_gin_bwd1(const void* g, const float* z1, const float* cA, const float* cB, const float* cC,
+extern "C" int gsatb_tc_gin_bwd1(const void* g, const void* z1, const float* cA, const float* cB, const float* cC,
                                  const void* w1t_bf16, void* dz1, float* dx, int64_t N, int H1, int Kin,
                                  gsatb_stream_t stream) {
     if (N < 0 || H1 <= 0 || Kin <= 0) return GSATB_EINVAL;
     if (N == 0) return GSATB_OK;
     if (!g || !z1 || !cA || !cB || !cC || !w1t_bf16 || !dz1 || !dx) return GSATB_EINVAL;
     if (H1 % 8 != 0 || H1 > 512) return GSATB_ESHAPE;
-    OpGinBwd1::Params p{(const uint16_t*)g, z1, cA, cB, cC, (uint16_t*)dz1, dx, H1, Kin};
+    OpGinBwd1::Params p{(const uint16_t*)g, (const uint16_t*)z1, cA, cB, cC, (uint16_t*)dz1, dx, H1, Kin};
     return launch<OpGinBwd1>(w1t_bf16, uniform_tiling(N), H1, Kin, p, (cudaStream_t)stream);
 }

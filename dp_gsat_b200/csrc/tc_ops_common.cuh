@@ -123,6 +123,25 @@ __device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int l
     }
 }
 
+// Same, bf16 output: two buffers of 32 rows x 128 channels x 2 bytes (16 KiB per group).
+template <class F>
+__device__ __forceinline__ void epi_emit_bf16(const EpiCtx& cx, uint16_t* out, int ld, F f) {
+    const int nchunks = (cx.cnt + 31) >> 5;
+    if (nchunks == 0) epi_release_acc(cx);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+        float v[32];
+        tc::tmem_ld_32x32(cx.taddr + c * 32, v);
+        tc::tmem_ld_wait();
+        if (c == nchunks - 1) epi_release_acc(cx);
+        uint16_t* buf = reinterpret_cast<uint16_t*>(cx.stage) + (c & 1) * (32 * 128);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) buf[j * 128 + cx.gtid] = float_to_bf16_bits(f(c * 32 + j, v[j]));
+        epi_sync(cx);
+        stage_store<2>(cx, reinterpret_cast<const uint8_t*>(buf), out + cx.r0 * ld, ld, c * 32, min(32, cx.cnt - c * 32));
+    }
+}
+
 // Per-warp copy of the tile's graph boundaries (local row offsets) in the epilogue scratch: bnd[0..nseg]
 __device__ __forceinline__ int load_segments(const Tiling& tl, int tile, int64_t r0, uint8_t* misc, int q, int lane,
                                              const int*& bnd, int& g0) {

@@ -176,16 +176,15 @@ class GIN(tnn.Module):
         fused = self.precision == 'bf16' and x.shape[1] % 8 == 0 and x.shape[1] <= 128
         for i in range(self.n_layers):
             if fused:
-                # K3 aggregation, then the node MLP + ReLU on the tensor cores (tc.gin_mlp_relu)
+                # K3 aggregation (bf16 out) chained into the node MLP + ReLU + dropout on the tensor cores
                 from . import tc
-                agg = ops.gin_aggregate(x, edge_atten, gi, self.convs[i].initial_eps)
                 dm = None
                 if self.masks is not None and self.training and self.dropout_p > 0:
                     dm = self.masks.get(f'{mask_key}.{i}', (x.shape[0], self.convs[i].nn[3].weight.shape[0]),
                                         self.dropout_p).to(device=x.device, dtype=torch.uint8)
                 self._calls += 1
-                x = tc.gin_mlp_relu(agg, self.convs[i].nn, self.training, self.dropout_p,
-                                    self.seed * 7919 + self._calls, dm)      # ReLU + dropout fused in the epilogue
+                x = tc.gin_layer(x, edge_atten, gi, self.convs[i], self.training, self.dropout_p,
+                                 self.seed * 7919 + self._calls, dm)         # ReLU + dropout fused in the epilogue
                 continue
             x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
             x = self.relu(x)

@@ -41,9 +41,29 @@ def linear(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_
         part = torch.empty(int(lib().cdll.gsatb_tc_stat_partials_elems(out_features)), dtype=torch.float32,
                            device=x.device)
         stats = torch.empty(2 * out_features, dtype=torch.float64, device=x.device)
-    lib().call('gsatb_tc_linear_fwd', ptr(x), K, ptr(in_scale), ptr(in_shift), ptr(wp), ptr(bias), ptr(out),
+    lib().call('gsatb_tc_linear_fwd', ptr(x), int(x.dtype == torch.bfloat16), K, ptr(in_scale), ptr(in_shift), ptr(wp),
+               ptr(bias), ptr(out),
                out_features, int(relu_out), ptr(part), ptr(stats), ptr(drop_mask), ctypes.c_uint64(drop_seed),
                ctypes.c_float(pdrop), rows, K, out_features, stream())
+    return (out, stats) if want_stats else out
+
+
+def linear_bf16(x16: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_features: int,
+                out_bf16: bool = True, relu_out: bool = False, want_stats: bool = False, pdrop: float = 0.0,
+                drop_seed: int = 0, drop_mask: Optional[torch.Tensor] = None):
+    """out = drop(act(x16 W^T + bias)) with the B operand fed by TMA straight from the bf16 activations (four epilogue
+    groups); bf16 or fp32 output; optional per-channel (sum z, sum z^2) in fp64, taken from the fp32 accumulators."""
+    x16 = x16.contiguous()
+    rows, K = x16.shape
+    out = torch.empty((rows, out_features), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x16.device)
+    part = stats = None
+    if want_stats:
+        part = torch.empty(int(lib().cdll.gsatb_tc_stat_partials_elems(out_features)), dtype=torch.float32,
+                           device=x16.device)
+        stats = torch.empty(2 * out_features, dtype=torch.float64, device=x16.device)
+    lib().call('gsatb_tc_linear_bf16_fwd', ptr(x16), K, ptr(wp), ptr(bias), ptr(out), int(out_bf16), out_features,
+               int(relu_out), ptr(part), ptr(stats), ptr(drop_mask), ctypes.c_uint64(drop_seed), ctypes.c_float(pdrop),
+               rows, K, out_features, stream())
     return (out, stats) if want_stats else out
 
 
@@ -170,79 +190,93 @@ def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: 
     return _FusedExtractor.apply(emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps)
 
 
+def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
+                     drop_seed, drop_mask):
+    """Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(agg)))))) on bf16 ``agg16`` [N, K].  Linear1 is a TMA-fed tcgen05
+    GEMM whose epilogue accumulates the BatchNorm batch statistics from the fp32 accumulators and stores z1 as bf16;
+    BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU and the dropout into its epilogue."""
+    N = agg16.shape[0]
+    H1, H = w1.shape[0], w2.shape[0]
+    w1p, w2p = prep_weight(w1), prep_weight(w2)
+    if training:
+        z1, stats = linear_bf16(agg16, w1p, b1, H1, want_stats=True)
+        mean64 = stats[:H1] / N
+        var64 = (stats[H1:] / N - mean64 * mean64).clamp_min(0.0)
+        mean, var = mean64.float(), var64.float()
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var * (N / max(N - 1, 1)), alpha=momentum)
+            nbt.add_(1)
+    else:
+        z1 = linear_bf16(agg16, w1p, b1, H1)
+        mean, var = running_mean.clone(), running_var.clone()
+    rstd = torch.rsqrt(var + eps)
+    scale = (gamma * rstd).contiguous()
+    shift = (beta - mean * scale).contiguous()
+    p = float(pdrop) if training else 0.0
+    a1 = torch.empty_like(z1)
+    lib().call('gsatb_bn_relu_bf16', ptr(z1), ptr(scale), ptr(shift), ptr(a1), N, H1, stream())
+    h = linear_bf16(a1, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=p, drop_seed=drop_seed, drop_mask=drop_mask)
+    return h, (z1, a1, mean, rstd, scale, shift, p)
+
+
+def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p):
+    """-> (d agg fp32 [N, K], dW1, db1, dgamma, dbeta, dW2, db2)."""
+    N, Kin = agg16.shape
+    H1, H = w1.shape[0], w2.shape[0]
+    dev = agg16.device
+    L = lib()
+    dh = dh.contiguous()
+    d2 = torch.empty((N, H), dtype=torch.bfloat16, device=dev)
+    g = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+    part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
+    stats = torch.empty(2 * H1, dtype=torch.float32, device=dev)
+    L.call('gsatb_tc_gin_bwd2', ptr(dh), ptr(h), ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
+           ptr(prep_weight(w2, transpose=True)), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
+           ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
+    dbeta, dgamma = stats[:H1], stats[H1:]
+    coef = gamma * rstd
+    if training:      # dz1 = coef * (g - dbeta/N - xhat * dgamma/N),  xhat = (z1 - mean) * rstd
+        cA = coef
+        cB = -coef * rstd * (dgamma / N)
+        cC = -coef * (dbeta / N) - cB * mean
+    else:             # running statistics are constants: dz1 = coef * g
+        cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
+    dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+    dagg = torch.empty((N, Kin), dtype=torch.float32, device=dev)
+    L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA.contiguous()), ptr(cB.contiguous()), ptr(cC.contiguous()),
+           ptr(prep_weight(w1, transpose=True)), ptr(dz1), ptr(dagg), N, H1, Kin, stream())
+    ones = torch.ones((1, N), dtype=torch.bfloat16, device=dev)
+    dW2 = _mm_f32(d2.t(), a1)
+    db2 = _mm_f32(ones, d2).view(-1)
+    dW1 = _mm_f32(dz1.t(), agg16)
+    db1 = _mm_f32(ones, dz1).view(-1)
+    return dagg, dW1, db1, dgamma.clone(), dbeta.clone(), dW2, db2
+
+
 class _GinMlpFused(torch.autograd.Function):
     """GIN node MLP  Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(x))))))  (reference src/models/gin.py:55-62 + the
-    ReLU / Dropout of :50-52) on tcgen05.  Forward: Linear1's epilogue accumulates the BatchNorm batch statistics per
-    channel (thread-local, deterministic); BatchNorm + ReLU are folded into Linear2's operand load; the outer ReLU and
-    the dropout into its epilogue.  Backward: gsatb_tc_gin_bwd2 / gin_bwd1 (masks, BatchNorm backward statistics and
-    the per-channel BatchNorm backward folded into operand loads / epilogues); weight gradients are plain library
-    GEMMs on the bf16 operands those kernels write out."""
+    ReLU / Dropout of :50-52) on tcgen05, for an fp32 input ``x`` (rounded to bf16 operands here).  Weight gradients
+    are plain library GEMMs on the bf16 operands the kernels write out."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
                 drop_seed, drop_mask):
-        x = x.contiguous()
-        N, K = x.shape
-        H1, H = w1.shape[0], w2.shape[0]
-        w1p, w2p = prep_weight(w1), prep_weight(w2)
-        if training:
-            z1, stats = linear(x, w1p, b1, H1, want_stats=True)
-            mean64 = stats[:H1] / N
-            var64 = (stats[H1:] / N - mean64 * mean64).clamp_min(0.0)
-            mean, var = mean64.float(), var64.float()
-            with torch.no_grad():
-                running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                running_var.mul_(1 - momentum).add_(var * (N / max(N - 1, 1)), alpha=momentum)
-                nbt.add_(1)
-        else:
-            z1 = linear(x, w1p, b1, H1)
-            mean, var = running_mean.clone(), running_var.clone()
-        rstd = torch.rsqrt(var + eps)
-        scale = (gamma * rstd).contiguous()
-        shift = (beta - mean * scale).contiguous()
-        p = float(pdrop) if training else 0.0
-        h = linear(z1, w2p, b2, H, in_scale=scale, in_shift=shift, relu_out=True, pdrop=p, drop_seed=drop_seed,
-                   drop_mask=drop_mask)
-        ctx.save_for_backward(x, z1, h, w1, w2, gamma, mean, rstd, scale, shift)
+        agg16 = x.contiguous().bfloat16()
+        h, (z1, a1, mean, rstd, scale, shift, p) = _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean,
+                                                                    running_var, nbt, training, momentum, eps, pdrop,
+                                                                    drop_seed, drop_mask)
+        ctx.save_for_backward(agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift)
         ctx.cfg = (bool(training), p)
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        x, z1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
         training, p = ctx.cfg
-        N, Kin = x.shape
-        H1, H = w1.shape[0], w2.shape[0]
-        dev = x.device
-        L = lib()
-        dh = dh.contiguous()
-        d2 = torch.empty((N, H), dtype=torch.bfloat16, device=dev)
-        g = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
-        a1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
-        part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
-        stats = torch.empty(2 * H1, dtype=torch.float32, device=dev)
-        L.call('gsatb_tc_gin_bwd2', ptr(dh), ptr(h), ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
-               ptr(prep_weight(w2, transpose=True)), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
-               ptr(g), ptr(a1), ptr(part), ptr(stats), N, H, H1, stream())
-        dbeta, dgamma = stats[:H1], stats[H1:]
-        coef = gamma * rstd
-        if training:      # dz1 = coef * (g - dbeta/N - xhat * dgamma/N),  xhat = (z1 - mean) * rstd
-            cA = coef
-            cB = -coef * rstd * (dgamma / N)
-            cC = -coef * (dbeta / N) - cB * mean
-        else:             # running statistics are constants: dz1 = coef * g
-            cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
-        dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
-        dx = torch.empty((N, Kin), dtype=torch.float32, device=dev)
-        L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA.contiguous()), ptr(cB.contiguous()), ptr(cC.contiguous()),
-               ptr(prep_weight(w1, transpose=True)), ptr(dz1), ptr(dx), N, H1, Kin, stream())
-        ones = torch.ones((1, N), dtype=torch.bfloat16, device=dev)
-        dW2 = _mm_f32(d2.t(), a1)
-        db2 = _mm_f32(ones, d2).view(-1)
-        dW1 = _mm_f32(dz1.t(), x.bfloat16())
-        db1 = _mm_f32(ones, dz1).view(-1)
-        return (dx, dW1, db1, dgamma.clone(), dbeta.clone(), dW2, db2, None, None, None, None, None, None, None, None,
-                None)
+        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd,
+                                                                    scale, shift, training, p)
+        return (dagg, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None, None, None, None)
 
 
 def gin_mlp_relu(x, seq, training: bool, pdrop: float = 0.0, drop_seed: int = 0, drop_mask=None):
@@ -252,3 +286,49 @@ def gin_mlp_relu(x, seq, training: bool, pdrop: float = 0.0, drop_seed: int = 0,
                               bn.running_var, bn.num_batches_tracked, training and bn.training,
                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, pdrop if training else 0.0,
                               drop_seed, drop_mask)
+
+
+class _GinLayerFused(torch.autograd.Function):
+    """One whole attention-aware GIN layer of the reference (GINConv.forward, src/models/conv_layers.py:14-34, with
+    its nn = GIN.MLP, then the ReLU / Dropout of src/models/gin.py:50-52):  K3 aggregation written as bf16 straight
+    into the operand layout of the node MLP -> the tcgen05 MLP above.  Backward chains the MLP backward (d agg in
+    fp32) into K3's backward (dx, d edge_atten)."""
+
+    @staticmethod
+    def forward(ctx, x, att, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, gi, conv_eps, training,
+                momentum, eps, pdrop, drop_seed, drop_mask):
+        x = x.contiguous()
+        N, K = x.shape
+        att_flat = None if att is None else att.contiguous().view(-1)
+        agg16 = torch.empty((N, K), dtype=torch.bfloat16, device=x.device)
+        lib().call('gsatb_gin_aggregate_fwd_bf16', ptr(x), ptr(att_flat), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
+                   ptr(gi.src_by_dst), ctypes.c_float(conv_eps), ptr(agg16), N, gi.E, K, stream())
+        h, (z1, a1, mean, rstd, scale, shift, p) = _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean,
+                                                                    running_var, nbt, training, momentum, eps, pdrop,
+                                                                    drop_seed, drop_mask)
+        ctx.save_for_backward(x, att_flat, agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift)
+        ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, att_flat, agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        training, p, gi, conv_eps, att_shape = ctx.cfg
+        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd,
+                                                                    scale, shift, training, p)
+        N, K = x.shape
+        need_att = att_flat is not None and ctx.needs_input_grad[1]
+        dx = torch.empty_like(x)
+        datt = torch.empty(gi.E, dtype=torch.float32, device=x.device) if need_att else None
+        lib().call('gsatb_gin_aggregate_bwd', ptr(dagg), ptr(x), ptr(att_flat), ptr(gi.rowptr_src), ptr(gi.eid_by_src),
+                   ptr(gi.dst_by_src), ctypes.c_float(conv_eps), ptr(dx), ptr(datt), N, gi.E, K, stream())
+        return (dx, datt.view(att_shape) if need_att else None, dW1, db1, dgamma, dbeta, dW2, db2) + (None,) * 11
+
+
+def gin_layer(x, edge_atten, gi, conv, training: bool, pdrop: float = 0.0, drop_seed: int = 0, drop_mask=None):
+    """``dropout(relu(conv(x, edge_index, edge_atten=edge_atten)))`` for conv = GINConv(GIN.MLP(...))."""
+    lin1, bn, _, lin2 = conv.nn[0], conv.nn[1], conv.nn[2], conv.nn[3]
+    return _GinLayerFused.apply(x, edge_atten, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight, lin2.bias,
+                                bn.running_mean, bn.running_var, bn.num_batches_tracked, gi, conv.initial_eps,
+                                training and bn.training, bn.momentum if bn.momentum is not None else 0.1, bn.eps,
+                                pdrop if training else 0.0, drop_seed, drop_mask)

@@ -88,6 +88,11 @@ int gsatb_index_build(const int64_t* edge_index /* [2,E] */, const int64_t* batc
 int gsatb_gin_aggregate_fwd(const float* x, const float* att, const int32_t* rowptr_dst, const int32_t* eid_by_dst,
                             const int32_t* src_by_dst, float eps, float* out, int64_t N, int64_t E, int H,
                             gsatb_stream_t stream);
+/* Same forward with the result rounded to bf16 [N,H] (the operand layout of the tensor-core node MLP): saves a quarter
+ * of the kernel's traffic and the separate cast pass in bf16 precision mode. */
+int gsatb_gin_aggregate_fwd_bf16(const float* x, const float* att, const int32_t* rowptr_dst,
+                                 const int32_t* eid_by_dst, const int32_t* src_by_dst, float eps, void* out_bf16,
+                                 int64_t N, int64_t E, int H, gsatb_stream_t stream);
 int gsatb_gin_aggregate_bwd(const float* gout, const float* x, const float* att, const int32_t* rowptr_src,
                             const int32_t* eid_by_src, const int32_t* dst_by_src, float eps, float* dx,
                             float* datt /* [nullable] */, int64_t N, int64_t E, int H, gsatb_stream_t stream);
@@ -206,10 +211,21 @@ size_t gsatb_tc_stat_partials_elems(int OUT);
 /* Development aid: device buffer [148][16] int64 (zeroed by the caller) that the tensor-core kernels fill with
  * per-role cycle counters (see csrc/tc_ops.cu); NULL switches it off (the default). */
 int gsatb_tc_set_profile_buffer(void* buf);
-int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const float* in_shift, const void* w_bf16_padded,
+int gsatb_tc_linear_fwd(const void* x, int x_is_bf16, int ldx, const float* in_scale, const float* in_shift, const void* w_bf16_padded,
                         const float* bias, float* out, int ldo, int relu_out, float* stat_partials, double* stats,
                         const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, int64_t rows, int K, int OUT,
                         gsatb_stream_t stream);
+
+/* gsatb_tc_linear_bf16_fwd: out = drop(act(x_bf16 W^T + bias)) with the B operand loaded by TMA straight from the
+ * row-major bf16 activations (both Linears of the GIN node MLP: K3's bf16 aggregation, then a1); out is bf16
+ * (out_is_bf16) or fp32; optional BatchNorm statistics as above, taken from the fp32 accumulators before rounding.
+ * gsatb_bn_relu_bf16: a1 = ReLU(z1 * scale + shift) (BatchNorm folded per channel), bf16 in / bf16 out. */
+int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void* w_bf16_padded, const float* bias, void* out,
+                             int out_is_bf16, int ldo, int relu_out, float* stat_partials, double* stats,
+                             const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, int64_t rows, int K, int OUT,
+                             gsatb_stream_t stream);
+int gsatb_bn_relu_bf16(const void* z_bf16, const float* scale, const float* shift, void* a_bf16, int64_t rows, int C,
+                       gsatb_stream_t stream);
 
 /* GIN node MLP backward (autograd of src/models/gin.py:55-62 + the ReLU / Dropout of gin.py:50-52):
  *   gin_bwd2: d2 = dh*(h>0)*drop_scale (written as bf16 [N,H]); da1 = d2 W2 on tcgen05 (w2t = prep(W2, transpose));
@@ -217,11 +233,11 @@ int gsatb_tc_linear_fwd(const float* x, int ldx, const float* in_scale, const fl
  *             stats[H1:2H1] = sum_rows g*xhat (BatchNorm backward), deterministic two-stage reduction
  *   gin_bwd1: dz1 = cA*g + cB*z1 + cC (BatchNorm backward folded per channel; written as bf16 [N,H1]);
  *             dx = dz1 W1 on tcgen05 (w1t = prep(W1, transpose)), fp32 [N,Kin] */
-int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16_padded, const float* z1,
+int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16_padded, const void* z1,
                       const float* bn_scale, const float* bn_shift, const float* mean, const float* rstd, void* d2,
                       void* g, void* a1, float* stat_partials, float* stats, int64_t N, int H, int H1,
                       gsatb_stream_t stream);
-int gsatb_tc_gin_bwd1(const void* g, const float* z1, const float* cA, const float* cB, const float* cC,
+int gsatb_tc_gin_bwd1(const void* g, const void* z1, const float* cA, const float* cB, const float* cC,
                       const void* w1t_bf16_padded, void* dz1, float* dx, int64_t N, int H1, int Kin,
                       gsatb_stream_t stream);
 

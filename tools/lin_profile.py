@@ -10,6 +10,6 @@ xl = torch.randn(rows, 128, device=dev)
 wl = tc.prep_weight(torch.randn(128, 128, device=dev) / 11)
 ol = torch.empty(rows, 128, device=dev)
 for _ in range(3):
-    L.call('gsatb_tc_linear_fwd', ptr(xl), 128, None, None, ptr(wl), None, ptr(ol), 128, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, 128, 128, stream())
+    L.call('gsatb_tc_linear_fwd', ptr(xl), 0, 128, None, None, ptr(wl), None, ptr(ol), 128, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, 128, 128, stream())
 torch.cuda.synchronize()
 print('ok')

@@ -67,7 +67,7 @@ ol = torch.empty(gi.E, 128, device=dev)
 
 
 def klin():
-    L.call('gsatb_tc_linear_fwd', ptr(xl), 128, None, None, ptr(wl), None, ptr(ol), 128, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), gi.E, 128, 128, stream())
+    L.call('gsatb_tc_linear_fwd', ptr(xl), 0, 128, None, None, ptr(wl), None, ptr(ol), 128, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), gi.E, 128, 128, stream())
 
 
 for name, fn in (('ext_fwd2 (eval, no dropout)', k2_nodrop), ('linear 128x128 on E rows', klin)):

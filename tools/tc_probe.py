@@ -27,7 +27,7 @@ def run(rows, K, OUT, stats=False, scale=False, relu=False):
     wp = prep(w)
     part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(OUT)), device=dev) if stats else None
     st = torch.empty(2 * OUT, dtype=torch.float64, device=dev) if stats else None
-    L.call('gsatb_tc_linear_fwd', ptr(x), K, ptr(sc), ptr(shf), ptr(wp), ptr(b), ptr(out), OUT, int(relu), ptr(part),
+    L.call('gsatb_tc_linear_fwd', ptr(x), 0, K, ptr(sc), ptr(shf), ptr(wp), ptr(b), ptr(out), OUT, int(relu), ptr(part),
            ptr(st), None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, K, OUT, stream())
     torch.cuda.synchronize()
     xin = torch.relu(x * sc + shf) if scale else x
@@ -56,11 +56,11 @@ if __name__ == '__main__':
     x = torch.randn(rows, K, device=dev); w = torch.randn(OUT, K, device=dev) / 11; b = torch.zeros(OUT, device=dev)
     out = torch.empty(rows, OUT, device=dev); wp = prep(w)
     for _ in range(3):
-        L.call('gsatb_tc_linear_fwd', ptr(x), K, None, None, ptr(wp), ptr(b), ptr(out), OUT, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, K, OUT, stream())
+        L.call('gsatb_tc_linear_fwd', ptr(x), 0, K, None, None, ptr(wp), ptr(b), ptr(out), OUT, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, K, OUT, stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        L.call('gsatb_tc_linear_fwd', ptr(x), K, None, None, ptr(wp), ptr(b), ptr(out), OUT, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, K, OUT, stream())
+        L.call('gsatb_tc_linear_fwd', ptr(x), 0, K, None, None, ptr(wp), ptr(b), ptr(out), OUT, 0, None, None, None, ctypes.c_uint64(0), ctypes.c_float(0.0), rows, K, OUT, stream())
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f'node linear 4.9M x 128 x 128: {ms:.3f} ms, {rows*(K+OUT)*4/ms/1e6:.0f} GB/s algorithmic, {2*rows*K*OUT/ms/1e9:.1f} TFLOP/s')
