@@ -180,8 +180,8 @@ def kernel_models(N, E, G, H):
         'gsatb_tc_linear_fwd': (8.0 * N * H, 2.0 * N * H * H),
         'gsatb_tc_gin_bwd2': (N * (4.0 * H + 4 * H + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
         'gsatb_tc_gin_bwd1': (N * (2.0 * H + 2 * H + 2 * H + 4 * H), 2.0 * N * H * H),
-        'gsatb_tc_ext_fwd1': (4.0 * N * H + 8.0 * E + 2.0 * E * C1, 2.0 * E * 2 * H * C1),
-        'gsatb_tc_ext_fwd2': (2.0 * E * C1 + 2.0 * E * C1 + 2.0 * E * H + 4.0 * E, 2.0 * E * C1 * H),
+        'gsatb_tc_ext_fwd1': (2.0 * E * 2 * H + 2.0 * E * C1, 2.0 * E * 2 * H * C1),
+        'gsatb_tc_ext_fwd2': (2.0 * E * C1 + 2.0 * E * H + 4.0 * E, 2.0 * E * C1 * H),
         'gsatb_tc_ext_bwd_head': (4.0 * E + 2.0 * E * H + 2.0 * E * H, 8.0 * E * H),
         'gsatb_tc_ext_bwd1': (2.0 * E * H + 2.0 * E * C1 + 2.0 * E * C1, 2.0 * E * H * C1),
         'gsatb_tc_linear_bf16in_fwd': (2.0 * E * C1 + 4.0 * E * 2 * H, 2.0 * E * C1 * 2 * H),

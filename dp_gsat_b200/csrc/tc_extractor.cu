@@ -2,13 +2,15 @@
 // cat(emb[col], emb[row]) -> Linear -> InstanceNorm(batch[col]) -> ReLU -> Dropout -> Linear -> InstanceNorm -> ReLU
 // -> Dropout -> Linear(H, 1)).
 //
-// Two launches over graph-aligned tiles (whole graphs, <= 128 rows per tile, so every per-graph InstanceNorm closes
+// Launches over graph-aligned tiles (whole graphs, <= 128 rows per tile, so every per-graph InstanceNorm closes
 // inside the tile's accumulator):
-//   ext_fwd1: gather emb[src] | emb[dst] straight into the swizzled B operand (the [E, 2H] concat is never
-//             materialised) -> GEMM1 on tcgen05 -> per-graph InstanceNorm in the epilogue (thread = channel, the
-//             tile's rows are its TMEM columns) -> xhat1 stored as bf16 [E, C1] (+ rstd1 [G, C1] for backward)
-//   ext_fwd2: xhat1 -> ReLU -> Dropout fused into the operand load -> GEMM2 -> InstanceNorm -> ReLU -> Dropout ->
-//             dot with w3 (+ b3) reduced across channels with a shuffle transpose -> one logit per row
+//   make_f12: f12 = [emb[src] | emb[dst]] gathered and rounded to bf16 [E, 2H] (also the operand of dW1 in backward)
+//   ext_fwd1: f12 (TMA-fed B operand, four epilogue groups) -> GEMM1 on tcgen05 -> per-graph InstanceNorm in the
+//             epilogue (thread = channel, the tile's rows are its TMEM columns) -> xhat1 stored as bf16 [E, C1]
+//             (+ rstd1 [G, C1] for backward)
+//   make_h1 : h1 = Dropout(ReLU(xhat1)) as bf16 [E, C1] (elementwise; also the operand of dW2 in backward)
+//   ext_fwd2: h1 (TMA-fed B operand, four epilogue groups) -> GEMM2 -> InstanceNorm -> ReLU -> Dropout -> dot with w3
+//             (+ b3) reduced across channels with a shuffle transpose -> one logit per row
 // The Linear biases in front of an InstanceNorm cancel exactly (the norm subtracts the per-graph mean), so b1 and b2
 // are not read; their gradients are exactly zero.
 #include "tc_ops_common.cuh"
@@ -113,32 +115,15 @@ __device__ __forceinline__ void instance_norm_rows(uint32_t taddr, const int* bn
 // ------------------------------------------------------------------------------------------------------------
 struct OpExtFwd1 {
     struct Params {
-        const float* emb;       // [N, H]
-        const int32_t* src;     // [E] nullable: node mode (rows are nodes, K = H)
-        const int32_t* dst;
-        int H;
         uint16_t* xhat;         // bf16 bits [rows, C]
         float* rstd;            // [G, C]
         int C;
         float eps;
     };
     struct EpiState {};
-    static constexpr int UNROLL = 8;
-    struct Raw {
-        float v[8];
-    };
-    __device__ static void load8(const Params& p, int64_t grow, int k, int K, Raw& r) {
-        if (p.src) {
-            const int node = k < p.H ? __ldg(p.src + grow) : __ldg(p.dst + grow);
-            load8_f32(p.emb + (int64_t)node * p.H, k < p.H ? k : k - p.H, p.H, r.v);
-        } else {
-            load8_f32(p.emb + grow * p.H, k, K, r.v);
-        }
-    }
-    __device__ static void transform8(const Params&, Raw& r, int64_t, int, int, uint32_t o[4]) { pack8(r.v, o); }
+    static constexpr bool TMA_B = true;      // B operand = f12 = [emb[src] | emb[dst]] (or emb rows) as bf16, from make_f12
     // staging: two buffers of 32 rows x 128 channels bf16 (16 KiB per group); the emit pass of the InstanceNorm fills
     // one 32-row chunk, the group stores it as whole rows while the channel threads fill the other buffer.
-    static constexpr bool TMA_B = false;
     static constexpr int STAGE_BYTES = 16384;
     __device__ static void epi_init(const Params&, EpiState&, int, bool, bool) {}
     __device__ static void epi_prefetch(const Params&, const Tiling&, const EpiCtx&) {}
@@ -172,9 +157,6 @@ struct OpExtFwd1 {
 // ------------------------------------------------------------------------------------------------------------
 struct OpExtFwd2 {
     struct Params {
-        const uint16_t* xhat1;   // bf16 bits [rows, C1]
-        int C1;
-        Dropout drop1;
         const float* w3;         // [H]
         const float* b3;         // [1] nullable
         uint16_t* xhat2;         // bf16 bits [rows, H]
@@ -183,42 +165,11 @@ struct OpExtFwd2 {
         float* logit;            // [rows]
         int H;
         float eps;
-        uint16_t* h1_out;        // bf16 [rows, C1] nullable: the operand rows as fed to GEMM2
     };
     struct EpiState {
         uint32_t par;
     };
-    static constexpr int UNROLL = 8;
-    struct Raw {
-        uint4 q;
-    };
-    __device__ static void load8(const Params& p, int64_t grow, int k, int, Raw& r) {
-        r.q = __ldg(reinterpret_cast<const uint4*>(p.xhat1 + grow * p.C1 + k));
-    }
-    __device__ static void transform8(const Params& p, Raw& r, int64_t grow, int k, int, uint32_t o[4]) {
-        float v[8];
-        unpack8(r.q, v);
-        uint32_t keep = 0xFFu;
-        if (p.drop1.enabled) {
-            if (p.drop1.mask) {                      // injected keep mask: 8 bytes of the row (C1 % 8 == 0)
-                const uint2 mb = __ldg(reinterpret_cast<const uint2*>(p.drop1.mask + grow * p.C1 + k));
-                keep = 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    keep |= ((((i < 4 ? mb.x : mb.y) >> (8 * (i & 3))) & 0xFFu) != 0u ? 1u : 0u) << i;
-            } else {
-                keep = 0u;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    keep |= (hash_keep(p.drop1, (uint32_t)grow, hash_ch_term(p.drop1, k + i)) ? 1u : 0u) << i;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? fmaxf(v[i], 0.f) * p.drop1.scale : 0.f;
-        pack8(v, o);
-        if (p.h1_out) *reinterpret_cast<uint4*>(p.h1_out + grow * p.C1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-    static constexpr bool TMA_B = false;
+    static constexpr bool TMA_B = true;       // B operand = h1 = Dropout(ReLU(xhat1)), bf16 [rows, C1], written by make_h1
     static constexpr int STAGE_BYTES = 16384;      // as OpExtFwd1: two 32-row bf16 chunk buffers for xhat2
     __device__ static void epi_init(const Params&, EpiState& st, int, bool, bool first) {
         if (first) st.par = 0;
@@ -310,35 +261,29 @@ extern "C" int gsatb_tile_plan_host(const int32_t* seg_ptr_host, int64_t G, int 
     return GSATB_OK;
 }
 
-extern "C" int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int32_t* dst, const void* w1_bf16,
-                                 const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
-                                 int num_tiles, void* xhat1, float* rstd1, int64_t rows, int H, int C1, float eps,
-                                 gsatb_stream_t stream) {
-    if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
+extern "C" int gsatb_tc_ext_fwd1(const void* f12, const void* w1_bf16, const int32_t* tile_row, const int32_t* tile_seg,
+                                 const int32_t* seg_ptr, int num_tiles, void* xhat1, float* rstd1, int64_t rows, int K,
+                                 int C1, float eps, gsatb_stream_t stream) {
+    if (rows < 0 || K <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || num_tiles == 0) return GSATB_OK;
-    if (!emb || !w1_bf16 || !tile_row || !tile_seg || !seg_ptr || !xhat1 || !rstd1) return GSATB_EINVAL;
-    if ((src == nullptr) != (dst == nullptr)) return GSATB_EINVAL;
-    if (H % 8 != 0) return GSATB_ESHAPE;
-    const int K = src ? 2 * H : H;
-    if (K > 512) return GSATB_ESHAPE;
-    OpExtFwd1::Params p{emb, src, dst, H, (uint16_t*)xhat1, rstd1, C1, eps};
+    if (!f12 || !w1_bf16 || !tile_row || !tile_seg || !seg_ptr || !xhat1 || !rstd1) return GSATB_EINVAL;
+    if (K % 8 != 0 || K > 512) return GSATB_ESHAPE;
+    OpExtFwd1::Params p{(uint16_t*)xhat1, rstd1, C1, eps};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
-    return launch<OpExtFwd1>(w1_bf16, tl, K, C1, p, (cudaStream_t)stream);
+    return launch<OpExtFwd1>(w1_bf16, tl, K, C1, p, (cudaStream_t)stream, f12, K);
 }
 
-extern "C" int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16, const float* w3, const float* b3,
-                                 const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
+extern "C" int gsatb_tc_ext_fwd2(const void* h1, const void* w2_bf16, const float* w3, const float* b3,
+                                 const uint8_t* mask2, uint64_t seed, float pdrop, int training,
                                  const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr,
-                                 int num_tiles, void* xhat2, float* rstd2, float* logit, void* h1_out, int64_t rows,
-                                 int C1, int H, float eps, gsatb_stream_t stream) {
+                                 int num_tiles, void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H,
+                                 float eps, gsatb_stream_t stream) {
     if (rows < 0 || H <= 0 || C1 <= 0 || num_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || num_tiles == 0) return GSATB_OK;
-    if (!xhat1 || !w2_bf16 || !w3 || !tile_row || !tile_seg || !seg_ptr || !xhat2 || !rstd2 || !logit)
+    if (!h1 || !w2_bf16 || !w3 || !tile_row || !tile_seg || !seg_ptr || !xhat2 || !rstd2 || !logit)
         return GSATB_EINVAL;
     if (C1 % 8 != 0 || C1 > 512 || H > 128) return GSATB_ESHAPE;
-    OpExtFwd2::Params p{(const uint16_t*)xhat1, C1, make_dropout(mask1, seed * 2 + 1, pdrop, training), w3, b3,
-                        (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps,
-                        (uint16_t*)h1_out};
+    OpExtFwd2::Params p{w3, b3, (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
-    return launch<OpExtFwd2>(w2_bf16, tl, C1, H, p, (cudaStream_t)stream);
+    return launch<OpExtFwd2>(w2_bf16, tl, C1, H, p, (cudaStream_t)stream, h1, C1);
 }

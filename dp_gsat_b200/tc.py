@@ -89,17 +89,27 @@ def extractor_forward(emb: torch.Tensor, gi: GraphIndex, w1: torch.Tensor, w2: t
     xhat2 = torch.empty((rows, H), dtype=torch.bfloat16, device=dev)
     rstd2 = torch.empty((gi.G, H), dtype=torch.float32, device=dev)
     logit = torch.empty((rows, 1), dtype=torch.float32, device=dev)
-    # Dropout(ReLU(xhat1)) as fed to GEMM2, written by the operand producers for the weight gradient dW2 = dz2^T h1
-    h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev) if keep_h1 else None
     L = lib()
-    L.call('gsatb_tc_ext_fwd1', ptr(emb), ptr(gi.src) if edge_mode else None, ptr(gi.dst) if edge_mode else None,
-           ptr(w1p), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T, ptr(xhat1), ptr(rstd1), rows, H, C1,
-           ctypes.c_float(eps), stream())
+    # f12 = [emb[src] | emb[dst]] as bf16: the B operand of GEMM1 (TMA-fed) and, in backward, of dW1 = dz1^T f12
+    Kin = 2 * H if edge_mode else H
+    f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
+    L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None, ptr(gi.dst) if edge_mode else None,
+           ptr(f12), rows, H, stream())
+    L.call('gsatb_tc_ext_fwd1', ptr(f12), ptr(w1p), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T, ptr(xhat1),
+           ptr(rstd1), rows, Kin, C1, ctypes.c_float(eps), stream())
+    if not keep_h1:
+        f12 = None
     w3f = w3.detach().reshape(-1).contiguous()
-    L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), ptr(mask1), ptr(mask2),
-           ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T,
-           ptr(xhat2), ptr(rstd2), ptr(logit), ptr(h1), rows, C1, H, ctypes.c_float(eps), stream())
-    return logit, dict(xhat1=xhat1, rstd1=rstd1, xhat2=xhat2, rstd2=rstd2, plan=plan, h1=h1)
+    # h1 = Dropout(ReLU(xhat1)): the B operand of GEMM2 (TMA-fed) and, in backward, of dW2 = dz2^T h1
+    h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
+    L.call('gsatb_tc_ext_make_h1', ptr(xhat1), ptr(mask1), ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training),
+           ptr(h1), rows, C1, stream())
+    L.call('gsatb_tc_ext_fwd2', ptr(h1), ptr(w2p), ptr(w3f), ptr(b3), ptr(mask2), ctypes.c_uint64(seed),
+           ctypes.c_float(pdrop), int(training), ptr(tile_row), ptr(tile_seg), ptr(seg_ptr), T, ptr(xhat2), ptr(rstd2),
+           ptr(logit), rows, C1, H, ctypes.c_float(eps), stream())
+    if not keep_h1:
+        h1 = None
+    return logit, dict(xhat1=xhat1, rstd1=rstd1, xhat2=xhat2, rstd2=rstd2, plan=plan, h1=h1, f12=f12)
 
 
 class _FusedExtractor(torch.autograd.Function):
@@ -155,11 +165,14 @@ class _FusedExtractor(torch.autograd.Function):
         dW2 = _mm_f32(dz2.t(), h1)
         del h1
         sv['h1'] = None
-        f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
-        L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None,
-               ptr(gi.dst) if edge_mode else None, ptr(f12), rows, H, stream())
+        f12 = sv.get('f12')
+        if f12 is None:
+            f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
+            L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None,
+                   ptr(gi.dst) if edge_mode else None, ptr(f12), rows, H, stream())
         dW1 = _mm_f32(dz1.t(), f12)
         del f12
+        sv['f12'] = None
         # input gradient: d f12 = dz1 W1, then the deterministic scatter back to the nodes
         w1t = prep_weight(w1, transpose=True)         # [Kin, C1]
         df = torch.empty((rows, Kin), dtype=torch.float32, device=dev)

@@ -247,23 +247,25 @@ int gsatb_tc_gin_bwd1(const void* g, const void* z1, const float* cA, const floa
  * Tiles are graph-aligned: gsatb_tile_plan_host packs consecutive graphs into tiles of <= 128 rows / <= 32 graphs
  * from the HOST copy of edge_ptr (node_ptr in node mode); it returns GSATB_ESHAPE when one graph alone exceeds a
  * tile (the caller then uses the unfused segnorm path).
- *   ext_fwd1: rows = edges: B operand = [emb[src] | emb[dst]] gathered on the fly (src == NULL: node mode, B =
- *             emb rows); xhat1 = InstanceNorm(B W1^T) stored as bf16 [rows, C1]; rstd1 [G, C1]
- *   ext_fwd2: logit = (Dropout(ReLU(InstanceNorm(Dropout(ReLU(xhat1)) W2^T))) . w3) + b3; also xhat2 bf16 [rows, H]
- *             and rstd2 [G, H] for backward.  mask1 [rows, C1] / mask2 [rows, H] (uint8 keep masks) are optional
- *             injected dropout masks; otherwise a counter hash of (seed, element index) decides, and backward can
- *             regenerate it.  h1_out [nullable]: bf16 [rows, C1] copy of Dropout(ReLU(xhat1)) as fed to GEMM2, kept
- *             for the weight gradient dW2 = dz2^T h1 (saves the re-materialisation pass gsatb_tc_ext_make_h1).
+ *   make_f12: f12 = [emb[src] | emb[dst]] gathered on the fly and rounded to bf16 [rows, K = 2H] (src == NULL: node
+ *             mode, f12 = emb rows, K = H) (gsatb_tc_ext_make_f12, declared with the backward ops: f12 is also the
+ *             operand of dW1 = dz1^T f12)
+ *   ext_fwd1: xhat1 = InstanceNorm(f12 W1^T) stored as bf16 [rows, C1]; rstd1 [G, C1]; f12 is the TMA-fed B operand
+ *   make_h1 : h1 = Dropout(ReLU(xhat1)) as bf16 [rows, C1] (gsatb_tc_ext_make_h1, declared with the backward ops:
+ *             h1 is also the operand of dW2 = dz2^T h1).  mask1 [rows, C1] (uint8 keep mask) is an optional injected
+ *             dropout mask; otherwise a counter hash of (seed, element index) decides, and backward regenerates it.
+ *   ext_fwd2: logit = (Dropout(ReLU(InstanceNorm(h1 W2^T))) . w3) + b3 with h1 as the TMA-fed B operand (four epilogue
+ *             groups); also xhat2 bf16 [rows, H] and rstd2 [G, H] for backward.  mask2 [rows, H] optional as mask1.
  * ---------------------------------------------------------------------------------------------------------- */
 int gsatb_tile_plan_host(const int32_t* seg_ptr_host, int64_t G, int max_rows, int max_seg, int32_t* tile_row,
                          int32_t* tile_seg, int32_t* num_tiles);
-int gsatb_tc_ext_fwd1(const float* emb, const int32_t* src, const int32_t* dst, const void* w1_bf16_padded,
+int gsatb_tc_ext_fwd1(const void* f12, const void* w1_bf16_padded, const int32_t* tile_row, const int32_t* tile_seg,
+                      const int32_t* seg_ptr, int num_tiles, void* xhat1, float* rstd1, int64_t rows, int K, int C1,
+                      float eps, gsatb_stream_t stream);
+int gsatb_tc_ext_fwd2(const void* h1, const void* w2_bf16_padded, const float* w3, const float* b3,
+                      const uint8_t* mask2, uint64_t seed, float pdrop, int training,
                       const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles,
-                      void* xhat1, float* rstd1, int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
-int gsatb_tc_ext_fwd2(const void* xhat1, const void* w2_bf16_padded, const float* w3, const float* b3,
-                      const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop, int training,
-                      const int32_t* tile_row, const int32_t* tile_seg, const int32_t* seg_ptr, int num_tiles,
-                      void* xhat2, float* rstd2, float* logit, void* h1_out, int64_t rows, int C1, int H, float eps,
+                      void* xhat2, float* rstd2, float* logit, int64_t rows, int C1, int H, float eps,
                       gsatb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------

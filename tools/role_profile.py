@@ -30,16 +30,18 @@ xhat2 = torch.empty((gi.E, H), dtype=torch.bfloat16, device=dev)
 rstd2 = torch.empty((gi.G, H), device=dev)
 logit = torch.empty((gi.E, 1), device=dev)
 w3f = w3.reshape(-1).contiguous()
+f12buf = (torch.randn((gi.E, 2 * H), device=dev) / 4).bfloat16()
+h1buf = torch.zeros((gi.E, C1), dtype=torch.bfloat16, device=dev)
 
 
 def k1():
-    L.call('gsatb_tc_ext_fwd1', ptr(emb), ptr(gi.src), ptr(gi.dst), ptr(w1p), ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T,
-           ptr(xhat1), ptr(rstd1), gi.E, H, C1, ctypes.c_float(1e-5), stream())
+    L.call('gsatb_tc_ext_fwd1', ptr(f12buf), ptr(w1p), ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T,
+           ptr(xhat1), ptr(rstd1), gi.E, 2 * H, C1, ctypes.c_float(1e-5), stream())
 
 
 def k2():
-    L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), None, None, ctypes.c_uint64(1), ctypes.c_float(0.5), 1,
-           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), None, gi.E, C1, H, ctypes.c_float(1e-5), stream())
+    L.call('gsatb_tc_ext_fwd2', ptr(h1buf), ptr(w2p), ptr(w3f), ptr(b3), None, ctypes.c_uint64(1), ctypes.c_float(0.5), 1,
+           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), gi.E, C1, H, ctypes.c_float(1e-5), stream())
 
 
 for name, fn in (('ext_fwd1', k1), ('ext_fwd2', k2)):
@@ -57,8 +59,8 @@ for name, fn in (('ext_fwd1', k1), ('ext_fwd2', k2)):
 
 
 def k2_nodrop():
-    L.call('gsatb_tc_ext_fwd2', ptr(xhat1), ptr(w2p), ptr(w3f), ptr(b3), None, None, ctypes.c_uint64(1), ctypes.c_float(0.5), 0,
-           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), None, gi.E, C1, H, ctypes.c_float(1e-5), stream())
+    L.call('gsatb_tc_ext_fwd2', ptr(h1buf), ptr(w2p), ptr(w3f), ptr(b3), None, ctypes.c_uint64(1), ctypes.c_float(0.5), 0,
+           ptr(tile_row), ptr(tile_seg), ptr(gi.edge_ptr), T, ptr(xhat2), ptr(rstd2), ptr(logit), gi.E, C1, H, ctypes.c_float(1e-5), stream())
 
 
 xl = torch.randn(gi.E, 128, device=dev)
