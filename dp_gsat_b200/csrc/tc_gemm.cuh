@@ -39,7 +39,7 @@ constexpr int EPI_WARP0 = 4, PRO_WARP0 = 12, PRO_WARPS = 8;
 constexpr int MAX_SEG = 32;                   // graphs per tile the InstanceNorm epilogues support
 constexpr int MISC_PER_GROUP = 6144;          // epilogue scratch per group: segment tables + reductions
 constexpr int EPI_BAR0 = 8;                   // named barriers EPI_BAR0 + grp: epilogue-group syncs around the staging buffer
-constexpr int EPI_REGS = 120, PRO_REGS = 104; // setmaxnreg budgets of the producer layout (see the kernel)
+constexpr int CTL_REGS = 56, EPI_REGS = 104, PRO_REGS = 104, EPI4_REGS = 104;   // setmaxnreg budgets (see the kernel)
 constexpr int ACC_BAR0 = 3;                   // named barriers ACC_BAR0 + grp: accumulator-full wait of a group
 
 struct Tiling {
@@ -259,12 +259,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
     const int slots_per_tile = sh.ORDER == 0 ? sh.SPT : sh.NMB;      // accumulator indices a tile advances by
 
     // Register budget per role (the kernel is launched with 96 registers x 640 threads): the four control warps keep
-    // 32 and hand the rest to the warps that hold tiles of data in registers.
-    //   producer layout: 128 x 32 + 256 x 120 (epilogue) + 256 x 104 (producers) = 61440
-    //   TMA-B layout:    128 x 32 + 512 x 112 (epilogue)                         = 61440
+    // 56 (32 made the single-thread MMA issue loop spill to local memory, which put ~1000 cycles between MMA
+    // batches) and hand the rest to the warps that hold tiles of data in registers.
+    //   producer layout: 128 x 56 + 256 x 104 (epilogue) + 256 x 104 (producers) = 60416 <= 61440
+    //   TMA-B layout:    128 x 56 + 512 x 104 (epilogue)                        = 60416
     // (each setmaxnreg is the first statement of its role's branch: ptxas allocates registers per region)
     if (warp < 4) {
-      tc::reg_dec<32>();
+      tc::reg_dec<CTL_REGS>();
       if (warp == 0) {
         // ===================== TMA producer: W K-blocks =====================
         if (lane == 0) {
@@ -360,7 +361,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
       }
     } else if (warp < EPI_WARP0 + 4 * NGRP) {
         // ===================== epilogue: NGRP warpgroups, one per accumulator slot =====================
-        if (TMA_B) tc::reg_inc<112>();
+        if (TMA_B) tc::reg_inc<EPI4_REGS>();
         else tc::reg_inc<EPI_REGS>();
         const int grp = (warp - EPI_WARP0) >> 2;
         const int q = (warp - EPI_WARP0) & 3;               // == warp % 4: the TMEM lane quarter this warp may access
