@@ -117,7 +117,7 @@ struct OpExtBwd1 {
         const int64_t r0 = cx.r0;
         const bool use_mask = p.drop1.enabled && p.drop1.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop1.mask + r0 * p.C1 + chc : nullptr;
-        const uint32_t cht = hash_ch_term(p.drop1, chc);
+        const uint32_t dseed = dropout_seed(p.drop1);
         const uint32_t row0 = (uint32_t)r0;
         uint16_t* xs = reinterpret_cast<uint16_t*>(cx.stage) + cx.gtid;      // [row][128]
         float m1[MAX_SEG], m2[MAX_SEG];
@@ -150,10 +150,8 @@ struct OpExtBwd1 {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 keep |= (__ldg(mk + (int64_t)min(c * 32 + j, cnt - 1) * p.C1) != 0 ? 1u : 0u) << j;
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                keep |= (hash_keep(p.drop1, row0 + (uint32_t)(c * 32 + j), cht) ? 1u : 0u) << j;
+                        } else {       // word scheme (as make_h1 drew it): bit j = keep(row c*32 + j, this channel)
+                            keep = dropout_rows32(p.drop1, row0 + (uint32_t)(c * 32), (uint32_t)cx.ch >> 5, dseed, cx.lane);
                         }
                     }
                     gt = 0u;
@@ -249,9 +247,15 @@ __global__ void k_ext_make_h1(const uint16_t* __restrict__ xhat1, Dropout drop1,
         const uint4 q = __ldg(reinterpret_cast<const uint4*>(xhat1 + row * C1 + k));
         float v[8];
         unpack8(q, v);
+        if (drop1.enabled && !drop1.mask) {      // word scheme: one call covers the 32 channels around k
+            const uint32_t bits = dropout_word(drop1, (uint32_t)row, (uint32_t)k >> 5, dropout_seed(drop1)) >> (k & 31);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            v[j] = (v[j] > 0.f && dropout_keep(drop1, row, k + j, C1)) ? v[j] * drop1.scale : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = (v[j] > 0.f && ((bits >> j) & 1u)) ? v[j] * drop1.scale : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[j] = (v[j] > 0.f && dropout_keep(drop1, row, k + j, C1)) ? v[j] * drop1.scale : 0.f;
+        }
         uint32_t o[4];
         pack8(v, o);
         *reinterpret_cast<uint4*>(h1 + row * C1 + k) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -299,7 +303,7 @@ extern "C" int gsatb_tc_ext_bwd1(const void* dz2, const void* w2t_bf16, const vo
     if (rows == 0 || num_tiles == 0) return GSATB_OK;
     if (!dz2 || !w2t_bf16 || !xhat1 || !rstd1 || !tile_row || !tile_seg || !seg_ptr || !dz1) return GSATB_EINVAL;
     if (H % 8 != 0 || H > 512) return GSATB_ESHAPE;
-    OpExtBwd1::Params p{(const uint16_t*)xhat1, rstd1, make_dropout(mask1, seed * 2 + 1, pdrop, training),
+    OpExtBwd1::Params p{(const uint16_t*)xhat1, rstd1, make_dropout(mask1, seed * 2 + 1, pdrop, training, 1),
                         (uint16_t*)dz1, C1};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
     return launch<OpExtBwd1>(w2t_bf16, tl, H, C1, p, (cudaStream_t)stream, dz2, H);
@@ -324,7 +328,7 @@ extern "C" int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uin
     int64_t blocks = (rows * (C1 / 8) + 255) / 256;
     if (blocks > (int64_t)GSATB_NUM_SMS * 32) blocks = (int64_t)GSATB_NUM_SMS * 32;
     k_ext_make_h1<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const uint16_t*)xhat1, make_dropout(mask1, seed * 2 + 1, pdrop, training), (uint16_t*)h1, rows, C1);
+        (const uint16_t*)xhat1, make_dropout(mask1, seed * 2 + 1, pdrop, training, 1), (uint16_t*)h1, rows, C1);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }

@@ -68,7 +68,8 @@ struct OpLinear {
         const float b = (ch_ok && p.bias) ? __ldg(p.bias + ch) : 0.f;
         const bool use_mask = p.drop.enabled && p.drop.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (ch_ok ? ch : 0) : nullptr;
-        const uint32_t cht = hash_ch_term(p.drop, ch);
+        const uint32_t dseed = dropout_seed(p.drop);
+        uint32_t keepw = 0u;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         epi_emit_f32<32>(cx, p.out, p.ldo, [&](int col, float acc) {
             const bool ok = col < cnt;
@@ -83,8 +84,10 @@ struct OpLinear {
             }
             if (p.relu_out) z = fmaxf(z, 0.f);
             if (p.drop.enabled) {
-                const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false)
-                                        : hash_keep(p.drop, (uint32_t)(r0 + col), cht);
+                // word scheme: the keep bits of 32 rows of this channel are drawn at the first column of each chunk
+                if (!use_mask && (col & 31) == 0)
+                    keepw = dropout_rows32(p.drop, (uint32_t)(r0 + col), (uint32_t)ch >> 5, dseed, cx.lane);
+                const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false) : ((keepw >> (col & 31)) & 1u) != 0;
                 z = k ? z * p.drop.scale : 0.f;
             }
             return z;
@@ -132,7 +135,8 @@ struct OpLinearBf16 {
         const float b = (cx.ch_ok && p.bias) ? __ldg(p.bias + cx.ch) : 0.f;
         const bool use_mask = p.drop.enabled && p.drop.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (cx.ch_ok ? cx.ch : 0) : nullptr;
-        const uint32_t cht = hash_ch_term(p.drop, cx.ch);
+        const uint32_t dseed = dropout_seed(p.drop);
+        uint32_t keepw = 0u;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         auto f = [&](int col, float acc) {
             const bool ok = col < cnt;
@@ -147,8 +151,10 @@ struct OpLinearBf16 {
             }
             if (p.relu_out) z = fmaxf(z, 0.f);
             if (p.drop.enabled) {
-                const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false)
-                                        : hash_keep(p.drop, (uint32_t)(r0 + col), cht);
+                // word scheme: the keep bits of 32 rows of this channel are drawn at the first column of each chunk
+                if (!use_mask && (col & 31) == 0)
+                    keepw = dropout_rows32(p.drop, (uint32_t)(r0 + col), (uint32_t)cx.ch >> 5, dseed, cx.lane);
+                const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false) : ((keepw >> (col & 31)) & 1u) != 0;
                 z = k ? z * p.drop.scale : 0.f;
             }
             return z;
@@ -249,7 +255,7 @@ extern "C" int gsatb_tc_linear_fwd(const void* x, int x_is_bf16, int ldx, const 
         return GSATB_EALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     OpLinear::Params p{x_is_bf16 ? nullptr : (const float*)x, x_is_bf16 ? (const uint16_t*)x : nullptr, ldx, in_scale, in_shift, bias, out, ldo, relu_out, stat_partials, OUT,
-                       make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f)};
+                       make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f, 1)};
     Tiling tl = uniform_tiling(rows);
     if (stat_partials)
         cudaMemsetAsync(stat_partials, 0, gsatb_tc_stat_partials_elems(OUT) * sizeof(float), st);
@@ -275,7 +281,7 @@ extern "C" int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void*
     Tiling tl = uniform_tiling(rows);
     if (stat_partials)
         cudaMemsetAsync(stat_partials, 0, gsatb_tc_stat_partials_elems(OUT) * sizeof(float), st);
-    const Dropout drop = make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f);
+    const Dropout drop = make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f, 1);
     int rc;
     if (out_is_bf16) {
         OpLinearBf16<true>::Params p{bias, out, ldo, relu_out, stat_partials, OUT, drop};

@@ -40,8 +40,10 @@ struct Dropout {
     const uint8_t* mask;   // nullable
     uint32_t seed;
     uint32_t thr24;        // drop when (hash >> 8) < thr24 ;  thr24 = p * 2^24
-    float scale;           // 1 / (1 - p)   (1 when disabled)
+    float scale;           // 1 / (1 - p)   (1 when disabled; word mode: 256 / (256 - thr8), the exact keep rate)
     int enabled;
+    uint32_t thr8;         // word mode: drop when the element's 8-bit uniform < thr8 ;  thr8 = round(p * 256)
+    int word;              // 1: "word" scheme (dropout_word), 0: per-element hash (hash_keep)
     const unsigned long long* step;   // nullable device step counter folded into the seed (gsatb_set_step_counter)
 };
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -72,7 +74,49 @@ __device__ __forceinline__ bool dropout_keep(const Dropout& d, int64_t row, int 
     return hash_keep(d, (uint32_t)row, hash_ch_term(d, ch));
 }
 
-inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int training) {
+// The effective 32-bit seed of this launch (host seed + optional device step counter).
+__device__ __forceinline__ uint32_t dropout_seed(const Dropout& d) {
+    return d.seed + (d.step ? (uint32_t)__ldg(d.step) * 0x9E3779B1u : 0u);
+}
+// "Word" scheme: ONE call yields the keep bits of 32 consecutive channels (32*wc .. 32*wc+31) of a row -- bit b = keep
+// (row, 32*wc + b).  p = 0.5 is a single hash (every bit of a good hash is a fair coin); any other p compares an 8-bit
+// uniform, held bit-sliced in 8 hashes, against thr8 with bitwise ops (p is quantised to 1/256 and the kept values are
+// scaled by the exact keep rate, so the estimator stays unbiased).  Per-element hashing cost ~10 instructions per
+// element in the issue-bound epilogues; this costs 0.3 (p = 0.5) to 3.
+__device__ __forceinline__ uint32_t dropout_word(const Dropout& d, uint32_t row, uint32_t wc, uint32_t seed) {
+    const uint32_t base = row * 0x9E3779B1u + wc * 0x7FEB352Du + seed;
+    if (d.thr8 == 128u) return mix32(base);
+    uint32_t lt = 0u, eq = 0xffffffffu;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        const uint32_t h = mix32(base + (uint32_t)(i + 1) * 0x632BE5ABu);
+        if ((d.thr8 >> i) & 1u) {
+            lt |= eq & ~h;
+            eq &= h;
+        } else {
+            eq &= ~h;
+        }
+    }
+    return d.thr8 >= 256u ? 0u : ~lt;      // keep = not (U < thr8)
+}
+// 32 x 32 bit-matrix transpose across a warp: in: lane r holds word r (bit c = element (r, c)); out: lane c holds the
+// bits of column c (bit r = element (r, c)).  Five shuffle / mask steps.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t mlow = s == 16 ? 0x0000FFFFu : s == 8 ? 0x00FF00FFu : s == 4 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = (lane & s) ? ((x & ~mlow) | ((y >> s) & mlow)) : ((x & mlow) | ((y << s) & ~mlow));
+    }
+    return x;
+}
+// Keep bits of 32 consecutive ROWS (row0 .. row0+31) for THIS thread's channel, for an epilogue warp whose 32 lanes own
+// the 32 channels of word column wc (lane = channel & 31): bit j = keep(row0 + j, channel).  Warp-collective.
+__device__ __forceinline__ uint32_t dropout_rows32(const Dropout& d, uint32_t row0, uint32_t wc, uint32_t seed, int lane) {
+    return warp_transpose32(dropout_word(d, row0 + (uint32_t)lane, wc, seed), lane);
+}
+
+inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int training, int word = 0) {
     Dropout d;
     d.mask = mask;
     d.seed = (uint32_t)(seed * 0x9E3779B97F4A7C15ull >> 32) ^ (uint32_t)seed;
@@ -81,6 +125,10 @@ inline Dropout make_dropout(const uint8_t* mask, uint64_t seed, float pdrop, int
     double t = (double)pdrop * 16777216.0;
     d.thr24 = (uint32_t)(t < 0 ? 0 : (t > 16777216.0 ? 16777216.0 : t));
     d.step = gsatb_step_counter_ref();
+    d.word = word;
+    double t8 = (double)pdrop * 256.0 + 0.5;
+    d.thr8 = (uint32_t)(t8 < 0 ? 0 : (t8 > 256.0 ? 256.0 : t8));
+    if (word && d.enabled && !mask && d.thr8 < 256u) d.scale = 256.f / (float)(256u - d.thr8);
     return d;
 }
 

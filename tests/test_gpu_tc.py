@@ -238,3 +238,27 @@ def test_gsat_step_bf16_mode_tracks_oracle(G):
     cos = float(torch.dot(go_flat, gg_flat) / (go_flat.norm() * gg_flat.norm()))
     assert cos > 0.97, cos
     assert torch.isfinite(gg_flat).all()
+
+
+@pytest.mark.parametrize('p', [0.5, 0.3, 0.1])
+def test_word_dropout_rate_and_scale(G, p):
+    """The 'word' dropout scheme of the tensor-core epilogues (one hash per 32 channels at p = 0.5, a bit-sliced 8-bit
+    comparison otherwise): keep rate = 1 - round(256 p) / 256, kept values scaled by the exact inverse keep rate, masks
+    differ between rows / channels / seeds, and the same seed regenerates the same mask."""
+    from dp_gsat_b200 import tc
+    rows, K = 4096, 128
+    x = torch.ones(rows, K, device='cuda').bfloat16()
+    w = tc.prep_weight(torch.eye(K, device='cuda'))
+    out = tc.linear_bf16(x, w, None, K, out_bf16=False, pdrop=p, drop_seed=11)
+    again = tc.linear_bf16(x, w, None, K, out_bf16=False, pdrop=p, drop_seed=11)
+    other = tc.linear_bf16(x, w, None, K, out_bf16=False, pdrop=p, drop_seed=12)
+    assert torch.equal(out, again) and not torch.equal(out, other)
+    thr8 = int(p * 256 + 0.5)
+    keep_rate = 1.0 - thr8 / 256.0
+    kept = out != 0
+    assert abs(float(kept.float().mean()) - keep_rate) < 4e-3
+    assert torch.allclose(out[kept], torch.full_like(out[kept], 1.0 / keep_rate), rtol=1e-6)
+    # no structure along rows or channels: every row / channel mean is close to the keep rate
+    assert float((kept.float().mean(0) - keep_rate).abs().max()) < 0.05
+    assert float((kept.float().mean(1) - keep_rate).abs().max()) < 0.2
+    assert abs(float(out.mean()) - 1.0) < 1e-2          # unbiased
