@@ -187,6 +187,7 @@ def kernel_models(N, E, G, H):
         'gsatb_tc_linear_bf16in_fwd': (2.0 * E * C1 + 4.0 * E * 2 * H, 2.0 * E * C1 * 2 * H),
         'gsatb_tc_ext_make_f12': (4.0 * N * H + 8.0 * E + 2.0 * E * 2 * H, 0.0),
         'gsatb_tc_ext_make_h1': (4.0 * E * C1, 0.0),
+        'gsatb_linear_small_dw': (4.0 * N * H + 40.0 * N, 2.0 * N * H * 11),
         'gsatb_gather_concat_bwd': (4.0 * E * 2 * H + 8.0 * E + 4.0 * N * H, 2.0 * E * H),
         'gsatb_sample_avg_info_fwd': (20.0 * E, 0.0),
         'gsatb_sample_avg_info_bwd': (20.0 * E, 0.0),

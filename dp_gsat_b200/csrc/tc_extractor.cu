@@ -189,7 +189,8 @@ struct OpExtFwd2 {
         const float w3 = ch_ok ? __ldg(p.w3 + ch) : 0.f;
         uint16_t* st16 = reinterpret_cast<uint16_t*>(cx.stage) + cx.gtid;
         const bool use_mask = p.drop2.enabled && p.drop2.mask != nullptr;
-        const uint32_t hash_ch = hash_ch_term(p.drop2, ch);
+        const uint32_t dseed = dropout_seed(p.drop2);
+        uint32_t keepw = 0xffffffffu;      // word scheme: keep bits of the chunk's 32 rows for this channel
         float a[32];
         instance_norm_rows(
             cx.taddr, bnd, nseg, p.eps,
@@ -198,7 +199,7 @@ struct OpExtFwd2 {
                 if (in) st16[((c & 1) * 32 + j) * 128] = bits;
                 float h = fmaxf(xh, 0.f);
                 const bool keep = use_mask ? (in && ch_ok ? __ldg(p.drop2.mask + (r0 + col) * p.H + ch) != 0 : false)
-                                           : hash_keep(p.drop2, (uint32_t)(r0 + col), hash_ch);
+                                           : ((keepw >> j) & 1u) != 0;
                 h = (!p.drop2.enabled || keep) ? h * p.drop2.scale : 0.f;
                 a[j] = (in && ch_ok) ? h * w3 : a[j];
             },
@@ -207,6 +208,8 @@ struct OpExtFwd2 {
             },
             [&](int c) {
                 if (c == nchunks - 1) epi_release_acc(cx);
+                if (p.drop2.enabled && !use_mask)
+                    keepw = dropout_rows32(p.drop2, (uint32_t)(r0 + c * 32), (uint32_t)ch >> 5, dseed, lane);   // warp-uniform
 #pragma unroll
                 for (int j = 0; j < 32; ++j) a[j] = 0.f;
             },
@@ -283,7 +286,7 @@ extern "C" int gsatb_tc_ext_fwd2(const void* h1, const void* w2_bf16, const floa
     if (!h1 || !w2_bf16 || !w3 || !tile_row || !tile_seg || !seg_ptr || !xhat2 || !rstd2 || !logit)
         return GSATB_EINVAL;
     if (C1 % 8 != 0 || C1 > 512 || H > 128) return GSATB_ESHAPE;
-    OpExtFwd2::Params p{w3, b3, (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training), logit, H, eps};
+    OpExtFwd2::Params p{w3, b3, (uint16_t*)xhat2, rstd2, make_dropout(mask2, seed * 2 + 2, pdrop, training, 1), logit, H, eps};
     Tiling tl{rows, num_tiles, tile_row, tile_seg, seg_ptr};
     return launch<OpExtFwd2>(w2_bf16, tl, C1, H, p, (cudaStream_t)stream, h1, C1);
 }

@@ -16,44 +16,78 @@ namespace {
 using namespace tcg;
 
 // ---- head -------------------------------------------------------------------------------------------------------
+// CTA = one graph x one 128-channel block, thread = channel.  The graph's [rows][128 channels] block of xhat2 is staged
+// in shared memory with 16-byte cp.async loads, both passes read it at 2 bytes (conflict-free), pass 1 overwrites it in
+// place with dz2 and the CTA stores it as whole rows (the first version read / wrote global memory at 2 bytes with a
+// row stride and was latency bound at 21 % of its HBM roofline).  Graphs have at most 128 rows here (tile plan).
 __global__ void __launch_bounds__(128)
 k_ext_bwd_head(const float* __restrict__ dlogit, const uint16_t* __restrict__ xhat2, const float* __restrict__ rstd2,
                const float* __restrict__ w3, const int32_t* __restrict__ seg_ptr, Dropout drop2,
                uint16_t* __restrict__ dz2, float* __restrict__ dw3_part, int H) {
+    __shared__ __align__(16) uint16_t tile[TILE_ROWS * 128];
+    __shared__ float s_dl[TILE_ROWS];
     const int g = blockIdx.x;
-    const int ch = blockIdx.y * 128 + threadIdx.x;
-    if (ch >= H) return;
+    const int ch0 = blockIdx.y * 128, tid = threadIdx.x, lane = tid & 31;
+    const int ch = ch0 + tid;
+    const bool ch_ok = ch < H;               // no early exit: the dropout words are drawn warp-collectively
+    const int chc = ch_ok ? ch : 0;
+    const int cw = min(128, H - ch0);        // channels of this block (multiple of 8)
     const int b0 = __ldg(seg_ptr + g), b1 = __ldg(seg_ptr + g + 1);
-    const int n = b1 - b0;
+    const int n = min(b1 - b0, TILE_ROWS);
     if (n <= 0) {
-        dw3_part[(int64_t)g * H + ch] = 0.f;
+        if (ch_ok) dw3_part[(int64_t)g * H + ch] = 0.f;
         return;
     }
-    const float w = __ldg(w3 + ch);
-    const uint32_t cht = hash_ch_term(drop2, ch);
+    const int cpr = cw / 8;                  // 16-byte chunks per staged row
+    for (int i = tid; i < n * cpr; i += 128) {
+        const int row = i / cpr, k = i % cpr;
+        cp_async16(tile + row * 128 + k * 8, xhat2 + (int64_t)(b0 + row) * H + ch0 + k * 8);
+    }
+    cp_async_commit();
+    for (int j = tid; j < n; j += 128) s_dl[j] = __ldg(dlogit + b0 + j);
+    const float w = __ldg(w3 + chc);
+    const uint32_t dseed = dropout_seed(drop2);
     const bool use_mask = drop2.enabled && drop2.mask != nullptr;
+    const float rs = __ldg(rstd2 + (int64_t)g * H + chc);
+    cp_async_wait<0>();
+    __syncthreads();
     float s1 = 0.f, s2 = 0.f, dw = 0.f;
-    for (int r = b0; r < b1; ++r) {
-        const float x = bf16_bits_to_float(__ldg(xhat2 + (int64_t)r * H + ch));
-        const bool keep = !drop2.enabled || (use_mask ? __ldg(drop2.mask + (int64_t)r * H + ch) != 0
-                                                       : hash_keep(drop2, (uint32_t)r, cht));
-        const float dl = __ldg(dlogit + r);
-        const float gate = (x > 0.f && keep) ? drop2.scale : 0.f;
-        const float dxh = dl * w * gate;
-        s1 += dxh;
-        s2 = fmaf(dxh, x, s2);
-        dw = fmaf(dl, x * gate, dw);
+    uint16_t* col = tile + tid;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const float inv_n = 1.f / (float)n;
+        const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+        for (int blk = 0; blk < n; blk += 32) {
+            // keep bits of rows b0+blk .. +31 for this channel (word scheme, as ext_fwd2 drew them)
+            uint32_t keep = 0xffffffffu;
+            if (drop2.enabled && !use_mask)
+                keep = dropout_rows32(drop2, (uint32_t)(b0 + blk), (uint32_t)ch >> 5, dseed, lane);   // ch >> 5: warp-uniform
+            const int nb = min(32, n - blk);
+#pragma unroll 4
+            for (int j = 0; j < nb; ++j) {
+                const int r = blk + j;
+                const float x = bf16_bits_to_float(col[r * 128]);
+                const bool k = use_mask ? __ldg(drop2.mask + (int64_t)(b0 + r) * H + chc) != 0 : ((keep >> j) & 1u) != 0;
+                const float gate = (x > 0.f && k && ch_ok) ? drop2.scale : 0.f;
+                const float dl = s_dl[r];
+                const float dxh = dl * w * gate;
+                if (pass == 0) {
+                    s1 += dxh;
+                    s2 = fmaf(dxh, x, s2);
+                    dw = fmaf(dl, x * gate, dw);
+                } else {
+                    col[r * 128] = float_to_bf16_bits(rs * (dxh - m1 - x * m2));
+                }
+            }
+        }
     }
-    const float inv_n = 1.f / (float)n;
-    const float m1 = s1 * inv_n, m2 = s2 * inv_n, rs = __ldg(rstd2 + (int64_t)g * H + ch);
-    for (int r = b0; r < b1; ++r) {
-        const float x = bf16_bits_to_float(__ldg(xhat2 + (int64_t)r * H + ch));
-        const bool keep = !drop2.enabled || (use_mask ? __ldg(drop2.mask + (int64_t)r * H + ch) != 0
-                                                       : hash_keep(drop2, (uint32_t)r, cht));
-        const float dxh = __ldg(dlogit + r) * w * ((x > 0.f && keep) ? drop2.scale : 0.f);
-        dz2[(int64_t)r * H + ch] = float_to_bf16_bits(rs * (dxh - m1 - x * m2));
+    __syncthreads();
+    for (int i = tid; i < n * cpr; i += 128) {
+        const int row = i / cpr, k = i % cpr;
+        *reinterpret_cast<uint4*>(dz2 + (int64_t)(b0 + row) * H + ch0 + k * 8) =
+            *reinterpret_cast<const uint4*>(tile + row * 128 + k * 8);
     }
-    dw3_part[(int64_t)g * H + ch] = dw;
+    if (ch_ok) dw3_part[(int64_t)g * H + ch] = dw;
 }
 
 // ---- shared pieces walker (same structure as the forward InstanceNorm) ---------------------------------------------
@@ -287,9 +321,11 @@ extern "C" int gsatb_tc_ext_bwd_head(const float* dlogit, const void* xhat2, con
     if (rows < 0 || G < 0 || H <= 0) return GSATB_EINVAL;
     if (rows == 0 || G == 0) return GSATB_OK;
     if (!dlogit || !xhat2 || !rstd2 || !w3 || !seg_ptr || !dz2 || !dw3_part) return GSATB_EINVAL;
+    if (H % 8 != 0) return GSATB_ESHAPE;
+    if (!gsatb_aligned16(xhat2) || !gsatb_aligned16(dz2)) return GSATB_EALIGN;
     dim3 grid((unsigned)G, (unsigned)((H + 127) / 128));
     k_ext_bwd_head<<<grid, 128, 0, (cudaStream_t)stream>>>(dlogit, (const uint16_t*)xhat2, rstd2, w3, seg_ptr,
-                                                          make_dropout(mask2, seed * 2 + 2, pdrop, training),
+                                                          make_dropout(mask2, seed * 2 + 2, pdrop, training, 1),
                                                           (uint16_t*)dz2, dw3_part, H);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;

@@ -313,3 +313,38 @@ class _PnaAggregate(torch.autograd.Function):
 def pna_aggregate(x, edge_feat, edge_atten, gi: GraphIndex, aggregators):
     """[N, A*(2H+He)] multi-aggregation of m_e = cat(x_i, x_j, edge_feat) * edge_atten over incoming edges."""
     return _PnaAggregate.apply(x, edge_feat, edge_atten, gi, [AGG_CODES[a] for a in aggregators])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# node encoder Linear(x_dim, H) with a small x_dim  (reference src/models/gin.py:22-25, pna.py:20-25)
+# ------------------------------------------------------------------------------------------------------------
+class _SmallLinear(torch.autograd.Function):
+    """y = x W^T + b for a narrow x [N, F] (F < 16).  Forward is the library GEMM; the weight / bias gradient (a K = N
+    reduction the library runs as a slow large-K sgemm) is gsatb_linear_small_dw."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = _f32c(g)
+        xc = _f32c(x)
+        N, F_ = xc.shape
+        H = weight.shape[0]
+        L = lib()
+        dW = torch.empty_like(weight)
+        db = torch.empty(H, dtype=torch.float32, device=g.device) if ctx.has_bias else None
+        ws_bytes = int(L.cdll.gsatb_linear_small_dw_workspace(N, H, F_))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+        L.call('gsatb_linear_small_dw', ptr(g), ptr(xc), ptr(dW), ptr(db), N, H, F_, ptr(ws), ctypes.c_size_t(ws_bytes),
+               stream())
+        dx = g @ weight if ctx.needs_input_grad[0] else None
+        return dx, dW, db
+
+
+def small_linear(x, weight, bias):
+    return _SmallLinear.apply(x, weight, bias)

@@ -125,6 +125,13 @@ int gsatb_gather_concat_bwd(const float* g, const int32_t* rowptr_src, const int
                             const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N, int H,
                             gsatb_stream_t stream);
 
+/* Weight / bias gradient of a Linear layer with a small input width (F + 1 <= 16): the node encoder Linear(x_dim, H)
+ * of src/models/gin.py:22-25 / pna.py:20-25.  dW[h,f] = sum_n g[n,h] x[n,f], db[h] = sum_n g[n,h] (db nullable);
+ * replaces the library's large-K fp32 sgemm in autograd; deterministic (per-CTA partials reduced in a fixed order). */
+size_t gsatb_linear_small_dw_workspace(int64_t N, int H, int F);
+int gsatb_linear_small_dw(const float* g, const float* x, float* dW /* [H,F] */, float* db /* [H] */, int64_t N, int H,
+                          int F, void* ws, size_t ws_bytes, gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K2  concrete (Gumbel-sigmoid) sampling + undirected reverse-edge average + information loss.  Replaces
  *   concrete_sample / sampling          src/run_gsat.py:866-885   example/gsat.py:94-103

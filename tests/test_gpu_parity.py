@@ -566,3 +566,22 @@ def test_cuda_graph_training_step(G):
     step.disable_cuda_graph()
     _, loss_e, _, _ = step(b, 0)                                                       # eager path still works afterwards
     assert np.isfinite(float(loss_e))
+
+
+@pytest.mark.parametrize('N,F_,H', [(1000, 10, 64), (33333, 14, 128), (777, 9, 80), (5, 1, 4)])
+def test_small_linear_weight_gradient(G, N, F_, H):
+    """Node-encoder Linear (src/models/gin.py:22-25): own K = N weight / bias gradient kernel against autograd."""
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(N, F_, generator=g)
+    lin = torch.nn.Linear(F_, H)
+    w = torch.randn(N, H, generator=g)
+    (lin(x) * w).sum().backward()
+    lg = torch.nn.Linear(F_, H).cuda()
+    lg.load_state_dict(lin.state_dict())
+    xg = x.cuda().requires_grad_(True)
+    out = G.ops.small_linear(xg, lg.weight, lg.bias)
+    (out * w.cuda()).sum().backward()
+    assert close(out, lin(x), 1e-5, 1e-6)
+    assert close(lg.weight.grad, lin.weight.grad, 1e-4, 1e-5)
+    assert close(lg.bias.grad, lin.bias.grad, 1e-4, 1e-5)
+    assert close(xg.grad, w @ lin.weight.detach(), 1e-4, 1e-5)
