@@ -70,7 +70,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-i', str(self.idx), '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '-i', str(self.idx), '-lms', '50'], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -97,7 +97,17 @@ class Clocks:
                     if v.lower().startswith('active'):
                         reasons.add(name)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm),
+                'window': 'identical untimed steps (>= 0.7 s, sampler already running) + the timed region'}
+
+
+def preload(run_one, sync, seconds=0.7):
+    """Keep the GPU under the SAME load for `seconds` before the timed region, so that the nvidia-smi sampler (which
+    needs ~100 ms to produce its first row) sees the clocks the timed steps run at even when K steps last < 0.1 s."""
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        run_one()
+        sync()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -309,6 +319,7 @@ def run_b200(a):
         clocks = Clocks(local)
         if rank == 0:
             clocks.start()
+        preload(lambda: step(data, 0), barrier)
         barrier()
         ev0.record()
         for _ in range(a.steps):
@@ -332,10 +343,13 @@ def run_b200(a):
             return 'bf16' if args[5] else 'fp32'
         return ''
     L.timer_tag = tag
-    launches0 = L.launches
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+    L.timer_all = False                       # (the preload steps are not part of the per-kernel statistics)
+    preload(lambda: step(data, 0), barrier)
+    L.timer, L.timer_all = {}, True
+    launches0 = L.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
