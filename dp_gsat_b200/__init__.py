@@ -6,9 +6,12 @@ message-passing path, exposed through the reference's own Python surfaces.
 There is no CPU path and no eager fallback: importing the package loads libgsat_b200.so and fails loudly if it
 has not been built (``python -m dp_gsat_b200.build``).
 """
+import sys as _sys
+
 from ._lib import lib as _lib
 
-_lib()  # fail at import time if the CUDA library is missing or does not export the declared C ABI
+if 'dp_gsat_b200.build' not in getattr(_sys, 'orig_argv', []):     # `python -m dp_gsat_b200.build` creates the library
+    _lib()  # fail at import time if the CUDA library is missing or does not export the declared C ABI
 
 from .data import Batch  # noqa: E402
 from .index import GraphIndex, get_graph_index, clear_index_cache  # noqa: E402

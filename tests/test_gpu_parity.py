@@ -121,13 +121,15 @@ def test_gin_aggregate_fwd_bwd(G, H, with_att):
         assert_close(ad.grad, ar.grad, what='datt')
 
 
-def test_gin_aggregate_high_degree_and_isolated(G):
-    """A star (degree 500 > one 32-lane fetch), isolated nodes and self loops."""
+@pytest.mark.parametrize('deg,H', [(500, 64), (3000, 64), (3000, 300), (1500, 128)])
+def test_gin_aggregate_high_degree_and_isolated(G, deg, H):
+    """A star (degree 500: many batches of one row; degree >= 1500: the row's tile holds more edges than the staged
+    entry list, so the tile takes the unstaged path), isolated nodes and self loops."""
     g = torch.Generator().manual_seed(0)
-    N, H = 600, 64
-    hub = torch.zeros(500, dtype=torch.int64)
-    leaves = torch.arange(1, 501)
-    ei = torch.cat([torch.stack([leaves, hub]), torch.stack([hub, leaves]), torch.tensor([[7, 550], [7, 550]])], 1)
+    N = deg + 100
+    hub = torch.zeros(deg, dtype=torch.int64)
+    leaves = torch.arange(1, deg + 1)
+    ei = torch.cat([torch.stack([leaves, hub]), torch.stack([hub, leaves]), torch.tensor([[7, deg + 50], [7, deg + 50]])], 1)
     x = torch.randn(N, H, generator=g)
     att = torch.rand(ei.shape[1], 1, generator=g)
     xr, ar = x.clone().requires_grad_(True), att.clone().requires_grad_(True)
