@@ -36,7 +36,7 @@ def parse():
     ap.add_argument('--graphs', type=int, default=196000, help='BA-2Motifs-shaped graphs in the global batch (cfg4)')
     ap.add_argument('--hidden', type=int, default=128)
     ap.add_argument('--layers', type=int, default=2)
-    ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
                     help='bf16: tcgen05 MLPs (bf16 operands, fp32 accumulate); fp32: strict library-sgemm path')
     ap.add_argument('--cuda-graph', default='auto', choices=['auto', 'on', 'off'],
@@ -371,13 +371,32 @@ def run_b200(a):
         ms_step, clk, launches = float(ms_graph.item()) / a.steps, clk_graph, launches_graph
     value = E_global / (ms_step * 1e-3)
 
-    # end-to-end through the public API from pinned host buffers
+    # end-to-end through the public API from pinned host buffers.  Every step's inputs are copied host -> device inside
+    # the timed region; as a data loader would, the copy of step i+1 is issued on a copy stream while step i computes
+    # (double buffering), the K0 index build of the fresh tensors and the D2H read of the loss are in the step.
     G.clear_index_cache()
     e2e_steps = max(1, a.e2e_steps)
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+
+    def fetch():
+        with torch.cuda.stream(copy_stream):
+            d = shard_host.to(dev, non_blocking=True)                  # H2D of one step's inputs
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        for t in (d.x, d.edge_index, d.batch, d.y, d.edge_attr, d.edge_label):
+            if t is not None:
+                t.record_stream(main_stream)                           # allocated on the copy stream, used on the main one
+        return d, ev
+
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        d = shard_host.to(dev, non_blocking=True)          # H2D of this step's inputs
+    nxt = fetch()
+    for i in range(e2e_steps):
+        d, ev = nxt
+        main_stream.wait_event(ev)
+        if i + 1 < e2e_steps:
+            nxt = fetch()
         _, loss, _, _ = step(d, 0)                          # index build (K0) + step
         loss_host = float(loss.item())                      # D2H of the step's result
     barrier()
@@ -386,7 +405,8 @@ def run_b200(a):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e = {'value': E_global / float(t_e2e.item()), 'unit': UNIT, 'h2d_bytes_per_step': shard_host.nbytes() * world,
            'd2h_bytes_per_step': 4 * world, 'ms_per_step': float(t_e2e.item()) * 1e3, 'steps': e2e_steps,
-           'last_loss': loss_host}
+           'last_loss': loss_host,
+           'how': 'pinned host batch -> H2D (copy stream, prefetched one step ahead) -> K0 index build -> step -> loss.item()'}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
