@@ -20,9 +20,10 @@ from .nn import (GIN, GINConv, ExtractorMLP, MLP, BatchSequential, InstanceNorm,
 from .gsat import (GSAT, is_undirected, transpose, reorder_like, get_r, concrete_sample,  # noqa: E402
                    lift_node_att_to_edge_att, gumbel_sigmoid, f1_sparsity_loss, info_loss)
 from .pna import PNA, PNAConvSimple  # noqa: E402
+from .dual import line_graph_dual  # noqa: E402
 from . import ops  # noqa: E402
 
 __all__ = ['Batch', 'GraphIndex', 'get_graph_index', 'clear_index_cache', 'GIN', 'GINConv', 'ExtractorMLP', 'MLP',
            'BatchSequential', 'InstanceNorm', 'Criterion', 'get_model', 'get_preds', 'AtomEncoder', 'BondEncoder',
            'GSAT', 'is_undirected', 'transpose', 'reorder_like', 'get_r', 'concrete_sample',
-           'lift_node_att_to_edge_att', 'gumbel_sigmoid', 'f1_sparsity_loss', 'info_loss', 'ops', 'PNA', 'PNAConvSimple']
+           'lift_node_att_to_edge_att', 'gumbel_sigmoid', 'f1_sparsity_loss', 'info_loss', 'ops', 'PNA', 'PNAConvSimple', 'line_graph_dual']

@@ -324,3 +324,46 @@ extern "C" int gsatb_index_build(const int64_t* edge_index, const int64_t* batch
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }
+
+// ---- stable sort of edge ids by one int32 key (used by the line-graph builder: members of a source group in primal
+// edge order) ------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_iota(int32_t* __restrict__ v, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+}  // namespace
+
+extern "C" size_t gsatb_stable_order_workspace(int64_t E) {
+    int64_t numTiles = (E + RS_TILE - 1) / RS_TILE;
+    if (numTiles < 1) numTiles = 1;
+    const size_t pad = 256;
+    size_t bytes = 5 * (((size_t)(E > 0 ? E : 1) * 4 + pad - 1) / pad * pad);      // ident + 2 (key,val) pairs
+    bytes += ((size_t)256 * numTiles * 4 + pad - 1) / pad * pad + 256 * 4 + pad;
+    return bytes;
+}
+
+// order[p] = id of the p-th element in ascending key order, ties in ascending id order (stable LSD radix sort)
+extern "C" int gsatb_stable_order(const int32_t* keys, int64_t E, int64_t key_range, int32_t* order, void* ws,
+                                  size_t ws_bytes, gsatb_stream_t stream) {
+    if (E < 0 || key_range < 0 || E >= (1ll << 31) - 1) return GSATB_EINVAL;
+    if (E == 0) return GSATB_OK;
+    if (!keys || !order || !ws) return GSATB_EINVAL;
+    if (ws_bytes < gsatb_stable_order_workspace(E)) return GSATB_EWS_TOO_SMALL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t pad = 256;
+    const size_t seg = ((size_t)E * 4 + pad - 1) / pad * pad;
+    char* w = (char*)ws;
+    int32_t* ident = (int32_t*)w;
+    Pair P0{(int32_t*)(w + seg), (int32_t*)(w + 2 * seg)};
+    Pair P1{(int32_t*)(w + 3 * seg), (int32_t*)(w + 4 * seg)};
+    const int numTiles = (int)((E + RS_TILE - 1) / RS_TILE);
+    uint32_t* hist = (uint32_t*)(w + 5 * seg);
+    uint32_t* totals = (uint32_t*)((char*)hist + ((size_t)256 * numTiles * 4 + pad - 1) / pad * pad);
+    k_iota<<<grid1d(E, 256), 256, 0, st>>>(ident, E);
+    const int passes = (bits_for(key_range > 1 ? key_range : 2) + 7) / 8;
+    Pair r = radix_sort_pairs(keys, ident, P0, P1, E, passes, numTiles, hist, totals, st);
+    cudaMemcpyAsync(order, r.v, (size_t)E * 4, cudaMemcpyDeviceToDevice, st);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}

@@ -125,6 +125,29 @@ int gsatb_gather_concat_bwd(const float* g, const int32_t* rowptr_src, const int
                             const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N, int H,
                             gsatb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Line-graph ("dual") builder of the fork.  Replaces the Python dict loops of
+ *   src/datasets/mutag_dual.py:342-378 (group primal edges by first endpoint, all ordered pairs inside a group)
+ *   and, with halve = 1, the relabelling of :536-548 (both directions of a primal edge share one dual node)
+ * on top of K0's CSC row pointers of the PRIMAL graph and `members` = gsatb_stable_order(src): the edges grouped by
+ * source node, each group in primal edge order (K0's own eid_by_src orders a group by destination).  One dual node per directed primal edge e (halve: per edge pair e >> 1);
+ * groups in order of first appearance of their source node; inside a group with members m_0 < m_1 < ... the dual
+ * edges (m_i, m_j), (m_j, m_i) for i < j, i outer.  Two calls because E_d = sum_v d(v)(d(v)-1) is data dependent:
+ *   count: offs[e] [E] (int64 exclusive prefix of the group sizes, laid out by first appearance), total[0] = E_d
+ *   fill : dual_edge_index int64 [2, Ed], dual_batch int64 [E] (halve: [E/2]) = node_graph[src[.]]   [nullable]
+ * Bit-exact against oracle/gsat_oracle.py::line_graph_dual.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* order[p] = id of the p-th edge in ascending `keys` order, ties in ascending id order (stable LSD radix sort of K0). */
+size_t gsatb_stable_order_workspace(int64_t E);
+int gsatb_stable_order(const int32_t* keys, int64_t E, int64_t key_range, int32_t* order, void* ws, size_t ws_bytes,
+                       gsatb_stream_t stream);
+size_t gsatb_line_graph_workspace(int64_t N, int64_t E);
+int gsatb_line_graph_count(const int32_t* src, const int32_t* rowptr_src, const int32_t* members, int64_t N, int64_t E,
+                           int64_t* offs, int64_t* total, void* ws, size_t ws_bytes, gsatb_stream_t stream);
+int gsatb_line_graph_fill(const int32_t* src, const int32_t* rowptr_src, const int32_t* members, const int64_t* offs,
+                          const int64_t* node_graph, int64_t N, int64_t E, int halve, int64_t* dual_edge_index,
+                          int64_t Ed, int64_t* dual_batch, gsatb_stream_t stream);
+
 /* Weight / bias gradient of a Linear layer with a small input width (F + 1 <= 16): the node encoder Linear(x_dim, H)
  * of src/models/gin.py:22-25 / pna.py:20-25.  dW[h,f] = sum_n g[n,h] x[n,f], db[h] = sum_n g[n,h] (db nullable);
  * replaces the library's large-K fp32 sgemm in autograd; deterministic (per-CTA partials reduced in a fixed order). */

@@ -649,3 +649,36 @@ class GSAT(nn.Module):
     sampling = staticmethod(lambda logits, training, noise_u=None: concrete_sample(logits, 1, training, noise_u))
     get_r = staticmethod(get_r)
     lift_node_att_to_edge_att = staticmethod(lift_node_att_to_edge_att)
+
+
+# --------------------------------------------------------------------------
+# line-graph ("dual") construction of the fork
+# --------------------------------------------------------------------------
+
+
+def line_graph_dual(edge_index: torch.Tensor, batch: torch.Tensor, halve: bool = False):
+    """Restatement of reference src/datasets/mutag_dual.py:342-378 (``group_by_first`` + ``add_pairs_from_group``),
+    with dual nodes identified by their index in the primal edge list, and -- ``halve`` -- of the relabelling of
+    :536-548 (``dual_dict = {pair: idx // 2 + 1}``: consecutive rows, the two directions of a primal edge, share one
+    id; 0-based here).  Plain Python loops on purpose: small cases only.
+
+    Returns (dual_edge_index int64 [2, E_d], dual_batch int64 [E] or [E/2])."""
+    src = edge_index[0].tolist()
+    E = len(src)
+    group_by_first = {}                      # dict insertion order == order of first appearance (mutag_dual.py:351-353)
+    for idx, a in enumerate(src):
+        group_by_first.setdefault(a, []).append(idx)
+    dual_edges = []
+    for group in group_by_first.values():    # mutag_dual.py:374-376
+        if len(group) > 1:
+            for i in range(len(group)):      # add_pairs_from_group, mutag_dual.py:363-372
+                for j in range(i + 1, len(group)):
+                    e1, e2 = group[i], group[j]
+                    if halve:
+                        e1, e2 = e1 // 2, e2 // 2
+                    dual_edges.append([e1, e2])
+                    dual_edges.append([e2, e1])
+    dual_ei = torch.tensor(dual_edges, dtype=torch.int64).t().contiguous() if dual_edges \
+        else torch.zeros((2, 0), dtype=torch.int64)
+    node_of_dual = edge_index[0][::2] if halve else edge_index[0]
+    return dual_ei, batch[node_of_dual].clone()

@@ -587,3 +587,35 @@ def test_small_linear_weight_gradient(G, N, F_, H):
     assert close(lg.weight.grad, lin.weight.grad, 1e-4, 1e-5)
     assert close(lg.bias.grad, lin.bias.grad, 1e-4, 1e-5)
     assert close(xg.grad, w @ lin.weight.detach(), 1e-4, 1e-5)
+
+
+@pytest.mark.parametrize('case', ['kat4', 'mutag', 'ba2motifs', 'shuffled', 'directed', 'empty'])
+@pytest.mark.parametrize('halve', [False, True])
+def test_line_graph_dual_bit_exact(G, case, halve):
+    """GPU line-graph builder against the restated reference loops: bit-exact dual edge list
+    (same order) and dual batch vector."""
+    from dp_gsat_b200.data import ba2motifs_batch, load_mutag_fixture
+    if case == 'kat4':
+        ei = torch.tensor([[0, 1, 0, 2, 1, 3, 0, 3, 1, 2], [1, 0, 2, 0, 3, 1, 3, 0, 2, 1]])
+        batch = torch.zeros(4, dtype=torch.int64)
+    elif case == 'mutag':
+        src, dst, ng = load_mutag_fixture(os.path.join(GOLDEN, 'mutag_slice.npz'))
+        keep = ng[src] < 96
+        ei, batch = torch.from_numpy(np.stack([src[keep], dst[keep]])), torch.from_numpy(ng)
+    elif case == 'empty':
+        ei, batch = torch.zeros((2, 0), dtype=torch.int64), torch.zeros(3, dtype=torch.int64)
+    else:
+        b = ba2motifs_batch(60, seed=4)
+        ei, batch = b.edge_index, b.batch
+        if case == 'shuffled':       # rows shuffled in pairs: groups no longer appear in node order
+            perm = torch.randperm(ei.shape[1] // 2, generator=torch.Generator().manual_seed(0))
+            ei = ei[:, torch.stack([2 * perm, 2 * perm + 1], 1).reshape(-1)]
+        elif case == 'directed':
+            ei = ei[:, ::2].contiguous()
+    if halve and (case == 'directed' or ei.shape[1] % 2):
+        pytest.skip('halve needs both directions of every edge as consecutive rows')
+    exp_ei, exp_b = O.line_graph_dual(ei, batch, halve=halve)
+    got_ei, got_b = G.line_graph_dual(ei.cuda(), batch.cuda(), halve=halve)
+    assert got_ei.dtype == torch.int64 and got_b.dtype == torch.int64
+    assert torch.equal(got_ei.cpu(), exp_ei)
+    assert torch.equal(got_b.cpu(), exp_b)

@@ -148,3 +148,34 @@ def test_oracle_step_runs_and_is_deterministic():
         outs.append((edge_att.detach(), loss.detach(), clf.convs[0].nn[0].weight.grad.clone()))
     assert all(torch.equal(a, c) for a, c in zip(*outs))
     assert outs[0][0].shape == (b.num_edges, 1) and torch.isfinite(outs[0][1])
+
+
+def test_line_graph_dual_oracle_matches_vectorised_builder_and_known_answer():
+    """The dual-graph oracle (reference mutag_dual.py:342-378 restated with its dict loops) against (1) the 4-node
+    example of the comment at mutag_dual.py:181-193 and (2) the vectorised numpy builder of data.py on the committed
+    Mutagenicity slice."""
+    import numpy as np
+    from oracle import gsat_oracle as O
+    # edges (1,2),(2,1),(1,3),(3,1),(2,4),(4,2),(1,4),(4,1),(2,3),(3,2) -> 0-based
+    ei = torch.tensor([[0, 1, 0, 2, 1, 3, 0, 3, 1, 2], [1, 0, 2, 0, 3, 1, 3, 0, 2, 1]])
+    batch = torch.zeros(4, dtype=torch.int64)
+    dei, db = O.line_graph_dual(ei, batch)
+    # groups by first endpoint in order of first appearance: 0:[0,2,6] 1:[1,4,8] 2:[3,9] 3:[5,7]
+    exp = [(0, 2), (2, 0), (0, 6), (6, 0), (2, 6), (6, 2), (1, 4), (4, 1), (1, 8), (8, 1), (4, 8), (8, 4), (3, 9), (9, 3),
+           (5, 7), (7, 5)]
+    assert dei.t().tolist() == [list(p) for p in exp]
+    assert db.tolist() == [0] * 10
+    deh, dbh = O.line_graph_dual(ei, batch, halve=True)
+    assert deh.t().tolist() == [[a // 2, b // 2] for a, b in exp] and dbh.numel() == 5
+    # E_d = sum_v d(v) (d(v) - 1)
+    deg = torch.bincount(ei[0], minlength=4)
+    assert dei.shape[1] == int((deg * (deg - 1)).sum())
+    from dp_gsat_b200.data import load_mutag_fixture, line_graph_dual as np_dual
+    import os
+    from tests.conftest import GOLDEN
+    src, dst, ng = load_mutag_fixture(os.path.join(GOLDEN, 'mutag_slice.npz'))
+    keep = ng[src] < 40
+    ds, dd, dng = np_dual(src[keep], dst[keep], ng)
+    dei2, db2 = O.line_graph_dual(torch.from_numpy(np.stack([src[keep], dst[keep]])), torch.from_numpy(ng))
+    assert np.array_equal(dei2[0].numpy(), ds) and np.array_equal(dei2[1].numpy(), dd)
+    assert np.array_equal(db2.numpy(), dng)
