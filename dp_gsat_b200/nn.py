@@ -135,6 +135,35 @@ class GINConv(tnn.Module):
         return self.nn(out)
 
 
+class GINEConv(tnn.Module):
+    """src/models/conv_layers.py:37-66 over torch_geometric GINEConv(nn, eps=0., train_eps=False, edge_dim): message
+    relu(x_j + lin(edge_attr)) * edge_atten; ``lin`` = Linear(edge_dim, in_channels) when edge_dim is given; ``eps`` is
+    a buffer, present in the state_dict (keys: nn.*, eps, lin.weight, lin.bias)."""
+
+    def __init__(self, nn: tnn.Module, eps: float = 0.0, train_eps: bool = False, edge_dim: Optional[int] = None):
+        super().__init__()
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:
+            raise NotImplementedError('train_eps=True is never used by the reference (gin.py:38)')
+        self.register_buffer('eps', torch.tensor([eps]))
+        if edge_dim is not None:
+            first = nn[0] if isinstance(nn, tnn.Sequential) else nn
+            in_channels = first.in_features if hasattr(first, 'in_features') else first.in_channels
+            self.lin = tnn.Linear(edge_dim, in_channels)
+        else:
+            self.lin = None
+
+    def forward(self, x, edge_index, edge_attr=None, edge_atten=None, size=None, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(edge_index, None, num_nodes=x.shape[0])
+        if self.lin is None and x.size(-1) != edge_attr.size(-1):
+            raise ValueError("Node and edge feature dimensionalities do not match. Consider setting the 'edge_dim' "
+                             "attribute of 'GINEConv'")
+        ef = self.lin(edge_attr) if self.lin is not None else edge_attr
+        out = ops.gine_aggregate(x, ef, edge_atten, gi, self.initial_eps)
+        return self.nn(out)
+
+
 class GIN(tnn.Module):
     """src/models/gin.py:12-81."""
 
@@ -145,16 +174,22 @@ class GIN(tnn.Module):
         self.edge_attr_dim = edge_attr_dim
         self.dropout_p = model_config['dropout_p']
         self.use_edge_attr = model_config.get('use_edge_attr', True)
+        self.with_edges = edge_attr_dim != 0 and self.use_edge_attr
         if model_config.get('atom_encoder', False):
             self.node_encoder = AtomEncoder(emb_dim=hidden_size)
+            if self.with_edges:
+                self.edge_encoder = BondEncoder(emb_dim=hidden_size)
         else:
             self.node_encoder = tnn.Linear(x_dim, hidden_size)
-        if edge_attr_dim != 0 and self.use_edge_attr:
-            raise NotImplementedError('GINEConv (edge features in GIN) is a SURVEY §8f "next" row, not built yet')
+            if self.with_edges:
+                self.edge_encoder = tnn.Linear(edge_attr_dim, hidden_size)
         self.convs = tnn.ModuleList()
         self.relu = tnn.ReLU()
         for _ in range(self.n_layers):
-            self.convs.append(GINConv(GIN.MLP(hidden_size, hidden_size)))
+            if self.with_edges:      # gin.py:36-38
+                self.convs.append(GINEConv(GIN.MLP(hidden_size, hidden_size), edge_dim=hidden_size))
+            else:
+                self.convs.append(GINConv(GIN.MLP(hidden_size, hidden_size)))
         self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
         self.masks = None     # parity tests inject dropout masks here
         self.precision = 'fp32'   # 'bf16': node MLPs on tcgen05 (tc.gin_mlp_relu); 'fp32': strict library path
@@ -173,7 +208,11 @@ class GIN(tnn.Module):
     def get_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin'):
         gi = get_graph_index(edge_index, batch)
         x = _encode_once(self, x)
-        fused = self.precision == 'bf16' and x.shape[1] % 8 == 0 and x.shape[1] <= 128
+        if edge_attr is not None and self.use_edge_attr and self.with_edges:
+            edge_attr = self.edge_encoder(edge_attr)          # gin.py:46-47, 66-67
+        else:
+            edge_attr = None
+        fused = self.precision == 'bf16' and x.shape[1] % 8 == 0 and x.shape[1] <= 128 and not self.with_edges
         for i in range(self.n_layers):
             if fused:
                 # K3 aggregation (bf16 out) chained into the node MLP + ReLU + dropout on the tensor cores
@@ -186,7 +225,7 @@ class GIN(tnn.Module):
                 x = tc.gin_layer(x, edge_atten, gi, self.convs[i], self.training, self.dropout_p,
                                  self.seed * 7919 + self._calls, dm)         # ReLU + dropout fused in the epilogue
                 continue
-            x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten, _index=gi)
+            x = self.convs[i](x, edge_index, edge_attr=edge_attr, edge_atten=edge_atten, _index=gi)
             x = self.relu(x)
             x = _dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
         return x

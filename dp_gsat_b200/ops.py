@@ -62,6 +62,45 @@ def gin_aggregate(x, edge_atten, gi: GraphIndex, eps: float = 0.0):
     return _GinAggregate.apply(x, edge_atten, gi, float(eps))
 
 
+class _GineAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, edge_feat, att, gi: GraphIndex, eps: float):
+        x, ef = _f32c(x), _f32c(edge_feat)
+        att_flat = None if att is None else _f32c(att).view(-1)
+        N, H = x.shape
+        if N != gi.N or ef.shape != (gi.E, H) or (att_flat is not None and att_flat.numel() != gi.E):
+            raise ValueError('x / edge features / edge_atten do not match the graph index')
+        out = torch.empty_like(x)
+        lib().call('gsatb_gine_aggregate_fwd', ptr(x), ptr(ef), ptr(att_flat), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
+                   ptr(gi.src_by_dst), ctypes.c_float(eps), ptr(out), N, gi.E, H, stream())
+        ctx.gi, ctx.eps = gi, eps
+        ctx.att_shape = None if att is None else att.shape
+        ctx.save_for_backward(x, ef, att_flat)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, ef, att_flat = ctx.saved_tensors
+        gi = ctx.gi
+        gout = _f32c(gout)
+        N, H = x.shape
+        need_ef = ctx.needs_input_grad[1]
+        need_att = ctx.needs_input_grad[2] and att_flat is not None
+        dx = torch.empty_like(x)
+        def_ = torch.empty_like(ef) if need_ef else None
+        datt = torch.empty(gi.E, dtype=torch.float32, device=x.device) if need_att else None
+        lib().call('gsatb_gine_aggregate_bwd', ptr(gout), ptr(x), ptr(ef), ptr(att_flat), ptr(gi.rowptr_src),
+                   ptr(gi.eid_by_src), ptr(gi.dst_by_src), ctypes.c_float(ctx.eps), ptr(dx), ptr(def_), ptr(datt), N,
+                   gi.E, H, stream())
+        return dx, def_, (datt.view(ctx.att_shape) if need_att else None), None, None
+
+
+def gine_aggregate(x, edge_feat, edge_atten, gi: GraphIndex, eps: float = 0.0):
+    """out[i] = sum_{e: dst(e)=i} relu(x[src(e)] + edge_feat[e]) * edge_atten[e] + (1+eps) * x[i]  (GINEConv message,
+    reference src/models/conv_layers.py:37-66)."""
+    return _GineAggregate.apply(x, edge_feat, edge_atten, gi, float(eps))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # K5  readout   (global_add_pool / global_mean_pool, reference src/models/gin.py:34,53, pna.py:47,62)
 # ------------------------------------------------------------------------------------------------------------

@@ -97,6 +97,19 @@ int gsatb_gin_aggregate_bwd(const float* gout, const float* x, const float* att,
                             const int32_t* eid_by_src, const int32_t* dst_by_src, float eps, float* dx,
                             float* datt /* [nullable] */, int64_t N, int64_t E, int H, gsatb_stream_t stream);
 
+/* Attention-aware GINEConv message passing (src/models/conv_layers.py:37-66 over PyG
+ * GINEConv):  out[i] = sum_{e: dst(e)=i} relu(x[src(e)] + edge_feat[e]) * att[e] + (1+eps) x[i], with
+ * edge_feat = lin(edge_attr) [E,H] computed by the caller.  bwd: t_e = att_e g[dst(e)] 1[x[src] + edge_feat[e] > 0];
+ * dx[j] = sum_e t_e + (1+eps) g[j]; dedge_feat[e] = t_e [nullable]; datt[e] = <relu(x[src]+edge_feat[e]), g[dst]>
+ * [nullable].  att [nullable].  Deterministic (CSR / CSC walks in edge order). */
+int gsatb_gine_aggregate_fwd(const float* x, const float* edge_feat, const float* att, const int32_t* rowptr_dst,
+                             const int32_t* eid_by_dst, const int32_t* src_by_dst, float eps, float* out, int64_t N,
+                             int64_t E, int H, gsatb_stream_t stream);
+int gsatb_gine_aggregate_bwd(const float* gout, const float* x, const float* edge_feat, const float* att,
+                             const int32_t* rowptr_src, const int32_t* eid_by_src, const int32_t* dst_by_src, float eps,
+                             float* dx, float* dedge_feat, float* datt, int64_t N, int64_t E, int H,
+                             gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K5  graph readout.  Replaces global_add_pool / global_mean_pool (src/models/gin.py:34,53, pna.py:47,62).
  * ---------------------------------------------------------------------------------------------------------- */

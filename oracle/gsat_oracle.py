@@ -309,6 +309,30 @@ class GINConv(nn.Module):
         return self.nn(out)
 
 
+class GINEConv(nn.Module):
+    """conv_layers.py:37-66 on top of PyG GINEConv(nn, eps=0, train_eps=False, edge_dim): lin = Linear(edge_dim,
+    in_channels) when edge_dim is given; message (x_j + lin(edge_attr)).relu() * edge_atten; aggr 'add'."""
+
+    def __init__(self, mlp: nn.Module, eps: float = 0.0, edge_dim: Optional[int] = None):
+        super().__init__()
+        self.nn = mlp
+        self.register_buffer('eps', torch.tensor([eps]))
+        in_channels = mlp[0].in_features if isinstance(mlp, nn.Sequential) else getattr(mlp, 'in_features', None)
+        self.lin = nn.Linear(edge_dim, in_channels) if edge_dim is not None else None
+
+    def forward(self, x, edge_index, edge_attr=None, edge_atten=None, size=None):
+        x_j = x.index_select(0, edge_index[0])
+        if self.lin is None and x_j.size(-1) != edge_attr.size(-1):
+            raise ValueError("Node and edge feature dimensionalities do not match. Consider setting the 'edge_dim' "
+                             "attribute of 'GINEConv'")
+        ea = self.lin(edge_attr) if self.lin is not None else edge_attr            # :57-58
+        m = (x_j + ea).relu()                                                       # :59
+        msg = m * edge_atten if edge_atten is not None else m                       # :61-64
+        out = scatter_sum(msg, edge_index[1], x.shape[0])
+        out = out + (1 + self.eps.to(x.dtype)) * x                                  # :46-48
+        return self.nn(out)
+
+
 def gin_mlp(in_channels: int, out_channels: int) -> nn.Sequential:
     """gin.py:55-62."""
     return nn.Sequential(nn.Linear(in_channels, out_channels), nn.BatchNorm1d(out_channels),
@@ -428,7 +452,7 @@ class BondEncoder(_SumEmbedding):
 
 
 class GIN(nn.Module):
-    """gin.py:12-81 (GINConv branch: edge_attr_dim == 0 or use_edge_attr False)."""
+    """gin.py:12-81 (GINConv, or GINEConv when edge_attr_dim != 0 and use_edge_attr)."""
 
     def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
         super().__init__()
@@ -437,21 +461,28 @@ class GIN(nn.Module):
         self.edge_attr_dim = edge_attr_dim
         self.dropout_p = model_config['dropout_p']
         self.use_edge_attr = model_config.get('use_edge_attr', True)
+        self.with_edges = edge_attr_dim != 0 and self.use_edge_attr
         if model_config.get('atom_encoder', False):
             self.node_encoder = AtomEncoder(hidden)
+            if self.with_edges:
+                self.edge_encoder = BondEncoder(hidden)
         else:
             self.node_encoder = nn.Linear(x_dim, hidden)
-        if edge_attr_dim != 0 and self.use_edge_attr:
-            raise NotImplementedError('GINEConv is a SURVEY §8f "next" row')
-        self.convs = nn.ModuleList([GINConv(gin_mlp(hidden, hidden)) for _ in range(self.n_layers)])
+            if self.with_edges:
+                self.edge_encoder = nn.Linear(edge_attr_dim, hidden)
+        if self.with_edges:                      # gin.py:36-38
+            self.convs = nn.ModuleList([GINEConv(gin_mlp(hidden, hidden), edge_dim=hidden) for _ in range(self.n_layers)])
+        else:
+            self.convs = nn.ModuleList([GINConv(gin_mlp(hidden, hidden)) for _ in range(self.n_layers)])
         self.fc_out = nn.Sequential(nn.Linear(hidden, 1 if num_class == 2 and not multi_label else num_class))
         self.masks: Optional[MaskSource] = None
         self._pass = 0
 
     def get_emb(self, x, edge_index, batch, edge_attr=None, edge_atten=None, mask_key: str = 'gin'):
         x = self.node_encoder(x)
+        edge_attr = self.edge_encoder(edge_attr) if (edge_attr is not None and self.with_edges) else None   # gin.py:66-67
         for i in range(self.n_layers):
-            x = self.convs[i](x, edge_index, edge_attr=None, edge_atten=edge_atten)
+            x = self.convs[i](x, edge_index, edge_attr=edge_attr, edge_atten=edge_atten)
             x = F.relu(x)
             x = dropout(x, self.dropout_p, self.training, self.masks, f'{mask_key}.{i}')
         return x

@@ -619,3 +619,96 @@ def test_line_graph_dual_bit_exact(G, case, halve):
     assert got_ei.dtype == torch.int64 and got_b.dtype == torch.int64
     assert torch.equal(got_ei.cpu(), exp_ei)
     assert torch.equal(got_b.cpu(), exp_b)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GINEConv: GIN with edge features
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('H,with_att', [(16, True), (64, True), (128, False), (300, True)])
+def test_gine_aggregate_fwd_bwd(G, H, with_att):
+    """relu(x_j + edge_feat) * edge_atten summed over incoming edges + (1+eps) x, forward and all three gradients,
+    against the oracle's GINEConv (reference conv_layers.py:37-66) with an identity nn and no lin."""
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(40, seed=9)
+    g = torch.Generator().manual_seed(H)
+    N, E = b.num_nodes, b.num_edges
+    x, ef = torch.randn(N, H, generator=g), torch.randn(E, H, generator=g)
+    att = torch.rand(E, 1, generator=g) if with_att else None
+    w = torch.randn(N, H, generator=g)
+    xr, er = x.clone().requires_grad_(True), ef.clone().requires_grad_(True)
+    ar = att.clone().requires_grad_(True) if with_att else None
+    ref = O.GINEConv(torch.nn.Identity())(xr, b.edge_index, edge_attr=er, edge_atten=ar)
+    (ref * w).sum().backward()
+    gi = G.get_graph_index(b.edge_index.cuda(), b.batch.cuda(), b.num_graphs)
+    xd, ed = x.cuda().requires_grad_(True), ef.cuda().requires_grad_(True)
+    ad = att.cuda().requires_grad_(True) if with_att else None
+    out = G.ops.gine_aggregate(xd, ed, ad, gi, 0.0)
+    (out * w.cuda()).sum().backward()
+    assert_close(out, ref, atol_scale=2e-6, what='gine fwd')
+    assert_close(xd.grad, xr.grad, atol_scale=2e-6, what='gine dx')
+    assert_close(ed.grad, er.grad, atol_scale=2e-6, what='gine d edge_feat')
+    if with_att:
+        assert_close(ad.grad, ar.grad, atol_scale=2e-6, what='gine d att')
+    assert torch.equal(out, G.ops.gine_aggregate(xd, ed, ad, gi, 0.0))        # deterministic
+
+
+@pytest.mark.parametrize('atom_encoder', [True, False])
+def test_gsat_gin_with_edge_features_step_parity(G, atom_encoder):
+    """GSAT + GIN on a batch WITH edge features (reference gin.py:28-38: edge_encoder + GINEConv layers), whole step
+    against the oracle: state_dict keys (incl. convs.{l}.lin.*), edge attention, logits, loss, every gradient."""
+    import copy
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(48, seed=11, with_edge_attr=True)
+    if not atom_encoder:      # plain float features through Linear encoders
+        gen = torch.Generator().manual_seed(0)
+        b.x = torch.rand(b.num_nodes, 7, generator=gen)
+        b.edge_attr = torch.rand(b.num_edges, 5, generator=gen)
+    cfg = {'model_name': 'GIN', 'hidden_size': 64, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': True,
+           'atom_encoder': atom_encoder}
+    shared = {'learn_edge_att': True, 'extractor_dropout_p': 0.5}
+    x_dim, ea_dim = b.x.shape[1], b.edge_attr.shape[1]
+    torch.manual_seed(0)
+    clf_o, ext_o = O.get_model(x_dim, ea_dim, 2, False, cfg), O.ExtractorMLP(64, shared)
+    clf_g, ext_g = G.get_model(x_dim, ea_dim, 2, False, cfg, 'cuda'), G.ExtractorMLP(64, shared).cuda()
+    assert set(clf_g.state_dict().keys()) == set(clf_o.state_dict().keys())
+    assert 'convs.0.lin.weight' in clf_g.state_dict() and 'convs.1.eps' in clf_g.state_dict()
+    clf_g.load_state_dict(clf_o.state_dict())
+    ext_g.load_state_dict(ext_o.state_dict())
+    ms = O.MaskSource(2)
+    for m in (clf_o, ext_o, clf_g, ext_g):
+        m.masks = ms
+    go = O.GSAT(clf_o, ext_o, O.Criterion(2, False), learn_edge_att=True, final_r=0.7)
+    gg = G.GSAT(clf_g, ext_g, G.Criterion(2, False), learn_edge_att=True, final_r=0.7)
+    go64 = copy.deepcopy(go).double()
+    for m in (go, gg, go64):
+        m.train()
+    u = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
+    ea_o, loss_o, _, logit_o = go.forward_pass(b, 3, True, noise_u=u)
+    b64 = b.to('cpu')
+    if not atom_encoder:
+        b64.x, b64.edge_attr = b64.x.double(), b64.edge_attr.double()
+    ea_t, loss_t, _, logit_t = go64.forward_pass(b64, 3, True, noise_u=u.double())
+    ea_g, loss_g, _, logit_g = gg.forward_pass(b.to('cuda'), 3, True, noise_u=u.cuda())
+    loss_o.backward()
+    loss_t.backward()
+    loss_g.backward()
+
+    def check(g_val, o_val, t_val, what, rtol=2e-4, atol_scale=2e-5):
+        if close(g_val, o_val, rtol, atol_scale):
+            return
+        t = t_val.detach().cpu().double()
+        err_g = (g_val.detach().cpu().double() - t).abs().max().item()
+        err_o = (o_val.detach().cpu().double() - t).abs().max().item()
+        assert err_g <= 4 * err_o + 1e-7 * max(1.0, t.abs().max().item()), \
+            f'{what}: cuda-vs-fp64 {err_g:.3e} > 4 x oracle32-vs-fp64 {err_o:.3e}'
+    check(ea_g, ea_o, ea_t, 'edge_att')
+    check(logit_g, logit_o, logit_t, 'logits')
+    check(loss_g, loss_o, loss_t, 'loss')
+    named = lambda m: dict(list(m.clf.named_parameters()) + [('ext.' + k, v) for k, v in m.extractor.named_parameters()])
+    po, pt, pg = named(go), named(go64), named(gg)
+    assert po.keys() == pg.keys()
+    for k in po:
+        if po[k].grad is None:
+            assert pg[k].grad is None or float(pg[k].grad.abs().max()) == 0.0, k
+            continue
+        check(pg[k].grad, po[k].grad, pt[k].grad, f'grad {k}', rtol=1e-3, atol_scale=2e-4)
