@@ -161,6 +161,14 @@ int gsatb_line_graph_fill(const int32_t* src, const int32_t* rowptr_src, const i
                           const int64_t* node_graph, int64_t N, int64_t E, int halve, int64_t* dual_edge_index,
                           int64_t Ed, int64_t* dual_batch, gsatb_stream_t stream);
 
+/* On-device explanation metric: GSAT.get_precision_at_k, src/run_gsat.py:783-791 (a Python
+ * loop over graphs with boolean masks over all edges and a numpy argsort each, on .cpu() copies).
+ * precision[g] = (sum of exp_labels over the k highest-attention edges of graph g) / k, edges of a graph contiguous
+ * (edge_ptr from K0); ties go to the smaller edge index (unspecified in the reference: numpy's default argsort is not
+ * stable).  Graphs with fewer than k edges contribute all their edges and still divide by k, as the reference does. */
+int gsatb_precision_at_k(const float* att, const float* exp_labels, const int32_t* edge_ptr, int64_t G, int k,
+                         float* precision /* [G] */, gsatb_stream_t stream);
+
 /* Weight / bias gradient of a Linear layer with a small input width (F + 1 <= 16): the node encoder Linear(x_dim, H)
  * of src/models/gin.py:22-25 / pna.py:20-25.  dW[h,f] = sum_n g[n,h] x[n,f], db[h] = sum_n g[n,h] (db nullable);
  * replaces the library's large-K fp32 sgemm in autograd; deterministic (per-CTA partials reduced in a fixed order). */

@@ -713,3 +713,34 @@ def line_graph_dual(edge_index: torch.Tensor, batch: torch.Tensor, halve: bool =
         else torch.zeros((2, 0), dtype=torch.int64)
     node_of_dual = edge_index[0][::2] if halve else edge_index[0]
     return dual_ei, batch[node_of_dual].clone()
+
+
+# --------------------------------------------------------------------------
+# per-batch explanation metrics of the trainer
+# --------------------------------------------------------------------------
+
+
+def get_precision_at_k(att, exp_labels, k, batch, edge_index):
+    """src/run_gsat.py:783-791, verbatim structure (loop over graphs, boolean edge masks, argsort of -att); the
+    argsort is made stable (kind='stable') so that ties are defined: the smaller edge index wins."""
+    import numpy as np
+    att = att.detach().reshape(-1).cpu()
+    exp_labels = exp_labels.detach().reshape(-1).cpu()
+    precision_at_k = []
+    for i in range(int(batch.max()) + 1):
+        nodes_for_graph_i = batch == i
+        edges_for_graph_i = nodes_for_graph_i[edge_index[0]] & nodes_for_graph_i[edge_index[1]]
+        labels_for_graph_i = exp_labels[edges_for_graph_i]
+        mask_log_logits_for_graph_i = att[edges_for_graph_i]
+        top = np.argsort(-mask_log_logits_for_graph_i.numpy(), kind='stable')[:k]
+        precision_at_k.append(labels_for_graph_i[top].sum().item() / k)
+    return precision_at_k
+
+
+def get_delta_kl(exp_labels, att, eps=1e-6):
+    """src/run_gsat.py:793-800."""
+    p = exp_labels.float().clamp(min=eps, max=1 - eps)
+    r_uv = att.clamp(min=eps, max=1 - eps)
+    r = r_uv.mean().clamp(min=eps, max=1 - eps)
+    delta_kl = p * torch.log(r_uv / r) + (1 - p) * torch.log((1 - r_uv) / (1 - r))
+    return delta_kl.sum().item()

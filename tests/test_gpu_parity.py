@@ -712,3 +712,31 @@ def test_gsat_gin_with_edge_features_step_parity(G, atom_encoder):
             assert pg[k].grad is None or float(pg[k].grad.abs().max()) == 0.0, k
             continue
         check(pg[k].grad, po[k].grad, pt[k].grad, f'grad {k}', rtol=1e-3, atol_scale=2e-4)
+
+
+@pytest.mark.parametrize('k', [1, 5, 60])
+def test_on_device_metrics(G, k):
+    """precision@k per graph and delta-KL on the device (SURVEY section 8f row 3) against the reference's Python loops;
+    includes graphs with fewer than k edges, exact ties (attention averaged over reverse edges) and a 1500-edge graph."""
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(40, seed=2)
+    g = torch.Generator().manual_seed(k)
+    gi_att = torch.rand(b.num_edges, generator=g)
+    ref_idx = G.get_graph_index(b.edge_index.cuda(), b.batch.cuda(), b.num_graphs)
+    att = ((gi_att + gi_att[ref_idx.rev.cpu().long()]) / 2).view(-1, 1)          # tied in reverse-edge pairs
+    labels = ((b.edge_index[0] % 25 >= 20) & (b.edge_index[1] % 25 >= 20)).float()     # motif edges
+    exp = O.get_precision_at_k(att, labels, k, b.batch, b.edge_index)
+    got = G.get_precision_at_k(att.cuda(), labels.cuda(), k, b.batch.cuda(), b.edge_index.cuda(), b.num_graphs)
+    assert got.shape == (b.num_graphs,)
+    assert torch.allclose(got.cpu().double(), torch.tensor(exp, dtype=torch.float64), rtol=0, atol=1e-6)
+    dk = G.get_delta_kl(labels.cuda(), att.cuda().view(-1))
+    assert abs(float(dk) - O.get_delta_kl(labels, att.view(-1))) < 1e-3 * max(1.0, abs(O.get_delta_kl(labels, att.view(-1))))
+    # one big graph (several staging chunks)
+    n = 400
+    src = torch.randint(0, n, (1500,), generator=g)
+    dst = torch.randint(0, n, (1500,), generator=g)
+    ei, batch = torch.stack([src, dst]), torch.zeros(n, dtype=torch.int64)
+    a2, l2 = torch.rand(1500, generator=g), (torch.rand(1500, generator=g) > 0.5).float()
+    exp2 = O.get_precision_at_k(a2, l2, k, batch, ei)
+    got2 = G.get_precision_at_k(a2.cuda(), l2.cuda(), k, batch.cuda(), ei.cuda(), 1)
+    assert torch.allclose(got2.cpu().double(), torch.tensor(exp2, dtype=torch.float64), rtol=0, atol=1e-6)

@@ -260,5 +260,5 @@ def test_word_dropout_rate_and_scale(G, p):
     assert torch.allclose(out[kept], torch.full_like(out[kept], 1.0 / keep_rate), rtol=1e-6)
     # no structure along rows or channels: every row / channel mean is close to the keep rate
     assert float((kept.float().mean(0) - keep_rate).abs().max()) < 0.05
-    assert float((kept.float().mean(1) - keep_rate).abs().max()) < 0.2
+    assert float((kept.float().mean(1) - keep_rate).abs().max()) < 0.27      # 128 samples per row: 6 sigma
     assert abs(float(out.mean()) - 1.0) < 1e-2          # unbiased
