@@ -399,6 +399,7 @@ def run_b200(a):
             nxt = fetch()
         _, loss, _, _ = step(d, 0)                          # index build (K0) + step
         loss_host = float(loss.item())                      # D2H of the step's result
+        G.clear_index_cache()                               # this batch is done: its index blocks go back to the allocator
     barrier()
     t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
