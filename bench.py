@@ -188,7 +188,7 @@ def kernel_models(N, E, G, H):
         'gsatb_tc_linear_bf16_fwd:fp32': (6.0 * N * H, 2.0 * N * H * H),              # bf16 a1 in, fp32 h out
         'gsatb_bn_relu_bf16': (4.0 * N * H, 0.0),
         'gsatb_tc_linear_fwd': (8.0 * N * H, 2.0 * N * H * H),
-        'gsatb_tc_gin_bwd2': (N * (4.0 * H + 4 * H + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
+        'gsatb_tc_gin_bwd2': (N * (4.0 * H + H / 8.0 + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),   # dh, sign bits, z1 in; d2, g out
         'gsatb_tc_gin_bwd1': (N * (2.0 * H + 2 * H + 2 * H + 4 * H), 2.0 * N * H * H),
         'gsatb_tc_ext_fwd1': (2.0 * E * 2 * H + 2.0 * E * C1, 2.0 * E * 2 * H * C1),
         'gsatb_tc_ext_fwd2': (2.0 * E * C1 + 2.0 * E * H + 4.0 * E, 2.0 * E * C1 * H),

@@ -121,6 +121,7 @@ struct OpLinearBf16 {
         float* stat_partials;    // nullable: [gridDim * 4 groups][2][OUT]
         int OUT;
         Dropout drop;
+        uint32_t* posmask;       // nullable: [rows, ceil(OUT/32)] bit c%32 of word (row, c/32) = (out[row, c] > 0)
     };
     struct EpiState {
         float s1, s2;
@@ -136,7 +137,7 @@ struct OpLinearBf16 {
         const bool use_mask = p.drop.enabled && p.drop.mask != nullptr;
         const uint8_t* mk = use_mask ? p.drop.mask + r0 * p.OUT + (cx.ch_ok ? cx.ch : 0) : nullptr;
         const uint32_t dseed = dropout_seed(p.drop);
-        uint32_t keepw = 0u;
+        uint32_t keepw = 0u, posw = 0u;
         float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
         auto f = [&](int col, float acc) {
             const bool ok = col < cnt;
@@ -156,6 +157,18 @@ struct OpLinearBf16 {
                     keepw = dropout_rows32(p.drop, (uint32_t)(r0 + col), (uint32_t)cx.ch >> 5, dseed, cx.lane);
                 const bool k = use_mask ? (ok ? __ldg(mk + (int64_t)col * p.OUT) != 0 : false) : ((keepw >> (col & 31)) & 1u) != 0;
                 z = k ? z * p.drop.scale : 0.f;
+            }
+            if (p.posmask) {     // sign bits of the layer output for the backward pass (it needs nothing else of h):
+                // each thread collects the bits of its channel over the chunk's 32 rows, a warp bit-matrix transpose
+                // turns them into one 32-channel word per row
+                posw |= ((z > 0.f && cx.ch_ok) ? 1u : 0u) << (col & 31);
+                if ((col & 31) == 31) {
+                    const uint32_t roww = warp_transpose32(posw, cx.lane);
+                    const int row = col - 31 + cx.lane;
+                    const int W = (p.OUT + 31) >> 5;       // words per row; warps past the last word column write nothing
+                    if (row < cnt && (cx.ch >> 5) < W) p.posmask[(r0 + row) * (int64_t)W + (cx.ch >> 5)] = roww;
+                    posw = 0u;
+                }
             }
             return z;
         };
@@ -270,8 +283,8 @@ extern "C" int gsatb_tc_linear_fwd(const void* x, int x_is_bf16, int ldx, const 
 
 extern "C" int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void* w_bf16, const float* bias, void* out,
                                         int out_is_bf16, int ldo, int relu_out, float* stat_partials, double* stats,
-                                        const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, int64_t rows, int K,
-                                        int OUT, gsatb_stream_t stream) {
+                                        const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, uint32_t* posmask_out,
+                                        int64_t rows, int K, int OUT, gsatb_stream_t stream) {
     if (rows < 0 || K <= 0 || OUT <= 0) return GSATB_EINVAL;
     if (rows == 0) return GSATB_OK;
     if (!x_bf16 || !w_bf16 || !out) return GSATB_EINVAL;
@@ -284,10 +297,10 @@ extern "C" int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void*
     const Dropout drop = make_dropout(drop_mask, drop_seed, pdrop, pdrop > 0.f, 1);
     int rc;
     if (out_is_bf16) {
-        OpLinearBf16<true>::Params p{bias, out, ldo, relu_out, stat_partials, OUT, drop};
+        OpLinearBf16<true>::Params p{bias, out, ldo, relu_out, stat_partials, OUT, drop, posmask_out};
         rc = launch<OpLinearBf16<true>>(w_bf16, tl, K, OUT, p, st, x_bf16, ldx);
     } else {
-        OpLinearBf16<false>::Params p{bias, out, ldo, relu_out, stat_partials, OUT, drop};
+        OpLinearBf16<false>::Params p{bias, out, ldo, relu_out, stat_partials, OUT, drop, posmask_out};
         rc = launch<OpLinearBf16<false>>(w_bf16, tl, K, OUT, p, st, x_bf16, ldx);
     }
     if (rc != GSATB_OK) return rc;

@@ -145,7 +145,7 @@ inline Tiling uniform_tiling(int64_t rows) {
 
 // Stream one accumulator block out as fp32 rows through the group's staging buffer: two buffers of RB rows x 128
 // channels x 4 bytes (RB = 32: 32 KiB per group, RB = 16: 16 KiB).  f(col, acc) is the value of element
-// (row r0 + col, this thread's channel); it is called for every column of a chunk that has at least one valid row.
+// (row r0 + col, this thread's channel); it is called, in column order, for all 32 columns of every chunk.
 template <int RB, class F>
 __device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int ld, F f) {
     constexpr int HALVES = 32 / RB;
@@ -160,10 +160,14 @@ __device__ __forceinline__ void epi_emit_f32(const EpiCtx& cx, float* out, int l
 #pragma unroll
         for (int h = 0; h < HALVES; ++h) {
             const int lo = c * 32 + h * RB, n = min(RB, cx.cnt - lo);
+            // f runs for every column of the chunk (it may be warp-collective / keep per-chunk state); rows past the
+            // tile end are computed and dropped
+#pragma unroll
+            for (int j = 0; j < RB; ++j) v[h * RB + j] = f(lo + j, v[h * RB + j]);
             if (n > 0) {       // uniform across the group
                 float* buf = reinterpret_cast<float*>(cx.stage) + (HALVES == 1 ? (c & 1) : h) * (RB * 128);
 #pragma unroll
-                for (int j = 0; j < RB; ++j) buf[j * 128 + cx.gtid] = f(lo + j, v[h * RB + j]);
+                for (int j = 0; j < RB; ++j) buf[j * 128 + cx.gtid] = v[h * RB + j];
                 epi_sync(cx);  // buffer staged; also orders the previous copy-out of the OTHER buffer before its re-use
                 stage_store<4>(cx, reinterpret_cast<const uint8_t*>(buf), out + cx.r0 * ld, ld, lo, n);
             }

@@ -50,7 +50,7 @@ def linear(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_
 
 def linear_bf16(x16: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], out_features: int,
                 out_bf16: bool = True, relu_out: bool = False, want_stats: bool = False, pdrop: float = 0.0,
-                drop_seed: int = 0, drop_mask: Optional[torch.Tensor] = None):
+                drop_seed: int = 0, drop_mask: Optional[torch.Tensor] = None, posmask: Optional[torch.Tensor] = None):
     """out = drop(act(x16 W^T + bias)) with the B operand fed by TMA straight from the bf16 activations (four epilogue
     groups); bf16 or fp32 output; optional per-channel (sum z, sum z^2) in fp64, taken from the fp32 accumulators."""
     x16 = x16.contiguous()
@@ -63,7 +63,7 @@ def linear_bf16(x16: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor
         stats = torch.empty(2 * out_features, dtype=torch.float64, device=x16.device)
     lib().call('gsatb_tc_linear_bf16_fwd', ptr(x16), K, ptr(wp), ptr(bias), ptr(out), int(out_bf16), out_features,
                int(relu_out), ptr(part), ptr(stats), ptr(drop_mask), ctypes.c_uint64(drop_seed), ctypes.c_float(pdrop),
-               rows, K, out_features, stream())
+               ptr(posmask), rows, K, out_features, stream())
     return (out, stats) if want_stats else out
 
 
@@ -204,7 +204,7 @@ def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: 
 
 
 def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
-                     drop_seed, drop_mask):
+                     drop_seed, drop_mask, keep_sign: bool = True):
     """Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(agg)))))) on bf16 ``agg16`` [N, K].  Linear1 is a TMA-fed tcgen05
     GEMM whose epilogue accumulates the BatchNorm batch statistics from the fp32 accumulators and stores z1 as bf16;
     BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU and the dropout into its epilogue."""
@@ -229,11 +229,14 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     p = float(pdrop) if training else 0.0
     a1 = torch.empty_like(z1)
     lib().call('gsatb_bn_relu_bf16', ptr(z1), ptr(scale), ptr(shift), ptr(a1), N, H1, stream())
-    h = linear_bf16(a1, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=p, drop_seed=drop_seed, drop_mask=drop_mask)
-    return h, (z1, a1, mean, rstd, scale, shift, p)
+    # sign bits of h: all the backward pass needs of the layer output (4 bytes per 32 channels instead of 128)
+    posmask = torch.empty((N, (H + 31) // 32), dtype=torch.int32, device=agg16.device) if keep_sign else None
+    h = linear_bf16(a1, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=p, drop_seed=drop_seed, drop_mask=drop_mask,
+                    posmask=posmask)
+    return h, (z1, a1, mean, rstd, scale, shift, p, posmask)
 
 
-def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p):
+def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p, posmask=None):
     """-> (d agg fp32 [N, K], dW1, db1, dgamma, dbeta, dW2, db2)."""
     N, Kin = agg16.shape
     H1, H = w1.shape[0], w2.shape[0]
@@ -244,7 +247,8 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     g = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
     part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
     stats = torch.empty(2 * H1, dtype=torch.float32, device=dev)
-    L.call('gsatb_tc_gin_bwd2', ptr(dh), ptr(h), ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
+    L.call('gsatb_tc_gin_bwd2', ptr(dh), None if posmask is not None else ptr(h), ptr(posmask),
+           ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
            ptr(prep_weight(w2, transpose=True)), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
            ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
     dbeta, dgamma = stats[:H1], stats[H1:]
@@ -276,19 +280,19 @@ class _GinMlpFused(torch.autograd.Function):
     def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
                 drop_seed, drop_mask):
         agg16 = x.contiguous().bfloat16()
-        h, (z1, a1, mean, rstd, scale, shift, p) = _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean,
-                                                                    running_var, nbt, training, momentum, eps, pdrop,
-                                                                    drop_seed, drop_mask)
-        ctx.save_for_backward(agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift)
+        h, (z1, a1, mean, rstd, scale, shift, p, posmask) = _gin_mlp_forward(
+            agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
+            drop_seed, drop_mask)
+        ctx.save_for_backward(agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
         ctx.cfg = (bool(training), p)
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
         training, p = ctx.cfg
-        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p)
+        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
+                                                                    scale, shift, training, p, posmask)
         return (dagg, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None, None, None, None)
 
 
@@ -316,19 +320,19 @@ class _GinLayerFused(torch.autograd.Function):
         agg16 = torch.empty((N, K), dtype=torch.bfloat16, device=x.device)
         lib().call('gsatb_gin_aggregate_fwd_bf16', ptr(x), ptr(att_flat), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
                    ptr(gi.src_by_dst), ctypes.c_float(conv_eps), ptr(agg16), N, gi.E, K, stream())
-        h, (z1, a1, mean, rstd, scale, shift, p) = _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean,
-                                                                    running_var, nbt, training, momentum, eps, pdrop,
-                                                                    drop_seed, drop_mask)
-        ctx.save_for_backward(x, att_flat, agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift)
+        h, (z1, a1, mean, rstd, scale, shift, p, posmask) = _gin_mlp_forward(
+            agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
+            drop_seed, drop_mask)
+        ctx.save_for_backward(x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
         ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape)
         return h
 
     @staticmethod
     def backward(ctx, dh):
-        x, att_flat, agg16, z1, a1, h, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
+        x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
         training, p, gi, conv_eps, att_shape = ctx.cfg
-        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p)
+        dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
+                                                                    scale, shift, training, p, posmask)
         N, K = x.shape
         need_att = att_flat is not None and ctx.needs_input_grad[1]
         dx = torch.empty_like(x)

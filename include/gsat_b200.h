@@ -270,21 +270,24 @@ int gsatb_tc_linear_fwd(const void* x, int x_is_bf16, int ldx, const float* in_s
 /* gsatb_tc_linear_bf16_fwd: out = drop(act(x_bf16 W^T + bias)) with the B operand loaded by TMA straight from the
  * row-major bf16 activations (both Linears of the GIN node MLP: K3's bf16 aggregation, then a1); out is bf16
  * (out_is_bf16) or fp32; optional BatchNorm statistics as above, taken from the fp32 accumulators before rounding.
+ * posmask_out [nullable]: uint32 [rows, ceil(OUT/32)], bit c%32 of word (row, c/32) = (out[row, c] > 0): the only
+ * thing the backward pass needs of the layer output h (gsatb_tc_gin_bwd2 then reads 4 bytes instead of 128 per row).
  * gsatb_bn_relu_bf16: a1 = ReLU(z1 * scale + shift) (BatchNorm folded per channel), bf16 in / bf16 out. */
 int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void* w_bf16_padded, const float* bias, void* out,
                              int out_is_bf16, int ldo, int relu_out, float* stat_partials, double* stats,
-                             const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, int64_t rows, int K, int OUT,
-                             gsatb_stream_t stream);
+                             const uint8_t* drop_mask, uint64_t drop_seed, float pdrop, uint32_t* posmask_out,
+                             int64_t rows, int K, int OUT, gsatb_stream_t stream);
 int gsatb_bn_relu_bf16(const void* z_bf16, const float* scale, const float* shift, void* a_bf16, int64_t rows, int C,
                        gsatb_stream_t stream);
 
 /* GIN node MLP backward (autograd of src/models/gin.py:55-62 + the ReLU / Dropout of gin.py:50-52):
- *   gin_bwd2: d2 = dh*(h>0)*drop_scale (written as bf16 [N,H]); da1 = d2 W2 on tcgen05 (w2t = prep(W2, transpose));
+ *   gin_bwd2: d2 = dh*(h>0)*drop_scale (written as bf16 [N,H]; the sign of h from posmask when given, else from h); da1 = d2 W2 on tcgen05 (w2t = prep(W2, transpose));
  *             g = da1*(ReLU(BN(z1))>0) and a1 = ReLU(BN(z1)) written as bf16 [N,H1]; stats[0:H1] = sum_rows g,
  *             stats[H1:2H1] = sum_rows g*xhat (BatchNorm backward), deterministic two-stage reduction
  *   gin_bwd1: dz1 = cA*g + cB*z1 + cC (BatchNorm backward folded per channel; written as bf16 [N,H1]);
  *             dx = dz1 W1 on tcgen05 (w1t = prep(W1, transpose)), fp32 [N,Kin] */
-int gsatb_tc_gin_bwd2(const float* dh, const float* h, float drop_scale, const void* w2t_bf16_padded, const void* z1,
+int gsatb_tc_gin_bwd2(const float* dh, const float* h /* [nullable if posmask] */, const uint32_t* posmask /* [nullable] */,
+                      float drop_scale, const void* w2t_bf16_padded, const void* z1,
                       const float* bn_scale, const float* bn_shift, const float* mean, const float* rstd, void* d2,
                       void* g, void* a1, float* stat_partials, float* stats, int64_t N, int H, int H1,
                       gsatb_stream_t stream);
