@@ -101,13 +101,27 @@ class Clocks:
                 'window': 'identical untimed steps (>= 0.7 s, sampler already running) + the timed region'}
 
 
-def preload(run_one, sync, seconds=0.7):
-    """Keep the GPU under the SAME load for `seconds` before the timed region, so that the nvidia-smi sampler (which
-    needs ~100 ms to produce its first row) sees the clocks the timed steps run at even when K steps last < 0.1 s."""
+def preload(run_one, sync, world, dev, seconds=0.7):
+    """Keep the GPU under the SAME load for about `seconds` before the timed region, so that the nvidia-smi sampler
+    (which needs ~100 ms to produce its first row) sees the clocks the timed steps run at even when K steps last
+    < 0.1 s.  The number of extra steps is AGREED across ranks (every step holds collectives: a per-rank, wall-clock
+    bounded loop would let ranks run different counts and dead-lock): two steps are timed, the maximum over ranks is
+    all-reduced, and every rank derives the same count from it."""
+    import math
+    sync()
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
+    run_one()
+    run_one()
+    sync()
+    t = torch.tensor([(time.perf_counter() - t0) / 2.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n = int(max(1, min(500, math.ceil(seconds / max(float(t.item()), 1e-5)))))
+    for _ in range(n):
         run_one()
-        sync()
+    sync()
+    return n
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -319,7 +333,7 @@ def run_b200(a):
         clocks = Clocks(local)
         if rank == 0:
             clocks.start()
-        preload(lambda: step(data, 0), barrier)
+        preload(lambda: step(data, 0), barrier, world, dev)
         barrier()
         ev0.record()
         for _ in range(a.steps):
@@ -347,7 +361,7 @@ def run_b200(a):
     if rank == 0:
         clocks.start()
     L.timer_all = False                       # (the preload steps are not part of the per-kernel statistics)
-    preload(lambda: step(data, 0), barrier)
+    preload(lambda: step(data, 0), barrier, world, dev)
     L.timer, L.timer_all = {}, True
     launches0 = L.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

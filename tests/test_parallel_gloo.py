@@ -76,3 +76,36 @@ def test_flat_bucket_views():
     lin(torch.ones(1, 3)).sum().backward()
     assert b.flat.numel() == 8 and torch.equal(b.flat[:6].view(2, 3), lin.weight.grad)
     assert lin.weight.grad.data_ptr() == b.flat.data_ptr()
+
+
+def _preload_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import importlib.util
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('_bench', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    buf = torch.zeros(1)
+
+    def step():                      # a "training step": different speed per rank, one collective inside
+        time.sleep(0.002 * (1 + 3 * rank))
+        dist.all_reduce(buf)
+        calls.append(1)
+
+    n = bench.preload(step, dist.barrier, world, torch.device('cpu'), seconds=0.08)
+    dist.barrier()
+    out[rank] = (n, len(calls))
+    dist.destroy_process_group()
+
+
+def test_bench_preload_runs_the_same_number_of_steps_on_every_rank():
+    """bench.preload keeps the GPU loaded before the timed region; every step holds collectives, so the number of extra
+    steps must be agreed across ranks (a per-rank wall-clock loop dead-locked the 2-GPU bench once)."""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_preload_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == out[1]
+    assert out[0][0] >= 1 and out[0][1] == out[0][0] + 2

@@ -114,3 +114,39 @@ for name, fn in (('ext_bwd1', kbwd1), ('linear_bf16in 512->256', kbf16in)):
     tiles = max(d[8].item(), 1)
     print(f'{name}: {e0.elapsed_time(e1):.3f} ms, B-buffers/CTA {tiles:.0f}; cycles per B buffer: ' +
           ', '.join(f'{n}={d[i].item() / tiles:.0f}' for i, n in enumerate(names[:8])))
+
+
+x16 = (torch.randn(gi.N, 128, device=dev)).bfloat16()
+o32 = torch.empty(gi.N, 128, device=dev)
+o16 = torch.empty(gi.N, 128, device=dev, dtype=torch.bfloat16)
+pm = torch.empty(gi.N, 4, device=dev, dtype=torch.int32)
+bias = torch.zeros(128, device=dev)
+
+
+def klin16():
+    L.call('gsatb_tc_linear_bf16_fwd', ptr(x16), 128, ptr(wl), ptr(bias), ptr(o16), 1, 128, 0, None, None, None, ctypes.c_uint64(0),
+           ctypes.c_float(0.0), None, gi.N, 128, 128, stream())
+
+
+def klin32():
+    L.call('gsatb_tc_linear_bf16_fwd', ptr(x16), 128, ptr(wl), ptr(bias), ptr(o32), 0, 128, 1, None, None, None, ctypes.c_uint64(3),
+           ctypes.c_float(0.3), ptr(pm), gi.N, 128, 128, stream())
+
+
+def klin32_plain():
+    L.call('gsatb_tc_linear_bf16_fwd', ptr(x16), 128, ptr(wl), ptr(bias), ptr(o32), 0, 128, 0, None, None, None, ctypes.c_uint64(3),
+           ctypes.c_float(0.0), None, gi.N, 128, 128, stream())
+
+
+for name, fn in (('linear_bf16 -> bf16 (Linear1)', klin16), ('linear_bf16 -> fp32 relu+dropout+posmask (Linear2)', klin32),
+                 ('linear_bf16 -> fp32 plain', klin32_plain)):
+    for _ in range(2):
+        fn()
+    dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    L.cdll.gsatb_tc_set_profile_buffer(ctypes.c_void_p(dbg.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    L.cdll.gsatb_tc_set_profile_buffer(None)
+    d = dbg.double().mean(0).cpu()
+    print(f'{name}: {e0.elapsed_time(e1):.3f} ms on N={gi.N} rows; cycles per CTA: ' +
+          ', '.join(f'{n}={d[i].item():.0f}' for i, n in enumerate(names[:6])))
