@@ -1,6 +1,12 @@
 // Shared device helpers for libgsat_b200 (sm_100a only).
 #pragma once
+#ifdef GSATB_HOST_SIM
+// tests/simt/: the same kernel source compiled by g++ against a host SIMT emulator (threads = fibers, real
+// __syncthreads / *_sync rendezvous) for the CPU-side kernel-logic tests.  Never defined in the product build.
+#include "simt.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/gsat_b200.h"
 
@@ -17,15 +23,28 @@
 // randomness on every replay although its kernel arguments are frozen.  Host-side accessor, defined in api.cu.
 const unsigned long long*& gsatb_step_counter_ref();
 
+// Kernel launch on `stream` (no dynamic shared memory).  KERNEL must be a plain identifier: name a template
+// instantiation through a local function pointer first (`auto k = k_foo<4, true>;`).
+#ifdef GSATB_HOST_SIM
+#define GSATB_LAUNCH(KERNEL, GRID, BLOCK, STREAM, ...) \
+    simt::launch(dim3(GRID), dim3(BLOCK), [&]() { KERNEL(__VA_ARGS__); })
+#else
+#define GSATB_LAUNCH(KERNEL, GRID, BLOCK, STREAM, ...) KERNEL<<<(GRID), (BLOCK), 0, (STREAM)>>>(__VA_ARGS__)
+#endif
+
 static inline bool gsatb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // 128-bit streaming load through the read-only path without L1 allocation (data touched once).
 __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+#ifdef GSATB_HOST_SIM
+    return *p;
+#else
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
+#endif
 }
 // 128-bit gather load through the read-only path, L1-allocating (neighbour rows are re-used inside a CTA).
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }

@@ -4,6 +4,8 @@ state_dict keys), backed by the sm_100a kernels of libgsat_b200.so.
   reference file                         -> here
   src/models/conv_layers.py:14-34  GINConv            -> GINConv
   src/models/gin.py:12-81          GIN                -> GIN
+  src/models/conv_layers.py:37-92  GINEConv, LEConv   -> GINEConv, LEConv
+  src/models/spmotif_gnn.py:9-87   SPMotifNet         -> SPMotifNet
   src/utils/get_model.py:7-68      get_model/Criterion/BatchSequential/MLP -> same names
   torch_geometric InstanceNorm / global_add_pool / global_mean_pool        -> InstanceNorm / ops.global_*_pool
   src/run_gsat.py:888-927, example/gsat.py:120-139  ExtractorMLP           -> ExtractorMLP
@@ -164,6 +166,87 @@ class GINEConv(tnn.Module):
         return self.nn(out)
 
 
+class LEConv(tnn.Module):
+    """src/models/conv_layers.py:69-92 over torch_geometric 2.0.3 LEConv(in_channels, out_channels, bias=True):
+    lin1 (bias), lin2 (no bias), lin3 (bias) -- the same state_dict keys; message (a_j - b_i) * edge_weight * edge_atten
+    summed over incoming edges, plus lin3(x).  The three Linears are library GEMMs; the message passing, the root
+    term and their backward are kernels of csrc/leconv.cu."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin1 = tnn.Linear(in_channels, out_channels, bias=bias)
+        self.lin2 = tnn.Linear(in_channels, out_channels, bias=False)
+        self.lin3 = tnn.Linear(in_channels, out_channels, bias=bias)
+
+    def forward(self, x, edge_index, edge_weight=None, edge_atten=None, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(edge_index, None, num_nodes=x.shape[0])
+        return ops.le_aggregate(self.lin1(x), self.lin2(x), edge_weight, edge_atten, gi, add=self.lin3(x))
+
+
+class SPMotifNet(tnn.Module):
+    """src/models/spmotif_gnn.py:9-87 (same attribute names, state_dict keys and method signatures)."""
+
+    def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
+        super().__init__()
+        self.n_layers = model_config['n_layers']
+        hidden_size = model_config['hidden_size']
+        self.edge_attr_dim = edge_attr_dim
+        self.node_emb = tnn.Linear(x_dim, hidden_size)
+        self.convs = tnn.ModuleList()
+        self.relus = tnn.ModuleList()
+        for _ in range(self.n_layers):
+            self.convs.append(LEConv(in_channels=hidden_size, out_channels=hidden_size))
+            self.relus.append(tnn.ReLU())
+        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
+                                     tnn.Linear(2 * hidden_size, num_class))
+        self.conf_mlp = tnn.Sequential(tnn.Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
+                                       tnn.Linear(2 * hidden_size, 3))
+        self.cq = tnn.Linear(3, 3)
+        self.conf_fw = tnn.Sequential(self.conf_mlp, self.cq)
+
+    def pool(self, x, batch, _index: Optional[GraphIndex] = None):
+        gi = _index if _index is not None else get_graph_index(_no_edges(batch.device), batch)
+        return ops.global_mean_pool(x, gi)
+
+    def forward(self, x, edge_index, batch, edge_attr, edge_atten=None):
+        node_x = self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten=edge_atten)
+        return self.get_causal_pred(self.pool(node_x, batch, get_graph_index(edge_index, batch)))
+
+    def get_emb(self, x, edge_index, batch, edge_attr, edge_atten=None):
+        return self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten=edge_atten)
+
+    def get_pred_from_emb(self, emb, batch):
+        return self.fc_out(self.pool(emb, batch))
+
+    def get_node_reps(self, x, edge_index, edge_attr, batch, edge_atten):
+        gi = get_graph_index(edge_index, batch)
+        x = _encode_once(self, x, 'node_emb')
+        for conv, relu in zip(self.convs, self.relus):
+            x = relu(conv(x=x, edge_index=edge_index, edge_weight=edge_attr, edge_atten=edge_atten, _index=gi))
+        return x
+
+    def get_graph_rep(self, x, edge_index, edge_attr, batch, edge_atten):
+        node_x = self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten=edge_atten)
+        return self.pool(node_x, batch, get_graph_index(edge_index, batch))
+
+    def get_causal_pred(self, causal_graph_x):
+        return self.fc_out(causal_graph_x)
+
+    def get_conf_pred(self, conf_graph_x):
+        return self.conf_fw(conf_graph_x)
+
+    def get_comb_pred(self, causal_graph_x, conf_graph_x):
+        causal_pred = self.fc_out(causal_graph_x)
+        conf_pred = self.conf_mlp(conf_graph_x).detach()
+        return torch.sigmoid(conf_pred) * causal_pred
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            for param in self.parameters():
+                param.uniform_(-1.0, 1.0)
+
+
 class GIN(tnn.Module):
     """src/models/gin.py:12-81."""
 
@@ -242,22 +325,22 @@ class GIN(tnn.Module):
         return self.fc_out(self.pool(emb, batch))
 
 
-def _encode_once(model, x):
+def _encode_once(model, x, attr: str = 'node_encoder'):
     """node_encoder(x), shared between the two GNN passes of ONE GSAT.forward_pass (get_emb, then clf: same input,
     same weights, no dropout in front of it -- example/gsat.py:75,86), so the encoder GEMM and its weight-gradient
     GEMM run once per step instead of twice.  GSAT.forward_pass opens / closes the scope (``_enc_scope``); outside
     of it every call encodes afresh."""
     scope = getattr(model, '_enc_scope', None)
     if scope is None:
-        return _encode(model, x)
+        return _encode(model, x, attr)
     key = (x.data_ptr(), tuple(x.shape), x._version, torch.is_grad_enabled())
     if scope.get('key') != key:
-        scope['key'], scope['out'] = key, _encode(model, x)
+        scope['key'], scope['out'] = key, _encode(model, x, attr)
     return scope['out']
 
 
-def _encode(model, x):
-    enc = model.node_encoder
+def _encode(model, x, attr: str = 'node_encoder'):
+    enc = getattr(model, attr)
     if isinstance(enc, tnn.Linear) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 \
             and x.shape[1] < 16 and enc.out_features % 4 == 0:
         return ops.small_linear(x, enc.weight, enc.bias)      # own kernel for the K = N weight-gradient reduction
@@ -386,6 +469,8 @@ def get_model(x_dim, edge_attr_dim, num_class, multi_label, model_config, device
     elif model_config['model_name'] == 'PNA':
         from .pna import PNA
         model = PNA(x_dim, edge_attr_dim, num_class, multi_label, model_config)
+    elif model_config['model_name'] == 'SPMotifNet':
+        model = SPMotifNet(x_dim, edge_attr_dim, num_class, multi_label, model_config)
     else:
         raise ValueError('[ERROR] Unknown model name!')
     return model.to(device)

@@ -101,6 +101,50 @@ def gine_aggregate(x, edge_feat, edge_atten, gi: GraphIndex, eps: float = 0.0):
     return _GineAggregate.apply(x, edge_feat, edge_atten, gi, float(eps))
 
 
+class _LeAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, edge_weight, att, add, gi: GraphIndex):
+        a, b, add = _f32c(a), _f32c(b), _f32c(add)
+        w_flat = None if edge_weight is None else _f32c(edge_weight).reshape(-1)
+        att_flat = None if att is None else _f32c(att).reshape(-1)
+        N, H = a.shape
+        if N != gi.N or b.shape != a.shape or (add is not None and add.shape != a.shape) \
+                or (w_flat is not None and w_flat.numel() != gi.E) or (att_flat is not None and att_flat.numel() != gi.E):
+            raise ValueError('a / b / edge_weight / edge_atten do not match the graph index')
+        out = torch.empty_like(a)
+        lib().call('gsatb_le_aggregate_fwd', ptr(a), ptr(b), ptr(w_flat), ptr(att_flat), ptr(gi.rowptr_dst),
+                   ptr(gi.eid_by_dst), ptr(gi.src_by_dst), ptr(add), ptr(out), N, gi.E, H, stream())
+        ctx.gi = gi
+        ctx.w_shape = None if edge_weight is None else edge_weight.shape
+        ctx.att_shape = None if att is None else att.shape
+        ctx.has_add = add is not None
+        ctx.save_for_backward(a, b, w_flat, att_flat)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b, w_flat, att_flat = ctx.saved_tensors
+        gi = ctx.gi
+        gout = _f32c(gout)
+        N, H = a.shape
+        need_w = ctx.needs_input_grad[2] and w_flat is not None
+        need_att = ctx.needs_input_grad[3] and att_flat is not None
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        dw = torch.empty(gi.E, dtype=torch.float32, device=a.device) if need_w else None
+        datt = torch.empty(gi.E, dtype=torch.float32, device=a.device) if need_att else None
+        lib().call('gsatb_le_aggregate_bwd', ptr(gout), ptr(a), ptr(b), ptr(w_flat), ptr(att_flat), ptr(gi.rowptr_src),
+                   ptr(gi.eid_by_src), ptr(gi.dst_by_src), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst), ptr(da), ptr(db),
+                   ptr(dw), ptr(datt), N, gi.E, H, stream())
+        return (da, db, (dw.view(ctx.w_shape) if need_w else None), (datt.view(ctx.att_shape) if need_att else None),
+                (gout if ctx.has_add else None), None)
+
+
+def le_aggregate(a, b, edge_weight, edge_atten, gi: GraphIndex, add=None):
+    """out[i] = sum_{e: dst(e)=i} ((a[src(e)] - b[i]) * edge_weight[e]) * edge_atten[e] + add[i]  (LEConv message and
+    root term, reference src/models/conv_layers.py:69-92); edge_weight, edge_atten and add are optional."""
+    return _LeAggregate.apply(a, b, edge_weight, edge_atten, add, gi)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # K5  readout   (global_add_pool / global_mean_pool, reference src/models/gin.py:34,53, pna.py:47,62)
 # ------------------------------------------------------------------------------------------------------------

@@ -110,6 +110,23 @@ int gsatb_gine_aggregate_bwd(const float* gout, const float* x, const float* edg
                              float* dx, float* dedge_feat, float* datt, int64_t N, int64_t E, int H,
                              gsatb_stream_t stream);
 
+/* Attention-aware LEConv message passing (src/models/conv_layers.py:69-92 over PyG LEConv,
+ * the layer of SPMotifNet, src/models/spmotif_gnn.py:20-23,58-63):
+ *   out[i] = sum_{e: dst(e)=i} ((a[src(e)] - b[i]) * edge_weight[e]) * att[e] + add[i]
+ * with a = lin1(x), b = lin2(x), add = lin3(x) [N,H] computed by the caller; edge_weight [E], att [E], add [nullable]
+ * (an absent factor is 1).  bwd: da[j] = sum_{e: src(e)=j} (g[dst(e)] att[e]) edge_weight[e];
+ * db[i] = -sum_{e: dst(e)=i} (g[i] att[e]) edge_weight[e]; datt[e] = <(a[src]-b[dst]) edge_weight[e], g[dst]>
+ * [nullable]; dedge_weight[e] = <a[src]-b[dst], g[dst] att[e]> [nullable]; d add = g (the caller's).
+ * Deterministic (CSR / CSC walks in edge order). */
+int gsatb_le_aggregate_fwd(const float* a, const float* b, const float* edge_weight, const float* att,
+                           const int32_t* rowptr_dst, const int32_t* eid_by_dst, const int32_t* src_by_dst,
+                           const float* add, float* out, int64_t N, int64_t E, int H, gsatb_stream_t stream);
+int gsatb_le_aggregate_bwd(const float* gout, const float* a, const float* b, const float* edge_weight,
+                           const float* att, const int32_t* rowptr_src, const int32_t* eid_by_src,
+                           const int32_t* dst_by_src, const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* da,
+                           float* db, float* dedge_weight, float* datt, int64_t N, int64_t E, int H,
+                           gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K5  graph readout.  Replaces global_add_pool / global_mean_pool (src/models/gin.py:34,53, pna.py:47,62).
  * ---------------------------------------------------------------------------------------------------------- */

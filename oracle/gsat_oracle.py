@@ -333,6 +333,27 @@ class GINEConv(nn.Module):
         return self.nn(out)
 
 
+class LEConv(nn.Module):
+    """conv_layers.py:69-92 on top of PyG 2.0.3 LEConv(in_channels, out_channels, bias=True): lin1 = Linear(in, out,
+    bias), lin2 = Linear(in, out, bias=False), lin3 = Linear(in, out, bias); aggr 'add'; message
+    (a_j - b_i) [* edge_weight.view(-1, 1)] [* edge_atten]; out = propagate(...) + lin3(x)."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.lin1 = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin2 = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin3 = nn.Linear(in_channels, out_channels, bias=bias)
+
+    def forward(self, x, edge_index, edge_weight=None, edge_atten=None):
+        a, b = self.lin1(x), self.lin2(x)                                           # :76-77
+        out = a.index_select(0, edge_index[0]) - b.index_select(0, edge_index[1])   # a_j - b_i, :86
+        m = out if edge_weight is None else out * edge_weight.view(-1, 1)           # :87
+        if edge_atten is not None:                                                  # :89-92
+            m = m * edge_atten
+        return scatter_sum(m, edge_index[1], x.shape[0]) + self.lin3(x)             # :80-82
+
+
 def gin_mlp(in_channels: int, out_channels: int) -> nn.Sequential:
     """gin.py:55-62."""
     return nn.Sequential(nn.Linear(in_channels, out_channels), nn.BatchNorm1d(out_channels),
@@ -545,12 +566,58 @@ class PNA(nn.Module):
         return self.fc_out(global_mean_pool(emb, batch))
 
 
+class SPMotifNet(nn.Module):
+    """spmotif_gnn.py:9-87 (LEConv backbone of "Discovering Invariant Rationales"; global_mean_pool readout)."""
+
+    def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
+        super().__init__()
+        self.n_layers = model_config['n_layers']
+        hidden = model_config['hidden_size']
+        self.edge_attr_dim = edge_attr_dim
+        self.node_emb = nn.Linear(x_dim, hidden)
+        self.convs = nn.ModuleList([LEConv(hidden, hidden) for _ in range(self.n_layers)])
+        self.relus = nn.ModuleList([nn.ReLU() for _ in range(self.n_layers)])
+        self.fc_out = nn.Sequential(nn.Linear(hidden, 2 * hidden), nn.ReLU(), nn.Linear(2 * hidden, num_class))
+        self.conf_mlp = nn.Sequential(nn.Linear(hidden, 2 * hidden), nn.ReLU(), nn.Linear(2 * hidden, 3))
+        self.cq = nn.Linear(3, 3)
+        self.conf_fw = nn.Sequential(self.conf_mlp, self.cq)
+
+    def get_node_reps(self, x, edge_index, edge_attr, batch, edge_atten):
+        x = self.node_emb(x)
+        for conv, relu in zip(self.convs, self.relus):
+            x = relu(conv(x, edge_index, edge_weight=edge_attr, edge_atten=edge_atten))      # :60-62
+        return x
+
+    def get_emb(self, x, edge_index, batch, edge_attr, edge_atten=None):
+        return self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten=edge_atten)
+
+    def forward(self, x, edge_index, batch, edge_attr, edge_atten=None):
+        return self.fc_out(global_mean_pool(self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten), batch))
+
+    def get_pred_from_emb(self, emb, batch):
+        return self.fc_out(global_mean_pool(emb, batch))
+
+    def get_graph_rep(self, x, edge_index, edge_attr, batch, edge_atten):
+        return global_mean_pool(self.get_node_reps(x, edge_index, edge_attr, batch, edge_atten), batch)
+
+    def get_causal_pred(self, causal_graph_x):
+        return self.fc_out(causal_graph_x)
+
+    def get_conf_pred(self, conf_graph_x):
+        return self.conf_fw(conf_graph_x)
+
+    def get_comb_pred(self, causal_graph_x, conf_graph_x):
+        return torch.sigmoid(self.conf_mlp(conf_graph_x).detach()) * self.fc_out(causal_graph_x)
+
+
 def get_model(x_dim, edge_attr_dim, num_class, multi_label, model_config, device='cpu'):
     """get_model.py:7-16."""
     if model_config['model_name'] == 'GIN':
         model = GIN(x_dim, edge_attr_dim, num_class, multi_label, model_config)
     elif model_config['model_name'] == 'PNA':
         model = PNA(x_dim, edge_attr_dim, num_class, multi_label, model_config)
+    elif model_config['model_name'] == 'SPMotifNet':
+        model = SPMotifNet(x_dim, edge_attr_dim, num_class, multi_label, model_config)
     else:
         raise ValueError('[ERROR] Unknown model name!')
     return model.to(device)

@@ -1,0 +1,163 @@
+"""GPU suite, part 3 (-m gpu): the SURVEY section 8f rows built last -- LEConv / SPMotifNet (row 2, second half), the
+fused atom / bond encoders and the device-side batch collate (row 4) -- through the C ABI against the CPU oracle on
+the same seeded inputs.  Same bars as tests/test_gpu_parity.py: indices bit-exact, fp32 values rtol 1e-5, whole-step
+losses / gradients with the fp64-ground-truth criterion.  The file sorts after the other GPU files on purpose: these
+kernels were written after the round's GPU budget was spent and had only been run on the host SIMT emulator
+(tests/test_simt_kernels.py) when they were committed."""
+import copy
+
+import pytest
+import torch
+
+from oracle import gsat_oracle as O
+from tests.test_gpu_parity import assert_close, close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def G():
+    import dp_gsat_b200 as g
+    assert torch.cuda.is_available()
+    return g
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# LEConv / SPMotifNet (reference conv_layers.py:69-92, spmotif_gnn.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('H,with_w,with_att', [(16, True, True), (32, True, True), (64, False, True), (128, True, False),
+                                               (300, True, True), (4, False, False)])
+def test_le_aggregate_fwd_bwd(G, H, with_w, with_att):
+    """((a_j - b_i) * edge_weight) * edge_atten summed over incoming edges + lin3 term, forward and all five gradients,
+    against the oracle's LEConv lines with the Linears factored out."""
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(40, seed=5)
+    g = torch.Generator().manual_seed(H)
+    N, E = b.num_nodes, b.num_edges
+    a, bb, add = (torch.randn(N, H, generator=g) for _ in range(3))
+    w = (torch.rand(E, 1, generator=g) + 0.5) if with_w else None
+    att = torch.rand(E, 1, generator=g) if with_att else None
+    gout = torch.randn(N, H, generator=g)
+
+    leaf = lambda t, dev=None: None if t is None else (t.clone() if dev is None else t.to(dev)).requires_grad_(True)
+    ar, br, dr, wr, tr = leaf(a), leaf(bb), leaf(add), leaf(w), leaf(att)
+    m = ar[b.edge_index[0]] - br[b.edge_index[1]]
+    if with_w:
+        m = m * wr.view(-1, 1)
+    if with_att:
+        m = m * tr
+    ref = O.scatter_sum(m, b.edge_index[1], N) + dr
+    (ref * gout).sum().backward()
+
+    gi = G.get_graph_index(b.edge_index.cuda(), b.batch.cuda(), b.num_graphs)
+    ad, bd, dd, wd, td = (leaf(t, 'cuda') for t in (a, bb, add, w, att))
+    out = G.ops.le_aggregate(ad, bd, wd, td, gi, add=dd)
+    (out * gout.cuda()).sum().backward()
+    assert_close(out, ref, atol_scale=2e-6, what='le fwd')
+    assert_close(ad.grad, ar.grad, atol_scale=2e-6, what='le da')
+    assert_close(bd.grad, br.grad, atol_scale=2e-6, what='le db')
+    assert_close(dd.grad, dr.grad, atol_scale=2e-6, what='le dadd')
+    if with_w:
+        assert_close(wd.grad, wr.grad, atol_scale=4e-6, what='le d edge_weight')
+    if with_att:
+        assert_close(td.grad, tr.grad, atol_scale=4e-6, what='le d att')
+    assert torch.equal(out, G.ops.le_aggregate(ad, bd, wd, td, gi, add=dd))        # deterministic
+    # without the root term, and isolated nodes / empty edge set
+    out2 = G.ops.le_aggregate(ad.detach(), bd.detach(), None, None, gi)
+    ref2 = O.scatter_sum(a[b.edge_index[0]] - bb[b.edge_index[1]], b.edge_index[1], N)
+    assert_close(out2, ref2, atol_scale=2e-6, what='le fwd plain')
+    gi0 = G.get_graph_index(torch.zeros((2, 0), dtype=torch.int64, device='cuda'), b.batch.cuda(), b.num_graphs)
+    out0 = G.ops.le_aggregate(ad.detach(), bd.detach(), None, None, gi0, add=dd.detach())
+    assert torch.equal(out0.cpu(), add)
+
+
+def _spmotif_batch(n_graphs=48, seed=3):
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(n_graphs, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    b.x = torch.rand(b.num_nodes, 4, generator=g)                       # spmotif.py:56
+    b.edge_attr = torch.rand(b.num_edges, 1, generator=g) + 0.5         # spmotif.py:57 uses ones; weights here
+    b.y = torch.randint(0, 3, (b.num_graphs,), generator=g)             # 3 motif classes, long labels
+    return b
+
+
+def test_leconv_layer_and_state_dict(G):
+    b = _spmotif_batch(12)
+    torch.manual_seed(0)
+    ref = O.LEConv(32, 32)
+    dev = G.LEConv(32, 32).cuda()
+    assert set(dev.state_dict().keys()) == set(ref.state_dict().keys()) == \
+        {'lin1.weight', 'lin1.bias', 'lin2.weight', 'lin3.weight', 'lin3.bias'}
+    dev.load_state_dict(ref.state_dict())
+    x = torch.randn(b.num_nodes, 32, generator=torch.Generator().manual_seed(1))
+    att = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(2))
+    want = ref(x, b.edge_index, edge_weight=b.edge_attr, edge_atten=att)
+    got = dev(x.cuda(), b.edge_index.cuda(), edge_weight=b.edge_attr.cuda(), edge_atten=att.cuda())
+    assert_close(got, want, rtol=2e-5, atol_scale=4e-6, what='LEConv layer')
+
+
+@pytest.mark.parametrize('learn_edge_att', [True, False])
+def test_gsat_spmotifnet_step_parity(G, learn_edge_att):
+    """GSAT + SPMotifNet (LEConv backbone, mean-pool readout, 3-class cross-entropy) whole step against the oracle:
+    state_dict keys, edge attention, logits, loss, every parameter gradient."""
+    b = _spmotif_batch()
+    cfg = {'model_name': 'SPMotifNet', 'hidden_size': 32, 'n_layers': 2}
+    shared = {'learn_edge_att': learn_edge_att, 'extractor_dropout_p': 0.5}
+    torch.manual_seed(0)
+    clf_o, ext_o = O.get_model(4, 1, 3, False, cfg), O.ExtractorMLP(32, shared)
+    clf_g, ext_g = G.get_model(4, 1, 3, False, cfg, 'cuda'), G.ExtractorMLP(32, shared).cuda()
+    assert isinstance(clf_g, G.SPMotifNet)
+    assert set(clf_g.state_dict().keys()) == set(clf_o.state_dict().keys())
+    assert {'node_emb.weight', 'convs.0.lin2.weight', 'convs.1.lin3.bias', 'fc_out.2.weight', 'conf_mlp.0.weight',
+            'cq.weight', 'conf_fw.0.2.bias', 'conf_fw.1.weight'} <= set(clf_g.state_dict().keys())
+    clf_g.load_state_dict(clf_o.state_dict())
+    ext_g.load_state_dict(ext_o.state_dict())
+    ms = O.MaskSource(2)
+    for m in (ext_o, ext_g):
+        m.masks = ms
+    go = O.GSAT(clf_o, ext_o, O.Criterion(3, False), learn_edge_att=learn_edge_att, final_r=0.7)
+    gg = G.GSAT(clf_g, ext_g, G.Criterion(3, False), learn_edge_att=learn_edge_att, final_r=0.7)
+    go64 = copy.deepcopy(go).double()
+    for m in (go, gg, go64):
+        m.train()
+    rows = b.num_edges if learn_edge_att else b.num_nodes
+    u = torch.rand(rows, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
+    ea_o, loss_o, _, logit_o = go.forward_pass(b, 3, True, noise_u=u)
+    b64 = b.to('cpu')
+    b64.x, b64.edge_attr = b64.x.double(), b64.edge_attr.double()
+    ea_t, loss_t, _, logit_t = go64.forward_pass(b64, 3, True, noise_u=u.double())
+    ea_g, loss_g, _, logit_g = gg.forward_pass(b.to('cuda'), 3, True, noise_u=u.cuda())
+    assert logit_g.shape == (b.num_graphs, 3)
+    loss_o.backward()
+    loss_t.backward()
+    loss_g.backward()
+
+    def check(g_val, o_val, t_val, what, rtol=2e-4, atol_scale=2e-5):
+        if close(g_val, o_val, rtol, atol_scale):
+            return
+        t = t_val.detach().cpu().double()
+        err_g = (g_val.detach().cpu().double() - t).abs().max().item()
+        err_o = (o_val.detach().cpu().double() - t).abs().max().item()
+        assert err_g <= 4 * err_o + 1e-7 * max(1.0, t.abs().max().item()), \
+            f'{what}: cuda-vs-fp64 {err_g:.3e} > 4 x oracle32-vs-fp64 {err_o:.3e}'
+    check(ea_g, ea_o, ea_t, 'edge_att')
+    check(logit_g, logit_o, logit_t, 'logits')
+    check(loss_g, loss_o, loss_t, 'loss')
+    named = lambda m: dict(list(m.clf.named_parameters()) + [('ext.' + k, v) for k, v in m.extractor.named_parameters()])
+    po, pt, pg = named(go), named(go64), named(gg)
+    assert po.keys() == pg.keys()
+    for k in po:
+        if po[k].grad is None:
+            assert pg[k].grad is None or float(pg[k].grad.abs().max()) == 0.0, k
+            continue
+        check(pg[k].grad, po[k].grad, pt[k].grad, f'grad {k}', rtol=1e-3, atol_scale=2e-4)
+    # the other reference entry points of the class
+    emb = gg.clf.get_emb(b.x.cuda(), b.edge_index.cuda(), b.batch.cuda(), b.edge_attr.cuda())
+    emb_o = go.clf.get_emb(b.x, b.edge_index, b.batch, b.edge_attr)
+    assert_close(emb, emb_o, rtol=2e-4, atol_scale=2e-5, what='get_emb')
+    assert_close(gg.clf.get_pred_from_emb(emb, b.batch.cuda()), go.clf.get_pred_from_emb(emb_o, b.batch), rtol=2e-4,
+                 atol_scale=2e-5, what='get_pred_from_emb')
+    gx = gg.clf.get_graph_rep(b.x.cuda(), b.edge_index.cuda(), b.edge_attr.cuda(), b.batch.cuda(), None)
+    assert_close(gg.clf.get_comb_pred(gx, gx), go.clf.get_comb_pred(gx.cpu(), gx.cpu()), rtol=2e-4, atol_scale=2e-5,
+                 what='get_comb_pred')
+    assert gg.clf.get_conf_pred(gx).shape == (b.num_graphs, 3)

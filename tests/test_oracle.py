@@ -179,3 +179,33 @@ def test_line_graph_dual_oracle_matches_vectorised_builder_and_known_answer():
     dei2, db2 = O.line_graph_dual(torch.from_numpy(np.stack([src[keep], dst[keep]])), torch.from_numpy(ng))
     assert np.array_equal(dei2[0].numpy(), ds) and np.array_equal(dei2[1].numpy(), dd)
     assert np.array_equal(db2.numpy(), dng)
+
+
+def test_leconv_and_spmotifnet_oracle_known_answers():
+    """LEConv restatement (conv_layers.py:69-92): with no weights / attention the layer is the dense identity
+    A^T lin1(x) - deg_in * lin2(x) + lin3(x); attention == 0 leaves only lin3(x); fp64 gradcheck of the message;
+    SPMotifNet (spmotif_gnn.py) state_dict keys as in the reference class."""
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(3, seed=0)
+    N, E = b.num_nodes, b.num_edges
+    torch.manual_seed(0)
+    conv = O.LEConv(8, 8).double()
+    x = torch.randn(N, 8, dtype=torch.float64)
+    A = torch.zeros(N, N, dtype=torch.float64)
+    A.index_put_((b.edge_index[1], b.edge_index[0]), torch.ones(E, dtype=torch.float64), accumulate=True)
+    dense = A @ conv.lin1(x) - A.sum(1, keepdim=True) * conv.lin2(x) + conv.lin3(x)
+    assert torch.allclose(conv(x, b.edge_index), dense, atol=1e-12)
+    assert torch.allclose(conv(x, b.edge_index, edge_atten=torch.zeros(E, 1, dtype=torch.float64)), conv.lin3(x))
+    w = torch.rand(E, 1, dtype=torch.float64)
+    assert torch.allclose(conv(x, b.edge_index, edge_weight=w, edge_atten=2 * torch.ones(E, 1, dtype=torch.float64)),
+                          conv(x, b.edge_index, edge_weight=2 * w), atol=1e-12)
+    xs = x[:, :8].clone().requires_grad_(True)
+    ws, ts = w.clone().requires_grad_(True), torch.rand(E, 1, dtype=torch.float64).requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a, c, d: conv(a, b.edge_index, edge_weight=c, edge_atten=d), (xs, ws, ts))
+    net = O.get_model(4, 1, 3, False, {'model_name': 'SPMotifNet', 'hidden_size': 16, 'n_layers': 2})
+    keys = set(net.state_dict().keys())
+    assert {'node_emb.weight', 'convs.0.lin1.bias', 'convs.0.lin2.weight', 'convs.1.lin3.weight', 'fc_out.0.weight',
+            'fc_out.2.bias', 'conf_mlp.2.weight', 'cq.bias', 'conf_fw.0.0.weight', 'conf_fw.1.bias'} <= keys
+    assert 'convs.0.lin2.bias' not in keys
+    out = net(torch.rand(N, 4), b.edge_index, b.batch, torch.ones(E, 1))
+    assert out.shape == (3, 3)

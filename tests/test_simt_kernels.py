@@ -1,0 +1,214 @@
+"""Kernel-logic tests on the host SIMT emulator (tests/simt): the SAME .cu sources the product library is built from,
+compiled by g++ with -DGSATB_HOST_SIM, called through the same C ABI with host pointers, against the CPU oracle.
+They check indexing, masks, sub-warp shuffles and reduction order without a GPU; the `-m gpu` suite repeats the
+comparisons on the real device (tests/test_gpu_z_next_rows.py)."""
+import pytest
+import torch
+
+from oracle import gsat_oracle as O
+from tests.simt.simlib import sim, guarded, intact
+
+OK = 0
+
+
+def _graph(n_graphs=6, seed=0):
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(n_graphs, seed=seed)
+    return b, O.build_index_oracle(b.edge_index, b.batch)
+
+
+def test_emulator_known_answers():
+    """The emulator itself (tests/simt/selftest.cpp): barriers + shared memory, sub-warp shuffles with divergent trip
+    counts, ballot / up / down / broadcast shuffles in a partial last warp, 3-D grids."""
+    import ctypes
+    c = sim().cdll
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    x = torch.arange(1000, dtype=torch.int32)
+    out = torch.zeros(3, dtype=torch.int32)
+    c.simt_selftest_block_sum(P(x), P(out), 1000, 3, 256)
+    assert int(out.sum()) == 999 * 1000 // 2
+    for lpr in (1, 2, 4, 8, 16, 32):
+        v = torch.arange(128, dtype=torch.float32) + 1
+        o = torch.zeros(128 // lpr)
+        c.simt_selftest_subwarp(P(v), P(o), lpr, 2, 64)
+        grp = v.view(-1, lpr).sum(1)
+        trips = torch.tensor([sum(range(1, g % 3 + 2)) for g in range(128 // lpr)], dtype=torch.float32)
+        assert torch.equal(o, grp * trips), lpr
+    o = torch.zeros(160, dtype=torch.int32)
+    c.simt_selftest_ballot(P(o))
+    o = o.view(40, 4)
+    full = sum(1 << l for l in range(32) if l % 3 == 0)
+    last = sum(1 << l for l in range(8) if (32 + l) % 3 == 0)
+    for t in range(40):
+        lane, base, width = t % 32, t - t % 32, (32 if t < 32 else 8)
+        assert (int(o[t, 0]) & 0xffffffff) == (full if t < 32 else last)
+        assert int(o[t, 1]) == (t - 1 if lane >= 1 else t)
+        assert int(o[t, 2]) == (t + 2 if lane + 2 < width else t) or (t >= 32 and lane + 2 < 32)
+        assert int(o[t, 3]) == base + 5
+    o = torch.zeros(12, dtype=torch.int32)
+    c.simt_selftest_grid3(P(o))
+    assert torch.equal(o, torch.full((12,), sum(range(8)), dtype=torch.int32))
+    for name in ('gsatb_le_aggregate_fwd', 'gsatb_le_aggregate_bwd'):
+        assert sim().has(name)
+
+
+@pytest.mark.parametrize('H', [4, 16, 64, 132, 300])
+@pytest.mark.parametrize('with_w,with_att,with_add', [(True, True, True), (False, True, False), (True, False, True),
+                                                      (False, False, False)])
+def test_leconv_aggregate_on_emulator(H, with_w, with_att, with_add):
+    b, ix = _graph(5 if H > 64 else 9, seed=H)
+    N, E = b.num_nodes, b.num_edges
+    g = torch.Generator().manual_seed(H + 1)
+    a, bb = torch.randn(N, H, generator=g), torch.randn(N, H, generator=g)
+    w = torch.rand(E, generator=g) + 0.5 if with_w else None
+    att = torch.rand(E, 1, generator=g) if with_att else None
+    add = torch.randn(N, H, generator=g) if with_add else None
+    gout = torch.randn(N, H, generator=g)
+    # oracle: the message / aggregation lines of conv_layers.py:69-92 with identity linears
+    ar, br = a.clone().requires_grad_(True), bb.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True) if with_w else None
+    tr = att.clone().requires_grad_(True) if with_att else None
+    m = ar[b.edge_index[0]] - br[b.edge_index[1]]
+    if with_w:
+        m = m * wr.view(-1, 1)
+    if with_att:
+        m = m * tr
+    ref = O.scatter_sum(m, b.edge_index[1], N)
+    if with_add:
+        ref = ref + add
+    (ref * gout).sum().backward()
+
+    out = guarded((N, H))
+    rc = sim().call('gsatb_le_aggregate_fwd', a, bb, w, None if att is None else att.view(-1).contiguous(),
+                    ix['rowptr_dst'], ix['eid_by_dst'], ix['src_by_dst'], add, out, N, E, H, None)
+    assert rc == OK and intact(out)
+    assert torch.allclose(out, ref.detach(), rtol=1e-5, atol=1e-5)
+
+    da, db = guarded((N, H)), guarded((N, H))
+    dw = guarded((E,)) if with_w else None
+    datt = guarded((E,)) if with_att else None
+    rc = sim().call('gsatb_le_aggregate_bwd', gout, a, bb, w, None if att is None else att.view(-1).contiguous(),
+                    ix['rowptr_src'], ix['eid_by_src'], ix['dst_by_src'], ix['rowptr_dst'], ix['eid_by_dst'],
+                    da, db, dw, datt, N, E, H, None)
+    assert rc == OK and intact(da) and intact(db)
+    assert torch.allclose(da, ar.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(db, br.grad, rtol=1e-5, atol=1e-5)
+    if with_w:
+        assert intact(dw) and torch.allclose(dw, wr.grad, rtol=1e-5, atol=2e-5 * H ** 0.5)
+    if with_att:
+        assert intact(datt) and torch.allclose(datt, tr.grad.view(-1), rtol=1e-5, atol=2e-5 * H ** 0.5)
+
+
+def test_leconv_argument_checks_on_emulator():
+    b, ix = _graph(2)
+    N, E = b.num_nodes, b.num_edges
+    x = torch.zeros(N, 6)
+    out = torch.zeros(N, 6)
+    rc = sim().call('gsatb_le_aggregate_fwd', x, x, None, None, ix['rowptr_dst'], ix['eid_by_dst'], ix['src_by_dst'],
+                    None, out, N, E, 6, None)
+    assert rc == -2                       # GSATB_ESHAPE: width not a multiple of 4
+    rc = sim().call('gsatb_le_aggregate_fwd', None, x, None, None, ix['rowptr_dst'], ix['eid_by_dst'],
+                    ix['src_by_dst'], None, out, N, E, 8, None)
+    assert rc == -1                       # GSATB_EINVAL
+    rc = sim().call('gsatb_le_aggregate_fwd', None, None, None, None, None, None, None, None, None, 0, 0, 8, None)
+    assert rc == OK                       # empty batch
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the Python autograd wrappers on top of the emulated library: argument order of the ctypes calls (every pointer is a
+# void* there, nothing else would catch a swapped pair before the GPU run), saved tensors, gradient routing
+# ---------------------------------------------------------------------------------------------------------------
+class _SimBackedLib:
+    """Stands in for dp_gsat_b200._lib._Lib inside these tests only: same .call() contract, emulated kernels."""
+    launches = 0
+    timer = None
+
+    def call(self, name, *args):
+        rc = sim().call(name, *args)
+        if rc != 0:
+            raise (ValueError if rc in (-1, -2, -3, -6) else RuntimeError)(f'{name} failed with code {rc}')
+
+
+class _FakeIndex:
+    """The GraphIndex attributes the wrappers read, filled from the oracle's index specification."""
+
+    def __init__(self, batch_obj):
+        ix = O.build_index_oracle(batch_obj.edge_index, batch_obj.batch)
+        for k, v in ix.items():
+            setattr(self, k, v)
+        self.N, self.E, self.G = batch_obj.num_nodes, batch_obj.num_edges, batch_obj.num_graphs
+
+
+@pytest.fixture
+def sim_ops(monkeypatch):
+    import dp_gsat_b200.ops as ops
+
+    def f32c(t):
+        if t is None:
+            return None
+        assert t.dtype == torch.float32
+        return t.contiguous()
+    fake = _SimBackedLib()
+    monkeypatch.setattr(ops, 'lib', lambda: fake)
+    monkeypatch.setattr(ops, '_f32c', f32c)
+    monkeypatch.setattr(ops, 'stream', lambda: None)
+    return ops
+
+
+@pytest.mark.parametrize('with_w,with_att,with_add', [(True, True, True), (False, True, False), (True, False, True)])
+def test_le_aggregate_autograd_wrapper_on_emulator(sim_ops, with_w, with_att, with_add):
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(7, seed=4)
+    gi = _FakeIndex(b)
+    N, E, H = b.num_nodes, b.num_edges, 32
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    a, bb, add, gout = mk(N, H), mk(N, H), (mk(N, H) if with_add else None), mk(N, H)
+    w = torch.rand(E, 1, generator=g) + 0.5 if with_w else None
+    att = torch.rand(E, 1, generator=g) if with_att else None
+    leaf = lambda t: None if t is None else t.clone().requires_grad_(True)
+    ar, br, dr, wr, tr = leaf(a), leaf(bb), leaf(add), leaf(w), leaf(att)
+    m = ar[b.edge_index[0]] - br[b.edge_index[1]]
+    if with_w:
+        m = m * wr.view(-1, 1)
+    if with_att:
+        m = m * tr
+    ref = O.scatter_sum(m, b.edge_index[1], N)
+    if with_add:
+        ref = ref + dr
+    (ref * gout).sum().backward()
+    a2, b2, d2, w2, t2 = leaf(a), leaf(bb), leaf(add), leaf(w), leaf(att)
+    out = sim_ops.le_aggregate(a2, b2, w2, t2, gi, add=d2)
+    (out * gout).sum().backward()
+    tol = dict(rtol=1e-5, atol=2e-5)
+    assert torch.allclose(out, ref, **tol)
+    assert torch.allclose(a2.grad, ar.grad, **tol) and torch.allclose(b2.grad, br.grad, **tol)
+    if with_add:
+        assert torch.allclose(d2.grad, dr.grad, **tol)
+    if with_w:
+        assert w2.grad.shape == w.shape and torch.allclose(w2.grad, wr.grad, rtol=1e-5, atol=2e-4)
+    if with_att:
+        assert t2.grad.shape == att.shape and torch.allclose(t2.grad, tr.grad, rtol=1e-5, atol=2e-4)
+
+
+def test_leconv_module_on_emulator(sim_ops):
+    """nn.LEConv (reference conv_layers.py:69-92) end to end on the emulated kernels: same parameters as the oracle
+    layer, forward and parameter gradients."""
+    import dp_gsat_b200 as G
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(5, seed=1)
+    gi = _FakeIndex(b)
+    torch.manual_seed(0)
+    ref = O.LEConv(16, 16)
+    dev = G.LEConv(16, 16)
+    dev.load_state_dict(ref.state_dict())
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(b.num_nodes, 16, generator=g)
+    w, att = torch.rand(b.num_edges, 1, generator=g), torch.rand(b.num_edges, 1, generator=g)
+    want = ref(x, b.edge_index, edge_weight=w, edge_atten=att)
+    got = dev(x, b.edge_index, edge_weight=w, edge_atten=att, _index=gi)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    want.square().sum().backward()
+    got.square().sum().backward()
+    for (k, p), (_, q) in zip(dev.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-4), k
