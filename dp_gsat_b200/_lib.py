@@ -92,7 +92,8 @@ class _Lib:
     # kernels launched per C-ABI call (index_build: see csrc/index_build.cu -- 5 fixed + 2 orders x (2 sorts x
     # 3 kernels x passes + 3) + 1; counted with passes=3)
     KERNELS_PER_CALL = {'gsatb_index_build': 5 + 2 * (2 * 3 * 3 + 3) + 1, 'gsatb_sample_avg_info_fwd': 2,
-                        'gsatb_le_aggregate_bwd': 2}       # by source (da, d att, d w) + by destination (db)
+                        'gsatb_le_aggregate_bwd': 2,       # by source (da, d att, d w) + by destination (db)
+                        'gsatb_embedding_sum_bwd': 2}      # per-CTA slabs + fixed-order reduction
 
     def call(self, name: str, *args):
         """Call an int-returning entry point; raise on a non-zero code."""

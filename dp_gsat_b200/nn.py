@@ -359,8 +359,32 @@ ATOM_FEATURE_DIMS = [119, 4, 12, 12, 10, 6, 6, 2, 2]
 BOND_FEATURE_DIMS = [5, 6, 2]
 
 
-class AtomEncoder(tnn.Module):
-    """ogb 1.3.2 AtomEncoder: sum of 9 embedding tables."""
+class _SumEmbeddingEncoder(tnn.Module):
+    """Sum of one embedding table per integer feature column (ogb 1.3.2 AtomEncoder / BondEncoder).
+
+    ``fused = True`` runs the whole encoder as ONE gather-sum kernel forward and one deterministic backward into the
+    tables (csrc/encoders.cu, SURVEY section 8f row 4) instead of K embedding lookups + K-1 adds and K scatter-adds;
+    results are bit-identical forward (same addition order).  It is opt-in this round: the kernels were written after
+    the round's GPU time was spent and have so far only run on the host SIMT emulator and in tests/test_gpu_z_next_rows.py
+    (``fused = False`` keeps the library embedding lookups the earlier GPU parity runs used)."""
+    fused = False
+    _list_name = ''
+
+    def _tables(self):
+        return [emb.weight for emb in getattr(self, self._list_name)]
+
+    def forward(self, x):
+        if self.fused:
+            return ops.embedding_sum(x, self._tables(), getattr(self, 'oob_flag', None))
+        out = 0
+        for i, emb in enumerate(getattr(self, self._list_name)):
+            out = out + emb(x[:, i])
+        return out
+
+
+class AtomEncoder(_SumEmbeddingEncoder):
+    """ogb 1.3.2 AtomEncoder: sum of 9 embedding tables (state_dict keys atom_embedding_list.{k}.weight)."""
+    _list_name = 'atom_embedding_list'
 
     def __init__(self, emb_dim):
         super().__init__()
@@ -370,15 +394,10 @@ class AtomEncoder(tnn.Module):
             tnn.init.xavier_uniform_(emb.weight.data)
             self.atom_embedding_list.append(emb)
 
-    def forward(self, x):
-        out = 0
-        for i, emb in enumerate(self.atom_embedding_list):
-            out = out + emb(x[:, i])
-        return out
 
-
-class BondEncoder(tnn.Module):
-    """ogb 1.3.2 BondEncoder."""
+class BondEncoder(_SumEmbeddingEncoder):
+    """ogb 1.3.2 BondEncoder: sum of 3 embedding tables (state_dict keys bond_embedding_list.{k}.weight)."""
+    _list_name = 'bond_embedding_list'
 
     def __init__(self, emb_dim):
         super().__init__()
@@ -387,12 +406,6 @@ class BondEncoder(tnn.Module):
             emb = tnn.Embedding(d, emb_dim)
             tnn.init.xavier_uniform_(emb.weight.data)
             self.bond_embedding_list.append(emb)
-
-    def forward(self, edge_attr):
-        out = 0
-        for i, emb in enumerate(self.bond_embedding_list):
-            out = out + emb(edge_attr[:, i])
-        return out
 
 
 class ExtractorMLP(tnn.Module):

@@ -13,13 +13,17 @@ from .index import GraphIndex
 MODE_TRAINING, MODE_AVERAGE, MODE_INFO_ON_EDGE_ATT, MODE_NO_INFO = 1, 2, 4, 8
 
 
+def _require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError('CUDA tensor expected (dp_gsat_b200 has no CPU path)')
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
     if t.dtype != torch.float32:
         raise ValueError(f'fp32 tensor expected, got {t.dtype}')
-    if not t.is_cuda:
-        raise RuntimeError('CUDA tensor expected (dp_gsat_b200 has no CPU path)')
+    _require_cuda(t)
     return t.contiguous()
 
 
@@ -431,3 +435,48 @@ class _SmallLinear(torch.autograd.Function):
 
 def small_linear(x, weight, bias):
     return _SmallLinear.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fused categorical encoders  (ogb AtomEncoder / BondEncoder, reference src/models/gin.py:22-25, pna.py:20-23)
+# ------------------------------------------------------------------------------------------------------------
+class _EmbeddingSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, table_cat, offsets_host: torch.Tensor, oob_flag):
+        if idx.dtype != torch.int64 or idx.dim() != 2:
+            raise ValueError(f'int64 [M, K] feature indices expected, got {idx.dtype} {tuple(idx.shape)}')
+        _require_cuda(idx)
+        idx, table_cat = idx.contiguous(), _f32c(table_cat)
+        (M, K), (R, H) = idx.shape, table_cat.shape
+        if offsets_host.numel() != K + 1 or int(offsets_host[K]) != R:
+            raise ValueError('feature offsets do not match the index width / the concatenated tables')
+        out = torch.empty((M, H), dtype=torch.float32, device=idx.device)
+        lib().call('gsatb_embedding_sum_fwd', ptr(idx), ptr(table_cat), ctypes.c_void_p(offsets_host.data_ptr()), ptr(out),
+                   ptr(oob_flag), M, K, H, stream())
+        ctx.save_for_backward(idx)
+        ctx.offsets_host, ctx.R = offsets_host, R
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        gout = _f32c(gout)
+        (M, K), H, R = idx.shape, gout.shape[1], ctx.R
+        L = lib()
+        ws_bytes = int(L.cdll.gsatb_embedding_sum_bwd_workspace(M, R, H))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=gout.device)
+        dtable = torch.empty((R, H), dtype=torch.float32, device=gout.device)
+        L.call('gsatb_embedding_sum_bwd', ptr(gout), ptr(idx), ctypes.c_void_p(ctx.offsets_host.data_ptr()), ptr(dtable),
+               M, K, H, ptr(ws), ctypes.c_size_t(ws_bytes), stream())
+        return None, dtable, None, None
+
+
+def embedding_sum(idx, tables, oob_flag=None):
+    """out[m] = sum_k tables[k][idx[m, k]] in ONE kernel (and one deterministic backward into the tables), additions in
+    feature order.  ``tables``: the K embedding weights [dim_k, H]; their gradients arrive through the row-wise
+    concatenation.  ``oob_flag``: optional int32 [1] device word, set to 1 when an index was outside its table
+    (the index is clamped: memory safe, the caller decides when to look at the flag)."""
+    sizes = [int(t.shape[0]) for t in tables]
+    offs = torch.zeros(len(sizes) + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(torch.tensor(sizes, dtype=torch.int64), 0).to(torch.int32)
+    return _EmbeddingSum.apply(idx, torch.cat(list(tables), dim=0), offs, oob_flag)

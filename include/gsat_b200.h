@@ -364,6 +364,42 @@ int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed,
 int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* dst, void* f12, int64_t rows, int H,
                           gsatb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * the step BEFORE the path -- feature encoders and batch collate on the device.
+ *
+ * Fused categorical encoders.  Replace ogb AtomEncoder / BondEncoder as called by src/models/gin.py:22-25,45-47 and
+ * pna.py:20-23,53-55 (K embedding gathers + K-1 adds; K scatter-adds backward):
+ *   out[m,:] = sum_{k<K} table_cat[feat_row_offset[k] + idx[m,k], :]      idx int64 [M,K], table_cat [R,H], out [M,H]
+ * table_cat = the K embedding tables concatenated row-wise; feat_row_offset_host = K+1 HOST ints (first row of each
+ * table, last = R), K <= 16.  Sums run in feature order (bit-identical to the reference's out = 0 + e_0 + e_1 ...).
+ * An index outside its table is clamped and reported by OR-ing 1 into *oob_flag [nullable].
+ * bwd: dtable_cat[r,:] = sum of gout rows whose index hits r -- deterministic (per-CTA shared-memory slabs, one thread
+ * per channel, then a fixed-order reduction); ws >= gsatb_embedding_sum_bwd_workspace(M, R, H) bytes.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_embedding_sum_fwd(const int64_t* idx, const float* table_cat, const int32_t* feat_row_offset_host, float* out,
+                            int32_t* oob_flag, int64_t M, int K, int H, gsatb_stream_t stream);
+size_t gsatb_embedding_sum_bwd_workspace(int64_t M, int R, int H);
+int gsatb_embedding_sum_bwd(const float* gout, const int64_t* idx, const int32_t* feat_row_offset_host,
+                            float* dtable_cat, int64_t M, int K, int H, void* ws, size_t ws_bytes,
+                            gsatb_stream_t stream);
+
+/* Device-side batch collate.  Replaces the host-side torch_geometric DataLoader collate the reference runs for every
+ * batch (src/utils/get_data_loaders.py:130-145; Batch.from_data_list semantics) for a dataset held
+ * in HBM in packed form: graph g owns rows [ds_ptr[g], ds_ptr[g+1]) of each per-node / per-edge tensor and
+ * ds_edge_index [2, E_ds] holds graph-local node ids.  ids [B] = the graphs of the batch in order; out_ptr [B+1] =
+ * exclusive prefix sum of their row counts (out_ptr[B] == rows_out).  All pointers are device pointers.
+ *   collate_rows:       out[out_ptr[b] + r, :] = src[ds_ptr[ids[b]] + r, :], rows of row_bytes (multiple of 4) bytes;
+ *                       out_batch[out row] = b [nullable]; ds_ptr == NULL: one row per graph (per-graph labels);
+ *                       row_bytes == 0: only out_batch is written.
+ *   collate_edge_index: out[:, out_edge_ptr[b] + e] = ds_edge_index[:, ds_edge_ptr[ids[b]] + e] + out_node_ptr[b].
+ * ---------------------------------------------------------------------------------------------------------- */
+int gsatb_collate_rows(const void* src, int64_t row_bytes, const int64_t* ds_ptr, const int64_t* ids,
+                       const int64_t* out_ptr, int64_t B, int64_t rows_out, void* out, int64_t* out_batch,
+                       gsatb_stream_t stream);
+int gsatb_collate_edge_index(const int64_t* ds_edge_index, int64_t E_ds, const int64_t* ds_edge_ptr, const int64_t* ids,
+                             const int64_t* out_edge_ptr, const int64_t* out_node_ptr, int64_t B, int64_t E_out,
+                             int64_t* out_edge_index, gsatb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

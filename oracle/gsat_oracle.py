@@ -811,3 +811,31 @@ def get_delta_kl(exp_labels, att, eps=1e-6):
     r = r_uv.mean().clamp(min=eps, max=1 - eps)
     delta_kl = p * torch.log(r_uv / r) + (1 - p) * torch.log((1 - r_uv) / (1 - r))
     return delta_kl.sum().item()
+
+
+# --------------------------------------------------------------------------
+# batch collate of the reference's loaders
+# --------------------------------------------------------------------------
+
+
+def collate_data_list(graphs):
+    """torch_geometric 2.0.3 ``Batch.from_data_list`` as the reference's DataLoaders apply it
+    (src/utils/get_data_loaders.py:130-145): every per-node / per-edge / per-graph tensor concatenated along dim 0,
+    ``edge_index`` concatenated along dim 1 after adding the cumulative node count of the preceding graphs, ``batch`` =
+    index of the owning graph for every node.  ``graphs``: objects with x, edge_index (graph-local ids), y and optional
+    edge_attr / edge_label / node_label.  Returns a dict of tensors."""
+    xs, eis, batch, ys, eas, els, nls = [], [], [], [], [], [], []
+    offset = 0
+    for i, g in enumerate(graphs):
+        n = g.x.shape[0]
+        xs.append(g.x)
+        eis.append(g.edge_index + offset)                       # __inc__('edge_index') = num_nodes
+        batch.append(torch.full((n,), i, dtype=torch.long))
+        ys.append(g.y)
+        eas.append(getattr(g, 'edge_attr', None))
+        els.append(getattr(g, 'edge_label', None))
+        nls.append(getattr(g, 'node_label', None))
+        offset += n
+    opt = lambda parts: None if any(p is None for p in parts) else torch.cat(parts, dim=0)
+    return {'x': torch.cat(xs, 0), 'edge_index': torch.cat(eis, 1), 'batch': torch.cat(batch, 0), 'y': torch.cat(ys, 0),
+            'edge_attr': opt(eas), 'edge_label': opt(els), 'node_label': opt(nls), 'num_graphs': len(graphs)}

@@ -161,3 +161,162 @@ def test_gsat_spmotifnet_step_parity(G, learn_edge_att):
     assert_close(gg.clf.get_comb_pred(gx, gx), go.clf.get_comb_pred(gx.cpu(), gx.cpu()), rtol=2e-4, atol_scale=2e-5,
                  what='get_comb_pred')
     assert gg.clf.get_conf_pred(gx).shape == (b.num_graphs, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused atom / bond encoders (reference gin.py:22-25, pna.py:20-23 over ogb 1.3.2)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,H,dims', [(1, 4, [3]), (5000, 80, [119, 4, 12, 12, 10, 6, 6, 2, 2]), (14001, 64, [5, 6, 2]),
+                                      (3000, 300, [119, 4, 12, 12, 10, 6, 6, 2, 2]), (2000, 132, [400, 7]),
+                                      (300000, 128, [119, 4, 12, 12, 10, 6, 6, 2, 2])])
+def test_embedding_sum_fwd_bwd(G, M, H, dims):
+    """One gather-sum kernel against the reference's loop (x_embedding = 0; x_embedding += emb_k(x[:, k])): forward
+    bit-exact, table gradients within fp32 reordering; tables beyond one shared-memory window, widths that are not a
+    multiple of the 64-channel slab, and a row count that uses every row chunk (300 000)."""
+    g = torch.Generator().manual_seed(M + H)
+    idx = torch.stack([torch.randint(0, d, (M,), generator=g) for d in dims], dim=1).contiguous()
+    tables = [torch.randn(d, H, generator=g) for d in dims]
+    ref = 0
+    for k in range(len(dims)):
+        ref = ref + tables[k][idx[:, k]]
+    gout = torch.randn(M, H, generator=g)
+    # gradient ground truth in fp64: a table row can collect 10^5 rows, where fp32 index_add itself is 1e-5 off
+    t64 = [t.double().requires_grad_(True) for t in tables]
+    sum((t64[k][idx[:, k]] * gout.double()).sum() for k in range(len(dims))).backward()
+    dev_tables = [t.detach().cuda().requires_grad_(True) for t in tables]
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    out = G.ops.embedding_sum(idx.cuda(), dev_tables, flag)
+    (out * gout.cuda()).sum().backward()
+    assert torch.equal(out.cpu(), ref)
+    assert int(flag.item()) == 0
+    for k, (td, tr) in enumerate(zip(dev_tables, t64)):
+        assert_close(td.grad, tr.grad, rtol=1e-5, atol_scale=2e-6, what=f'd table {k}')
+    out2 = G.ops.embedding_sum(idx.cuda(), dev_tables, flag)
+    assert torch.equal(out, out2)
+    g1 = [t.grad.clone() for t in dev_tables]
+    for t in dev_tables:
+        t.grad = None
+    (out2 * gout.cuda()).sum().backward()
+    assert all(torch.equal(a, t.grad) for a, t in zip(g1, dev_tables))           # deterministic backward
+
+
+def test_embedding_sum_out_of_range_is_clamped_and_flagged(G):
+    dims, H = [3, 5], 8
+    idx = torch.tensor([[0, 4], [3, 1], [-1, 7]], dtype=torch.int64, device='cuda')
+    tables = [torch.arange(3 * H, dtype=torch.float32, device='cuda').view(3, H),
+              100 + torch.arange(5 * H, dtype=torch.float32, device='cuda').view(5, H)]
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    out = G.ops.embedding_sum(idx, tables, flag)
+    assert int(flag.item()) == 1
+    assert torch.equal(out[1], tables[0][2] + tables[1][1]) and torch.equal(out[2], tables[0][0] + tables[1][4])
+    with pytest.raises(ValueError):
+        G.ops.embedding_sum(idx.int(), tables, flag)
+    with pytest.raises(RuntimeError):
+        G.ops.embedding_sum(idx.cpu(), [t.cpu() for t in tables], None)
+
+
+@pytest.mark.parametrize('model_name', ['PNA', 'GIN'])
+def test_fused_encoders_inside_the_step(G, model_name):
+    """GSAT step on a molhiv-shaped batch with atom / bond encoders: fused encoder kernels (one launch each way) against
+    the library-lookup path of the same modules (which tests/test_gpu_parity.py pins to the oracle)."""
+    from dp_gsat_b200.data import molhiv_like_batch, in_degree_histogram
+    b = molhiv_like_batch(64, seed=13, with_edge_attr=True)
+    cfg = {'model_name': model_name, 'hidden_size': 80 if model_name == 'PNA' else 64, 'n_layers': 2, 'dropout_p': 0.0,
+           'use_edge_attr': True, 'atom_encoder': True, 'aggregators': ['mean', 'min', 'max', 'std'], 'scalers': False,
+           'deg': in_degree_histogram(b)}
+    shared = {'learn_edge_att': True, 'extractor_dropout_p': 0.0}
+    H = cfg['hidden_size']
+    torch.manual_seed(0)
+    clf = G.get_model(9, 3, 2, False, cfg, 'cuda')
+    ext = G.ExtractorMLP(H, shared).cuda()
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.7)
+    gsat.train()
+    d = b.to('cuda')
+    u = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10).cuda()
+    res = {}
+    for fused in (False, True):
+        clf.node_encoder.fused = clf.edge_encoder.fused = fused
+        gsat.zero_grad(set_to_none=True)
+        edge_att, loss, _, logits = gsat.forward_pass(d, 3, True, noise_u=u)
+        loss.backward()
+        res[fused] = (edge_att.detach().clone(), loss.detach().clone(), logits.detach().clone(),
+                      {k: p.grad.clone() for k, p in clf.named_parameters() if p.grad is not None})
+    for i, what in ((0, 'edge_att'), (1, 'loss'), (2, 'logits')):        # the encoders' forward bits are identical
+        assert_close(res[True][i], res[False][i], rtol=1e-6, atol_scale=1e-7, what=what)
+    assert res[True][3].keys() == res[False][3].keys()
+    assert any(k.startswith('node_encoder.atom_embedding_list') for k in res[True][3])
+    assert any(k.startswith('edge_encoder.bond_embedding_list') for k in res[True][3])
+    for k in res[True][3]:
+        assert_close(res[True][3][k], res[False][3][k], rtol=1e-4, atol_scale=1e-5, what=f'grad {k}')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-side batch collate (SURVEY section 8f row 4; reference get_data_loaders.py:130-145 over PyG collate)
+# ---------------------------------------------------------------------------------------------------------------
+def _graphs(n_graphs=40, seed=0):
+    from dp_gsat_b200.data import molhiv_like_batch
+    from dp_gsat_b200.loader import split_batch
+    b = molhiv_like_batch(n_graphs, seed=seed, with_edge_attr=True)
+    b.edge_label = (torch.arange(b.num_edges) % 3 == 0).float()
+    b.node_label = torch.arange(b.num_nodes, dtype=torch.float32)
+    return b, split_batch(b)
+
+
+@pytest.mark.parametrize('ids', [[0], [3, 1, 4, 1, 5, 9, 2, 6], list(range(40)), list(range(39, -1, -1))])
+def test_device_collate_bit_exact(G, ids):
+    _, graphs = _graphs()
+    ds = G.PackedDataset.from_data_list(graphs, device='cuda')
+    got = ds.collate(ids)
+    want = O.collate_data_list([graphs[i] for i in ids])
+    assert got.num_graphs == len(ids)
+    for k in ('x', 'edge_index', 'batch', 'y', 'edge_attr', 'edge_label', 'node_label'):
+        t = getattr(got, k)
+        assert t.is_cuda and t.dtype == want[k].dtype and torch.equal(t.cpu(), want[k]), k
+
+
+def test_device_collate_edge_cases_and_loader(G):
+    g = torch.Generator().manual_seed(0)
+    graphs = []
+    for n, e in ((3, 4), (1, 0), (5, 7), (2, 0), (4, 12), (700, 3000)):
+        graphs.append(G.Graph(torch.rand(n, 5, generator=g), torch.randint(0, n, (2, e), generator=g),
+                              torch.randint(0, 3, (1,), generator=g)))
+    ds = G.PackedDataset.from_data_list(graphs, device='cuda')
+    for ids in ([1], [1, 3], [0, 1, 2, 3, 4, 5], [5, 3, 4, 1, 5]):
+        got, want = ds.collate(ids), O.collate_data_list([graphs[i] for i in ids])
+        for k in ('x', 'edge_index', 'batch', 'y'):
+            assert torch.equal(getattr(got, k).cpu(), want[k]), (ids, k)
+        assert got.edge_attr is None and got.edge_label is None
+    batches = list(G.DeviceLoader(ds, ids=[4, 3, 2, 1, 0], batch_size=2))
+    assert [bb.num_graphs for bb in batches] == [2, 2, 1]
+    assert torch.equal(batches[2].x.cpu(), graphs[0].x)
+    with pytest.raises(IndexError):
+        ds.collate([6])
+
+
+def test_step_on_a_device_collated_batch_equals_the_host_batch(G):
+    """The loader feeds the path: a GSAT-GIN step on a batch gathered on the device gives the same bits as the step on
+    the host-built batch copied over (the reference's route)."""
+    from dp_gsat_b200.data import ba2motifs_batch
+    from dp_gsat_b200.loader import split_batch
+    full = ba2motifs_batch(96, seed=4)
+    graphs = split_batch(full)
+    ds = G.PackedDataset.from_data_list(graphs, device='cuda')
+    ids = list(range(16, 80))
+    host = O.collate_data_list([graphs[i] for i in ids])
+    hb = G.Batch(host['x'], host['edge_index'], host['batch'], host['y'], None, host['edge_label'], len(ids)).to('cuda')
+    db = ds.collate(ids)
+    cfg = {'model_name': 'GIN', 'hidden_size': 64, 'n_layers': 2, 'dropout_p': 0.0, 'use_edge_attr': False}
+    torch.manual_seed(0)
+    clf = G.get_model(full.x.shape[1], 0, 2, False, cfg, 'cuda')
+    ext = G.ExtractorMLP(64, {'learn_edge_att': True, 'extractor_dropout_p': 0.0}).cuda()
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.7)
+    gsat.train()
+    u = torch.rand(db.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10).cuda()
+    out = []
+    for batch in (hb, db):
+        edge_att, loss, _, logits = gsat.forward_pass(batch, 0, True, noise_u=u)
+        out.append((edge_att.detach().clone(), loss.detach().clone(), logits.detach().clone()))
+    for k in ('x', 'edge_index', 'batch', 'y', 'edge_label'):
+        assert torch.equal(getattr(hb, k), getattr(db, k)), k
+    for a, c, what in zip(out[0], out[1], ('edge_att', 'loss', 'logits')):
+        assert_close(a, c, rtol=1e-6, atol_scale=1e-7, what=what)

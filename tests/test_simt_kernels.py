@@ -123,6 +123,13 @@ class _SimBackedLib:
     launches = 0
     timer = None
 
+    @property
+    def cdll(self):
+        c = sim().cdll
+        c.gsatb_embedding_sum_bwd_workspace.restype = sim().protos['gsatb_embedding_sum_bwd_workspace'][0]
+        c.gsatb_embedding_sum_bwd_workspace.argtypes = sim().protos['gsatb_embedding_sum_bwd_workspace'][1]
+        return c
+
     def call(self, name, *args):
         rc = sim().call(name, *args)
         if rc != 0:
@@ -143,15 +150,12 @@ class _FakeIndex:
 def sim_ops(monkeypatch):
     import dp_gsat_b200.ops as ops
 
-    def f32c(t):
-        if t is None:
-            return None
-        assert t.dtype == torch.float32
-        return t.contiguous()
+    import dp_gsat_b200.loader as loader
     fake = _SimBackedLib()
-    monkeypatch.setattr(ops, 'lib', lambda: fake)
-    monkeypatch.setattr(ops, '_f32c', f32c)
-    monkeypatch.setattr(ops, 'stream', lambda: None)
+    for mod in (ops, loader):
+        monkeypatch.setattr(mod, 'lib', lambda: fake)
+        monkeypatch.setattr(mod, 'stream', lambda: None)
+    monkeypatch.setattr(ops, '_require_cuda', lambda t: None)       # host tensors: the emulated kernels take host pointers
     return ops
 
 
@@ -212,3 +216,128 @@ def test_leconv_module_on_emulator(sim_ops):
     got.square().sum().backward()
     for (k, p), (_, q) in zip(dev.named_parameters(), ref.named_parameters()):
         assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-4), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused atom / bond encoders, device-side collate
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,H,dims', [(1, 4, [3]), (37, 16, [5, 6, 2]), (700, 80, [119, 4, 12, 12, 10, 6, 6, 2, 2]),
+                                      (300, 132, [200, 7]), (0, 8, [4, 4])])
+def test_embedding_sum_on_emulator(M, H, dims):
+    """out[m] = sum_k table_k[idx[m, k]]: forward BIT-exact against the reference's loop (ogb AtomEncoder.forward:
+    x_embedding = 0; x_embedding += emb_k(x[:, k])), backward against autograd of the same loop; tables larger than one
+    shared-memory window (200 rows) and widths that are not a multiple of the 64-channel slab included."""
+    g = torch.Generator().manual_seed(M + H)
+    K = len(dims)
+    idx = torch.stack([torch.randint(0, d, (M,), generator=g) for d in dims], dim=1).contiguous()
+    tables = [torch.randn(d, H, generator=g).requires_grad_(True) for d in dims]
+    ref = 0
+    for k in range(K):
+        ref = ref + tables[k][idx[:, k]]
+    gout = torch.randn(M, H, generator=g)
+    if M:
+        (ref * gout).sum().backward()
+    offs = torch.zeros(K + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(torch.tensor(dims), 0).to(torch.int32)
+    cat = torch.cat([t.detach() for t in tables], 0).contiguous()
+    out, flag = guarded((M, H)), torch.zeros(1, dtype=torch.int32)
+    rc = sim().call('gsatb_embedding_sum_fwd', idx, cat, offs, out, flag, M, K, H, None)
+    assert rc == OK and intact(out) and int(flag) == 0
+    if M:
+        assert torch.equal(out, ref.detach())
+    R = int(offs[-1])
+    c = _SimBackedLib().cdll
+    ws_bytes = int(c.gsatb_embedding_sum_bwd_workspace(M, R, H))
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8)
+    dt = guarded((R, H))
+    import ctypes
+    rc = sim().call('gsatb_embedding_sum_bwd', gout, idx, offs, dt, M, K, H, ws, ctypes.c_size_t(ws_bytes), None)
+    assert rc == OK and intact(dt)
+    want = torch.cat([t.grad if t.grad is not None else torch.zeros_like(t) for t in tables], 0)
+    assert torch.allclose(dt, want, rtol=1e-5, atol=1e-5)
+    rc = sim().call('gsatb_embedding_sum_bwd', gout, idx, offs, dt, M, K, H, ws, ctypes.c_size_t(16), None)
+    assert rc == -4                                       # GSATB_EWS_TOO_SMALL
+
+
+def test_embedding_sum_clamps_and_flags_out_of_range_indices():
+    dims, H = [3, 5], 8
+    idx = torch.tensor([[0, 4], [3, 1], [-1, 7]], dtype=torch.int64)          # 3 >= dims[0], -1, 7 >= dims[1]
+    cat = torch.arange(8 * H, dtype=torch.float32).view(8, H).contiguous()
+    offs = torch.tensor([0, 3, 8], dtype=torch.int32)
+    out, flag = guarded((3, H)), torch.zeros(1, dtype=torch.int32)
+    assert sim().call('gsatb_embedding_sum_fwd', idx, cat, offs, out, flag, 3, 2, H, None) == OK
+    assert int(flag) == 1 and intact(out)
+    assert torch.equal(out[0], cat[0] + cat[3 + 4])
+    assert torch.equal(out[1], cat[2] + cat[3 + 1])                         # clamped to the last row of table 0
+    assert torch.equal(out[2], cat[0] + cat[3 + 4])                         # clamped to row 0 / the last row of table 1
+    bad = torch.tensor([0, 3, 3], dtype=torch.int32)                          # an empty table
+    assert sim().call('gsatb_embedding_sum_fwd', idx, cat, bad, out, flag, 3, 2, H, None) == -1
+
+
+def test_fused_encoders_autograd_wrapper_on_emulator(sim_ops):
+    """nn.AtomEncoder / BondEncoder with fused = True against their own library-lookup path (the reference's loop):
+    forward bit-exact, the gradient of every table within fp32 reordering."""
+    import dp_gsat_b200 as G
+    from dp_gsat_b200.data import molhiv_like_batch
+    b = molhiv_like_batch(6, seed=3, with_edge_attr=True)
+    for enc, idx in ((G.AtomEncoder(20), b.x), (G.BondEncoder(12), b.edge_attr)):
+        w = torch.randn(idx.shape[0], enc._tables()[0].shape[1], generator=torch.Generator().manual_seed(1))
+        enc.fused = False
+        ref = enc(idx)
+        (ref * w).sum().backward()
+        want = [t.grad.clone() for t in enc._tables()]
+        enc.zero_grad()
+        enc.fused = True
+        out = enc(idx)
+        assert torch.equal(out, ref)
+        (out * w).sum().backward()
+        for t, g0 in zip(enc._tables(), want):
+            assert torch.allclose(t.grad, g0, rtol=1e-5, atol=1e-5)
+
+
+def _sample_graphs(seed=0):
+    from dp_gsat_b200.data import molhiv_like_batch
+    from dp_gsat_b200.loader import split_batch
+    b = molhiv_like_batch(9, seed=seed, with_edge_attr=True)
+    b.edge_label = (torch.arange(b.num_edges) % 3 == 0).float()
+    b.node_label = torch.arange(b.num_nodes, dtype=torch.float32)
+    return split_batch(b)
+
+
+@pytest.mark.parametrize('ids', [[0], [3, 1, 4, 1, 5], list(range(9)), [8, 7, 6, 5, 4, 3, 2, 1, 0]])
+def test_device_collate_on_emulator(sim_ops, ids):
+    """PackedDataset.collate(ids) (csrc/collate.cu) is bit-identical to the restated PyG Batch.from_data_list of the
+    same graphs: x, edge_index with cumulative node offsets, batch vector, y, edge_attr, edge / node labels; repeated
+    ids, reversed order and single-graph batches included."""
+    from dp_gsat_b200.loader import PackedDataset
+    graphs = _sample_graphs()
+    ds = PackedDataset.from_data_list(graphs, device='cpu')
+    got = ds.collate(ids)
+    want = O.collate_data_list([graphs[i] for i in ids])
+    assert got.num_graphs == len(ids)
+    for k in ('x', 'edge_index', 'batch', 'y', 'edge_attr', 'edge_label', 'node_label'):
+        assert torch.equal(getattr(got, k), want[k]), k
+        assert getattr(got, k).dtype == want[k].dtype
+
+
+def test_device_collate_edge_cases_on_emulator(sim_ops):
+    """Graphs without edges, a dataset without optional tensors, float features, the loader's batching."""
+    from dp_gsat_b200.loader import PackedDataset, DeviceLoader, Graph
+    g = torch.Generator().manual_seed(0)
+    graphs = []
+    for n, e in ((3, 4), (1, 0), (5, 7), (2, 0), (4, 12)):
+        ei = torch.randint(0, n, (2, e), generator=g)
+        graphs.append(Graph(torch.rand(n, 5, generator=g), ei, torch.randint(0, 3, (1,), generator=g)))
+    ds = PackedDataset.from_data_list(graphs, device='cpu')
+    for ids in ([1], [1, 3], [0, 1, 2, 3, 4], [3, 4, 1]):
+        got, want = ds.collate(ids), O.collate_data_list([graphs[i] for i in ids])
+        for k in ('x', 'edge_index', 'batch', 'y'):
+            assert torch.equal(getattr(got, k), want[k]), (ids, k)
+        assert got.edge_attr is None and got.edge_label is None
+    batches = list(DeviceLoader(ds, ids=[4, 3, 2, 1, 0], batch_size=2))
+    assert [b.num_graphs for b in batches] == [2, 2, 1]
+    assert torch.equal(batches[2].x, graphs[0].x)
+    with pytest.raises(IndexError):
+        ds.collate([5])
+    with pytest.raises(ValueError):
+        PackedDataset.from_data_list([Graph(torch.rand(2, 3), torch.tensor([[0], [2]]), torch.zeros(1))], device='cpu')
