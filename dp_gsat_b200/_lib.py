@@ -125,6 +125,17 @@ def lib() -> _Lib:
     return _LIB
 
 
+def require_cuda(t) -> None:
+    """Every op of this package takes CUDA tensors: there is no CPU path to fall back to."""
+    if not t.is_cuda:
+        raise RuntimeError('CUDA tensor expected (dp_gsat_b200 has no CPU path)')
+
+
+def device_guard(device):
+    """Context manager that makes ``device`` current for raw C-ABI calls issued inside it."""
+    return torch.cuda.device(device)
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     if t is None:

@@ -12,7 +12,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import lib, ptr, stream
+from ._lib import lib, ptr, stream, require_cuda, device_guard
 
 
 class GraphIndex:
@@ -21,8 +21,7 @@ class GraphIndex:
                  '_flags_host', 'device', '_plans')
 
     def __init__(self, edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: Optional[int] = None):
-        if not edge_index.is_cuda:
-            raise RuntimeError('GraphIndex needs CUDA tensors (no CPU path)')
+        require_cuda(edge_index)
         if edge_index.dtype != torch.int64 or batch.dtype != torch.int64:
             raise ValueError('edge_index and batch must be int64, as in the reference')
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -47,7 +46,7 @@ class GraphIndex:
         L = lib()
         ws_bytes = int(L.cdll.gsatb_index_build_workspace(N, E, G))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             L.call('gsatb_index_build', ptr(edge_index), ptr(batch), N, E, G, ptr(self.src), ptr(self.dst),
                    ptr(self.rev), ptr(self.rowptr_dst), ptr(self.eid_by_dst), ptr(self.src_by_dst),
                    ptr(self.rowptr_src), ptr(self.eid_by_src), ptr(self.dst_by_src), ptr(self.node_ptr),

@@ -7,15 +7,10 @@ from typing import Optional
 
 import torch
 
-from ._lib import lib, ptr, stream
+from ._lib import lib, ptr, stream, require_cuda
 from .index import GraphIndex
 
 MODE_TRAINING, MODE_AVERAGE, MODE_INFO_ON_EDGE_ATT, MODE_NO_INFO = 1, 2, 4, 8
-
-
-def _require_cuda(t: torch.Tensor) -> None:
-    if not t.is_cuda:
-        raise RuntimeError('CUDA tensor expected (dp_gsat_b200 has no CPU path)')
 
 
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -23,7 +18,7 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
         return None
     if t.dtype != torch.float32:
         raise ValueError(f'fp32 tensor expected, got {t.dtype}')
-    _require_cuda(t)
+    require_cuda(t)
     return t.contiguous()
 
 
@@ -445,7 +440,7 @@ class _EmbeddingSum(torch.autograd.Function):
     def forward(ctx, idx, table_cat, offsets_host: torch.Tensor, oob_flag):
         if idx.dtype != torch.int64 or idx.dim() != 2:
             raise ValueError(f'int64 [M, K] feature indices expected, got {idx.dtype} {tuple(idx.shape)}')
-        _require_cuda(idx)
+        require_cuda(idx)
         idx, table_cat = idx.contiguous(), _f32c(table_cat)
         (M, K), (R, H) = idx.shape, table_cat.shape
         if offsets_host.numel() != K + 1 or int(offsets_host[K]) != R:

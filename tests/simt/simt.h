@@ -9,6 +9,7 @@
 // MASK and REDUCTION LOGIC of a kernel without a GPU; it says nothing about races between warps (the schedule is
 // deterministic) or about performance.  The product library never includes this file.
 #pragma once
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <algorithm>
@@ -52,12 +53,27 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrComputeCapabilityMajor = 75 };
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 10; return cudaSuccess; }   // "sm_100"
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {      // launches run to completion,
+    std::memset(p, v, n);                                                                // so stream order is call order
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+    std::memmove(d, s, n);
+    return cudaSuccess;
+}
 
 namespace simt {
 
 struct Fiber {
-    ucontext_t ctx;
+    ucontext_t ctx;      // first entry only (makecontext); afterwards fibers switch with _setjmp / _longjmp, which --
+    jmp_buf jb;          // unlike swapcontext -- do not make a sigprocmask system call per switch
+    bool started;
     bool done;
 };
 struct WarpBarrier {
@@ -72,6 +88,7 @@ struct Warp {
 
 struct State {
     ucontext_t sched;
+    jmp_buf sched_jb;
     std::vector<Fiber> fibers;
     std::vector<Warp> warps;
     std::vector<char> stacks;
@@ -95,7 +112,7 @@ constexpr size_t kStackBytes = 256 * 1024;
 }
 inline void yield() {
     State& s = S();
-    swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+    if (_setjmp(s.fibers[s.cur].jb) == 0) _longjmp(s.sched_jb, 1);
 }
 inline void trampoline() {
     State& s = S();
@@ -103,7 +120,20 @@ inline void trampoline() {
     s.fibers[s.cur].done = true;
     --s.live;
     ++s.progress;
-    swapcontext(&s.fibers[s.cur].ctx, &s.sched);
+    _longjmp(s.sched_jb, 1);
+}
+// scheduler side: run fiber t until it yields or finishes
+inline void resume(int t) {
+    State& s = S();
+    Fiber& f = s.fibers[t];
+    if (_setjmp(s.sched_jb) == 0) {
+        if (!f.started) {
+            f.started = true;
+            setcontext(&f.ctx);
+        } else {
+            _longjmp(f.jb, 1);
+        }
+    }
 }
 inline int lane_id() { return S().cur & 31; }
 inline Warp& warp() { return S().warps[S().cur >> 5]; }
@@ -182,10 +212,11 @@ inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& bod
                     s.warps[t >> 5].exists |= 1u << (t & 31);
                     Fiber& f = s.fibers[t];
                     f.done = false;
+                    f.started = false;
                     getcontext(&f.ctx);
                     f.ctx.uc_stack.ss_sp = s.stacks.data() + (size_t)t * kStackBytes;
                     f.ctx.uc_stack.ss_size = kStackBytes;
-                    f.ctx.uc_link = &s.sched;
+                    f.ctx.uc_link = nullptr;            // the trampoline never returns
                     makecontext(&f.ctx, (void (*)())simt::trampoline, 0);
                 }
                 s.live = nthreads;
@@ -197,7 +228,7 @@ inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& bod
                         s.cur = t;
                         threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
                                           (unsigned)t / (block.x * block.y)};
-                        swapcontext(&s.sched, &s.fibers[t].ctx);
+                        resume(t);
                         if (s.block_arrived > 0 && s.block_arrived == s.live) {       // __syncthreads released
                             s.block_arrived = 0;
                             ++s.block_gen;
@@ -252,6 +283,18 @@ inline unsigned __ballot_sync(unsigned mask, int pred) {
     unsigned r = 0;
     for (int l = 0; l < 32; ++l)
         if (((mask & w.exists) >> l) & 1u) r |= (unsigned)(w.slot[l] & 1u) << l;
+    simt::warp_barrier(mask);
+    return r;
+}
+template <class T>
+inline unsigned __match_any_sync(unsigned mask, T v) {
+    simt::Warp& w = simt::warp();
+    const int lane = simt::lane_id();
+    w.slot[lane] = simt::to_bits(v);
+    simt::warp_barrier(mask);
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if ((((mask & w.exists) >> l) & 1u) && w.slot[l] == w.slot[lane]) r |= 1u << l;
     simt::warp_barrier(mask);
     return r;
 }

@@ -40,6 +40,13 @@ def test_no_cpu_fallback_in_product():
             dp_gsat_b200.get_graph_index(torch.zeros((2, 3), dtype=torch.int64), torch.zeros(2, dtype=torch.int64))
         with pytest.raises(RuntimeError):
             dp_gsat_b200.ops.gin_aggregate(torch.zeros(2, 4), None, None, 0.0)
+        with pytest.raises(RuntimeError):
+            dp_gsat_b200.ops.embedding_sum(torch.zeros((2, 1), dtype=torch.int64), [torch.zeros(3, 4)])
+        with pytest.raises(RuntimeError):
+            dp_gsat_b200.ops.le_aggregate(torch.zeros(2, 4), torch.zeros(2, 4), None, None, None)
+    for fn in os.listdir(pkg):          # the host SIMT emulator is test infrastructure: the product never references it
+        if fn.endswith('.py') or fn.endswith('.cu'):
+            assert 'tests.simt' not in open(os.path.join(pkg, fn)).read(), fn
 
 
 def test_generators_shapes():
