@@ -118,24 +118,6 @@ def test_leconv_argument_checks_on_emulator():
 # the Python autograd wrappers on top of the emulated library: argument order of the ctypes calls (every pointer is a
 # void* there, nothing else would catch a swapped pair before the GPU run), saved tensors, gradient routing
 # ---------------------------------------------------------------------------------------------------------------
-class _SimBackedLib:
-    """Stands in for dp_gsat_b200._lib._Lib inside these tests only: same .call() contract, emulated kernels."""
-    launches = 0
-    timer = None
-
-    @property
-    def cdll(self):
-        c = sim().cdll
-        c.gsatb_embedding_sum_bwd_workspace.restype = sim().protos['gsatb_embedding_sum_bwd_workspace'][0]
-        c.gsatb_embedding_sum_bwd_workspace.argtypes = sim().protos['gsatb_embedding_sum_bwd_workspace'][1]
-        return c
-
-    def call(self, name, *args):
-        rc = sim().call(name, *args)
-        if rc != 0:
-            raise (ValueError if rc in (-1, -2, -3, -6) else RuntimeError)(f'{name} failed with code {rc}')
-
-
 class _FakeIndex:
     """The GraphIndex attributes the wrappers read, filled from the oracle's index specification."""
 
@@ -148,14 +130,10 @@ class _FakeIndex:
 
 @pytest.fixture
 def sim_ops(monkeypatch):
+    """dp_gsat_b200.ops (and the rest of the package) on top of the emulated library, host tensors allowed."""
+    from tests.simt import emulate
+    emulate.patch_product(monkeypatch.setattr)
     import dp_gsat_b200.ops as ops
-
-    import dp_gsat_b200.loader as loader
-    fake = _SimBackedLib()
-    for mod in (ops, loader):
-        monkeypatch.setattr(mod, 'lib', lambda: fake)
-        monkeypatch.setattr(mod, 'stream', lambda: None)
-    monkeypatch.setattr(ops, '_require_cuda', lambda t: None)       # host tensors: the emulated kernels take host pointers
     return ops
 
 
@@ -246,8 +224,8 @@ def test_embedding_sum_on_emulator(M, H, dims):
     if M:
         assert torch.equal(out, ref.detach())
     R = int(offs[-1])
-    c = _SimBackedLib().cdll
-    ws_bytes = int(c.gsatb_embedding_sum_bwd_workspace(M, R, H))
+    from tests.simt.emulate import emulated_lib
+    ws_bytes = int(emulated_lib().cdll.gsatb_embedding_sum_bwd_workspace(M, R, H))
     ws = torch.zeros(ws_bytes, dtype=torch.uint8)
     dt = guarded((R, H))
     import ctypes
