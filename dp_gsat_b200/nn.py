@@ -119,6 +119,67 @@ def get_preds(logits, multi_label):
     return (logits.sigmoid() > 0.5).float()
 
 
+class _SyncBatchNormFn(torch.autograd.Function):
+    """BatchNorm1d over the rows of ALL ranks of a data-parallel group (the one cross-shard coupling
+    of the step).  Two-pass statistics (sum -> mean, then centred sum of squares), each one small all-reduce; backward
+    all-reduces (sum dy, sum dy * xhat).  The parameter gradients returned are the LOCAL sums: the step's gradient
+    all-reduce adds them up like every other parameter gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, momentum, eps, group):
+        import torch.distributed as dist
+        C = x.shape[1]
+        buf = torch.empty(C + 1, dtype=torch.float64, device=x.device)
+        buf[:C] = x.sum(0, dtype=torch.float64)
+        buf[C] = x.shape[0]
+        dist.all_reduce(buf, group=group)
+        n = buf[C].clone()
+        mean = (buf[:C] / n)
+        xc = x - mean.to(x.dtype)
+        sq = xc.square().sum(0, dtype=torch.float64)
+        dist.all_reduce(sq, group=group)
+        var = sq / n                                           # biased, as F.batch_norm normalises in training mode
+        rstd = torch.rsqrt(var + eps).to(x.dtype)
+        xhat = xc * rstd
+        with torch.no_grad():
+            running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+            running_var.mul_(1 - momentum).add_((var * (n / (n - 1).clamp_min(1))).to(running_var.dtype), alpha=momentum)
+            nbt.add_(1)
+        ctx.save_for_backward(xhat, gamma, rstd, n)
+        ctx.group = group
+        return xhat * gamma + beta
+
+    @staticmethod
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        xhat, gamma, rstd, n = ctx.saved_tensors
+        C = xhat.shape[1]
+        local = torch.empty(2 * C, dtype=torch.float64, device=dy.device)
+        local[:C] = dy.sum(0, dtype=torch.float64)
+        local[C:] = (dy * xhat).sum(0, dtype=torch.float64)
+        glob = local.clone()
+        dist.all_reduce(glob, group=ctx.group)
+        m_dy, m_dyx = (glob[:C] / n).to(dy.dtype), (glob[C:] / n).to(dy.dtype)
+        dx = (gamma * rstd) * (dy - m_dy - xhat * m_dyx)
+        return dx, local[C:].to(gamma.dtype), local[:C].to(gamma.dtype), None, None, None, None, None, None
+
+
+class BatchNorm1d(tnn.BatchNorm1d):
+    """torch.nn.BatchNorm1d as the reference builds it (gin.py:59; pna.py:45 through PyG BatchNorm: eps 1e-5, momentum
+    0.1, affine, running statistics -- same parameters, buffers and state_dict keys), plus an optional data-parallel
+    group: with ``sync_group`` set (parallel.enable_sync_batchnorm) the TRAINING-mode batch statistics span the rows of
+    every rank, which makes the graph-sharded N-GPU step compute exactly the single-device step (SURVEY section 8e);
+    ``sync_group = None`` (default) keeps shard-local statistics, the semantics of torch DDP."""
+    sync_group = None
+
+    def forward(self, x):
+        if self.sync_group is None or not self.training:
+            return super().forward(x)
+        return _SyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
+                                      self.num_batches_tracked, self.momentum if self.momentum is not None else 0.1,
+                                      self.eps, self.sync_group)
+
+
 class GINConv(tnn.Module):
     """src/models/conv_layers.py:14-34 over torch_geometric GINConv(nn, eps=0., train_eps=False): ``eps`` is a
     buffer, present in the state_dict."""
@@ -281,7 +342,7 @@ class GIN(tnn.Module):
 
     @staticmethod
     def MLP(in_channels: int, out_channels: int):
-        return tnn.Sequential(tnn.Linear(in_channels, out_channels), tnn.BatchNorm1d(out_channels),
+        return tnn.Sequential(tnn.Linear(in_channels, out_channels), BatchNorm1d(out_channels),
                               tnn.ReLU(inplace=True), tnn.Linear(out_channels, out_channels))
 
     def pool(self, x, batch, _index: Optional[GraphIndex] = None):

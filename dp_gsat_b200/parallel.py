@@ -5,7 +5,8 @@ over a single flat fp32 gradient bucket (NCCL over NVLink 5 / NVSwitch; payload 
 The reference has no distributed code at all (single device, src/run_gsat.py:1069); this is new capability.
 Loss terms are means over GLOBAL counts: the local info loss is weighted by E_local/E_global and the local
 prediction loss by G_local/G_global, so the SUM of the ranks' gradients equals the single-device gradient (up to
-BatchNorm, whose batch statistics are shard-local here, as in torch DDP).
+BatchNorm, whose batch statistics are shard-local by default, as in torch DDP; ``enable_sync_batchnorm`` /
+``TrainStep(sync_bn=True)`` all-reduce them for exact single-device math).
 
 The module is device-agnostic torch code, so the N>1 logic is covered on CPU with the gloo backend.
 """
@@ -54,13 +55,31 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
             dist.broadcast(t.data, src=src, group=group)
 
 
+def enable_sync_batchnorm(module: torch.nn.Module, group=None, enabled: bool = True) -> int:
+    """Make every BatchNorm1d of ``module`` (the GIN node MLPs, gin.py:59; PNA's per-layer norms, pna.py:45) take its
+    training-mode batch statistics over ALL ranks of ``group`` instead of over the local shard, so that the
+    graph-sharded step equals the single-device step exactly.  Costs two small all-reduces per
+    BatchNorm forward and one per backward (fp32 path), one each way on the tensor-core path.  Returns the number of
+    layers switched.  ``enabled=False`` restores shard-local statistics (DDP semantics, the default)."""
+    from .nn import BatchNorm1d
+    n = 0
+    for m in module.modules():
+        if isinstance(m, BatchNorm1d):
+            m.sync_group = (group if group is not None else dist.group.WORLD) if enabled else None
+            n += 1
+    return n
+
+
 class TrainStep:
     """forward_pass -> backward -> (all-reduce) -> Adam.step for one (sharded) batch.  ``gsat`` is any object with
     the reference's ``forward_pass(data, epoch, training)`` and the ``pred_scale`` / ``info_scale`` attributes."""
 
-    def __init__(self, gsat, lr: float = 1e-3, weight_decay: float = 0.0, group=None, fused_adam: Optional[bool] = None):
+    def __init__(self, gsat, lr: float = 1e-3, weight_decay: float = 0.0, group=None, fused_adam: Optional[bool] = None,
+                 sync_bn: bool = False):
         self.gsat = gsat
         self.group = group
+        if sync_bn and dist.is_available() and dist.is_initialized():
+            enable_sync_batchnorm(gsat.clf, group)
         params = list(gsat.extractor.parameters()) + list(gsat.clf.parameters())   # order of src/run_gsat.py:1007
         self.bucket = FlatGradBucket(params)
         if fused_adam is None:

@@ -203,8 +203,23 @@ def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: 
     return _FusedExtractor.apply(emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps)
 
 
+def _allreduce_stats(stats: torch.Tensor, n_local: int, group):
+    """Sum per-channel statistics and the row count over the data-parallel group (sync BatchNorm).
+    Returns the global row count as a 0-dim fp64 device tensor (no host sync: CUDA-graph capturable); ``stats`` is
+    updated in place.  group None -> (stats untouched, python int)."""
+    if group is None:
+        return n_local
+    import torch.distributed as dist
+    buf = torch.empty(stats.numel() + 1, dtype=torch.float64, device=stats.device)
+    buf[:-1] = stats
+    buf[-1:].fill_(float(n_local))
+    dist.all_reduce(buf, group=group)
+    stats.copy_(buf[:-1])
+    return buf[-1].clone()
+
+
 def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
-                     drop_seed, drop_mask, keep_sign: bool = True):
+                     drop_seed, drop_mask, keep_sign: bool = True, sync_group=None):
     """Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(agg)))))) on bf16 ``agg16`` [N, K].  Linear1 is a TMA-fed tcgen05
     GEMM whose epilogue accumulates the BatchNorm batch statistics from the fp32 accumulators and stores z1 as bf16;
     BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU and the dropout into its epilogue."""
@@ -213,12 +228,14 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     w1p, w2p = prep_weight(w1), prep_weight(w2)
     if training:
         z1, stats = linear_bf16(agg16, w1p, b1, H1, want_stats=True)
-        mean64 = stats[:H1] / N
-        var64 = (stats[H1:] / N - mean64 * mean64).clamp_min(0.0)
+        n_rows = _allreduce_stats(stats, N, sync_group)          # python int, or the group-wide count on the device
+        mean64 = stats[:H1] / n_rows
+        var64 = (stats[H1:] / n_rows - mean64 * mean64).clamp_min(0.0)
         mean, var = mean64.float(), var64.float()
+        unbias = N / max(N - 1, 1) if sync_group is None else (n_rows / (n_rows - 1).clamp_min(1)).float()
         with torch.no_grad():
             running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-            running_var.mul_(1 - momentum).add_(var * (N / max(N - 1, 1)), alpha=momentum)
+            running_var.mul_(1 - momentum).add_(var * unbias, alpha=momentum)
             nbt.add_(1)
     else:
         z1 = linear_bf16(agg16, w1p, b1, H1)
@@ -236,8 +253,10 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     return h, (z1, a1, mean, rstd, scale, shift, p, posmask)
 
 
-def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p, posmask=None):
-    """-> (d agg fp32 [N, K], dW1, db1, dgamma, dbeta, dW2, db2)."""
+def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p, posmask=None,
+                      sync_group=None):
+    """-> (d agg fp32 [N, K], dW1, db1, dgamma, dbeta, dW2, db2).  With ``sync_group`` the BatchNorm backward sums span
+    the group (the returned dgamma / dbeta stay the LOCAL sums: the step's gradient all-reduce adds them up)."""
     N, Kin = agg16.shape
     H1, H = w1.shape[0], w2.shape[0]
     dev = agg16.device
@@ -254,9 +273,15 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     dbeta, dgamma = stats[:H1], stats[H1:]
     coef = gamma * rstd
     if training:      # dz1 = coef * (g - dbeta/N - xhat * dgamma/N),  xhat = (z1 - mean) * rstd
+        if sync_group is not None:                   # sums and row count over every rank's rows
+            dbeta, dgamma = dbeta.clone(), dgamma.clone()                       # local sums -> parameter gradients
+            n_glob = _allreduce_stats(stats, N, sync_group)
+            m_dbeta, m_dgamma = (stats[:H1] / n_glob).float(), (stats[H1:] / n_glob).float()
+        else:
+            m_dbeta, m_dgamma = dbeta / N, dgamma / N
         cA = coef
-        cB = -coef * rstd * (dgamma / N)
-        cC = -coef * (dbeta / N) - cB * mean
+        cB = -coef * rstd * m_dgamma
+        cC = -coef * m_dbeta - cB * mean
     else:             # running statistics are constants: dz1 = coef * g
         cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
     dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
@@ -278,22 +303,22 @@ class _GinMlpFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
-                drop_seed, drop_mask):
+                drop_seed, drop_mask, sync_group=None):
         agg16 = x.contiguous().bfloat16()
         h, (z1, a1, mean, rstd, scale, shift, p, posmask) = _gin_mlp_forward(
             agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
-            drop_seed, drop_mask)
+            drop_seed, drop_mask, sync_group=sync_group)
         ctx.save_for_backward(agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
-        ctx.cfg = (bool(training), p)
+        ctx.cfg = (bool(training), p, sync_group)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        training, p = ctx.cfg
+        training, p, sync_group = ctx.cfg
         dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p, posmask)
-        return (dagg, dW1, db1, dgamma, dbeta, dW2, db2, None, None, None, None, None, None, None, None, None)
+                                                                    scale, shift, training, p, posmask, sync_group)
+        return (dagg, dW1, db1, dgamma, dbeta, dW2, db2) + (None,) * 10
 
 
 def gin_mlp_relu(x, seq, training: bool, pdrop: float = 0.0, drop_seed: int = 0, drop_mask=None):
@@ -302,7 +327,7 @@ def gin_mlp_relu(x, seq, training: bool, pdrop: float = 0.0, drop_seed: int = 0,
     return _GinMlpFused.apply(x, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight, lin2.bias, bn.running_mean,
                               bn.running_var, bn.num_batches_tracked, training and bn.training,
                               bn.momentum if bn.momentum is not None else 0.1, bn.eps, pdrop if training else 0.0,
-                              drop_seed, drop_mask)
+                              drop_seed, drop_mask, getattr(bn, 'sync_group', None))
 
 
 class _GinLayerFused(torch.autograd.Function):
@@ -313,7 +338,7 @@ class _GinLayerFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, att, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, gi, conv_eps, training,
-                momentum, eps, pdrop, drop_seed, drop_mask):
+                momentum, eps, pdrop, drop_seed, drop_mask, sync_group=None):
         x = x.contiguous()
         N, K = x.shape
         att_flat = None if att is None else att.contiguous().view(-1)
@@ -322,24 +347,24 @@ class _GinLayerFused(torch.autograd.Function):
                    ptr(gi.src_by_dst), ctypes.c_float(conv_eps), ptr(agg16), N, gi.E, K, stream())
         h, (z1, a1, mean, rstd, scale, shift, p, posmask) = _gin_mlp_forward(
             agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
-            drop_seed, drop_mask)
+            drop_seed, drop_mask, sync_group=sync_group)
         ctx.save_for_backward(x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
-        ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape)
+        ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape, sync_group)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        training, p, gi, conv_eps, att_shape = ctx.cfg
+        training, p, gi, conv_eps, att_shape, sync_group = ctx.cfg
         dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p, posmask)
+                                                                    scale, shift, training, p, posmask, sync_group)
         N, K = x.shape
         need_att = att_flat is not None and ctx.needs_input_grad[1]
         dx = torch.empty_like(x)
         datt = torch.empty(gi.E, dtype=torch.float32, device=x.device) if need_att else None
         lib().call('gsatb_gin_aggregate_bwd', ptr(dagg), ptr(x), ptr(att_flat), ptr(gi.rowptr_src), ptr(gi.eid_by_src),
                    ptr(gi.dst_by_src), ctypes.c_float(conv_eps), ptr(dx), ptr(datt), N, gi.E, K, stream())
-        return (dx, datt.view(att_shape) if need_att else None, dW1, db1, dgamma, dbeta, dW2, db2) + (None,) * 11
+        return (dx, datt.view(att_shape) if need_att else None, dW1, db1, dgamma, dbeta, dW2, db2) + (None,) * 12
 
 
 def gin_layer(x, edge_atten, gi, conv, training: bool, pdrop: float = 0.0, drop_seed: int = 0, drop_mask=None):
@@ -348,4 +373,4 @@ def gin_layer(x, edge_atten, gi, conv, training: bool, pdrop: float = 0.0, drop_
     return _GinLayerFused.apply(x, edge_atten, lin1.weight, lin1.bias, bn.weight, bn.bias, lin2.weight, lin2.bias,
                                 bn.running_mean, bn.running_var, bn.num_batches_tracked, gi, conv.initial_eps,
                                 training and bn.training, bn.momentum if bn.momentum is not None else 0.1, bn.eps,
-                                pdrop if training else 0.0, drop_seed, drop_mask)
+                                pdrop if training else 0.0, drop_seed, drop_mask, getattr(bn, 'sync_group', None))

@@ -318,3 +318,61 @@ def test_step_on_a_device_collated_batch_equals_the_host_batch(G):
         assert torch.equal(getattr(hb, k), getattr(db, k)), k
     for a, c, what in zip(out[0], out[1], ('edge_att', 'loss', 'logits')):
         assert_close(a, c, rtol=1e-6, atol_scale=1e-7, what=what)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sync BatchNorm over the data-parallel group, exercised on a single-rank group: the collective is the
+# identity, so the synced step must reproduce the default step (the 2-rank equality is in tests/test_parallel_gloo.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def single_rank_group():
+    import os
+    import socket
+    import torch.distributed as dist
+    if dist.is_initialized():
+        yield dist.group.WORLD
+        return
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    on_gpu = torch.zeros(1, device='cuda').is_cuda            # False in the emulator dry run (tests/simt/emulate.py)
+    dist.init_process_group('nccl' if on_gpu else 'gloo', rank=0, world_size=1)
+    yield dist.group.WORLD
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_sync_batchnorm_on_a_single_rank_group_equals_the_default(G, single_rank_group, precision):
+    from dp_gsat_b200.data import ba2motifs_batch
+    from dp_gsat_b200.parallel import enable_sync_batchnorm
+    b = ba2motifs_batch(64, seed=6)
+    b.x = torch.rand(b.x.shape, generator=torch.Generator().manual_seed(3))
+    cfg = {'model_name': 'GIN', 'hidden_size': 64, 'n_layers': 2, 'dropout_p': 0.0, 'use_edge_attr': False}
+    torch.manual_seed(0)
+    clf = G.get_model(b.x.shape[1], 0, 2, False, cfg, 'cuda')
+    ext = G.ExtractorMLP(64, {'learn_edge_att': True, 'extractor_dropout_p': 0.0}).cuda()
+    clf.precision = ext.precision = precision
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.7)
+    gsat.train()
+    d = b.to('cuda')
+    u = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10).cuda()
+    state = {k: v.clone() for k, v in clf.state_dict().items()}
+    res = {}
+    for sync in (False, True):
+        clf.load_state_dict(state)
+        assert enable_sync_batchnorm(clf, single_rank_group, enabled=sync) == 2
+        gsat.zero_grad(set_to_none=True)
+        _, loss, _, logits = gsat.forward_pass(d, 0, True, noise_u=u)
+        loss.backward()
+        res[sync] = (loss.detach().clone(), logits.detach().clone(),
+                     {k: p.grad.clone() for k, p in clf.named_parameters() if p.grad is not None},
+                     clf.convs[0].nn[1].running_var.clone())
+    enable_sync_batchnorm(clf, enabled=False)
+    rtol, scale = (2e-4, 2e-5) if precision == 'fp32' else (2e-2, 2e-3)
+    assert_close(res[True][0], res[False][0], rtol=rtol, atol_scale=scale, what='loss')
+    assert_close(res[True][1], res[False][1], rtol=rtol, atol_scale=scale, what='logits')
+    assert_close(res[True][3], res[False][3], rtol=rtol, atol_scale=scale, what='running_var')
+    for k in res[True][2]:
+        assert_close(res[True][2][k], res[False][2][k], rtol=10 * rtol, atol_scale=10 * scale, what=f'grad {k}')

@@ -109,3 +109,88 @@ def test_bench_preload_runs_the_same_number_of_steps_on_every_rank():
     mp.spawn(_preload_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0] == out[1]
     assert out[0][0] >= 1 and out[0][1] == out[0][0] + 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the PRODUCT model on two gloo ranks (kernels on the host SIMT emulator, tests/simt): loss weighting, flat bucket,
+# all-reduce and -- with sync BatchNorm -- exact equality of the sharded and the single-device step
+# ---------------------------------------------------------------------------------------------------------------
+def _product(seed, model_name='GIN'):
+    import dp_gsat_b200 as G
+    cfg = {'model_name': model_name, 'hidden_size': 16, 'n_layers': 2, 'dropout_p': 0.0, 'use_edge_attr': False,
+           'aggregators': ['mean', 'min', 'max', 'std'], 'scalers': False, 'deg': torch.ones(10)}
+    torch.manual_seed(seed)
+    clf = G.get_model(10, 0, 2, False, cfg, 'cpu')
+    ext = G.ExtractorMLP(16, {'learn_edge_att': True, 'extractor_dropout_p': 0.0})
+    g = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5)
+    g.train()                                    # BatchNorm in TRAINING mode: batch statistics matter
+    return g
+
+
+def _full_batch():
+    from dp_gsat_b200.data import ba2motifs_batch
+    full = ba2motifs_batch(12, seed=5)
+    full.x = torch.rand(full.x.shape, generator=torch.Generator().manual_seed(3))
+    u = torch.rand(full.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-6, 1 - 1e-6)
+    return full, u
+
+
+def _product_worker(rank, world, port, out, model_name, sync_bn):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests.simt import emulate
+    emulate.patch_product(setattr)
+    from dp_gsat_b200.data import shard_batch
+    from dp_gsat_b200.parallel import TrainStep, broadcast_parameters
+    torch.set_num_threads(1)
+    full, u_full = _full_batch()
+    g = _product(seed=rank, model_name=model_name)
+    broadcast_parameters(g.clf)
+    broadcast_parameters(g.extractor)
+    shard = shard_batch(full, rank, world)
+    e0 = sum(shard_batch(full, r, world).num_edges for r in range(rank))
+    step = TrainStep(g, lr=1e-2, fused_adam=False, sync_bn=sync_bn)
+    step(shard, 0, noise_u=u_full[e0:e0 + shard.num_edges])
+    if rank == 0:
+        bn = next(m for m in g.clf.modules() if isinstance(m, torch.nn.BatchNorm1d))
+        torch.save({'flat': step.bucket.flat.clone(), 'running_var': bn.running_var.clone(),
+                    'running_mean': bn.running_mean.clone()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('model_name', ['GIN', 'PNA'])
+def test_product_two_ranks_with_sync_batchnorm_equal_single_rank(tmp_path, monkeypatch, model_name):
+    """Graph-sharded step of the product model (emulated kernels) on 2 ranks with enable_sync_batchnorm == the
+    single-rank step on the whole batch: every parameter gradient and the BatchNorm running statistics."""
+    from tests.simt import emulate
+    from dp_gsat_b200.parallel import TrainStep
+    out = str(tmp_path / 'r0.pt')
+    mp.spawn(_product_worker, args=(2, _free_port(), out, model_name, True), nprocs=2, join=True)
+    got = torch.load(out)
+    emulate.patch_product(monkeypatch.setattr)
+    full, u_full = _full_batch()
+    g = _product(seed=0, model_name=model_name)
+    step = TrainStep(g, lr=1e-2, fused_adam=False)
+    step(full, 0, noise_u=u_full)
+    scale = float(step.bucket.flat.abs().max())
+    assert torch.allclose(got['flat'], step.bucket.flat, rtol=2e-4, atol=2e-6 * max(1.0, scale))
+    bn = next(m for m in g.clf.modules() if isinstance(m, torch.nn.BatchNorm1d))
+    assert torch.allclose(got['running_mean'], bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got['running_var'], bn.running_var, rtol=1e-5, atol=1e-6)
+
+
+def test_product_two_ranks_without_sync_batchnorm_differ(tmp_path, monkeypatch):
+    """The default (shard-local BatchNorm statistics, DDP semantics) is NOT the single-device step -- which is what
+    the sync option is for; this pins that the option actually changes the math."""
+    from tests.simt import emulate
+    from dp_gsat_b200.parallel import TrainStep
+    out = str(tmp_path / 'r0.pt')
+    mp.spawn(_product_worker, args=(2, _free_port(), out, 'GIN', False), nprocs=2, join=True)
+    got = torch.load(out)
+    emulate.patch_product(monkeypatch.setattr)
+    full, u_full = _full_batch()
+    g = _product(seed=0)
+    step = TrainStep(g, lr=1e-2, fused_adam=False)
+    step(full, 0, noise_u=u_full)
+    assert not torch.allclose(got['flat'], step.bucket.flat, rtol=2e-4, atol=1e-6)

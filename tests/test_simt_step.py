@@ -91,3 +91,12 @@ CASES = [
 @pytest.mark.parametrize('fn,kw', CASES)
 def test_gpu_test_body_on_the_emulator(G, fn, kw):
     fn(G, **kw)
+
+
+def test_sync_batchnorm_single_rank_body_on_the_emulator(G):
+    gen = Z.single_rank_group.__wrapped__()            # the fixture's generator: a one-rank gloo group here
+    group = next(gen)
+    try:
+        Z.test_sync_batchnorm_on_a_single_rank_group_equals_the_default(G, group, 'fp32')
+    finally:
+        next(gen, None)
