@@ -17,7 +17,7 @@ from .data import Batch  # noqa: E402
 from .index import GraphIndex, get_graph_index, clear_index_cache  # noqa: E402
 from .nn import (GIN, GINConv, GINEConv, LEConv, SPMotifNet, ExtractorMLP, MLP, BatchSequential, InstanceNorm, Criterion, get_model,  # noqa: E402
                  get_preds, AtomEncoder, BondEncoder)
-from .gsat import (GSAT, is_undirected, transpose, reorder_like, get_r, concrete_sample,  # noqa: E402
+from .gsat import (GSAT, DualGSAT, is_undirected, transpose, reorder_like, get_r, concrete_sample,  # noqa: E402
                    lift_node_att_to_edge_att, gumbel_sigmoid, f1_sparsity_loss, info_loss)
 from .pna import PNA, PNAConvSimple  # noqa: E402
 from .dual import line_graph_dual  # noqa: E402
@@ -27,6 +27,6 @@ from . import ops  # noqa: E402
 
 __all__ = ['Batch', 'GraphIndex', 'get_graph_index', 'clear_index_cache', 'GIN', 'GINConv', 'GINEConv', 'LEConv', 'SPMotifNet', 'ExtractorMLP', 'MLP',
            'BatchSequential', 'InstanceNorm', 'Criterion', 'get_model', 'get_preds', 'AtomEncoder', 'BondEncoder',
-           'GSAT', 'is_undirected', 'transpose', 'reorder_like', 'get_r', 'concrete_sample',
+           'GSAT', 'DualGSAT', 'is_undirected', 'transpose', 'reorder_like', 'get_r', 'concrete_sample',
            'lift_node_att_to_edge_att', 'gumbel_sigmoid', 'f1_sparsity_loss', 'info_loss', 'ops', 'PNA', 'PNAConvSimple', 'line_graph_dual', 'get_precision_at_k', 'get_delta_kl',
            'Graph', 'PackedDataset', 'DeviceLoader']

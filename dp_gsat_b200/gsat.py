@@ -203,3 +203,164 @@ class GSAT(tnn.Module):
     get_r = staticmethod(get_r)
     lift_node_att_to_edge_att = staticmethod(lift_node_att_to_edge_att)
     concrete_sample = staticmethod(concrete_sample)
+
+
+class DualGSAT(tnn.Module):
+    """The fork's GSAT class (src/run_gsat.py:33-149, 189-283, 610-637): a primal model and a dual (line-graph) model
+    trained together by ``dual_forward_pass(primal_data, dual_data, epoch, training)`` ->
+    ``(primal_edge_att, loss, loss_dict, primal_clf_logits)``.  Same attribute names (``primal_clf``,
+    ``dual_extractor``, ``primal_learn_edge_att``, ``dual_final_r`` ...) and the same loss composition: primal / dual
+    prediction losses, dual info loss against the scalar schedule r, primal info loss against the per-edge prior
+    ``sigmoid(dual_logits).detach()``, f1 sparsity loss of the dual attention against the primal edge labels, and the
+    0.3 / 0.7 mix of the dual attention into the primal edge attention after epoch 50.
+
+    Every gather / scatter / sampling step is a kernel of this library (K0 index, K1 extractor, fused sampler +
+    reverse-average + info loss, lift, K3 / K4 message passing, K5 pooling); the elementwise fork glue
+    (gumbel_sigmoid, f1 loss, the mix) is plain device-side PyTorch composed through autograd.  Not carried over (SURVEY
+    App. C): the per-batch ``.cpu().numpy()`` copies and plotting of :262-274 and the dead ``comb_att`` line that
+    raises NameError when ``primal_learn_edge_att`` is set.  ``from_reference_args`` takes the reference constructor's
+    28 positional arguments unchanged."""
+
+    def __init__(self, primal_clf, primal_extractor, dual_clf, dual_extractor, primal_num_class, primal_multi_label,
+                 dual_num_class, dual_multi_label, primal_method_config, primal_shared_config, dual_method_config,
+                 dual_shared_config, primal_optimizer=None, dual_optimizer=None, lazy_metrics: bool = False, seed: int = 0):
+        super().__init__()
+        from .nn import Criterion
+        self.primal_clf, self.primal_extractor, self.primal_optimizer = primal_clf, primal_extractor, primal_optimizer
+        self.dual_clf, self.dual_extractor, self.dual_optimizer = dual_clf, dual_extractor, dual_optimizer
+        self.primal_multi_label, self.dual_multi_label = primal_multi_label, dual_multi_label
+        self.primal_criterion = Criterion(primal_num_class, primal_multi_label)
+        self.dual_criterion = Criterion(dual_num_class, dual_multi_label)
+        for side, mc, sc in (('primal', primal_method_config, primal_shared_config),
+                             ('dual', dual_method_config, dual_shared_config)):
+            setattr(self, f'{side}_method_name', mc.get('method_name', 'GSAT'))
+            setattr(self, f'{side}_learn_edge_att', sc['learn_edge_att'])
+            setattr(self, f'{side}_k', sc.get('precision_k', 5))
+            setattr(self, f'{side}_epochs', mc.get('epochs', 0))
+            setattr(self, f'{side}_pred_loss_coef', mc['pred_loss_coef'])
+            setattr(self, f'{side}_info_loss_coef', mc['info_loss_coef'])
+            setattr(self, f'{side}_fix_r', mc.get('fix_r', None))
+            setattr(self, f'{side}_decay_interval', mc.get('decay_interval', None))
+            setattr(self, f'{side}_decay_r', mc.get('decay_r', None))
+            setattr(self, f'{side}_final_r', mc.get('final_r', 0.1))
+            setattr(self, f'{side}_init_r', mc.get('init_r', 0.9))
+        self.lazy_metrics, self.seed, self._step = lazy_metrics, seed, 0
+
+    @classmethod
+    def from_reference_args(cls, primal_clf, primal_extractor, primal_optimizer, primal_scheduler, primal_writer,
+                            primal_device, primal_model_dir, primal_dataset_name, primal_num_class, primal_multi_label,
+                            primal_random_state, primal_method_config, primal_shared_config, primal_model_config, dual_clf,
+                            dual_extractor, dual_optimizer, dual_scheduler, dual_writer, dual_device, dual_model_dir,
+                            dual_dataset_name, dual_num_class, dual_multi_label, dual_random_state, dual_method_config,
+                            dual_shared_config, dual_model_config):
+        """Argument order of the reference constructor (src/run_gsat.py:35-37); trainer-side objects are kept as
+        attributes but unused by the step."""
+        self = cls(primal_clf, primal_extractor, dual_clf, dual_extractor, primal_num_class, primal_multi_label,
+                   dual_num_class, dual_multi_label, primal_method_config, primal_shared_config, dual_method_config,
+                   dual_shared_config, primal_optimizer, dual_optimizer)
+        for side, vals in (('primal', (primal_scheduler, primal_writer, primal_device, primal_model_dir,
+                                       primal_dataset_name, primal_random_state, primal_model_config)),
+                           ('dual', (dual_scheduler, dual_writer, dual_device, dual_model_dir, dual_dataset_name,
+                                     dual_random_state, dual_model_config))):
+            for name, v in zip(('scheduler', 'writer', 'device', 'model_dir', 'dataset_name', 'random_state',
+                                'model_config'), vals):
+                setattr(self, f'{side}_{name}', v)
+        return self
+
+    def __loss__(self, primal_info, dual_att, primal_clf_logits, dual_clf_logits, primal_clf_labels, dual_clf_labels,
+                 epoch):
+        """src/run_gsat.py:121-149; ``primal_info`` is the (already reduced) primal info loss against the per-edge prior."""
+        primal_pred_loss = self.primal_criterion(primal_clf_logits, primal_clf_labels) * self.primal_pred_loss_coef
+        dual_pred_loss = self.dual_criterion(dual_clf_logits, dual_clf_labels) * self.dual_pred_loss_coef
+        dual_r = self.dual_fix_r if self.dual_fix_r else get_r(self.dual_decay_interval, self.dual_decay_r, epoch,
+                                                               final_r=self.dual_final_r, init_r=self.dual_init_r)
+        dual_info_loss = info_loss(dual_att, dual_r) * self.dual_info_loss_coef
+        primal_info_loss = primal_info * self.primal_info_loss_coef
+        loss = primal_pred_loss + dual_pred_loss + primal_info_loss + dual_info_loss
+        if self.lazy_metrics:
+            loss_dict = {'loss': loss.detach(), 'pred': dual_pred_loss.detach(), 'info': dual_info_loss.detach()}
+        else:       # the reference's dict: the dual entries overwrite the primal ones (:144-147)
+            loss_dict = {'loss': loss.item(), 'pred': dual_pred_loss.item(), 'info': dual_info_loss.item()}
+        return loss, loss_dict
+
+    def dual_forward_pass(self, primal_data, dual_data, epoch, training, noise=None):
+        for clf in (self.primal_clf, self.dual_clf):
+            clf._enc_scope = {}
+        try:
+            return self._dual_forward_pass(primal_data, dual_data, epoch, training, noise or {})
+        finally:
+            for clf in (self.primal_clf, self.dual_clf):
+                clf._enc_scope = None
+
+    def _dual_forward_pass(self, p, d, epoch, training, noise):
+        gi_p = get_graph_index(p.edge_index, p.batch, getattr(p, 'num_graphs', None) or None)
+        gi_d = get_graph_index(d.edge_index, d.batch, getattr(d, 'num_graphs', None) or None)
+        self._step += 1
+        off = self._step * (1 << 32)
+        # dual side first: its logits are the prior of the primal info loss
+        dual_emb = self.dual_clf.get_emb(d.x, d.edge_index, batch=d.batch, edge_attr=d.edge_attr)
+        dual_att_log_logits = self.dual_extractor(dual_emb, d.edge_index, d.batch, 'dual')
+        dual_node_att = gumbel_sigmoid(dual_att_log_logits, tau=0.1, noise_u=noise.get('dual_U'))[:, 0].unsqueeze(-1)
+        f1_loss = f1_sparsity_loss(dual_node_att, p.edge_label.float().to(dual_node_att.device))       # :226-227
+        if self.dual_learn_edge_att:
+            dual_edge_att = ops.gather_reverse(dual_node_att, gi_d.rev).add(dual_node_att).div(2) if gi_d.symmetric \
+                else dual_node_att                                                                     # :232-238
+        else:
+            dual_edge_att = ops.lift_node_att(dual_node_att, gi_d)                                     # :239-240
+        # primal side
+        primal_emb = self.primal_clf.get_emb(p.x, p.edge_index, batch=p.batch, edge_attr=p.edge_attr)
+        primal_att_log_logits = self.primal_extractor(primal_emb, p.edge_index, p.batch, 'primal')
+        primal_r = dual_att_log_logits.sigmoid().detach()                                              # :129
+        mix = epoch > 50
+        if self.primal_learn_edge_att:
+            # sampling + reverse average (+ the info loss on the averaged attention when nothing is mixed in) in ONE kernel
+            _, primal_edge_att, primal_info = ops.sample_avg_info(
+                primal_att_log_logits, training=training, rev=gi_p.rev, average=gi_p.symmetric, r=primal_r,
+                noise_u=noise.get('primal_u'), temp=1.0, info_on_edge_att=True, want_info=not mix, seed=self.seed,
+                offset=off)
+        else:
+            primal_node_att, _, _ = ops.sample_avg_info(
+                primal_att_log_logits, training=training, rev=None, average=False, noise_u=noise.get('primal_u'),
+                temp=1.0, want_info=False, seed=self.seed, offset=off)
+            primal_edge_att = ops.lift_node_att(primal_node_att, gi_p)                                 # :249
+            primal_info = None
+        if mix:                                                                                        # :252-253
+            primal_edge_att = 0.3 * dual_node_att + (1 - 0.3) * primal_edge_att
+            primal_info = None
+        if primal_info is None:
+            primal_info = info_loss(primal_edge_att, primal_r)                                         # :132
+        primal_clf_logits = self.primal_clf(p.x, p.edge_index, p.batch, edge_attr=p.edge_attr, edge_atten=primal_edge_att)
+        dual_clf_logits = self.dual_clf(d.x, d.edge_index, d.batch, edge_attr=d.edge_attr, edge_atten=dual_edge_att)
+        loss, loss_dict = self.__loss__(primal_info, dual_edge_att, primal_clf_logits, dual_clf_logits, p.y, d.y, epoch)
+        loss = loss + f1_loss                                                                          # :281
+        return primal_edge_att, loss, loss_dict, primal_clf_logits
+
+    def dual_eval_one_batch(self, primal_data, dual_data, epoch):
+        """src/run_gsat.py:610-618 (outputs stay on the device: no per-batch .cpu())."""
+        for m in (self.primal_extractor, self.primal_clf, self.dual_extractor, self.dual_clf):
+            m.eval()
+        with torch.no_grad():
+            att, loss, loss_dict, clf_logits = self.dual_forward_pass(primal_data, dual_data, epoch, training=False)
+        return att.detach().reshape(-1), loss_dict, clf_logits.detach()
+
+    def dual_train_one_batch(self, primal_data, dual_data, epoch):
+        """src/run_gsat.py:620-637."""
+        for m in (self.primal_extractor, self.primal_clf, self.dual_extractor, self.dual_clf):
+            m.train()
+        att, loss, loss_dict, clf_logits = self.dual_forward_pass(primal_data, dual_data, epoch, training=True)
+        self.primal_optimizer.zero_grad()
+        self.dual_optimizer.zero_grad()
+        loss.backward()
+        self.primal_optimizer.step()
+        self.dual_optimizer.step()
+        return att.detach().reshape(-1), loss_dict, clf_logits.detach()
+
+    @staticmethod
+    def sampling(att_log_logits, epoch, training, noise_u=None):
+        return concrete_sample(att_log_logits, 1, training, noise_u)
+
+    get_r = staticmethod(get_r)
+    gumbel_sigmoid = staticmethod(gumbel_sigmoid)
+    f1_sparsity_loss = staticmethod(f1_sparsity_loss)
+    lift_node_att_to_edge_att = staticmethod(lift_node_att_to_edge_att)
+    concrete_sample = staticmethod(concrete_sample)

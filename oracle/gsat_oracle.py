@@ -749,6 +749,79 @@ class GSAT(nn.Module):
     lift_node_att_to_edge_att = staticmethod(lift_node_att_to_edge_att)
 
 
+class DualGSAT(nn.Module):
+    """The fork's two-model step, run_gsat.py:33-149 (constructor fields, ``__loss__``) and :189-283
+    (``dual_forward_pass``): a primal GSAT and a dual (line-graph) GSAT trained together.  Dual nodes are primal
+    edges, so the dual "node attention" (one value per dual node, gumbel_sigmoid at tau 0.1) has one entry per primal
+    edge: it feeds the f1 loss against the primal edge labels (:226-227), the per-edge prior r of the primal info
+    loss (``primal_r = sigmoid(dual_logits).detach()``, :129) and, after epoch 50, the 0.3 / 0.7 mix into the primal
+    edge attention (:252-253).  Not restated: the numpy / plotting code of :262-274 and the dead ``comb_att`` line
+    (:270; it reads ``old_primal_edge_att``, which does not exist when primal_learn_edge_att is set -- SURVEY App. C).
+    ``noise``: optional dict of injected uniforms {'primal_u', 'dual_U'}."""
+
+    def __init__(self, primal_clf, primal_extractor, dual_clf, dual_extractor, primal_criterion, dual_criterion,
+                 primal_method_config, primal_shared_config, dual_method_config, dual_shared_config):
+        super().__init__()
+        self.primal_clf, self.primal_extractor = primal_clf, primal_extractor
+        self.dual_clf, self.dual_extractor = dual_clf, dual_extractor
+        self.primal_criterion, self.dual_criterion = primal_criterion, dual_criterion
+        for side, mc, sc in (('primal', primal_method_config, primal_shared_config),
+                             ('dual', dual_method_config, dual_shared_config)):
+            setattr(self, f'{side}_learn_edge_att', sc['learn_edge_att'])
+            setattr(self, f'{side}_pred_loss_coef', mc['pred_loss_coef'])
+            setattr(self, f'{side}_info_loss_coef', mc['info_loss_coef'])
+            setattr(self, f'{side}_fix_r', mc.get('fix_r', None))
+            setattr(self, f'{side}_decay_interval', mc.get('decay_interval', None))
+            setattr(self, f'{side}_decay_r', mc.get('decay_r', None))
+            setattr(self, f'{side}_final_r', mc.get('final_r', 0.1))
+            setattr(self, f'{side}_init_r', mc.get('init_r', 0.9))
+
+    def __loss__(self, primal_att, dual_att, primal_clf_logits, dual_clf_logits, primal_clf_labels, dual_clf_labels,
+                 dual_att_log_logits, epoch):
+        primal_pred_loss = self.primal_criterion(primal_clf_logits, primal_clf_labels)           # :122
+        dual_pred_loss = self.dual_criterion(dual_clf_logits, dual_clf_labels)                   # :124
+        dual_r = self.dual_fix_r if self.dual_fix_r else get_r(self.dual_decay_interval, self.dual_decay_r, epoch,
+                                                               final_r=self.dual_final_r, init_r=self.dual_init_r)
+        dual_info_loss = info_loss(dual_att, dual_r)                                             # :127
+        primal_r = dual_att_log_logits.sigmoid().detach()                                        # :129
+        primal_info_loss = info_loss(primal_att, primal_r)                                       # :132
+        primal_pred_loss = primal_pred_loss * self.primal_pred_loss_coef
+        primal_info_loss = primal_info_loss * self.primal_info_loss_coef
+        dual_pred_loss = dual_pred_loss * self.dual_pred_loss_coef
+        dual_info_loss = dual_info_loss * self.dual_info_loss_coef
+        loss = primal_pred_loss + dual_pred_loss + primal_info_loss + dual_info_loss             # :142
+        loss_dict = {'loss': loss.item(), 'pred': primal_pred_loss.item(), 'info': primal_info_loss.item()}
+        loss_dict.update({'loss': loss.item(), 'pred': dual_pred_loss.item(), 'info': dual_info_loss.item()})
+        return loss, loss_dict
+
+    def dual_forward_pass(self, primal_data, dual_data, epoch, training, noise=None):
+        noise = noise or {}
+        p, d = primal_data, dual_data
+        primal_emb = self.primal_clf.get_emb(p.x, p.edge_index, batch=p.batch, edge_attr=p.edge_attr)
+        primal_att_log_logits = self.primal_extractor(primal_emb, p.edge_index, p.batch, 'primal')
+        primal_node_att = concrete_sample(primal_att_log_logits, 1, training, noise.get('primal_u'))     # :204
+        dual_emb = self.dual_clf.get_emb(d.x, d.edge_index, batch=d.batch, edge_attr=d.edge_attr)
+        dual_att_log_logits = self.dual_extractor(dual_emb, d.edge_index, d.batch, 'dual')
+        dual_node_att = gumbel_sigmoid(dual_att_log_logits, tau=0.1, noise_u=noise.get('dual_U'))[:, 0].unsqueeze(-1)
+        f1_loss = f1_sparsity_loss(dual_node_att, p.edge_label.float())                                   # :226-227
+        if self.dual_learn_edge_att:
+            dual_edge_att = undirected_average(dual_node_att, d.edge_index)
+        else:
+            dual_edge_att = lift_node_att_to_edge_att(dual_node_att, d.edge_index)
+        if self.primal_learn_edge_att:
+            primal_edge_att = undirected_average(primal_node_att, p.edge_index)
+        else:
+            primal_edge_att = lift_node_att_to_edge_att(primal_node_att, p.edge_index)
+        if epoch > 50:                                                                                     # :252-253
+            primal_edge_att = 0.3 * dual_node_att + (1 - 0.3) * primal_edge_att
+        primal_clf_logits = self.primal_clf(p.x, p.edge_index, p.batch, edge_attr=p.edge_attr, edge_atten=primal_edge_att)
+        dual_clf_logits = self.dual_clf(d.x, d.edge_index, d.batch, edge_attr=d.edge_attr, edge_atten=dual_edge_att)
+        loss, loss_dict = self.__loss__(primal_edge_att, dual_edge_att, primal_clf_logits, dual_clf_logits, p.y, d.y,
+                                        dual_att_log_logits, epoch)
+        loss = loss + f1_loss                                                                              # :281
+        return primal_edge_att, loss, loss_dict, primal_clf_logits
+
+
 # --------------------------------------------------------------------------
 # line-graph ("dual") construction of the fork (SURVEY section 8f row 1)
 # --------------------------------------------------------------------------

@@ -115,6 +115,7 @@ def redirect_torch_to_cpu(setattr_fn):
     host tensors.  ``setattr_fn`` as in patch_product."""
     setattr_fn(torch.cuda, 'is_available', lambda: True)
     setattr_fn(torch.cuda, 'synchronize', lambda *a, **k: None)
+    setattr_fn(torch.cuda, 'is_current_stream_capturing', lambda: False)      # asked by torch.optim when cuda 'is available'
     setattr_fn(torch.Tensor, 'cuda', lambda self, *a, **k: self)
     setattr_fn(torch.nn.Module, 'cuda', lambda self, *a, **k: self)
     t_to, m_to = torch.Tensor.to, torch.nn.Module.to

@@ -376,3 +376,124 @@ def test_sync_batchnorm_on_a_single_rank_group_equals_the_default(G, single_rank
     assert_close(res[True][3], res[False][3], rtol=rtol, atol_scale=scale, what='running_var')
     for k in res[True][2]:
         assert_close(res[True][2][k], res[False][2][k], rtol=10 * rtol, atol_scale=10 * scale, what=f'grad {k}')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the fork's two-model step: GSAT.dual_forward_pass (reference src/run_gsat.py:121-149, 189-283)
+# ---------------------------------------------------------------------------------------------------------------
+def _primal_dual_pair(n_graphs=24, seed=8):
+    """A primal batch (BA-2Motifs-shaped, random features, motif edge labels) and its line-graph dual: one dual node
+    per directed primal edge (mutag_dual.py:342-378), dual features random, dual labels = primal labels."""
+    import numpy as np
+    import dp_gsat_b200 as G
+    from dp_gsat_b200.data import ba2motifs_batch, line_graph_dual, graph_contiguous_relabel
+    p = ba2motifs_batch(n_graphs, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    p.x = torch.rand(p.num_nodes, 10, generator=g)
+    src, dst = p.edge_index[0].numpy(), p.edge_index[1].numpy()
+    dsrc, ddst, dng = line_graph_dual(src, dst, p.batch.numpy())
+    dsrc, ddst = graph_contiguous_relabel(dsrc, ddst, dng)
+    d = G.Batch(torch.rand(p.num_edges, 7, generator=g), torch.from_numpy(np.stack([dsrc, ddst])),
+                torch.from_numpy(dng), p.y.clone(), None, torch.zeros(dsrc.shape[0]), n_graphs)
+    return p, d
+
+
+@pytest.mark.parametrize('primal_learn_edge_att,epoch', [(True, 3), (False, 3), (True, 60), (False, 60)])
+def test_dual_forward_pass_parity(G, primal_learn_edge_att, epoch):
+    """Whole fork step against the restated reference method: primal / dual attention paths (reverse average or lift),
+    gumbel_sigmoid dual attention, f1 loss, per-edge prior r, the epoch > 50 mix, loss and every gradient of all four
+    modules."""
+    p, d = _primal_dual_pair()
+    cfg = {'model_name': 'GIN', 'hidden_size': 32, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    sc_p = {'learn_edge_att': primal_learn_edge_att, 'extractor_dropout_p': 0.5, 'precision_k': 5}
+    sc_d = {'learn_edge_att': False, 'extractor_dropout_p': 0.5, 'precision_k': 5}
+    mc = {'method_name': 'GSAT', 'pred_loss_coef': 1, 'info_loss_coef': 1, 'epochs': 100, 'decay_interval': 10,
+          'decay_r': 0.1, 'final_r': 0.5, 'init_r': 0.9}
+    torch.manual_seed(0)
+    o_mods = (O.get_model(10, 0, 2, False, cfg), O.ExtractorMLP(32, sc_p, 'primal'),
+              O.get_model(7, 0, 2, False, cfg), O.ExtractorMLP(32, sc_d, 'dual'))
+    g_mods = (G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(32, sc_p, 'primal').cuda(),
+              G.get_model(7, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(32, sc_d, 'dual').cuda())
+    for mo, mg in zip(o_mods, g_mods):
+        assert set(mg.state_dict().keys()) == set(mo.state_dict().keys())
+        mg.load_state_dict(mo.state_dict())
+    ms = O.MaskSource(2)
+    for m in o_mods + g_mods:
+        m.masks = ms
+    go = O.DualGSAT(o_mods[0], o_mods[1], o_mods[2], o_mods[3], O.Criterion(2, False), O.Criterion(2, False), mc, sc_p,
+                    mc, sc_d)
+    gg = G.DualGSAT(g_mods[0], g_mods[1], g_mods[2], g_mods[3], 2, False, 2, False, mc, sc_p, mc, sc_d)
+    go64 = copy.deepcopy(go).double()
+    for m in (go, gg, go64):
+        m.train()
+    gen = torch.Generator().manual_seed(1)
+    rows_p = p.num_edges if primal_learn_edge_att else p.num_nodes
+    noise = {'primal_u': torch.rand(rows_p, 1, generator=gen).clamp(1e-10, 1 - 1e-10),
+             'dual_U': torch.rand(d.num_nodes, 1, generator=gen)}
+    cast = lambda n, f: {k: f(v) for k, v in n.items()}
+    ea_o, loss_o, ld_o, logit_o = go.dual_forward_pass(p, d, epoch, True, noise)
+    p64, d64 = p.to('cpu'), d.to('cpu')
+    p64.x, d64.x = p64.x.double(), d64.x.double()
+    ea_t, loss_t, _, logit_t = go64.dual_forward_pass(p64, d64, epoch, True, cast(noise, lambda v: v.double()))
+    ea_g, loss_g, ld_g, logit_g = gg.dual_forward_pass(p.to('cuda'), d.to('cuda'), epoch, True,
+                                                       cast(noise, lambda v: v.cuda()))
+    loss_o.backward()
+    loss_t.backward()
+    loss_g.backward()
+
+    def check(g_val, o_val, t_val, what, rtol=2e-4, atol_scale=2e-5):
+        if close(g_val, o_val, rtol, atol_scale):
+            return
+        t = t_val.detach().cpu().double()
+        err_g = (g_val.detach().cpu().double() - t).abs().max().item()
+        err_o = (o_val.detach().cpu().double() - t).abs().max().item()
+        assert err_g <= 4 * err_o + 1e-7 * max(1.0, t.abs().max().item()), \
+            f'{what}: cuda-vs-fp64 {err_g:.3e} > 4 x oracle32-vs-fp64 {err_o:.3e}'
+    check(ea_g, ea_o, ea_t, 'primal_edge_att')
+    check(logit_g, logit_o, logit_t, 'primal logits')
+    check(loss_g, loss_o, loss_t, 'loss')
+    assert set(ld_g.keys()) == set(ld_o.keys()) == {'loss', 'pred', 'info'}
+    for k in ld_o:
+        assert abs(ld_g[k] - ld_o[k]) <= 2e-4 * max(1.0, abs(ld_o[k])), k
+    names = ('primal_clf', 'primal_extractor', 'dual_clf', 'dual_extractor')
+    for name in names:
+        po = dict(getattr(go, name).named_parameters())
+        pt = dict(getattr(go64, name).named_parameters())
+        pg = dict(getattr(gg, name).named_parameters())
+        assert po.keys() == pg.keys()
+        for k in po:
+            if po[k].grad is None:
+                assert pg[k].grad is None or float(pg[k].grad.abs().max()) == 0.0, (name, k)
+                continue
+            check(pg[k].grad, po[k].grad, pt[k].grad, f'grad {name}.{k}', rtol=1e-3, atol_scale=2e-4)
+
+
+def test_dual_train_and_eval_one_batch(G):
+    """dual_train_one_batch / dual_eval_one_batch (run_gsat.py:610-637) and the 28-argument reference constructor."""
+    p, d = _primal_dual_pair(12, seed=2)
+    cfg = {'model_name': 'GIN', 'hidden_size': 32, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    sc = {'learn_edge_att': False, 'extractor_dropout_p': 0.5, 'precision_k': 5, 'num_viz_samples': 0, 'viz_interval': 10,
+          'viz_norm_att': True}
+    mc = {'method_name': 'GSAT', 'pred_loss_coef': 1, 'info_loss_coef': 1, 'epochs': 100, 'decay_interval': 10,
+          'decay_r': 0.1, 'final_r': 0.5, 'lr': 1e-3}
+    torch.manual_seed(0)
+    pc, pe = G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(32, sc, 'primal').cuda()
+    dc, de = G.get_model(7, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(32, sc, 'dual').cuda()
+    po = torch.optim.Adam(list(pe.parameters()) + list(pc.parameters()), lr=1e-2)
+    do = torch.optim.Adam(list(de.parameters()) + list(dc.parameters()), lr=1e-2)
+    gsat = G.DualGSAT.from_reference_args(pc, pe, po, None, None, 'cuda', None, 'mutag', 2, False, 0, mc, sc, cfg,
+                                          dc, de, do, None, None, 'cuda', None, 'mutag_dual', 2, False, 0, mc, sc, cfg)
+    assert gsat.primal_dataset_name == 'mutag' and gsat.dual_final_r == 0.5 and gsat.primal_learn_edge_att is False
+    pd_, dd_ = p.to('cuda'), d.to('cuda')
+    w0 = pc.convs[0].nn[0].weight.detach().clone()
+    losses = []
+    for epoch in range(4):
+        att, loss_dict, logits = gsat.dual_train_one_batch(pd_, dd_, epoch)
+        assert att.shape == (p.num_edges,) and logits.shape == (p.num_graphs, 1)
+        losses.append(loss_dict['loss'])
+    assert not torch.equal(w0, pc.convs[0].nn[0].weight.detach())
+    assert all(l == l for l in losses)                                          # finite
+    att, loss_dict, logits = gsat.dual_eval_one_batch(pd_, dd_, 4)
+    att2, _, logits2 = gsat.dual_eval_one_batch(pd_, dd_, 4)
+    assert torch.equal(att, att2) and torch.equal(logits, logits2)              # eval: no sampling noise, no dropout
+    assert float(att.min()) >= 0.0 and float(att.max()) <= 1.0

@@ -85,6 +85,12 @@ CASES = [
     _case(Z.test_device_collate_bit_exact, ids=[3, 1, 4, 1, 5, 9, 2, 6]),
     _case(Z.test_device_collate_edge_cases_and_loader),
     _case(Z.test_step_on_a_device_collated_batch_equals_the_host_batch),
+    # the fork's two-model step
+    _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=True, epoch=3),
+    _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=False, epoch=3),
+    _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=True, epoch=60),
+    _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=False, epoch=60),
+    _case(Z.test_dual_train_and_eval_one_batch),
 ]
 
 
