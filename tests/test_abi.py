@@ -87,3 +87,33 @@ def test_shard_bounds_balance_edges():
     assert max(p.num_edges for p in parts) - min(p.num_edges for p in parts) <= 52
     for p in parts:
         assert int(p.edge_index.max()) < p.num_nodes and int(p.batch.max()) == p.num_graphs - 1
+
+
+def test_every_entry_point_rejects_null_pointers_without_touching_the_device():
+    """Error behaviour of the C ABI (include/gsat_b200.h: 'return a negative GSATB_E* code, nothing throws across the
+    ABI'): every int-returning entry point called with NULL pointers and sizes of 1 must come back with GSATB_EINVAL
+    before any CUDA work -- on this GPU-less machine too.  Runs in a child process so that a crash is a test failure,
+    not the end of the test session."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, importlib.util, sys
+spec = importlib.util.spec_from_file_location('_b', sys.argv[1])
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+lib = ctypes.CDLL(m.LIB_PATH)
+bad = []
+for name, (restype, argtypes) in sorted(m.parse_header().items()):
+    if restype is not ctypes.c_int or name in ('gsatb_version', 'gsatb_check_device', 'gsatb_set_step_counter',
+                                               'gsatb_tc_set_profile_buffer'):
+        continue
+    fn = getattr(lib, name); fn.restype, fn.argtypes = restype, argtypes
+    args = [None if t is ctypes.c_void_p else (0.0 if t is ctypes.c_float else 1) for t in argtypes]
+    rc = fn(*args)
+    if rc != -1:
+        bad.append((name, rc))
+print('CHECKED', bad)
+sys.exit(1 if bad else 0)
+'''
+    r = subprocess.run([sys.executable, '-c', code, os.path.join(ROOT, 'dp_gsat_b200', '_lib.py')],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0 and 'CHECKED []' in r.stdout, r.stdout[-2000:]
