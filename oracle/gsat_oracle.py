@@ -17,7 +17,13 @@ only reference-side pins available are (1) the ``reorder_like`` runtime
 invariant (src/utils/utils.py:23), (2) the in-tree Mutagenicity topology
 (data/mutag_dual/raw/Mutagenicity_A.txt, a slice of which is committed under
 tests/golden/ by tests/golden/make_golden.py) whose consecutive rows are
-mutual reverses, and (3) analytic known answers (tests/test_oracle.py).
+mutual reverses, (3) analytic known answers (tests/test_oracle.py), and (4) the
+outputs of the reference's own first-party function / class bodies, extracted
+with ``ast`` and executed by tests/golden/make_golden.py and
+make_golden_fork.py (reorder_like, sampler, losses, MLP / ExtractorMLP, the
+conv layers' forward + message, SPMotifNet, the fork's __loss__ and
+dual_forward_pass) -- first-party code is pinned, the third-party wheels'
+semantics are not.
 
 Every public symbol cites the reference file:line it follows (paths relative
 to /root/reference).

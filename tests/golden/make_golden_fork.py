@@ -1,0 +1,197 @@
+"""Generate tests/golden/ref_fork.pt: outputs of the REFERENCE'S OWN class bodies for the fork-specific parts of the
+path, extracted with ``ast`` from /root/reference and executed unmodified.  Run ONCE in the build container, where
+/root/reference exists:   python tests/golden/make_golden_fork.py
+
+Pinned here (all first-party code of mihikamd/DP-GSAT):
+
+* ``GINConv`` / ``GINEConv`` / ``LEConv`` of src/models/conv_layers.py:14-92 -- their ``forward`` and ``message``
+  bodies, on stub base classes that supply what torch_geometric's bases supply (``nn``, ``eps``, ``lin``, ``lin1..3``
+  and a ``propagate`` that gathers x_j = x[edge_index[0]], x_i = x[edge_index[1]], calls the reference ``message`` and
+  scatter-adds into edge_index[1] -- SURVEY App. A.1; that third-party part stays UNPINNED);
+* ``SPMotifNet`` (src/models/spmotif_gnn.py:9-87), whole class, on the reference LEConv above;
+* the fork's ``GSAT`` class (src/run_gsat.py:33-283): ``__init__``, ``__loss__``, ``dual_forward_pass`` and the helpers
+  they call, with the reference's ``ExtractorMLP`` (:886-927), ``Criterion`` / ``MLP`` (src/utils/get_model.py) and
+  ``reorder_like`` (src/utils/utils.py); the GNN backbones inside are the oracle's GIN (PyG-dependent, unpinned).
+  Run with every module in eval mode (no dropout draws, BatchNorm on its running statistics) and ``training=True``, so
+  the only random draws are the sampler's uniform and gumbel_sigmoid's ``rand_like``, which are replayed from the same
+  seed and stored; epochs 3 and 57 (not multiples of 10: the plotting block of :394-426 stays off) cover both sides of
+  the ``epoch > 50`` mix.  ``primal_learn_edge_att`` is False in both (with True the reference body raises NameError
+  on ``old_primal_edge_att``).
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+from oracle import gsat_oracle as O  # noqa: E402
+from make_golden import _extract, _compile  # noqa: E402
+
+REF = '/root/reference'
+
+
+def _strip_annotations(node):
+    """The reference annotates with torch_geometric.typing names (Adj, OptTensor ...): drop annotations, keep bodies."""
+    for n in ast.walk(node):
+        if isinstance(n, ast.FunctionDef):
+            n.returns = None
+            for a in n.args.args + n.args.kwonlyargs:
+                a.annotation = None
+        if isinstance(n, ast.AnnAssign):      # `x: OptPairTensor = (x, x)` -> `x = (x, x)`
+            pass
+    class T(ast.NodeTransformer):
+        def visit_AnnAssign(self, n):
+            return ast.copy_location(ast.Assign(targets=[n.target], value=n.value), n) if n.value is not None else None
+    return ast.fix_missing_locations(T().visit(node))
+
+
+class _Propagate(nn.Module):
+    """What torch_geometric.nn.MessagePassing.propagate does for these layers (flow source_to_target, aggr 'add')."""
+
+    def propagate(self, edge_index, size=None, **kw):
+        args = {}
+        for k, v in kw.items():
+            if k in ('x', 'a', 'b'):
+                xs = v if isinstance(v, tuple) else (v, v)
+                args[k + '_j'] = xs[0].index_select(0, edge_index[0])
+                args[k + '_i'] = xs[1].index_select(0, edge_index[1])
+            else:
+                args[k] = v
+        import inspect
+        want = inspect.signature(self.message).parameters
+        msg = self.message(**{k: v for k, v in args.items() if k in want})
+        n = (kw['x'] if 'x' in kw else kw['b'])
+        n = (n[1] if isinstance(n, tuple) else n).shape[0]
+        return O.scatter_sum(msg, edge_index[1], n)
+
+
+class BaseGINConv(_Propagate):
+    def __init__(self, nn_, eps=0.0):
+        super().__init__()
+        self.nn = nn_
+        self.register_buffer('eps', torch.tensor([eps]))
+
+
+class BaseGINEConv(_Propagate):
+    def __init__(self, nn_, eps=0.0, edge_dim=None):
+        super().__init__()
+        self.nn = nn_
+        self.register_buffer('eps', torch.tensor([eps]))
+        self.lin = nn.Linear(edge_dim, nn_[0].in_features) if edge_dim is not None else None
+
+
+class BaseLEConv(_Propagate):
+    def __init__(self, in_channels, out_channels, bias=True):
+        super().__init__()
+        self.lin1 = nn.Linear(in_channels, out_channels, bias=bias)
+        self.lin2 = nn.Linear(in_channels, out_channels, bias=False)
+        self.lin3 = nn.Linear(in_channels, out_channels, bias=bias)
+
+
+def main():
+    gold = {}
+    quiet = lambda *a, **k: None
+    g = torch.Generator().manual_seed(0)
+
+    # ---- conv layers ------------------------------------------------------------------------------------------
+    convs = _extract(f'{REF}/src/models/conv_layers.py', ['GINConv', 'GINEConv', 'LEConv'])
+    ns = _compile([_strip_annotations(n) for n in convs.values()],
+                  {'torch': torch, 'Tensor': torch.Tensor, 'BaseGINConv': BaseGINConv, 'BaseGINEConv': BaseGINEConv,
+                   'BaseLEConv': BaseLEConv, 'print': quiet})
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(4, seed=1)
+    N, E, H = b.num_nodes, b.num_edges, 8
+    x = torch.randn(N, H, generator=g)
+    att = torch.rand(E, 1, generator=g)
+    ea = torch.randn(E, 5, generator=g)
+    w = torch.rand(E, 1, generator=g) + 0.5
+    gold['graph/edge_index'], gold['graph/batch'] = b.edge_index, b.batch
+    gold['graph/x'], gold['graph/att'], gold['graph/edge_attr'], gold['graph/edge_weight'] = x, att, ea, w
+    torch.manual_seed(1)
+    gin = ns['GINConv'](O.gin_mlp(H, H))
+    gin.eval()
+    gold['ginconv/state'] = {k: v.clone() for k, v in gin.state_dict().items()}
+    gold['ginconv/out_att'] = gin(x, b.edge_index, edge_atten=att).detach()
+    gold['ginconv/out_noatt'] = gin(x, b.edge_index).detach()
+    gine = ns['GINEConv'](O.gin_mlp(H, H), edge_dim=5)
+    gine.eval()
+    gold['gineconv/state'] = {k: v.clone() for k, v in gine.state_dict().items()}
+    gold['gineconv/out_att'] = gine(x, b.edge_index, edge_attr=ea, edge_atten=att).detach()
+    le = ns['LEConv'](H, H)
+    gold['leconv/state'] = {k: v.clone() for k, v in le.state_dict().items()}
+    gold['leconv/out_w_att'] = le(x, b.edge_index, edge_weight=w, edge_atten=att).detach()
+    gold['leconv/out_att'] = le(x, b.edge_index, edge_atten=att).detach()
+    gold['leconv/out_plain'] = le(x, b.edge_index).detach()
+
+    # ---- SPMotifNet -------------------------------------------------------------------------------------------
+    sp = _extract(f'{REF}/src/models/spmotif_gnn.py', ['SPMotifNet'])
+    ns_sp = _compile(sp.values(), {'torch': torch, 'Linear': nn.Linear, 'ReLU': nn.ReLU, 'ModuleList': nn.ModuleList,
+                                   'global_mean_pool': O.global_mean_pool, 'LEConv': ns['LEConv']})
+    torch.manual_seed(2)
+    net = ns_sp['SPMotifNet'](4, 1, 3, False, {'n_layers': 2, 'hidden_size': 16})
+    x4 = torch.rand(N, 4, generator=g)
+    gold['spmotif/state'] = {k: v.clone() for k, v in net.state_dict().items()}
+    gold['spmotif/x'] = x4
+    gold['spmotif/logits'] = net(x4, b.edge_index, b.batch, w, edge_atten=att).detach()
+    gold['spmotif/emb'] = net.get_emb(x4, b.edge_index, b.batch, w, edge_atten=att).detach()
+    gx = net.get_graph_rep(x4, b.edge_index, w, b.batch, att).detach()
+    gold['spmotif/comb_pred'] = net.get_comb_pred(gx, gx).detach()
+    gold['spmotif/conf_pred'] = net.get_conf_pred(gx).detach()
+
+    # ---- the fork's GSAT class: __loss__ + dual_forward_pass --------------------------------------------------
+    gm = _extract(f'{REF}/src/utils/get_model.py', ['Criterion', 'BatchSequential', 'MLP'])
+    ns_gm = _compile(gm.values(), {'nn': nn, 'F': F, 'InstanceNorm': O.InstanceNorm, 'print': quiet})
+    ns_u = {'torch': torch, 'sort_edge_index': O.sort_edge_index}
+    _compile(_extract(f'{REF}/src/utils/utils.py', ['reorder_like']).values(), ns_u)
+    run = _extract(f'{REF}/src/run_gsat.py', ['GSAT', 'ExtractorMLP'])
+    ns_run = _compile(run.values(), {
+        'torch': torch, 'nn': nn, 'F': F, 'np': np, 'Criterion': ns_gm['Criterion'], 'MLP': ns_gm['MLP'],
+        'is_undirected': O.is_undirected, 'transpose': O.transpose, 'reorder_like': ns_u['reorder_like'],
+        'print': quiet, 'input': quiet, 'plt': None, 'sns': None})
+    RefGSAT, RefExtractor = ns_run['GSAT'], ns_run['ExtractorMLP']
+
+    from tests.test_gpu_z_next_rows import _primal_dual_pair
+    p, d = _primal_dual_pair(6, seed=8)
+    cfg = {'model_name': 'GIN', 'hidden_size': 16, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    sc = {'learn_edge_att': False, 'extractor_dropout_p': 0.5, 'precision_k': 5, 'num_viz_samples': 0,
+          'viz_interval': 10, 'viz_norm_att': True}
+    mc = {'method_name': 'GSAT', 'pred_loss_coef': 1, 'info_loss_coef': 1, 'epochs': 100, 'decay_interval': 10,
+          'decay_r': 0.1, 'final_r': 0.5, 'init_r': 0.9}
+    torch.manual_seed(3)
+    pc, pe = O.get_model(10, 0, 2, False, cfg), RefExtractor(16, sc, 'primal')
+    dc, de = O.get_model(7, 0, 2, False, cfg), RefExtractor(16, sc, 'dual')
+    ref = RefGSAT(pc, pe, None, None, None, 'cpu', None, 'mutag', 2, False, 0, mc, sc, cfg,
+                  dc, de, None, None, None, 'cpu', None, 'mutag_dual', 2, False, 0, mc, sc, cfg)
+    for m in (pc, pe, dc, de):                  # (the reference class re-defines .train() as its training loop)
+        m.eval()
+    for name, m in (('primal_clf', pc), ('primal_extractor', pe), ('dual_clf', dc), ('dual_extractor', de)):
+        gold[f'dual/{name}/state'] = {k: v.clone() for k, v in m.state_dict().items()}
+    for side, data in (('primal', p), ('dual', d)):
+        for k in ('x', 'edge_index', 'batch', 'y', 'edge_label'):
+            gold[f'dual/{side}/{k}'] = getattr(data, k)
+    gold['dual/method_config'], gold['dual/shared_config'], gold['dual/model_config'] = mc, sc, cfg
+    for epoch in (3, 57):
+        seed = 100 + epoch
+        torch.manual_seed(seed)                       # the draws the body will make, in its order (:204, :222, :229)
+        u_primal = torch.empty(p.num_nodes, 1).uniform_(1e-10, 1 - 1e-10)
+        U_dual = torch.rand(d.num_nodes, 1)
+        torch.manual_seed(seed)
+        edge_att, loss, loss_dict, logits = ref.dual_forward_pass(p, d, epoch, True)
+        gold[f'dual/epoch{epoch}/primal_u'], gold[f'dual/epoch{epoch}/dual_U'] = u_primal, U_dual
+        gold[f'dual/epoch{epoch}/primal_edge_att'] = edge_att.detach()
+        gold[f'dual/epoch{epoch}/loss'] = loss.detach()
+        gold[f'dual/epoch{epoch}/logits'] = logits.detach()
+        gold[f'dual/epoch{epoch}/loss_dict'] = dict(loss_dict)
+    torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
+    print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))
+
+
+if __name__ == '__main__':
+    main()

@@ -209,3 +209,75 @@ def test_leconv_and_spmotifnet_oracle_known_answers():
     assert 'convs.0.lin2.bias' not in keys
     out = net(torch.rand(N, 4), b.edge_index, b.batch, torch.ones(E, 1))
     assert out.shape == (3, 3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fork-specific classes against the reference's own bodies (tests/golden/ref_fork.pt, made by make_golden_fork.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def fork_gold():
+    return torch.load(os.path.join(GOLDEN, 'ref_fork.pt'), weights_only=False)
+
+
+def test_conv_layers_against_reference_bodies(fork_gold):
+    """GINConv / GINEConv / LEConv forward + message (conv_layers.py:14-92) executed from the reference source."""
+    fg = fork_gold
+    ei, x, att = fg['graph/edge_index'], fg['graph/x'], fg['graph/att']
+    H = x.shape[1]
+    gin = O.GINConv(O.gin_mlp(H, H))
+    gin.load_state_dict(fg['ginconv/state'])
+    gin.eval()
+    assert torch.allclose(gin(x, ei, edge_atten=att), fg['ginconv/out_att'], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(gin(x, ei), fg['ginconv/out_noatt'], rtol=1e-6, atol=1e-6)
+    gine = O.GINEConv(O.gin_mlp(H, H), edge_dim=5)
+    gine.load_state_dict(fg['gineconv/state'])
+    gine.eval()
+    assert torch.allclose(gine(x, ei, edge_attr=fg['graph/edge_attr'], edge_atten=att), fg['gineconv/out_att'],
+                          rtol=1e-6, atol=1e-6)
+    le = O.LEConv(H, H)
+    le.load_state_dict(fg['leconv/state'])
+    w = fg['graph/edge_weight']
+    assert torch.allclose(le(x, ei, edge_weight=w, edge_atten=att), fg['leconv/out_w_att'], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(le(x, ei, edge_atten=att), fg['leconv/out_att'], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(le(x, ei), fg['leconv/out_plain'], rtol=1e-6, atol=1e-6)
+
+
+def test_spmotifnet_against_reference_class(fork_gold):
+    """SPMotifNet (spmotif_gnn.py:9-87), the whole reference class on the reference LEConv."""
+    fg = fork_gold
+    net = O.get_model(4, 1, 3, False, {'model_name': 'SPMotifNet', 'n_layers': 2, 'hidden_size': 16})
+    assert set(net.state_dict().keys()) == set(fg['spmotif/state'].keys())
+    net.load_state_dict(fg['spmotif/state'])
+    ei, batch, w, att, x4 = (fg['graph/edge_index'], fg['graph/batch'], fg['graph/edge_weight'], fg['graph/att'],
+                             fg['spmotif/x'])
+    assert torch.allclose(net(x4, ei, batch, w, edge_atten=att), fg['spmotif/logits'], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(net.get_emb(x4, ei, batch, w, edge_atten=att), fg['spmotif/emb'], rtol=1e-6, atol=1e-6)
+    gx = net.get_graph_rep(x4, ei, w, batch, att)
+    assert torch.allclose(net.get_comb_pred(gx, gx), fg['spmotif/comb_pred'], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(net.get_conf_pred(gx), fg['spmotif/conf_pred'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('epoch', [3, 57])
+def test_dual_forward_pass_against_reference_body(fork_gold, epoch):
+    """The fork's GSAT.__loss__ + dual_forward_pass (run_gsat.py:121-149, 189-283) executed from the reference source
+    with the reference ExtractorMLP / Criterion / MLP / reorder_like, on both sides of the epoch > 50 mix."""
+    from types import SimpleNamespace
+    fg = fork_gold
+    cfg, sc, mc = fg['dual/model_config'], fg['dual/shared_config'], fg['dual/method_config']
+    pc, pe = O.get_model(10, 0, 2, False, cfg), O.ExtractorMLP(cfg['hidden_size'], sc, 'primal')
+    dc, de = O.get_model(7, 0, 2, False, cfg), O.ExtractorMLP(cfg['hidden_size'], sc, 'dual')
+    for name, m in (('primal_clf', pc), ('primal_extractor', pe), ('dual_clf', dc), ('dual_extractor', de)):
+        assert set(m.state_dict().keys()) == set(fg[f'dual/{name}/state'].keys()), name
+        m.load_state_dict(fg[f'dual/{name}/state'])
+        m.eval()
+    g = O.DualGSAT(pc, pe, dc, de, O.Criterion(2, False), O.Criterion(2, False), mc, sc, mc, sc)
+    data = {side: SimpleNamespace(edge_attr=None, **{k: fg[f'dual/{side}/{k}'] for k in
+                                                     ('x', 'edge_index', 'batch', 'y', 'edge_label')})
+            for side in ('primal', 'dual')}
+    noise = {'primal_u': fg[f'dual/epoch{epoch}/primal_u'], 'dual_U': fg[f'dual/epoch{epoch}/dual_U']}
+    edge_att, loss, loss_dict, logits = g.dual_forward_pass(data['primal'], data['dual'], epoch, True, noise)
+    assert torch.allclose(edge_att, fg[f'dual/epoch{epoch}/primal_edge_att'], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(logits, fg[f'dual/epoch{epoch}/logits'], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(loss, fg[f'dual/epoch{epoch}/loss'], rtol=1e-5, atol=1e-6)
+    for k, v in fg[f'dual/epoch{epoch}/loss_dict'].items():
+        assert abs(loss_dict[k] - v) <= 1e-5 * max(1.0, abs(v)), k
