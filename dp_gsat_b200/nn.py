@@ -180,6 +180,18 @@ class BatchNorm1d(tnn.BatchNorm1d):
                                       self.eps, self.sync_group)
 
 
+class BatchNorm(tnn.Module):
+    """torch_geometric.nn.BatchNorm as the reference's PNA uses it (pna.py:8,45): a thin wrapper holding the
+    BatchNorm1d as ``self.module``, so that a PNA state_dict has the reference's ``batch_norms.{i}.module.*`` keys."""
+
+    def __init__(self, in_channels, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.module = BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
+
+    def forward(self, x):
+        return self.module(x)
+
+
 class GINConv(tnn.Module):
     """src/models/conv_layers.py:14-34 over torch_geometric GINConv(nn, eps=0., train_eps=False): ``eps`` is a
     buffer, present in the state_dict."""

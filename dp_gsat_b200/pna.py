@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .index import GraphIndex, get_graph_index
-from .nn import AtomEncoder, BatchNorm1d, BondEncoder, _dropout, _encode_once
+from .nn import AtomEncoder, BatchNorm, BondEncoder, _dropout, _encode_once
 
 
 def _scale_identity(src, deg, avg):
@@ -98,7 +98,7 @@ class PNA(tnn.Module):
         for _ in range(self.n_layers):
             self.convs.append(PNAConvSimple(in_channels=in_channels, out_channels=hidden_size, aggregators=aggregators,
                                             scalers=scalers, deg=deg, post_layers=1))
-            self.batch_norms.append(BatchNorm1d(hidden_size))
+            self.batch_norms.append(BatchNorm(hidden_size))
         self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, hidden_size // 2), tnn.ReLU(),
                                      tnn.Linear(hidden_size // 2, hidden_size // 4), tnn.ReLU(),
                                      tnn.Linear(hidden_size // 4, 1 if num_class == 2 and not multi_label else num_class))

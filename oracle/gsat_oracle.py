@@ -522,6 +522,19 @@ class GIN(nn.Module):
         return self.fc_out(global_add_pool(emb, batch))
 
 
+class BatchNorm(nn.Module):
+    """torch_geometric.nn.BatchNorm (2.0.3; pna.py:8,45): a wrapper that holds ``torch.nn.BatchNorm1d(C, eps=1e-5,
+    momentum=0.1, affine=True, track_running_stats=True)`` as ``self.module`` -- hence the ``batch_norms.{i}.module.*``
+    keys of a reference PNA checkpoint (from the published source, unpinned)."""
+
+    def __init__(self, in_channels, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+        super().__init__()
+        self.module = nn.BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
+
+    def forward(self, x):
+        return self.module(x)
+
+
 class PNA(nn.Module):
     """pna.py:12-78."""
 
@@ -548,7 +561,7 @@ class PNA(nn.Module):
         self.batch_norms = nn.ModuleList()
         for _ in range(self.n_layers):
             self.convs.append(PNAConvSimple(in_channels, hidden, aggregators, scalers, deg, post_layers=1))
-            self.batch_norms.append(nn.BatchNorm1d(hidden))
+            self.batch_norms.append(BatchNorm(hidden))
         self.fc_out = nn.Sequential(nn.Linear(hidden, hidden // 2), nn.ReLU(),
                                     nn.Linear(hidden // 2, hidden // 4), nn.ReLU(),
                                     nn.Linear(hidden // 4, 1 if num_class == 2 and not multi_label else num_class))

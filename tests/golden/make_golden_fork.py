@@ -9,6 +9,9 @@ Pinned here (all first-party code of mihikamd/DP-GSAT):
   and a ``propagate`` that gathers x_j = x[edge_index[0]], x_i = x[edge_index[1]], calls the reference ``message`` and
   scatter-adds into edge_index[1] -- SURVEY App. A.1; that third-party part stays UNPINNED);
 * ``SPMotifNet`` (src/models/spmotif_gnn.py:9-87), whole class, on the reference LEConv above;
+* ``PNAConvSimple`` with its aggregators and scalers (src/models/conv_layers.py:96-259; torch_scatter's ``scatter`` and
+  PyG's ``degree`` bound to the restatements) and the whole ``GIN`` / ``PNA`` backbone classes (src/models/gin.py,
+  pna.py) on those layers, with ogb's encoders and PyG's BatchNorm / pooling bound to the restatements;
 * the fork's ``GSAT`` class (src/run_gsat.py:33-283): ``__init__``, ``__loss__``, ``dual_forward_pass`` and the helpers
   they call, with the reference's ``ExtractorMLP`` (:886-927), ``Criterion`` / ``MLP`` (src/utils/get_model.py) and
   ``reorder_like`` (src/utils/utils.py); the GNN backbones inside are the oracle's GIN (PyG-dependent, unpinned).
@@ -144,6 +147,81 @@ def main():
     gx = net.get_graph_rep(x4, b.edge_index, w, b.batch, att).detach()
     gold['spmotif/comb_pred'] = net.get_comb_pred(gx, gx).detach()
     gold['spmotif/conf_pred'] = net.get_conf_pred(gx).detach()
+
+    # ---- PNAConvSimple with its aggregators / scalers, and the GIN / PNA backbones ------------------------------
+    tree = ast.parse(open(f'{REF}/src/models/conv_layers.py').read())
+    pna_nodes = [n for n in tree.body
+                 if (isinstance(n, (ast.FunctionDef, ast.ClassDef)) and (n.name.startswith(('aggregate_', 'scale_'))
+                                                                         or n.name == 'PNAConvSimple'))
+                 or (isinstance(n, ast.Assign) and getattr(n.targets[0], 'id', '') in ('AGGREGATORS', 'SCALERS'))]
+
+    class MessagePassing(_Propagate):
+        def __init__(self, aggr=None, node_dim=0, **kwargs):
+            super().__init__()
+
+        def propagate(self, edge_index, size=None, **kw):
+            x = kw['x']
+            msg = self.message(x_i=x.index_select(0, edge_index[1]), x_j=x.index_select(0, edge_index[0]),
+                               edge_attr=kw.get('edge_attr'), edge_atten=kw.get('edge_atten'))
+            return self.aggregate(msg, edge_index[1], dim_size=x.shape[0])
+
+    def scatter(src, index, dim, out, dim_size, reduce):          # torch_scatter.scatter (restated, unpinned)
+        assert dim == 0 and out is None
+        return {'sum': O.scatter_sum, 'mean': O.scatter_mean, 'min': O.scatter_min, 'max': O.scatter_max}[reduce](
+            src, index, dim_size)
+
+    def reset(module):
+        for m in module.modules():
+            if hasattr(m, 'reset_parameters') and m is not module:
+                m.reset_parameters()
+    ns_pna = _compile([_strip_annotations(n) for n in pna_nodes],
+                      {'torch': torch, 'MessagePassing': MessagePassing, 'scatter': scatter, 'degree': O.degree,
+                       'reset': reset, 'Linear': nn.Linear, 'ReLU': nn.ReLU, 'Sequential': nn.Sequential,
+                       'print': quiet})
+    from dp_gsat_b200.data import molhiv_like_batch, in_degree_histogram
+    mb = molhiv_like_batch(6, seed=4, with_edge_attr=True)
+    deg = in_degree_histogram(mb)
+    Hp = 8
+    xm = torch.randn(mb.num_nodes, Hp, generator=g)
+    eam = torch.randn(mb.num_edges, Hp, generator=g)
+    attm = torch.rand(mb.num_edges, 1, generator=g)
+    gold['mol/edge_index'], gold['mol/batch'], gold['mol/x_int'], gold['mol/edge_attr_int'] = (
+        mb.edge_index, mb.batch, mb.x, mb.edge_attr)
+    gold['mol/x'], gold['mol/edge_feat'], gold['mol/att'], gold['mol/deg'] = xm, eam, attm, deg
+    for tag, aggs, scalers in (('all_identity', ['mean', 'min', 'max', 'std', 'sum', 'var'], ['identity']),
+                               ('scaled', ['mean', 'min', 'max', 'std'],
+                                ['identity', 'amplification', 'attenuation', 'linear', 'inverse_linear'])):
+        torch.manual_seed(5)
+        conv = ns_pna['PNAConvSimple'](3 * Hp, Hp, aggs, scalers, deg, post_layers=1)
+        gold[f'pnaconv/{tag}/state'] = {k: v.clone() for k, v in conv.state_dict().items()}
+        gold[f'pnaconv/{tag}/out'] = conv(xm, mb.edge_index, eam, edge_atten=attm).detach()
+    torch.manual_seed(5)
+    conv = ns_pna['PNAConvSimple'](2 * Hp, Hp, ['mean', 'min', 'max', 'std'], ['identity'], deg, post_layers=2)
+    gold['pnaconv/noea/state'] = {k: v.clone() for k, v in conv.state_dict().items()}
+    gold['pnaconv/noea/out'] = conv(xm, mb.edge_index, None, edge_atten=None).detach()
+
+    model_ns = {'torch': torch, 'nn': nn, 'F': F, 'Linear': nn.Linear, 'ReLU': nn.ReLU, 'Sequential': nn.Sequential,
+                'ModuleList': nn.ModuleList, 'AtomEncoder': O.AtomEncoder, 'BondEncoder': O.BondEncoder,
+                'BatchNorm': O.BatchNorm, 'global_mean_pool': O.global_mean_pool, 'global_add_pool': O.global_add_pool,
+                'PNAConvSimple': ns_pna['PNAConvSimple'], 'GINConv': ns['GINConv'], 'GINEConv': ns['GINEConv'],
+                'input': quiet, 'print': quiet}
+    RefPNA = _compile(_extract(f'{REF}/src/models/pna.py', ['PNA']).values(), dict(model_ns))['PNA']
+    RefGIN = _compile(_extract(f'{REF}/src/models/gin.py', ['GIN']).values(), dict(model_ns))['GIN']
+    pna_cfg = {'model_name': 'PNA', 'hidden_size': 16, 'n_layers': 2, 'dropout_p': 0.3, 'atom_encoder': True,
+               'use_edge_attr': True, 'aggregators': ['mean', 'min', 'max', 'std'], 'scalers': False, 'deg': deg}
+    gin_cfg = {'model_name': 'GIN', 'hidden_size': 16, 'n_layers': 2, 'dropout_p': 0.3, 'atom_encoder': True,
+               'use_edge_attr': True}
+    for tag, Ref, cfg_ in (('pna', RefPNA, pna_cfg), ('gin', RefGIN, gin_cfg)):
+        torch.manual_seed(6)
+        m = Ref(9, 3, 2, False, cfg_)
+        m.eval()
+        gold[f'{tag}_model/config'] = cfg_
+        gold[f'{tag}_model/state'] = {k: v.clone() for k, v in m.state_dict().items()}
+        gold[f'{tag}_model/logits'] = m(mb.x, mb.edge_index, mb.batch, mb.edge_attr, edge_atten=attm).detach()
+        gold[f'{tag}_model/emb'] = m.get_emb(mb.x, mb.edge_index, mb.batch, mb.edge_attr, edge_atten=attm).detach()
+        m.train()                                     # training-mode BatchNorm (batch statistics); dropout off
+        m.dropout_p = 0.0
+        gold[f'{tag}_model/logits_train'] = m(mb.x, mb.edge_index, mb.batch, mb.edge_attr, edge_atten=attm).detach()
 
     # ---- the fork's GSAT class: __loss__ + dual_forward_pass --------------------------------------------------
     gm = _extract(f'{REF}/src/utils/get_model.py', ['Criterion', 'BatchSequential', 'MLP'])

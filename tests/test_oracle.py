@@ -281,3 +281,38 @@ def test_dual_forward_pass_against_reference_body(fork_gold, epoch):
     assert torch.allclose(loss, fg[f'dual/epoch{epoch}/loss'], rtol=1e-5, atol=1e-6)
     for k, v in fg[f'dual/epoch{epoch}/loss_dict'].items():
         assert abs(loss_dict[k] - v) <= 1e-5 * max(1.0, abs(v)), k
+
+
+@pytest.mark.parametrize('tag,aggs,scalers,with_ea,post_layers', [
+    ('all_identity', ['mean', 'min', 'max', 'std', 'sum', 'var'], ['identity'], True, 1),
+    ('scaled', ['mean', 'min', 'max', 'std'], ['identity', 'amplification', 'attenuation', 'linear', 'inverse_linear'],
+     True, 1),
+    ('noea', ['mean', 'min', 'max', 'std'], ['identity'], False, 2)])
+def test_pnaconv_against_reference_class(fork_gold, tag, aggs, scalers, with_ea, post_layers):
+    """PNAConvSimple.forward / message / aggregate, all six aggregators and five scalers (conv_layers.py:96-259)."""
+    fg = fork_gold
+    H = fg['mol/x'].shape[1]
+    conv = O.PNAConvSimple((3 if with_ea else 2) * H, H, aggs, scalers, fg['mol/deg'], post_layers=post_layers)
+    assert set(conv.state_dict().keys()) == set(fg[f'pnaconv/{tag}/state'].keys())
+    conv.load_state_dict(fg[f'pnaconv/{tag}/state'])
+    out = conv(fg['mol/x'], fg['mol/edge_index'], fg['mol/edge_feat'] if with_ea else None,
+               edge_atten=fg['mol/att'] if with_ea else None)
+    assert torch.allclose(out, fg[f'pnaconv/{tag}/out'], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('tag', ['pna', 'gin'])
+def test_backbones_against_reference_classes(fork_gold, tag):
+    """The whole GIN (gin.py:12-81) and PNA (pna.py:12-78) classes executed from the reference source: identical
+    state_dict keys (incl. PNA's ``batch_norms.{i}.module.*``), eval and training-mode outputs."""
+    fg = fork_gold
+    cfg = dict(fg[f'{tag}_model/config'])
+    m = O.get_model(9, 3, 2, False, cfg)
+    assert set(m.state_dict().keys()) == set(fg[f'{tag}_model/state'].keys())
+    m.load_state_dict(fg[f'{tag}_model/state'])
+    m.eval()
+    args = (fg['mol/x_int'], fg['mol/edge_index'], fg['mol/batch'], fg['mol/edge_attr_int'])
+    assert torch.allclose(m(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/logits'], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(m.get_emb(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/emb'], rtol=1e-5, atol=1e-5)
+    m.train()
+    m.dropout_p = 0.0
+    assert torch.allclose(m(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/logits_train'], rtol=1e-4, atol=1e-5)
