@@ -497,3 +497,103 @@ def test_dual_train_and_eval_one_batch(G):
     att2, _, logits2 = gsat.dual_eval_one_batch(pd_, dd_, 4)
     assert torch.equal(att, att2) and torch.equal(logits, logits2)              # eval: no sampling noise, no dropout
     assert float(att.min()) >= 0.0 and float(att.max()) <= 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# product directly against the outputs of the reference's OWN class bodies (tests/golden/ref_fork.pt, generated by
+# tests/golden/make_golden_fork.py from /root/reference): no oracle in between -- state_dict keys, shapes, outputs
+# ---------------------------------------------------------------------------------------------------------------
+_FORK_GOLD = {}
+
+
+def _fork_gold():
+    import os
+    from tests.conftest import GOLDEN
+    if not _FORK_GOLD:
+        raw = torch.load(os.path.join(GOLDEN, 'ref_fork.pt'), weights_only=False)
+        _FORK_GOLD.update({k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in raw.items()})
+    return _FORK_GOLD
+
+
+def _cfg_on_host(cfg):
+    return {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in cfg.items()}
+
+
+def _load(module, state):
+    assert set(module.state_dict().keys()) == set(state.keys())
+    for k, v in module.state_dict().items():
+        assert v.shape == state[k].shape, k
+    module.load_state_dict(state)
+    return module.cuda()
+
+
+def test_product_layers_reproduce_the_reference_layers(G):
+    fg = _fork_gold()
+    ei, x, att = fg['graph/edge_index'], fg['graph/x'], fg['graph/att']
+    H = x.shape[1]
+    tol = dict(rtol=1e-5, atol=1e-5)
+    gin = _load(G.GINConv(G.GIN.MLP(H, H)), fg['ginconv/state']).eval()
+    assert torch.allclose(gin(x, ei, edge_atten=att), fg['ginconv/out_att'], **tol)
+    assert torch.allclose(gin(x, ei), fg['ginconv/out_noatt'], **tol)
+    gine = _load(G.GINEConv(G.GIN.MLP(H, H), edge_dim=5), fg['gineconv/state']).eval()
+    assert torch.allclose(gine(x, ei, edge_attr=fg['graph/edge_attr'], edge_atten=att), fg['gineconv/out_att'], **tol)
+    le = _load(G.LEConv(H, H), fg['leconv/state'])
+    assert torch.allclose(le(x, ei, edge_weight=fg['graph/edge_weight'], edge_atten=att), fg['leconv/out_w_att'], **tol)
+    assert torch.allclose(le(x, ei, edge_atten=att), fg['leconv/out_att'], **tol)
+    assert torch.allclose(le(x, ei), fg['leconv/out_plain'], **tol)
+    Hm = fg['mol/x'].shape[1]
+    for tag, aggs, scalers, with_ea, post in (
+            ('all_identity', ['mean', 'min', 'max', 'std', 'sum', 'var'], ['identity'], True, 1),
+            ('scaled', ['mean', 'min', 'max', 'std'],
+             ['identity', 'amplification', 'attenuation', 'linear', 'inverse_linear'], True, 1),
+            ('noea', ['mean', 'min', 'max', 'std'], ['identity'], False, 2)):
+        conv = _load(G.PNAConvSimple((3 if with_ea else 2) * Hm, Hm, aggs, scalers, fg['mol/deg'].cpu(), post_layers=post),
+                     fg[f'pnaconv/{tag}/state'])
+        out = conv(fg['mol/x'], fg['mol/edge_index'], fg['mol/edge_feat'] if with_ea else None,
+                   edge_atten=fg['mol/att'] if with_ea else None)
+        assert torch.allclose(out, fg[f'pnaconv/{tag}/out'], rtol=1e-4, atol=1e-4), tag
+
+
+@pytest.mark.parametrize('tag', ['pna', 'gin', 'spmotif'])
+def test_product_backbones_reproduce_the_reference_classes(G, tag):
+    fg = _fork_gold()
+    if tag == 'spmotif':
+        net = _load(G.get_model(4, 1, 3, False, {'model_name': 'SPMotifNet', 'n_layers': 2, 'hidden_size': 16}, 'cuda'),
+                    fg['spmotif/state'])
+        ei, batch, w, att, x4 = (fg['graph/edge_index'], fg['graph/batch'], fg['graph/edge_weight'], fg['graph/att'],
+                                 fg['spmotif/x'])
+        assert torch.allclose(net(x4, ei, batch, w, edge_atten=att), fg['spmotif/logits'], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(net.get_emb(x4, ei, batch, w, edge_atten=att), fg['spmotif/emb'], rtol=1e-5, atol=1e-5)
+        gx = net.get_graph_rep(x4, ei, w, batch, att)
+        assert torch.allclose(net.get_comb_pred(gx, gx), fg['spmotif/comb_pred'], rtol=1e-5, atol=1e-5)
+        return
+    m = _load(G.get_model(9, 3, 2, False, _cfg_on_host(fg[f'{tag}_model/config']), 'cuda'), fg[f'{tag}_model/state']).eval()
+    args = (fg['mol/x_int'], fg['mol/edge_index'], fg['mol/batch'], fg['mol/edge_attr_int'])
+    assert torch.allclose(m(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/logits'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(m.get_emb(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/emb'], rtol=1e-4, atol=1e-5)
+    for fused in (False, True):                     # library lookups and the one-kernel encoders
+        m.node_encoder.fused = m.edge_encoder.fused = fused
+        m.train()
+        m.dropout_p = 0.0
+        assert torch.allclose(m(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/logits_train'], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('epoch', [3, 57])
+def test_product_dual_forward_pass_reproduces_the_reference_body(G, epoch):
+    fg = _fork_gold()
+    cfg, sc, mc = fg['dual/model_config'], fg['dual/shared_config'], fg['dual/method_config']
+    pc, pe = G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(cfg['hidden_size'], sc, 'primal').cuda()
+    dc, de = G.get_model(7, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(cfg['hidden_size'], sc, 'dual').cuda()
+    for name, m in (('primal_clf', pc), ('primal_extractor', pe), ('dual_clf', dc), ('dual_extractor', de)):
+        _load(m, fg[f'dual/{name}/state']).eval()
+    gsat = G.DualGSAT(pc, pe, dc, de, 2, False, 2, False, mc, sc, mc, sc)
+    data = {side: G.Batch(fg[f'dual/{side}/x'], fg[f'dual/{side}/edge_index'], fg[f'dual/{side}/batch'],
+                          fg[f'dual/{side}/y'], None, fg[f'dual/{side}/edge_label'],
+                          int(fg[f'dual/{side}/y'].shape[0])) for side in ('primal', 'dual')}
+    noise = {'primal_u': fg[f'dual/epoch{epoch}/primal_u'], 'dual_U': fg[f'dual/epoch{epoch}/dual_U']}
+    edge_att, loss, loss_dict, logits = gsat.dual_forward_pass(data['primal'], data['dual'], epoch, True, noise)
+    assert torch.allclose(edge_att, fg[f'dual/epoch{epoch}/primal_edge_att'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(logits, fg[f'dual/epoch{epoch}/logits'], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(loss, fg[f'dual/epoch{epoch}/loss'], rtol=1e-4, atol=1e-5)
+    for k, v in fg[f'dual/epoch{epoch}/loss_dict'].items():
+        assert abs(loss_dict[k] - v) <= 1e-4 * max(1.0, abs(v)), k

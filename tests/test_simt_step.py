@@ -91,6 +91,13 @@ CASES = [
     _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=True, epoch=60),
     _case(Z.test_dual_forward_pass_parity, primal_learn_edge_att=False, epoch=60),
     _case(Z.test_dual_train_and_eval_one_batch),
+    # product directly against the outputs of the reference's own class bodies (tests/golden/ref_fork.pt)
+    _case(Z.test_product_layers_reproduce_the_reference_layers),
+    _case(Z.test_product_backbones_reproduce_the_reference_classes, tag='pna'),
+    _case(Z.test_product_backbones_reproduce_the_reference_classes, tag='gin'),
+    _case(Z.test_product_backbones_reproduce_the_reference_classes, tag='spmotif'),
+    _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=3),
+    _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=57),
 ]
 
 
