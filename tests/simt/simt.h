@@ -70,11 +70,14 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 
 namespace simt {
 
+// One fiber per thread SLOT of a block, created once and reused by every block and launch (its body loops: run the
+// kernel for the (block, thread) the scheduler has set, report done, wait to be resumed for the next one).
 struct Fiber {
     ucontext_t ctx;      // first entry only (makecontext); afterwards fibers switch with _setjmp / _longjmp, which --
     jmp_buf jb;          // unlike swapcontext -- do not make a sigprocmask system call per switch
-    bool started;
-    bool done;
+    char* stack = nullptr;
+    bool started = false;
+    bool done = false;
 };
 struct WarpBarrier {
     uint32_t arrived = 0;
@@ -89,9 +92,8 @@ struct Warp {
 struct State {
     ucontext_t sched;
     jmp_buf sched_jb;
-    std::vector<Fiber> fibers;
+    std::vector<Fiber*> fibers;   // pool, grows to the largest block seen; addresses and stacks never move
     std::vector<Warp> warps;
-    std::vector<char> stacks;
     const std::function<void()>* body = nullptr;
     int cur = -1;
     int live = 0;                 // fibers not finished
@@ -112,20 +114,22 @@ constexpr size_t kStackBytes = 256 * 1024;
 }
 inline void yield() {
     State& s = S();
-    if (_setjmp(s.fibers[s.cur].jb) == 0) _longjmp(s.sched_jb, 1);
+    if (_setjmp(s.fibers[s.cur]->jb) == 0) _longjmp(s.sched_jb, 1);
 }
 inline void trampoline() {
     State& s = S();
-    (*s.body)();
-    s.fibers[s.cur].done = true;
-    --s.live;
-    ++s.progress;
-    _longjmp(s.sched_jb, 1);
+    for (;;) {                               // s.cur / threadIdx / blockIdx / s.body were set by the scheduler
+        (*s.body)();
+        s.fibers[s.cur]->done = true;
+        --s.live;
+        ++s.progress;
+        yield();                             // resumed when this slot gets its next (block, thread)
+    }
 }
 // scheduler side: run fiber t until it yields or finishes
 inline void resume(int t) {
     State& s = S();
-    Fiber& f = s.fibers[t];
+    Fiber& f = *s.fibers[t];
     if (_setjmp(s.sched_jb) == 0) {
         if (!f.started) {
             f.started = true;
@@ -199,8 +203,16 @@ inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& bod
     s.body = &body;
     s.block_dim = block;
     s.grid_dim = grid;
-    s.fibers.resize(nthreads);
-    s.stacks.resize((size_t)nthreads * kStackBytes);
+    while ((int)s.fibers.size() < nthreads) {                 // new thread slots: one context + stack each, made once
+        Fiber* f = new Fiber();
+        f->stack = static_cast<char*>(std::malloc(kStackBytes));
+        getcontext(&f->ctx);
+        f->ctx.uc_stack.ss_sp = f->stack;
+        f->ctx.uc_stack.ss_size = kStackBytes;
+        f->ctx.uc_link = nullptr;                             // the trampoline never returns
+        makecontext(&f->ctx, (void (*)())simt::trampoline, 0);
+        s.fibers.push_back(f);
+    }
     blockDim = block;
     gridDim = grid;
     for (unsigned bz = 0; bz < grid.z; ++bz)
@@ -210,21 +222,14 @@ inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& bod
                 s.warps.assign((nthreads + 31) / 32, Warp());
                 for (int t = 0; t < nthreads; ++t) {
                     s.warps[t >> 5].exists |= 1u << (t & 31);
-                    Fiber& f = s.fibers[t];
-                    f.done = false;
-                    f.started = false;
-                    getcontext(&f.ctx);
-                    f.ctx.uc_stack.ss_sp = s.stacks.data() + (size_t)t * kStackBytes;
-                    f.ctx.uc_stack.ss_size = kStackBytes;
-                    f.ctx.uc_link = nullptr;            // the trampoline never returns
-                    makecontext(&f.ctx, (void (*)())simt::trampoline, 0);
+                    s.fibers[t]->done = false;
                 }
                 s.live = nthreads;
                 s.block_arrived = 0;
                 while (s.live > 0) {
                     const uint64_t before = s.progress;
                     for (int t = 0; t < nthreads; ++t) {
-                        if (s.fibers[t].done) continue;
+                        if (s.fibers[t]->done) continue;
                         s.cur = t;
                         threadIdx = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y,
                                           (unsigned)t / (block.x * block.y)};
