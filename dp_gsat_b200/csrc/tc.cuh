@@ -1,6 +1,12 @@
 // sm_100a tensor-core plumbing: mbarrier, TMA, tcgen05 (MMA / TMEM alloc / ld / commit) inline-PTX wrappers and
 // the shared-memory / instruction descriptors for bf16 K-major SWIZZLE_128B operands.
 #pragma once
+#ifdef GSATB_HOST_SIM
+// tests/simt: host implementations of every PTX wrapper of this file (mbarrier words, named barriers, TMA boxes with
+// the SWIZZLE_128B pattern, tcgen05.mma / TMEM as plain arrays) for the CPU-side kernel-logic tests.  Never defined in
+// the product build.
+#include "tc_sim.h"
+#else
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -125,6 +131,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+}  // namespace tc
+#endif  // GSATB_HOST_SIM
+
+namespace tc {
 
 // ---- descriptors -------------------------------------------------------------------------------------------
 // K-major, SWIZZLE_128B operand tile: rows of 64 bf16 (128 B), 8-row atoms 1024 B apart (tile base 1024-aligned).

@@ -106,12 +106,19 @@ __device__ __forceinline__ void epi_release_acc(const EpiCtx& c) {
     tc::tc_fence_before();
     tc::mbar_arrive(c.acc_empty);
 }
+#ifdef GSATB_HOST_SIM      // tests/simt: the copy completes at once
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 // Asynchronously copy rows [row_lo, row_lo + nrows) x channels [ch0, ch0 + nch) of the row-major tensor `g`
 // (element size ES, leading dimension ld elements; g points at element (row 0 of the TILE, channel 0)) into `buf`
@@ -214,7 +221,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CU
           const Shape sh, const typename Op::Params p) {
     constexpr bool TMA_B = Op::TMA_B;
     constexpr int NGRP = TMA_B ? 4 : 2;
+#ifdef GSATB_HOST_SIM
+    uint8_t* smem_raw = simt::dyn_smem();
+#else
     extern __shared__ uint8_t smem_raw[];
+#endif
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const SmemLayout L = smem_layout(sh);
     uint8_t* sA = smem + L.a_off;

@@ -45,6 +45,7 @@ def line_graph_dual(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: O
     dual_ei = torch.empty((2, Ed), dtype=torch.int64, device=dev)
     nd = E // 2 if halve else E
     dual_batch = torch.empty(nd, dtype=torch.int64, device=dev)
+    batch_c = batch.contiguous()
     L.call('gsatb_line_graph_fill', ptr(gi.src), ptr(gi.rowptr_src), ptr(members), ptr(offs),
-           ptr(batch.contiguous()), N, E, int(halve), ptr(dual_ei), Ed, ptr(dual_batch), stream())
+           ptr(batch_c), N, E, int(halve), ptr(dual_ei), Ed, ptr(dual_batch), stream())
     return dual_ei, dual_batch

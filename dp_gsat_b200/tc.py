@@ -266,9 +266,12 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     g = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
     part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
     stats = torch.empty(2 * H1, dtype=torch.float32, device=dev)
+    # (operands are held in locals until the launch has been enqueued: a temporary passed as ptr(f(x)) is released
+    # before the call is made -- harmless with the stream-ordered caching allocator, but not something to lean on)
+    w2t = prep_weight(w2, transpose=True)
     L.call('gsatb_tc_gin_bwd2', ptr(dh), None if posmask is not None else ptr(h), ptr(posmask),
            ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
-           ptr(prep_weight(w2, transpose=True)), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
+           ptr(w2t), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
            ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
     dbeta, dgamma = stats[:H1], stats[H1:]
     coef = gamma * rstd
@@ -286,8 +289,9 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
         cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
     dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
     dagg = torch.empty((N, Kin), dtype=torch.float32, device=dev)
-    L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA.contiguous()), ptr(cB.contiguous()), ptr(cC.contiguous()),
-           ptr(prep_weight(w1, transpose=True)), ptr(dz1), ptr(dagg), N, H1, Kin, stream())
+    cA, cB, cC, w1t = cA.contiguous(), cB.contiguous(), cC.contiguous(), prep_weight(w1, transpose=True)
+    L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, Kin,
+           stream())
     ones = torch.ones((1, N), dtype=torch.bfloat16, device=dev)
     dW2 = _mm_f32(d2.t(), a1)
     db2 = _mm_f32(ones, d2).view(-1)

@@ -15,7 +15,8 @@ OUT_DIR = os.environ.get('GSATB_SIM_BUILD_DIR', os.path.join(HERE, 'build'))
 LIB = os.path.join(OUT_DIR, 'libgsat_sim.so')
 # every kernel source without tcgen05 / TMA / mbarrier PTX: the fp32 path of the step, K0, the line-graph builder, metrics
 SIM_SOURCES = ['aggregate.cu', 'gine.cu', 'leconv.cu', 'pna.cu', 'index_build.cu', 'line_graph.cu', 'sampler.cu',
-               'segnorm.cu', 'small_ops.cu', 'metrics.cu', 'encoders.cu', 'collate.cu', 'api.cu']
+               'segnorm.cu', 'small_ops.cu', 'metrics.cu', 'encoders.cu', 'collate.cu', 'api.cu',
+               'tc_ops.cu', 'tc_gin.cu', 'tc_extractor.cu', 'tc_extractor_bwd.cu']
 
 _LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<')
 
@@ -60,14 +61,13 @@ def rewrite_launches(txt: str) -> str:
             return out + txt[pos:]
         cfg_end = txt.index('>>>', m.end())
         cfg = _split_top(txt[m.end():cfg_end].replace('\\\n', ' '))
-        if len(cfg) >= 3 and cfg[2] not in ('0', ''):
-            raise ValueError(f'dynamic shared memory is not emulated: {m.group(0)} {cfg}')
+        smem = cfg[2] if len(cfg) >= 3 and cfg[2] else '0'
         a0 = cfg_end + 3
         while txt[a0] in ' \t\\\n':
             a0 += 1
         assert txt[a0] == '(', txt[m.start():a0 + 20]
         a1 = _match(txt, a0, '(', ')')
-        out += txt[pos:m.start()] + f'simt::launch(dim3({cfg[0]}), dim3({cfg[1]}), [&]() {{ {m.group(1)}{txt[a0:a1]}; }})'
+        out += txt[pos:m.start()] + f'simt::launch(dim3({cfg[0]}), dim3({cfg[1]}), [&]() {{ {m.group(1)}{txt[a0:a1]}; }}, {smem})'
         pos = a1
 
 
@@ -77,12 +77,17 @@ def sources():
 
 
 def build(force: bool = False) -> str:
-    deps = sources() + [os.path.join(HERE, 'simt.h'), os.path.join(HERE, 'cuda_bf16.h'), os.path.join(CSRC, 'common.cuh'),
+    deps = sources() + [os.path.join(HERE, h) for h in os.listdir(HERE) if h.endswith('.h')] + \
+        [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith('.cuh')] + [
                         os.path.join(ROOT, 'include', 'gsat_b200.h'), os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gen = os.path.join(OUT_DIR, 'gen')
     os.makedirs(gen, exist_ok=True)
+    for h in sorted(os.listdir(CSRC)):                      # headers may launch kernels too (tc_gemm.cuh)
+        if h.endswith('.cuh'):
+            with open(os.path.join(gen, h), 'w') as f:
+                f.write(f'#line 1 "{os.path.join(CSRC, h)}"\n' + rewrite_launches(open(os.path.join(CSRC, h)).read()))
     procs = []
     for s in sources():
         base = os.path.splitext(os.path.basename(s))[0]
@@ -90,7 +95,7 @@ def build(force: bool = False) -> str:
         with open(g, 'w') as f:
             f.write(f'#line 1 "{s}"\n' + rewrite_launches(open(s).read()))
         o = os.path.join(OUT_DIR, base + '.o')
-        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O1', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE', '-I', HERE, '-I', CSRC,
+        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O1', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE', '-I', HERE, '-I', gen, '-I', CSRC,
                '-Wno-attributes', '-Wno-unused', '-Wno-unknown-pragmas', '-c', g, '-o', o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

@@ -8,8 +8,8 @@ TEST INFRASTRUCTURE ONLY.  Two users:
   refuses CPU tensors (``_lib.require_cuda``) and has no CPU path.
 * ``python -m pytest -p tests.simt.emulate -m gpu tests/test_gpu_parity.py ...``: a DRY RUN of the GPU suites on a machine
   without a GPU.  As a pytest plugin this module additionally redirects ``.cuda()`` / ``device='cuda'`` in torch to the
-  CPU, so the GPU test bodies themselves execute (against the emulated kernels).  Tests that need the tcgen05 kernels,
-  CUDA graphs or BASELINE-size inputs are skipped.  A dry run is not a GPU result and is never reported as one.
+  CPU, so the GPU test bodies themselves execute (against the emulated kernels, the tcgen05 ones included).  Tests
+  that need CUDA graphs or BASELINE-size inputs are skipped.  A dry run is not a GPU result and is never reported as one.
 """
 from __future__ import annotations
 
@@ -36,7 +36,7 @@ class EmulatedLib:
         for name, (restype, argtypes) in self.protos.items():
             try:
                 fn = getattr(self.cdll, name)
-            except AttributeError:          # tcgen05 / TMA entry points are not part of the emulator build
+            except AttributeError:          # an entry point whose source is not part of the emulator build
                 self.missing.append(name)
                 continue
             fn.restype, fn.argtypes = restype, argtypes
@@ -58,7 +58,7 @@ class EmulatedLib:
 
     def call(self, name: str, *args):
         if name in self.missing:
-            raise NotImplementedError(f'{name}: tcgen05 / TMA kernels are not emulated')
+            raise NotImplementedError(f'{name} is not part of the emulator build')
         self.launches += 1
         rc = getattr(self.cdll, name)(*args)
         if rc != 0:
@@ -90,6 +90,10 @@ def patch_product(setattr_fn) -> EmulatedLib:
             setattr_fn(mod, 'require_cuda', lambda t: None)
         if hasattr(mod, 'device_guard'):
             setattr_fn(mod, 'device_guard', lambda dev: contextlib.nullcontext())
+    tc = importlib.import_module('dp_gsat_b200.tc')
+    setattr_fn(tc, 'lib', lambda: emu)
+    setattr_fn(tc, 'stream', lambda: None)
+    setattr_fn(tc, '_mm_f32', lambda a, b: a.float() @ b.float())      # torch.mm(out_dtype=) exists on CUDA only
     index = importlib.import_module('dp_gsat_b200.index')
     index.clear_index_cache()
     return emu
@@ -98,7 +102,7 @@ def patch_product(setattr_fn) -> EmulatedLib:
 # ---------------------------------------------------------------------------------------------------------------
 # pytest plugin: dry run of the GPU suites (-p tests.simt.emulate)
 # ---------------------------------------------------------------------------------------------------------------
-_SKIP_IN_DRY_RUN = ('test_gpu_tc.py', 'test_cuda_graph_training_step', 'test_large_batch_properties', 'one_big_graph',
+_SKIP_IN_DRY_RUN = ('test_cuda_graph_training_step', 'test_large_batch_properties', 'one_big_graph',
                     '300000')
 
 
@@ -133,8 +137,8 @@ def redirect_torch_to_cpu(setattr_fn):
         return m_to(self, *a, **k)
     setattr_fn(torch.Tensor, 'to', tensor_to)
     setattr_fn(torch.nn.Module, 'to', module_to)
-    for name in ('zeros', 'ones', 'empty', 'full', 'arange', 'tensor', 'rand', 'randn', 'randint', 'zeros_like',
-                 'empty_like', 'ones_like'):
+    for name in ('zeros', 'ones', 'empty', 'full', 'arange', 'tensor', 'as_tensor', 'rand', 'randn', 'randint', 'eye',
+                 'randperm', 'linspace', 'zeros_like', 'empty_like', 'ones_like', 'full_like', 'rand_like', 'randn_like'):
         orig = getattr(torch, name)
 
         def wrapped(*a, __orig=orig, **k):
@@ -153,4 +157,4 @@ def pytest_collection_modifyitems(config, items):
     import pytest
     for it in items:
         if any(s in it.nodeid for s in _SKIP_IN_DRY_RUN):
-            it.add_marker(pytest.mark.skip(reason='not part of the emulator dry run (tcgen05 / CUDA graph / full size)'))
+            it.add_marker(pytest.mark.skip(reason='not part of the emulator dry run (CUDA graph / full size)'))

@@ -1,7 +1,7 @@
 // Host-side SIMT emulator: TEST INFRASTRUCTURE ONLY (tests/simt/, `-m "not gpu"` suite).
 //
-// Lets a kernel source of dp_gsat_b200/csrc/ that is written against csrc/common.cuh and launched through
-// GSATB_LAUNCH be compiled by plain g++ (-DGSATB_HOST_SIM) and run on the CPU with CUDA's execution semantics:
+// Lets the kernel sources of dp_gsat_b200/csrc/ be compiled by plain g++ (-DGSATB_HOST_SIM; build_sim.py rewrites the
+// <<<...>>> launches in a generated copy) and run on the CPU with CUDA's execution semantics:
 // every thread of a block is a cooperative fiber (ucontext); blocks run one after the other; __syncthreads() and the
 // *_sync warp primitives are real rendezvous points (a lane named in a mask that never arrives is reported as a
 // dead-lock instead of hanging, a lane that calls with a mask it is not part of aborts).  Global / shared memory are
@@ -49,6 +49,8 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
@@ -89,9 +91,20 @@ struct Warp {
     std::unordered_map<uint32_t, WarpBarrier> bars;           // one rendezvous per distinct mask
 };
 
+struct NamedBarrier {
+    int arrived = 0;
+    uint64_t gen = 0;
+};
+constexpr size_t kDynSmemBytes = 256 * 1024;        // >= the 227 KiB a CTA can opt into
+constexpr uint32_t kTmemCols = 512;
+
 struct State {
     ucontext_t sched;
     jmp_buf sched_jb;
+    uint8_t* dyn_smem = nullptr;  // 1024-aligned dynamic shared memory of the running block
+    float* tmem = nullptr;        // [128 lanes][kTmemCols] tensor memory of the running block
+    uint32_t tmem_next = 0;       // bump allocator of TMEM columns
+    NamedBarrier named[16];
     std::vector<Fiber*> fibers;   // pool, grows to the largest block seen; addresses and stacks never move
     std::vector<Warp> warps;
     const std::function<void()>* body = nullptr;
@@ -187,7 +200,31 @@ inline T shfl_from(unsigned mask, T v, int src_lane) {
     return r;
 }
 
-inline void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+inline void launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes = 0);
+
+inline uint8_t* dyn_smem() { return S().dyn_smem; }
+inline float* tmem() { return S().tmem; }
+inline uint32_t tmem_alloc_cols(uint32_t ncols) {
+    State& s = S();
+    if (ncols < 32 || (ncols & (ncols - 1)) || s.tmem_next + ncols > kTmemCols) fail("tcgen05.alloc: bad column count");
+    const uint32_t base = s.tmem_next;
+    s.tmem_next += ncols;
+    return base;                                      // lane 0, column `base`
+}
+// bar.sync id, nthreads
+inline void named_barrier(int id, int nthreads) {
+    State& s = S();
+    if (id < 0 || id >= 16) fail("named barrier id out of range");
+    NamedBarrier& b = s.named[id];
+    ++s.progress;
+    if (++b.arrived == nthreads) {
+        b.arrived = 0;
+        ++b.gen;
+        return;
+    }
+    const uint64_t gen = b.gen;
+    while (b.gen == gen) yield();
+}
 
 }  // namespace simt
 
@@ -195,8 +232,13 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()>& body);
 inline uint3 threadIdx, blockIdx;
 inline dim3 blockDim, gridDim;
 
-inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& body, size_t dyn_smem_bytes) {
     State& s = S();
+    if (dyn_smem_bytes > kDynSmemBytes) fail("dynamic shared memory request too large");
+    if (!s.dyn_smem) {
+        s.dyn_smem = static_cast<uint8_t*>(std::aligned_alloc(1024, kDynSmemBytes));
+        s.tmem = static_cast<float*>(std::malloc(sizeof(float) * 128 * kTmemCols));
+    }
     const int nthreads = (int)(block.x * block.y * block.z);
     if (nthreads <= 0 || nthreads > 1024) fail("block size out of range");
     if (grid.x == 0 || grid.y == 0 || grid.z == 0 || grid.y > 65535 || grid.z > 65535) fail("grid size out of range");
@@ -219,6 +261,8 @@ inline void simt::launch(dim3 grid, dim3 block, const std::function<void()>& bod
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 blockIdx = uint3{bx, by, bz};
+                s.tmem_next = 0;
+                for (auto& nb : s.named) nb = NamedBarrier();
                 s.warps.assign((nthreads + 31) / 32, Warp());
                 for (int t = 0; t < nthreads; ++t) {
                     s.warps[t >> 5].exists |= 1u << (t & 31);
@@ -316,6 +360,20 @@ template <class T>
 inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }
 template <class T>
 inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
+inline long long clock64() { return 0; }
+inline float __uint_as_float(unsigned u) { return simt::from_bits<float>(simt::to_bits(u)); }
+inline unsigned __float_as_uint(float f) { return simt::from_bits<unsigned>(simt::to_bits(f)); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {       // PTX prmt, default mode
+    const uint64_t both = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned c = (sel >> (4 * i)) & 0xf;
+        unsigned byte = (unsigned)((both >> (8 * (c & 7))) & 0xff);
+        if (c & 8) byte = (byte & 0x80) ? 0xff : 0x00;                     // sign replication
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -4,16 +4,17 @@
 compiled by g++ against the emulator) and redirects `.cuda()` / `device='cuda'` to host tensors for the duration of one
 test; the functions called below are the `-m gpu` tests of tests/test_gpu_parity.py and tests/test_gpu_z_next_rows.py,
 unchanged, with the oracle as the checker.  What this tier proves and what it does not is stated in DESIGN.md section 2a:
-indexing, masks, warp-level reductions, argument order and autograd routing of every non-tensor-core kernel -- not the
-tcgen05 kernels, not inter-warp races, not speed.  It is not a GPU result.
+indexing, masks, warp-level reductions, argument order and autograd routing of every kernel, the tensor-core ones through
+functional models of mbarrier / TMA / tcgen05.mma / TMEM -- not inter-warp races, not the hardware's accumulation order,
+not speed.  It is not a GPU result.
 
-Left out on purpose: the tensor-core tests (tests/test_gpu_tc.py), the CUDA-graph test, the BASELINE-size property test,
-and two whole-step cases whose ill-conditioned BatchNorm statistics (constant BA-2Motifs features; see the docstring of
+Left out on purpose: the CUDA-graph test, the BASELINE-size property test, and two whole-step cases whose ill-conditioned BatchNorm statistics (constant BA-2Motifs features; see the docstring of
 test_gsat_step_parity.check) put the CPU library ops that replace torch's CUDA ops under emulation outside the bound.
 """
 import pytest
 
 import tests.test_gpu_parity as P
+import tests.test_gpu_tc as T
 import tests.test_gpu_z_next_rows as Z
 
 
@@ -72,6 +73,18 @@ CASES = [
     _case(P.test_gine_aggregate_fwd_bwd, H=64, with_att=True),
     _case(P.test_gsat_gin_with_edge_features_step_parity, atom_encoder=True),
     _case(P.test_on_device_metrics, k=5),
+    # the tensor-core path: tcgen05.mma / TMEM / TMA / mbarrier kernels on their host models (tests/simt/tc_sim.h)
+    _case(T.test_tc_linear_matches_bf16_reference, rows=1000, K=128, OUT=128),
+    _case(T.test_tc_linear_matches_bf16_reference, rows=3333, K=256, OUT=512),
+    _case(T.test_tc_linear_matches_bf16_reference, rows=777, K=80, OUT=80),
+    _case(T.test_fused_extractor_fwd_bwd, case='ba_edge_H64'),
+    _case(T.test_fused_extractor_fwd_bwd, case='ba_edge_H128'),
+    _case(T.test_fused_extractor_fwd_bwd, case='mol_node_H64'),
+    _case(T.test_fused_extractor_fwd_bwd, case='mol_edge_H80_p03'),
+    _case(T.test_fused_extractor_fwd_bwd, case='eval_mode'),
+    _case(T.test_gin_mlp_fused_matches_torch),
+    _case(T.test_gsat_step_bf16_mode_tracks_oracle),
+    _case(T.test_word_dropout_rate_and_scale, p=0.3),
     # SURVEY 8f rows built after the GPU budget was spent: emulator runs are all they have had so far
     _case(Z.test_le_aggregate_fwd_bwd, H=32, with_w=True, with_att=True),
     _case(Z.test_le_aggregate_fwd_bwd, H=300, with_w=True, with_att=True),
@@ -111,5 +124,6 @@ def test_sync_batchnorm_single_rank_body_on_the_emulator(G):
     group = next(gen)
     try:
         Z.test_sync_batchnorm_on_a_single_rank_group_equals_the_default(G, group, 'fp32')
+        Z.test_sync_batchnorm_on_a_single_rank_group_equals_the_default(G, group, 'bf16')
     finally:
         next(gen, None)
