@@ -28,16 +28,17 @@ class Batch:
     edge_label: Optional[torch.Tensor] = None
     num_graphs: int = 0
     _cache: dict = field(default_factory=dict, repr=False, compare=False)
+    node_label: Optional[torch.Tensor] = None      # per-node explanation labels (mutag.py / spmotif.py Data.node_label)
 
     def to(self, device, non_blocking: bool = False) -> "Batch":
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
         return Batch(mv(self.x), mv(self.edge_index), mv(self.batch), mv(self.y), mv(self.edge_attr),
-                     mv(self.edge_label), self.num_graphs)
+                     mv(self.edge_label), self.num_graphs, node_label=mv(self.node_label))
 
     def pin_memory(self) -> "Batch":
         pm = lambda t: None if t is None else t.pin_memory()
         return Batch(pm(self.x), pm(self.edge_index), pm(self.batch), pm(self.y), pm(self.edge_attr),
-                     pm(self.edge_label), self.num_graphs)
+                     pm(self.edge_label), self.num_graphs, node_label=pm(self.node_label))
 
     @property
     def num_nodes(self) -> int:
@@ -49,7 +50,7 @@ class Batch:
 
     def nbytes(self) -> int:
         tot = 0
-        for t in (self.x, self.edge_index, self.batch, self.y, self.edge_attr, self.edge_label):
+        for t in (self.x, self.edge_index, self.batch, self.y, self.edge_attr, self.edge_label, self.node_label):
             if t is not None:
                 tot += t.numel() * t.element_size()
         return tot

@@ -128,9 +128,7 @@ class PackedDataset:
         ds_ei = self.t['edge_index']
         L.call('gsatb_collate_edge_index', ptr(ds_ei), ds_ei.shape[1], ptr(self.edge_ptr), ptr(ids_dev),
                ptr(out_edge_ptr), ptr(out_node_ptr), B, E_out, ptr(ei), st)
-        b = Batch(x, ei, batch_vec, y, edge_attr, edge_label, B)
-        b.node_label = node_label
-        return b
+        return Batch(x, ei, batch_vec, y, edge_attr, edge_label, B, node_label=node_label)
 
 
 class DeviceLoader:

@@ -18,6 +18,17 @@ SIM_SOURCES = ['aggregate.cu', 'gine.cu', 'leconv.cu', 'pna.cu', 'index_build.cu
                'segnorm.cu', 'small_ops.cu', 'metrics.cu', 'encoders.cu', 'collate.cu', 'api.cu',
                'tc_ops.cu', 'tc_gin.cu', 'tc_extractor.cu', 'tc_extractor_bwd.cu']
 
+def _host_has_fma() -> bool:
+    try:
+        return ' fma ' in open('/proc/cpuinfo').read()
+    except OSError:
+        return False
+
+
+# nvcc contracts a * b + c into one FMA (-fmad=true, the default); let g++ do the same where the host can, so that
+# cancellation-prone expressions (E[m^2] - E[m]^2 in the PNA std aggregator, ...) round as they do on the device
+FMA_FLAGS = ['-mfma', '-ffp-contract=fast'] if _host_has_fma() else []
+
 _LAUNCH = re.compile(r'([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<')
 
 
@@ -95,7 +106,7 @@ def build(force: bool = False) -> str:
         with open(g, 'w') as f:
             f.write(f'#line 1 "{s}"\n' + rewrite_launches(open(s).read()))
         o = os.path.join(OUT_DIR, base + '.o')
-        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O1', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE', '-I', HERE, '-I', gen, '-I', CSRC,
+        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O1', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE'] + FMA_FLAGS + ['-I', HERE, '-I', gen, '-I', CSRC,
                '-Wno-attributes', '-Wno-unused', '-Wno-unknown-pragmas', '-c', g, '-o', o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

@@ -198,3 +198,16 @@ def test_product_two_ranks_without_sync_batchnorm_differ(tmp_path, monkeypatch):
     step = TrainStep(g, lr=1e-2, fused_adam=False)
     step(full, 0, noise_u=u_full)
     assert not torch.allclose(got['flat'], step.bucket.flat, rtol=2e-4, atol=1e-6)
+
+
+def test_bench_control_flow_on_two_ranks_without_a_gpu():
+    """bench.py's own b200 arm (warm-up, agreed pre-load, timed region, e2e loop, max over ranks, JSON line) on two gloo
+    ranks with the kernels on the emulator (tools/bench_dry_run.py): every rank issues the same collectives and the line
+    carries every contract key.  Timings are emulation and are not looked at."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'bench_dry_run.py'), '--ranks', '2', '--graphs', '48',
+                        '--steps', '1', '--warmup', '1'], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and 'control flow ok on 2 rank(s)' in r.stdout, r.stdout[-3000:]
