@@ -432,6 +432,15 @@ def run_b200(a):
         cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                         'sample': f'{n_graphs} graphs / {n_edges} edges per step of the same generator, 1 warm-up + 2 '
                                   f'timed steps, {sec:.2f} s/step; oracle/gsat_oracle.py on torch CPU'}
+        try:     # the reference's own thread setting (torch.set_num_threads(5), src/run_gsat.py:1049), half the sample
+            r5, e5, s5 = cpu_oracle_rate(a, max(200, n_graphs // 2), 1, 1, min(5, threads))
+            cpu_baseline['reference_thread_setting'] = {'value': r5, 'unit': UNIT, 'cores': min(5, threads),
+                                                        'sample': f'{e5} edges per step, 1 warm-up + 1 timed step, '
+                                                                  f'{s5:.2f} s/step'}
+        except Exception as exc:                          # an optional extra figure must never cost the bench line
+            cpu_baseline['reference_thread_setting'] = {'error': repr(exc)}
+        finally:
+            torch.set_num_threads(threads)
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
