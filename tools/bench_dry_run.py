@@ -81,7 +81,7 @@ def _worker(rank, world, port, a, out):
     spec.loader.exec_module(bench)
     sys.argv = ['bench.py', '--gpus', str(world), '--steps', str(a.steps), '--warmup', str(a.warmup), '--graphs',
                 str(a.graphs), '--hidden', str(a.hidden), '--precision', a.precision, '--cuda-graph', 'off',
-                '--no-cpu-baseline', '--e2e-steps', '2']
+                '--e2e-steps', '2'] + ([] if a.with_cpu_baseline else ['--no-cpu-baseline'])
     args = bench.parse()
     import io
     import contextlib
@@ -101,6 +101,7 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--warmup', type=int, default=1)
     ap.add_argument('--precision', default='bf16')
+    ap.add_argument('--with-cpu-baseline', action='store_true', help='also run the cpu_baseline leg (rank 0, N = 1)')
     a = ap.parse_args()
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -117,6 +118,9 @@ def main():
     missing = need - set(line)
     assert not missing, missing
     assert line['n_gpus'] == a.ranks and line['e2e']['h2d_bytes_per_step'] > 0
+    if a.with_cpu_baseline and a.ranks == 1:
+        cb = line['cpu_baseline']
+        assert cb['value'] > 0 and cb['reference_thread_setting']['value'] > 0, cb
     print(f"bench.py control flow ok on {a.ranks} rank(s): keys complete, n_gpus {line['n_gpus']}, "
           f"gpu_launches {line['gpu_launches']}, e2e steps {line['e2e']['steps']}  (timings are emulation: not reported)")
 
