@@ -283,7 +283,7 @@ extern "C" int gsatb_pna_aggregate_fwd(const float* x, const float* edge_feat, c
     if (N == 0) return GSATB_OK;
     if (!x || !rowptr_dst || !out || !stat_mean || !stat_msq || !argmin || !argmax || !agg_codes) return GSATB_EINVAL;
     if (E > 0 && (!eid_by_dst || !src_by_dst)) return GSATB_EINVAL;
-    if (He > 0 && !edge_feat) return GSATB_EINVAL;
+    if (He > 0 && E > 0 && !edge_feat) return GSATB_EINVAL;      // (an edgeless batch has an empty, null edge_feat)
     if (H % 4 != 0 || He % 4 != 0) return GSATB_ESHAPE;
     AggList aggs;
     if (!make_aggs(agg_codes, n_aggs, aggs)) return GSATB_EINVAL;

@@ -33,7 +33,10 @@ class Graph:
 
 def _rows(t: torch.Tensor) -> torch.Tensor:
     """[rows, ...] -> contiguous [rows, row_bytes / itemsize]."""
-    return t.reshape(t.shape[0], -1).contiguous()
+    width = 1
+    for d in t.shape[1:]:
+        width *= int(d)
+    return t.reshape(t.shape[0], width).contiguous()          # (explicit width: -1 is ambiguous for an empty tensor)
 
 
 class PackedDataset:
