@@ -322,3 +322,63 @@ def test_device_collate(G, shapes, data):
     got, want = ds.collate(ids), O.collate_data_list([graphs[i] for i in ids])
     for k in ('x', 'edge_index', 'batch', 'y', 'edge_attr', 'edge_label'):
         assert torch.equal(getattr(got, k), want[k]), k
+
+
+@st.composite
+def ragged_batches(draw):
+    """Many small graphs (down to zero rows), so that the graph-aligned tile plan of the fused extractor is exercised at
+    its limits: <= 128 rows and <= 32 graphs per tile, empty graphs inside and at the ends of a tile."""
+    n_graphs = draw(st.integers(1, 90))
+    style = draw(st.sampled_from(['tiny', 'mixed', 'large']))
+    hi = {'tiny': 5, 'mixed': 12, 'large': 60}[style]
+    # graphs of 1-3 rows are left out: InstanceNorm maps them to (almost) constants, the true gradient is ~0 and a
+    # relative comparison under bf16 rounding is meaningless; empty graphs (0 rows) stay in
+    sizes = [draw(st.sampled_from([0] + list(range(4, hi + 1)))) for _ in range(n_graphs)]
+    if sum(sizes) == 0:
+        sizes[0] = 4
+    src, dst, batch, off = [], [], [], 0
+    for g, n in enumerate(sizes):
+        batch += [g] * n
+        for a in range(n - 1):                      # a path, both directions: <= 2 (n - 1) <= 118 edges per graph
+            src += [off + a, off + a + 1]
+            dst += [off + a + 1, off + a]
+        off += n
+    ei = torch.tensor([src, dst], dtype=torch.int64).reshape(2, -1)
+    return ei, torch.tensor(batch, dtype=torch.int64), n_graphs
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
+                                                                 HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(ragged_batches(), st.booleans(), st.sampled_from([16, 64]), st.integers(0, 2 ** 31 - 1))
+def test_fused_tensor_core_extractor_on_ragged_batches(G, case, edge_mode, H, seed):
+    """The tcgen05 extractor (TMA-fed GEMMs, per-graph InstanceNorm inside graph-aligned accumulator tiles, backward
+    kernels) against the fp32 restatement with the same bf16 rounding points, forward and input gradient."""
+    from dp_gsat_b200 import tc
+    from tests.test_gpu_tc import _emulated_bf16_extractor, rel_l2
+    ei, batch, ng = case
+    rows = ei.shape[1] if edge_mode else batch.numel()
+    if rows == 0:
+        return
+    torch.manual_seed(seed % 1000)
+    ext_o = O.ExtractorMLP(H, {'learn_edge_att': edge_mode, 'extractor_dropout_p': 0.0})
+    ext_o.train()
+    mlp = ext_o.feature_extractor
+    lin = [getattr(mlp, str(i)) for i in (0, 4, 8)]
+    g = torch.Generator().manual_seed(seed)
+    emb = torch.relu(torch.randn(batch.numel(), H, generator=g))
+    wt = torch.randn(rows, 1, generator=g)
+    e_ref = emb.clone().requires_grad_(True)
+    out_ref = _emulated_bf16_extractor(e_ref, ei, batch, lin, edge_mode, 0.0, True, None, None)
+    (out_ref * wt).sum().backward()
+    gi = G.get_graph_index(ei, batch, ng)
+    if gi.tile_plan('edge' if edge_mode else 'node') is None:
+        return                                      # a graph larger than one tile: the module uses the unfused path
+    params = [t.detach().clone().requires_grad_(True) for t in
+              (lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias)]
+    e_got = emb.clone().requires_grad_(True)
+    out = tc.fused_extractor(e_got, *params, gi, edge_mode=edge_mode, pdrop=0.0, training=True, seed=1)
+    (out * wt).sum().backward()
+    assert torch.isfinite(out).all() and torch.isfinite(e_got.grad).all()
+    assert rel_l2(out, out_ref) <= 5e-2, rel_l2(out, out_ref)
+    assert rel_l2(e_got.grad, e_ref.grad) <= 0.1, rel_l2(e_got.grad, e_ref.grad)
+    assert rel_l2(params[4].grad, lin[2].weight.grad) <= 5e-2
