@@ -382,3 +382,70 @@ def test_fused_tensor_core_extractor_on_ragged_batches(G, case, edge_mode, H, se
     assert rel_l2(out, out_ref) <= 5e-2, rel_l2(out, out_ref)
     assert rel_l2(e_got.grad, e_ref.grad) <= 0.1, rel_l2(e_got.grad, e_ref.grad)
     assert rel_l2(params[4].grad, lin[2].weight.grad) <= 5e-2
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
+                                                                 HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(st.one_of(batches(allow_empty_graphs=True), ragged_batches()), st.sampled_from([16, 64, 128]), st.booleans(),
+       st.booleans(), st.integers(0, 2 ** 31 - 1))
+def test_fused_tensor_core_gin_layer_on_random_batches(G, case, H, with_att, training, seed):
+    """One whole attention-aware GIN layer on the tensor-core path (K3 aggregation written as bf16 -> Linear with
+    BatchNorm statistics in the epilogue -> BN + ReLU -> Linear + ReLU, and its backward kernels) against the same layer
+    from torch modules in fp32: row counts that are not a multiple of the 128-row tile, isolated nodes, no edges."""
+    from dp_gsat_b200 import tc
+    from tests.test_gpu_tc import rel_l2
+    ei, batch, ng = case
+    N, E = batch.numel(), ei.shape[1]
+    if N < 8:
+        return              # BatchNorm over a handful of rows is ill-conditioned under bf16 rounding (as InstanceNorm above)
+    torch.manual_seed(seed % 1000)
+    conv = G.GINConv(G.GIN.MLP(H, H))
+    conv.train(training)
+    lin1, bn, _, lin2 = conv.nn
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+    rm0, rv0 = bn.running_mean.clone(), bn.running_var.clone()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, H, generator=g)
+    att = torch.rand(E, 1, generator=g) if with_att else None
+    w = torch.randn(N, H, generator=g)
+    leaf = lambda t: None if t is None else t.clone().requires_grad_(True)
+
+    def restated(xr, ar):
+        """fp32 autograd restatement with the kernels' rounding points (bf16 GEMM operands, bf16-stored z1 / a1; the
+        BatchNorm statistics come from the fp32 accumulators): the ReLU gates see the same rounded values as the kernels
+        do, so no gate flips separate the two (against pure fp32 a handful of flipped gates dominate at small N)."""
+        msg = xr[ei[0]] * ar if ar is not None else xr[ei[0]]
+        agg = r_(O.scatter_sum(msg, ei[1], N) + xr)
+        z = agg @ r_(lin1.weight).t() + lin1.bias
+        if training:
+            mean, var = z.mean(0), z.var(0, unbiased=False)
+        else:
+            mean, var = rm0, rv0
+        scale = bn.weight * torch.rsqrt(var + bn.eps)
+        a1 = r_(torch.relu(r_(z) * scale + (bn.bias - mean * scale)))
+        return torch.relu(a1 @ r_(lin2.weight).t() + lin2.bias), z
+    from tests.test_gpu_tc import _RoundSTE
+    r_ = _RoundSTE.apply
+    xr, ar = leaf(x), leaf(att)
+    exp, z_ref = restated(xr, ar)
+    (exp * w).sum().backward()
+    want = {n: p.grad.clone() for n, p in conv.nn.named_parameters()}
+    conv.zero_grad()
+    gi = G.get_graph_index(ei, batch, ng)
+    xd, ad = leaf(x), leaf(att)
+    out = tc.gin_layer(xd, ad, gi, conv, training)
+    (out * w).sum().backward()
+    assert torch.isfinite(out).all() and torch.isfinite(xd.grad).all()
+    assert rel_l2(out, exp) < 2e-2, rel_l2(out, exp)
+    assert rel_l2(xd.grad, xr.grad) < 0.1, rel_l2(xd.grad, xr.grad)
+    if with_att and E:
+        assert rel_l2(ad.grad, ar.grad) < 0.1, rel_l2(ad.grad, ar.grad)
+    gscale = max(float(v.abs().max()) for v in want.values())
+    for n, p in conv.nn.named_parameters():
+        assert float((p.grad - want[n]).abs().max()) < 5e-2 * gscale, n
+    if training:
+        zz = z_ref.detach()
+        assert torch.allclose(bn.running_mean, 0.9 * rm0 + 0.1 * zz.mean(0), rtol=1e-3, atol=1e-4)
+        assert torch.allclose(bn.running_var, 0.9 * rv0 + 0.1 * zz.var(0, unbiased=True), rtol=1e-3, atol=1e-4)
