@@ -166,3 +166,14 @@ def get_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], num
 
 def clear_index_cache():
     _CACHE.clear()
+
+
+def set_index_cache_capacity(n: int) -> int:
+    """Number of batches whose GraphIndex stays cached (LRU).  The default (8) suits a resident batch or two per rank;
+    a loader that keeps every batch of an epoch resident (loader.DeviceLoader(cache=True)) raises it to its batch
+    count so that K0 runs once per batch for the whole training run, not once per epoch.  Returns the old value."""
+    global _CACHE_CAP
+    old, _CACHE_CAP = _CACHE_CAP, max(1, int(n))
+    while len(_CACHE) > _CACHE_CAP:
+        _CACHE.popitem(last=False)
+    return old

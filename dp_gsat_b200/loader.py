@@ -139,11 +139,19 @@ class DeviceLoader:
     runs them with shuffle=False) over a PackedDataset: yields device-resident Batch objects."""
 
     def __init__(self, dataset: PackedDataset, ids: Optional[Sequence[int]] = None, batch_size: int = 128,
-                 shuffle: bool = False, seed: int = 0, drop_last: bool = False):
+                 shuffle: bool = False, seed: int = 0, drop_last: bool = False, cache: bool = False):
+        """``cache=True`` (shuffle=False only -- the fork's loaders, get_data_loaders.py:133-135): every collated batch
+        stays resident and is handed out again in later epochs, at the same addresses.  The K0 index of a batch is then
+        built once for the whole run (the index cache is sized to the loader) and a step can be replayed as a CUDA graph
+        (parallel.TrainStep.enable_cuda_graph needs its inputs to stay put); costs one copy of the split in HBM."""
         self.dataset = dataset
         self.ids = np.arange(dataset.num_graphs, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         self.batch_size, self.shuffle, self.drop_last = int(batch_size), shuffle, drop_last
         self._rng = np.random.default_rng(seed)
+        if cache and shuffle:
+            raise ValueError('cache=True keeps the batches of an epoch resident: it needs shuffle=False')
+        self.cache = cache
+        self._batches = {}
 
     def __len__(self) -> int:
         n = len(self.ids)
@@ -151,8 +159,17 @@ class DeviceLoader:
 
     def __iter__(self):
         order = self._rng.permutation(self.ids) if self.shuffle else self.ids
+        if self.cache:
+            from .index import _CACHE_CAP, set_index_cache_capacity
+            if _CACHE_CAP < len(self) + 8:
+                set_index_cache_capacity(len(self) + 8)
         for i in range(len(self)):
-            yield self.dataset.collate(order[i * self.batch_size:(i + 1) * self.batch_size])
+            if not self.cache:
+                yield self.dataset.collate(order[i * self.batch_size:(i + 1) * self.batch_size])
+                continue
+            if i not in self._batches:
+                self._batches[i] = self.dataset.collate(order[i * self.batch_size:(i + 1) * self.batch_size])
+            yield self._batches[i]
 
 
 def split_batch(b: Batch) -> List[Graph]:

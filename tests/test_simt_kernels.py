@@ -319,3 +319,40 @@ def test_device_collate_edge_cases_on_emulator(sim_ops):
         ds.collate([5])
     with pytest.raises(ValueError):
         PackedDataset.from_data_list([Graph(torch.rand(2, 3), torch.tensor([[0], [2]]), torch.zeros(1))], device='cpu')
+
+
+def test_cached_loader_builds_each_batch_and_its_index_once(sim_ops):
+    """DeviceLoader(cache=True): the second epoch hands out the SAME resident batches (same addresses), so the K0 index of
+    every batch is built once for the whole run even when an epoch has more batches than the default index cache."""
+    import dp_gsat_b200 as G
+    from dp_gsat_b200.loader import PackedDataset, DeviceLoader, split_batch
+    from dp_gsat_b200.data import ba2motifs_batch
+    from tests.simt.emulate import emulated_lib
+    old_cap = G.set_index_cache_capacity(8)
+    try:
+        ds = PackedDataset.from_data_list(split_batch(ba2motifs_batch(24, seed=1)), device='cpu')
+        loader = DeviceLoader(ds, batch_size=2, cache=True)                  # 12 batches > the default capacity of 8
+        assert len(loader) == 12
+        calls = {'n': 0}
+        emu = emulated_lib()
+        orig = emu.call
+
+        def counting(name, *a):
+            calls['n'] += name == 'gsatb_index_build'
+            return orig(name, *a)
+        emu.call = counting
+        try:
+            first = [(b, G.get_graph_index(b.edge_index, b.batch, b.num_graphs)) for b in loader]
+            second = [(b, G.get_graph_index(b.edge_index, b.batch, b.num_graphs)) for b in loader]
+        finally:
+            emu.call = orig
+        assert calls['n'] == 12
+        for (b1, g1), (b2, g2) in zip(first, second):
+            assert b1 is b2 and g1 is g2 and b1.x.data_ptr() == b2.x.data_ptr()
+        with pytest.raises(ValueError):
+            DeviceLoader(ds, batch_size=2, cache=True, shuffle=True)
+        plain = list(DeviceLoader(ds, batch_size=2))
+        assert all(torch.equal(a.edge_index, b[0].edge_index) for a, b in zip(plain, first))
+    finally:
+        G.set_index_cache_capacity(old_cap)
+        G.clear_index_cache()
