@@ -19,7 +19,8 @@ Pinned here (all first-party code of mihikamd/DP-GSAT):
   the only random draws are the sampler's uniform and gumbel_sigmoid's ``rand_like``, which are replayed from the same
   seed and stored; epochs 3 and 57 (not multiples of 10: the plotting block of :394-426 stays off) cover both sides of
   the ``epoch > 50`` mix.  ``primal_learn_edge_att`` is False in both (with True the reference body raises NameError
-  on ``old_primal_edge_att``).
+  on ``old_primal_edge_att``, SURVEY App. C);
+* the trainer's per-batch explanation metrics ``get_precision_at_k`` / ``get_delta_kl`` (src/run_gsat.py:783-800).
 """
 import ast
 import os
@@ -267,6 +268,17 @@ def main():
         gold[f'dual/epoch{epoch}/loss'] = loss.detach()
         gold[f'dual/epoch{epoch}/logits'] = logits.detach()
         gold[f'dual/epoch{epoch}/loss_dict'] = dict(loss_dict)
+    # ---- per-batch explanation metrics of the trainer (run_gsat.py:783-800), tie-free attention ----------------------
+    gm_ = torch.Generator().manual_seed(9)
+    m_att = torch.rand(p.num_edges, generator=gm_)
+    m_lab = (torch.rand(p.num_edges, generator=gm_) < 0.3).float()
+    gold['metrics/att'], gold['metrics/labels'] = m_att, m_lab
+    gold['metrics/edge_index'], gold['metrics/batch'] = p.edge_index, p.batch
+    for k in (1, 5, 60):
+        gold[f'metrics/precision_at_{k}'] = torch.tensor(
+            RefGSAT.get_precision_at_k(None, m_att, m_lab, k, p.batch, p.edge_index), dtype=torch.float64)
+    gold['metrics/delta_kl'] = torch.tensor(RefGSAT.get_delta_kl(None, m_lab, m_att), dtype=torch.float64)
+
     torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
     print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))
 

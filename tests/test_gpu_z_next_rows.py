@@ -597,3 +597,16 @@ def test_product_dual_forward_pass_reproduces_the_reference_body(G, epoch):
     assert torch.allclose(loss, fg[f'dual/epoch{epoch}/loss'], rtol=1e-4, atol=1e-5)
     for k, v in fg[f'dual/epoch{epoch}/loss_dict'].items():
         assert abs(loss_dict[k] - v) <= 1e-4 * max(1.0, abs(v)), k
+
+
+def test_product_metrics_reproduce_the_reference_bodies(G):
+    """On-device precision@k / delta-KL against the outputs of the reference's own get_precision_at_k / get_delta_kl
+    (run_gsat.py:783-800, tie-free attention)."""
+    fg = _fork_gold()
+    att, lab, ei, batch = fg['metrics/att'], fg['metrics/labels'], fg['metrics/edge_index'], fg['metrics/batch']
+    ng = int(batch.max().item()) + 1
+    for k in (1, 5, 60):
+        got = G.get_precision_at_k(att.view(-1, 1), lab, k, batch, ei, ng)
+        assert torch.allclose(got.double().cpu(), fg[f'metrics/precision_at_{k}'].cpu(), rtol=0, atol=1e-6), k
+    dk = float(G.get_delta_kl(lab, att))
+    assert abs(dk - float(fg['metrics/delta_kl'])) < 1e-3 * abs(float(fg['metrics/delta_kl']))

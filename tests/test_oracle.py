@@ -316,3 +316,13 @@ def test_backbones_against_reference_classes(fork_gold, tag):
     m.train()
     m.dropout_p = 0.0
     assert torch.allclose(m(*args, edge_atten=fg['mol/att']), fg[f'{tag}_model/logits_train'], rtol=1e-4, atol=1e-5)
+
+
+def test_metrics_against_reference_bodies(fork_gold):
+    """get_precision_at_k / get_delta_kl (run_gsat.py:783-800) executed from the reference source (tie-free attention)."""
+    fg = fork_gold
+    att, lab, ei, batch = fg['metrics/att'], fg['metrics/labels'], fg['metrics/edge_index'], fg['metrics/batch']
+    for k in (1, 5, 60):
+        got = torch.tensor(O.get_precision_at_k(att, lab, k, batch, ei), dtype=torch.float64)
+        assert torch.allclose(got, fg[f'metrics/precision_at_{k}'], rtol=0, atol=1e-12), k
+    assert abs(O.get_delta_kl(lab, att) - float(fg['metrics/delta_kl'])) < 1e-4 * abs(float(fg['metrics/delta_kl']))

@@ -111,6 +111,7 @@ CASES = [
     _case(Z.test_product_backbones_reproduce_the_reference_classes, tag='spmotif'),
     _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=3),
     _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=57),
+    _case(Z.test_product_metrics_reproduce_the_reference_bodies),
 ]
 
 
