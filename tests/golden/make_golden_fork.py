@@ -20,6 +20,8 @@ Pinned here (all first-party code of mihikamd/DP-GSAT):
   seed and stored; epochs 3 and 57 (not multiples of 10: the plotting block of :394-426 stays off) cover both sides of
   the ``epoch > 50`` mix.  ``primal_learn_edge_att`` is False in both (with True the reference body raises NameError
   on ``old_primal_edge_att``, SURVEY App. C);
+* the line-graph construction loops of src/datasets/mutag_dual.py:342-378 (``group_by_first`` / ``add_pairs_from_group``),
+  executed as they stand on a primal edge list;
 * the trainer's per-batch explanation metrics ``get_precision_at_k`` / ``get_delta_kl`` (src/run_gsat.py:783-800).
 """
 import ast
@@ -278,6 +280,25 @@ def main():
         gold[f'metrics/precision_at_{k}'] = torch.tensor(
             RefGSAT.get_precision_at_k(None, m_att, m_lab, k, p.batch, p.edge_index), dtype=torch.float64)
     gold['metrics/delta_kl'] = torch.tensor(RefGSAT.get_delta_kl(None, m_lab, m_att), dtype=torch.float64)
+
+    # ---- the fork's line-graph ("dual") construction loops, src/datasets/mutag_dual.py:342-378 -------------------------
+    # statements of the dataset-reading method between those lines, executed as they stand on `dual_nodes` = the primal
+    # edge list; the (a, b) node pairs they emit are mapped back to primal-edge indices (unique: no duplicate edges)
+    tree = ast.parse(open(f'{REF}/src/datasets/mutag_dual.py').read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.lineno < 342 and n.end_lineno > 378][-1]
+    stmts = [st_ for st_ in fn.body if 342 <= st_.lineno and st_.end_lineno <= 378]
+    mod = ast.Module(body=stmts, type_ignores=[])
+    ast.fix_missing_locations(mod)
+    code = compile(mod, '<mutag_dual.py:342-378>', 'exec')
+    for tag, batch_obj in (('ba2motifs', p), ('mol', mb)):
+        prim = batch_obj.edge_index.t().contiguous().numpy()
+        ns_lg = {'np': np, 'dual_nodes': [tuple(r) for r in prim.tolist()], 'print': quiet, 'input': quiet}
+        exec(code, ns_lg)
+        lut = {tuple(r): i for i, r in enumerate(prim.tolist())}
+        assert len(lut) == prim.shape[0]
+        de = [[lut[tuple(np.asarray(e1).tolist())], lut[tuple(np.asarray(e2).tolist())]] for e1, e2 in ns_lg['dual_edges']]
+        gold[f'linegraph/{tag}/edge_index'], gold[f'linegraph/{tag}/batch'] = batch_obj.edge_index, batch_obj.batch
+        gold[f'linegraph/{tag}/dual_edge_index'] = torch.tensor(de, dtype=torch.int64).t().contiguous()
 
     torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
     print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))

@@ -610,3 +610,13 @@ def test_product_metrics_reproduce_the_reference_bodies(G):
         assert torch.allclose(got.double().cpu(), fg[f'metrics/precision_at_{k}'].cpu(), rtol=0, atol=1e-6), k
     dk = float(G.get_delta_kl(lab, att))
     assert abs(dk - float(fg['metrics/delta_kl'])) < 1e-3 * abs(float(fg['metrics/delta_kl']))
+
+
+@pytest.mark.parametrize('tag', ['ba2motifs', 'mol'])
+def test_product_line_graph_reproduces_the_reference_loops(G, tag):
+    """GPU line-graph builder against the dual edges the reference's own loops emit (mutag_dual.py:342-378), bit-exact."""
+    fg = _fork_gold()
+    ei, batch = fg[f'linegraph/{tag}/edge_index'], fg[f'linegraph/{tag}/batch']
+    got_ei, got_b = G.line_graph_dual(ei, batch, halve=False)
+    assert torch.equal(got_ei.cpu(), fg[f'linegraph/{tag}/dual_edge_index'].cpu())
+    assert torch.equal(got_b.cpu(), batch[ei[0]].cpu())

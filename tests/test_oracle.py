@@ -326,3 +326,17 @@ def test_metrics_against_reference_bodies(fork_gold):
         got = torch.tensor(O.get_precision_at_k(att, lab, k, batch, ei), dtype=torch.float64)
         assert torch.allclose(got, fg[f'metrics/precision_at_{k}'], rtol=0, atol=1e-12), k
     assert abs(O.get_delta_kl(lab, att) - float(fg['metrics/delta_kl'])) < 1e-4 * abs(float(fg['metrics/delta_kl']))
+
+
+@pytest.mark.parametrize('tag', ['ba2motifs', 'mol'])
+def test_line_graph_against_reference_loops(fork_gold, tag):
+    """The fork's dual construction (mutag_dual.py:342-378) executed from the reference source: same dual edges, same
+    order, as the oracle restatement and the vectorised host builder."""
+    from dp_gsat_b200.data import line_graph_dual
+    fg = fork_gold
+    ei, batch = fg[f'linegraph/{tag}/edge_index'], fg[f'linegraph/{tag}/batch']
+    want = fg[f'linegraph/{tag}/dual_edge_index']
+    got, got_b = O.line_graph_dual(ei, batch, halve=False)
+    assert torch.equal(got, want) and torch.equal(got_b, batch[ei[0]])
+    ds, dd, _ = line_graph_dual(ei[0].numpy(), ei[1].numpy(), batch.numpy())
+    assert torch.equal(torch.from_numpy(ds), want[0]) and torch.equal(torch.from_numpy(dd), want[1])

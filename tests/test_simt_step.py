@@ -112,6 +112,8 @@ CASES = [
     _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=3),
     _case(Z.test_product_dual_forward_pass_reproduces_the_reference_body, epoch=57),
     _case(Z.test_product_metrics_reproduce_the_reference_bodies),
+    _case(Z.test_product_line_graph_reproduces_the_reference_loops, tag='ba2motifs'),
+    _case(Z.test_product_line_graph_reproduces_the_reference_loops, tag='mol'),
 ]
 
 
