@@ -231,8 +231,13 @@ def test_embedding_sum_on_emulator(M, H, dims):
     import ctypes
     rc = sim().call('gsatb_embedding_sum_bwd', gout, idx, offs, dt, M, K, H, ws, ctypes.c_size_t(ws_bytes), None)
     assert rc == OK and intact(dt)
-    want = torch.cat([t.grad if t.grad is not None else torch.zeros_like(t) for t in tables], 0)
-    assert torch.allclose(dt, want, rtol=1e-5, atol=1e-5)
+    # ground truth in fp64 (the fp32 index_add of autograd is itself ~1e-5 off on rows that collect hundreds of terms,
+    # and its accumulation order depends on the thread count)
+    t64 = [t.detach().double().requires_grad_(True) for t in tables]
+    if M:
+        sum((t64[k][idx[:, k]] * gout.double()).sum() for k in range(K)).backward()
+    want = torch.cat([t.grad if t.grad is not None else torch.zeros_like(t) for t in t64], 0)
+    assert torch.allclose(dt.double(), want, rtol=1e-5, atol=2e-6 * max(1.0, float(want.abs().max())))
     rc = sim().call('gsatb_embedding_sum_bwd', gout, idx, offs, dt, M, K, H, ws, ctypes.c_size_t(16), None)
     assert rc == -4                                       # GSATB_EWS_TOO_SMALL
 
