@@ -152,10 +152,18 @@ def _product_worker(rank, world, port, out, model_name, sync_bn, precision='fp32
     e0 = sum(shard_batch(full, r, world).num_edges for r in range(rank))
     step = TrainStep(g, lr=1e-2, fused_adam=False, sync_bn=sync_bn)
     step(shard, 0, noise_u=u_full[e0:e0 + shard.num_edges])
+    local = None
+    if sync_bn:                                   # the same sharded step with shard-local statistics (DDP semantics)
+        g2 = _product(seed=0, model_name=model_name, precision=precision)
+        broadcast_parameters(g2.clf)
+        broadcast_parameters(g2.extractor)
+        step2 = TrainStep(g2, lr=1e-2, fused_adam=False)
+        step2(shard, 0, noise_u=u_full[e0:e0 + shard.num_edges])
+        local = step2.bucket.flat.clone()
     if rank == 0:
         bn = next(m for m in g.clf.modules() if isinstance(m, torch.nn.BatchNorm1d))
         torch.save({'flat': step.bucket.flat.clone(), 'running_var': bn.running_var.clone(),
-                    'running_mean': bn.running_mean.clone()}, out)
+                    'running_mean': bn.running_mean.clone(), 'flat_local_bn': local}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -182,22 +190,8 @@ def test_product_two_ranks_with_sync_batchnorm_equal_single_rank(tmp_path, monke
     bn = next(m for m in g.clf.modules() if isinstance(m, torch.nn.BatchNorm1d))
     assert torch.allclose(got['running_mean'], bn.running_mean, rtol=1e-5 if precision == 'fp32' else 1e-3, atol=1e-6)
     assert torch.allclose(got['running_var'], bn.running_var, rtol=1e-5 if precision == 'fp32' else 1e-3, atol=1e-6)
-
-
-def test_product_two_ranks_without_sync_batchnorm_differ(tmp_path, monkeypatch):
-    """The default (shard-local BatchNorm statistics, DDP semantics) is NOT the single-device step -- which is what
-    the sync option is for; this pins that the option actually changes the math."""
-    from tests.simt import emulate
-    from dp_gsat_b200.parallel import TrainStep
-    out = str(tmp_path / 'r0.pt')
-    mp.spawn(_product_worker, args=(2, _free_port(), out, 'GIN', False), nprocs=2, join=True)
-    got = torch.load(out)
-    emulate.patch_product(monkeypatch.setattr)
-    full, u_full = _full_batch()
-    g = _product(seed=0)
-    step = TrainStep(g, lr=1e-2, fused_adam=False)
-    step(full, 0, noise_u=u_full)
-    assert not torch.allclose(got['flat'], step.bucket.flat, rtol=2e-4, atol=1e-6)
+    # the default (shard-local statistics) is NOT the single-device step: the option actually changes the math
+    assert not torch.allclose(got['flat_local_bn'], step.bucket.flat, rtol=2e-4, atol=1e-6)
 
 
 def test_bench_control_flow_on_two_ranks_without_a_gpu():
