@@ -299,6 +299,15 @@ def main():
         de = [[lut[tuple(np.asarray(e1).tolist())], lut[tuple(np.asarray(e2).tolist())]] for e1, e2 in ns_lg['dual_edges']]
         gold[f'linegraph/{tag}/edge_index'], gold[f'linegraph/{tag}/batch'] = batch_obj.edge_index, batch_obj.batch
         gold[f'linegraph/{tag}/dual_edge_index'] = torch.tensor(de, dtype=torch.int64).t().contiguous()
+        if tag == 'mol':          # both directions of every edge are consecutive rows: the relabelling of :535-549 applies
+            stmts2 = [st_ for st_ in fn.body if 535 <= st_.lineno and st_.end_lineno <= 549]
+            mod2 = ast.Module(body=stmts2, type_ignores=[])
+            ast.fix_missing_locations(mod2)
+            ns2 = {'dual_node_lists': [ns_lg['dual_nodes']], 'dual_edge_lists': [ns_lg['dual_edges']], 'print': quiet,
+                   'input': quiet}
+            exec(compile(mod2, '<mutag_dual.py:535-549>', 'exec'), ns2)
+            halved = torch.tensor(ns2['dual_single_edge_lists'][0], dtype=torch.int64).t().contiguous() - 1   # 1-based ids
+            gold[f'linegraph/{tag}/dual_edge_index_halved'] = halved
 
     torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
     print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))

@@ -620,3 +620,6 @@ def test_product_line_graph_reproduces_the_reference_loops(G, tag):
     got_ei, got_b = G.line_graph_dual(ei, batch, halve=False)
     assert torch.equal(got_ei.cpu(), fg[f'linegraph/{tag}/dual_edge_index'].cpu())
     assert torch.equal(got_b.cpu(), batch[ei[0]].cpu())
+    if f'linegraph/{tag}/dual_edge_index_halved' in fg:          # the relabelling of mutag_dual.py:535-549
+        got_h, _ = G.line_graph_dual(ei, batch, halve=True)
+        assert torch.equal(got_h.cpu(), fg[f'linegraph/{tag}/dual_edge_index_halved'].cpu())

@@ -340,3 +340,6 @@ def test_line_graph_against_reference_loops(fork_gold, tag):
     assert torch.equal(got, want) and torch.equal(got_b, batch[ei[0]])
     ds, dd, _ = line_graph_dual(ei[0].numpy(), ei[1].numpy(), batch.numpy())
     assert torch.equal(torch.from_numpy(ds), want[0]) and torch.equal(torch.from_numpy(dd), want[1])
+    if f'linegraph/{tag}/dual_edge_index_halved' in fg:          # the one-id-per-undirected-edge relabelling, :535-549
+        got_h, _ = O.line_graph_dual(ei, batch, halve=True)
+        assert torch.equal(got_h, fg[f'linegraph/{tag}/dual_edge_index_halved'])
