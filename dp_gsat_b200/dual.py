@@ -5,8 +5,14 @@
   reference src/datasets/mutag_dual.py:536-548   optional relabelling: the two directions of a primal edge (consecutive
                                                  rows of the edge list) share one dual node id   (``halve=True``)
 
-The reference builds this with Python dict loops over every edge at dataset-processing time; here it is two kernels on
-top of the CSC that K0 already built for the primal batch.
+  reference src/datasets/ba_2motifs_dual.py:33-73  the dense-matrix variant: dual nodes = UNDIRECTED primal edges numbered
+                                                 in order of first appearance in the adjacency matrix, dual edges between
+                                                 edges that share a node, in dense_to_sparse (row-major) order
+                                                 (``line_graph_dual_dense``)
+
+The reference builds these with Python dict / matrix loops over every edge at dataset-processing time; here it is two
+kernels on top of the CSC that K0 already built for the primal batch (plus, for the dense variant, a rank and a sort of
+the dual edge keys on the device).
 """
 from __future__ import annotations
 
@@ -49,3 +55,37 @@ def line_graph_dual(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: O
     L.call('gsatb_line_graph_fill', ptr(gi.src), ptr(gi.rowptr_src), ptr(members), ptr(offs),
            ptr(batch_c), N, E, int(halve), ptr(dual_ei), Ed, ptr(dual_batch), stream())
     return dual_ei, dual_batch
+
+
+def line_graph_dual_dense(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: Optional[int] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The BA-2Motifs dual of the fork (reference src/datasets/ba_2motifs_dual.py:33-73) for a whole batch on the device.
+
+    Dual node = undirected primal edge {u, v}, numbered in the order the reference's scan of the adjacency matrix meets
+    it (rows ascending, columns ascending == ascending (min, max)), graph after graph; dual edge (i, j), i != j, for every
+    two edges that share a node, listed in ``dense_to_sparse`` order (ascending (i, j), no duplicates).  Needs a
+    symmetric, duplicate-free primal edge set without self loops (what a 0/1 adjacency matrix holds).
+
+    Returns (dual_edge_index int64 [2, E_d], dual_batch int64 [E/2], und_id int64 [E]: the dual node of every directed
+    primal edge)."""
+    gi = get_graph_index(edge_index, batch, num_graphs)
+    if not gi.symmetric or gi.has_duplicates:
+        raise ValueError('the dense dual needs a symmetric, duplicate-free primal edge set (a 0/1 adjacency matrix)')
+    src, dst = gi.src.long(), gi.dst.long()
+    if bool((src == dst).any()):
+        raise ValueError('the dense dual is defined for graphs without self loops (ba_2motifs_dual.py:44)')
+    E = gi.E
+    M = E // 2
+    order = gi.eid_by_src.long()                       # directed edges in ascending (src, dst): the matrix scan order
+    first = (src < dst)[order]                         # the scan numbers an edge when it meets its (min, max) entry
+    rank = torch.cumsum(first.long(), 0) - 1
+    und = torch.empty(E, dtype=torch.int64, device=edge_index.device)
+    und[order[first]] = rank[first]
+    rev = gi.rev.long()
+    und[rev[order[first]]] = rank[first]
+    pairs, _ = line_graph_dual(edge_index, batch, num_graphs)              # directed edges sharing their source node
+    key = torch.unique(und[pairs[0]] * max(M, 1) + und[pairs[1]])          # sorted: dense_to_sparse order
+    dual_ei = torch.stack([key // max(M, 1), key % max(M, 1)])
+    dual_batch = torch.empty(M, dtype=torch.int64, device=edge_index.device)
+    dual_batch[rank[first]] = batch[src[order[first]]]
+    return dual_ei, dual_batch, und

@@ -22,6 +22,8 @@ Pinned here (all first-party code of mihikamd/DP-GSAT):
   on ``old_primal_edge_att``, SURVEY App. C);
 * the line-graph construction loops of src/datasets/mutag_dual.py:342-378 (``group_by_first`` / ``add_pairs_from_group``),
   executed as they stand on a primal edge list;
+* the dense-matrix dual of src/datasets/ba_2motifs_dual.py:26-62 (edge numbering by adjacency scan, shared-node adjacency),
+  executed as it stands on BA-2Motifs-shaped adjacency matrices;
 * the trainer's per-batch explanation metrics ``get_precision_at_k`` / ``get_delta_kl`` (src/run_gsat.py:783-800).
 """
 import ast
@@ -308,6 +310,30 @@ def main():
             exec(compile(mod2, '<mutag_dual.py:535-549>', 'exec'), ns2)
             halved = torch.tensor(ns2['dual_single_edge_lists'][0], dtype=torch.int64).t().contiguous() - 1   # 1-based ids
             gold[f'linegraph/{tag}/dual_edge_index_halved'] = halved
+
+    # ---- the dense-matrix dual of src/datasets/ba_2motifs_dual.py:33-62 (+ dense_to_sparse of :69) ------------------------
+    tree = ast.parse(open(f'{REF}/src/datasets/ba_2motifs_dual.py').read())
+    fn2 = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == 'read_ba2motif_data'][0]
+    stmts3 = [st_ for st_ in fn2.body if 26 <= st_.lineno and st_.end_lineno <= 62]
+    mod3 = ast.Module(body=stmts3, type_ignores=[])
+    ast.fix_missing_locations(mod3)
+    from dp_gsat_b200.data import ba2motifs_batch as _ba
+    bb = _ba(5, seed=11)
+    n_per = 25
+    dense = np.zeros((bb.num_graphs, n_per, n_per))
+    gidx = bb.batch[bb.edge_index[0]].numpy()
+    dense[gidx, bb.edge_index[0].numpy() - gidx * n_per, bb.edge_index[1].numpy() - gidx * n_per] = 1.0
+    ns3 = {'np': np, 'torch': torch, 'dense_edges': dense, 'node_features': np.zeros((bb.num_graphs, n_per, 10)),
+           'print': quiet, 'input': quiet}
+    exec(compile(mod3, '<ba_2motifs_dual.py:26-62>', 'exec'), ns3)
+    duals, off = [], 0
+    for dd in ns3['dual_dense_edges_list']:
+        nz = torch.from_numpy(dd).nonzero().t().contiguous()          # dense_to_sparse: row-major non-zeros (:69)
+        duals.append(nz + off)                                        # collate: cumulative dual-node offsets
+        off += dd.shape[0]
+    gold['densedual/edge_index'], gold['densedual/batch'] = bb.edge_index, bb.batch
+    gold['densedual/dual_edge_index'] = torch.cat(duals, 1)
+    gold['densedual/dual_node_label'] = torch.cat(ns3['dual_node_label_lists'])
 
     torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
     print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))

@@ -623,3 +623,20 @@ def test_product_line_graph_reproduces_the_reference_loops(G, tag):
     if f'linegraph/{tag}/dual_edge_index_halved' in fg:          # the relabelling of mutag_dual.py:535-549
         got_h, _ = G.line_graph_dual(ei, batch, halve=True)
         assert torch.equal(got_h.cpu(), fg[f'linegraph/{tag}/dual_edge_index_halved'].cpu())
+
+
+def test_dense_dual_reproduces_the_reference_loops(G):
+    """line_graph_dual_dense against the dual adjacency the reference's own matrix loops build
+    (ba_2motifs_dual.py:26-62 + dense_to_sparse), bit-exact, incl. the motif node labels carried over by und_id."""
+    fg = _fork_gold()
+    ei, batch = fg['densedual/edge_index'], fg['densedual/batch']
+    dual_ei, dual_batch, und = G.line_graph_dual_dense(ei, batch)
+    assert torch.equal(dual_ei.cpu(), fg['densedual/dual_edge_index'].cpu())
+    src = ei[0]
+    assert torch.equal(dual_batch.cpu(), torch.zeros_like(dual_batch).cpu().scatter_(0, und.cpu(), batch[src].cpu()))
+    # the reference labels a dual node 1 when both endpoints are motif nodes (>= 20 inside the 25-node graph): :46-47
+    motif = ((ei[0] % 25 >= 20) & (ei[1] % 25 >= 20)).float()
+    lab = torch.zeros(dual_batch.numel(), device=und.device).scatter_(0, und, motif)
+    assert torch.equal(lab.cpu(), fg['densedual/dual_node_label'].cpu())
+    with pytest.raises(ValueError):
+        G.line_graph_dual_dense(ei[:, ei[0] < ei[1]].contiguous(), batch)          # not symmetric

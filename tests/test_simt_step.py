@@ -114,6 +114,7 @@ CASES = [
     _case(Z.test_product_metrics_reproduce_the_reference_bodies),
     _case(Z.test_product_line_graph_reproduces_the_reference_loops, tag='ba2motifs'),
     _case(Z.test_product_line_graph_reproduces_the_reference_loops, tag='mol'),
+    _case(Z.test_dense_dual_reproduces_the_reference_loops),
 ]
 
 
