@@ -89,3 +89,13 @@ def line_graph_dual_dense(edge_index: torch.Tensor, batch: torch.Tensor, num_gra
     dual_batch = torch.empty(M, dtype=torch.int64, device=edge_index.device)
     dual_batch[rank[first]] = batch[src[order[first]]]
     return dual_ei, dual_batch, und
+
+
+def dense_dual_node_features(x: torch.Tensor, edge_index: torch.Tensor, und_id: torch.Tensor) -> torch.Tensor:
+    """Features of the dense dual's nodes (reference src/datasets/ba_2motifs_dual.py:48): for the undirected primal edge
+    {u, v}, u < v, ``cat(x[u], x[v])``.  ``und_id`` as returned by line_graph_dual_dense."""
+    src, dst = edge_index[0], edge_index[1]
+    first = src < dst
+    out = torch.empty((int(und_id.numel()) // 2, 2 * x.shape[1]), dtype=x.dtype, device=x.device)
+    out[und_id[first]] = torch.cat([x[src[first]], x[dst[first]]], dim=1)
+    return out

@@ -323,7 +323,8 @@ def main():
     dense = np.zeros((bb.num_graphs, n_per, n_per))
     gidx = bb.batch[bb.edge_index[0]].numpy()
     dense[gidx, bb.edge_index[0].numpy() - gidx * n_per, bb.edge_index[1].numpy() - gidx * n_per] = 1.0
-    ns3 = {'np': np, 'torch': torch, 'dense_edges': dense, 'node_features': np.zeros((bb.num_graphs, n_per, 10)),
+    feats = np.random.default_rng(3).random((bb.num_graphs, n_per, 10)).astype(np.float32)
+    ns3 = {'np': np, 'torch': torch, 'dense_edges': dense, 'node_features': feats,
            'print': quiet, 'input': quiet}
     exec(compile(mod3, '<ba_2motifs_dual.py:26-62>', 'exec'), ns3)
     duals, off = [], 0
@@ -334,6 +335,8 @@ def main():
     gold['densedual/edge_index'], gold['densedual/batch'] = bb.edge_index, bb.batch
     gold['densedual/dual_edge_index'] = torch.cat(duals, 1)
     gold['densedual/dual_node_label'] = torch.cat(ns3['dual_node_label_lists'])
+    gold['densedual/x'] = torch.from_numpy(feats.reshape(-1, 10))
+    gold['densedual/dual_x'] = torch.from_numpy(np.concatenate(ns3['dual_node_features_list'], 0)).float()
 
     torch.save(gold, os.path.join(HERE, 'ref_fork.pt'))
     print('golden keys:', len(gold), 'size', os.path.getsize(os.path.join(HERE, 'ref_fork.pt')))

@@ -638,5 +638,7 @@ def test_dense_dual_reproduces_the_reference_loops(G):
     motif = ((ei[0] % 25 >= 20) & (ei[1] % 25 >= 20)).float()
     lab = torch.zeros(dual_batch.numel(), device=und.device).scatter_(0, und, motif)
     assert torch.equal(lab.cpu(), fg['densedual/dual_node_label'].cpu())
+    dual_x = G.dense_dual_node_features(fg['densedual/x'], ei, und)                 # cat(x[u], x[v]), u < v  (:48)
+    assert torch.equal(dual_x.cpu(), fg['densedual/dual_x'].cpu())
     with pytest.raises(ValueError):
         G.line_graph_dual_dense(ei[:, ei[0] < ei[1]].contiguous(), batch)          # not symmetric
