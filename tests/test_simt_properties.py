@@ -8,7 +8,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 from oracle import gsat_oracle as O
 
-SETTINGS = dict(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
+SETTINGS = dict(max_examples=10, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
                                                                         HealthCheck.too_slow])
 
 
@@ -347,7 +347,7 @@ def ragged_batches(draw):
     return ei, torch.tensor(batch, dtype=torch.int64), n_graphs
 
 
-@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
+@settings(max_examples=8, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
                                                                  HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(ragged_batches(), st.booleans(), st.sampled_from([16, 64]), st.integers(0, 2 ** 31 - 1))
 def test_fused_tensor_core_extractor_on_ragged_batches(G, case, edge_mode, H, seed):
@@ -384,7 +384,7 @@ def test_fused_tensor_core_extractor_on_ragged_batches(G, case, edge_mode, H, se
     assert rel_l2(params[4].grad, lin[2].weight.grad) <= 5e-2
 
 
-@settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
+@settings(max_examples=8, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture,
                                                                  HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(st.one_of(batches(allow_empty_graphs=True), ragged_batches()), st.sampled_from([16, 64, 128]), st.booleans(),
        st.booleans(), st.integers(0, 2 ** 31 - 1))
