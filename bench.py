@@ -248,6 +248,8 @@ def build_roofline(timer, N, E, G, H, steps, ms_step):
                 else:
                     row.update(bound='hbm', achieved=nbytes / sec / 1e9, peak=hbm, unit='GB/s')
                 row['frac'] = row['achieved'] / row['peak']
+                if row['unit'] == 'GB/s':                 # both the measured and the nominal 8 TB/s fraction
+                    row['frac_of_nominal_8TBs'] = row['achieved'] / 8000.0
                 row['algorithmic_bytes_per_launch'], row['flops_per_launch'] = nbytes, flops
             rows.append(row)
     rows.sort(key=lambda r: -r['share_of_step'])
