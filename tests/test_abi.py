@@ -117,3 +117,32 @@ sys.exit(1 if bad else 0)
     r = subprocess.run([sys.executable, '-c', code, os.path.join(ROOT, 'dp_gsat_b200', '_lib.py')],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert r.returncode == 0 and 'CHECKED []' in r.stdout, r.stdout[-2000:]
+
+
+def test_bench_roofline_table_from_recorded_events():
+    """bench.build_roofline on a recorded event table: dominant kernel = largest share of the step, achieved = algorithmic
+    bytes / launch time, fractions of the measured peak and of the nominal 8 TB/s, kernels without a byte model listed
+    without a fraction."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class Ev:
+        def __init__(self, t):
+            self.t = t
+
+        def elapsed_time(self, other):
+            return other.t - self.t
+    N, E, G, H = 4900000, 9996000, 196000, 128
+    timer = {'gsatb_gin_aggregate_fwd': [(Ev(0), Ev(1.0), 'att'), (Ev(2), Ev(3.0), 'noatt')],
+             'gsatb_tc_ext_bwd1': [(Ev(0), Ev(13.4), '')], 'gsatb_something_new': [(Ev(0), Ev(0.2), '')]}
+    r = bench.build_roofline(timer, N, E, G, H, 1, 92.0)
+    assert r['kernel'] == 'gsatb_tc_ext_bwd1' and r['bound'] == 'hbm' and r['unit'] == 'GB/s'
+    nbytes = bench.kernel_models(N, E, G, H)['gsatb_tc_ext_bwd1'][0]
+    assert abs(r['achieved'] - nbytes / 13.4e-3 / 1e9) < 1e-6 * r['achieved']
+    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12 and abs(r['frac_of_nominal_8TBs'] - r['achieved'] / 8000) < 1e-12
+    rows = {k['kernel']: k for k in r['kernels']}
+    assert rows['gsatb_gin_aggregate_fwd:att']['algorithmic_bytes_per_launch'] == 8.0 * N * H + 8.0 * E + 4.0 * N
+    assert 'frac' not in rows['gsatb_something_new']
+    assert abs(r['ours_share_of_step'] - (13.4 + 1.0 + 1.0 + 0.2) / 92.0) < 1e-9
