@@ -361,3 +361,24 @@ def test_cached_loader_builds_each_batch_and_its_index_once(sim_ops):
     finally:
         G.set_index_cache_capacity(old_cap)
         G.clear_index_cache()
+
+
+def test_device_step_counter_feeds_the_in_kernel_random_streams(sim_ops):
+    """gsatb_set_step_counter: the device-resident counter is added to the sampler's Philox offset INSIDE the kernel, which
+    is what lets a CUDA graph of the whole step (frozen kernel arguments) draw fresh noise on every replay."""
+    import dp_gsat_b200 as G
+    from tests.simt.emulate import emulated_lib
+    counter = emulated_lib().step_counter()
+    counter.zero_()
+    try:
+        logits = torch.zeros(4096, 1)
+        a = G.concrete_sample(logits, 1, True, seed=5, offset=100)
+        assert torch.equal(a, G.concrete_sample(logits, 1, True, seed=5, offset=100))      # same counter: same draw
+        counter.add_(1)
+        b = G.concrete_sample(logits, 1, True, seed=5, offset=100)
+        assert not torch.equal(a, b) and abs(float(b.mean()) - 0.5) < 0.03                 # fresh, still uniform noise
+        counter.sub_(1)
+        assert torch.equal(a, G.concrete_sample(logits, 1, True, seed=5, offset=100))
+        assert torch.equal(G.concrete_sample(logits, 1, False), torch.full_like(logits, 0.5))   # eval: no noise at all
+    finally:
+        counter.zero_()
