@@ -127,10 +127,24 @@ def preload(run_one, sync, world, dev, seconds=0.7):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU path (the oracle port of the reference's algorithm) -- cpu_baseline leg and --impl reference
 # ---------------------------------------------------------------------------------------------------------------
+def _data_module():
+    """The synthetic generators (dp_gsat_b200/data.py: numpy + torch only) loaded BY FILE, not through the package:
+    importing the package maps libgsat_b200.so, and the reference arm must not touch the product's library."""
+    import importlib.util
+    name = '_gsatb_data_standalone'
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, 'dp_gsat_b200', 'data.py'))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
 def cpu_oracle_rate(a, n_graphs, steps, warmup, threads):
     """edges/s of the oracle's training step on `n_graphs` BA-2Motifs graphs, host cores."""
     from oracle import gsat_oracle as O
-    from dp_gsat_b200.data import ba2motifs_batch
+    ba2motifs_batch = _data_module().ba2motifs_batch
     torch.set_num_threads(threads)
     cfg, shared = model_cfg(a)
     torch.manual_seed(0)

@@ -130,7 +130,37 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+// narrower variants: 16 / 8 consecutive columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// TMA store: shared memory box -> global tensor (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int crd0, int crd1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(desc),
+                 "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N committed store groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 }  // namespace tc
 #endif  // GSATB_HOST_SIM
@@ -148,9 +178,24 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// MN-major, SWIZZLE_128B operand tile: for every K index a 128-byte row of 64 consecutive M/N elements, 8 K-rows per
+// 1024-byte atom (tile base 1024-aligned); atoms of the next 8 K follow at the stride byte offset (1024), the next 64
+// M/N elements live `lbo_bytes` away (leading byte offset).  This is how a row-major [rows = K][channels] tile (dW
+// products, K = rows) and a channel-major [channels = K][rows] tile (activations produced by the swap-AB epilogues)
+// feed the tensor core without a transpose.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes & 0x3FFFFu) >> 4) << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32; a_mn / b_mn = 1 selects an MN-major operand (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // byte offset of element (row, k) inside one [rows x 64] bf16 K-block stored in the SWIZZLE_128B pattern
 __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {

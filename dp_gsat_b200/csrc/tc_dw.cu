@@ -1,0 +1,275 @@
+// Weight-gradient products on the tensor cores:  D[m, n] = sum_r A[r, m] * B[r, n]   (dW = dz^T h, K = rows), plus the
+// bias gradient  db[m] = sum_r A[r, m]  from the same pass.  Replaces the autograd weight-gradient GEMMs of
+// src/utils/get_model.py:57-68 (extractor MLP) and src/models/gin.py:55-62 (GIN node MLP) at src/run_gsat.py:634,
+// which round 1 ran as library GEMMs.
+//
+// Both operands are bf16 activations as the other kernels of the step leave them in HBM; each may be
+//   row-major     [rows, C]  (ld = elements per row)      -> TMA boxes of 64 channels x 64 rows = an MN-major
+//                                                            SWIZZLE_128B operand tile (K = rows runs across smem rows)
+//   channel-major [C, rows]  (ld = elements per channel)  -> TMA boxes of 64 rows x 128 channels = the usual K-major tile
+// so no transposed copy of an activation is ever made.
+//
+// Split-K over the rows: grid = (splits, slabs); a slab is one 128-channel block of A times up to 256 channels of B
+// (accumulator [128 lanes x n_chunk columns] in TMEM, + 16 columns for the bias gradient: A times a tile of ones).
+// Warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (accumulator -> fp32
+// partial in the workspace).  A second tiny kernel adds the partials in split order: deterministic.
+#include "tc_ops_common.cuh"
+
+namespace {
+
+using namespace tcg;
+
+constexpr int DW_THREADS = 256;
+constexpr int DW_KSTEP = 64;                 // rows per pipeline stage
+constexpr int DW_A_BYTES = 128 * 128;        // [128 channels x 64 rows] bf16
+constexpr int DW_ONES_BYTES = 16 * 128;      // 16 "channels" of ones x 64 rows (any layout of ones is ones)
+constexpr int DW_BIAS_COLS = 16;
+
+struct DwParams {
+    int64_t rows;
+    int M, N;            // channels of A (output rows of D) and of B (output columns of D)
+    int a_cm, b_cm;      // 1: channel-major operand
+    int n_chunk;         // B channels per slab: multiple of 64, <= 256
+    int n_chunks;        // slabs per A block
+    int splits;
+    int stages;
+    float* ws;           // [splits][slabs][128][n_chunk + 16]
+};
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const DwParams p) {
+#ifdef GSATB_HOST_SIM
+    uint8_t* smem_raw = simt::dyn_smem();
+#else
+    extern __shared__ uint8_t smem_raw[];
+#endif
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.n_chunk * 128;
+    const int stage_bytes = DW_A_BYTES + b_bytes;
+    uint8_t* ones = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + DW_ONES_BYTES);
+    uint64_t* full = bars;              // [stages <= 8]
+    uint64_t* empty = bars + 8;         // [stages]
+    uint64_t* acc_full = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, slab = blockIdx.y;
+    const int mb = slab / p.n_chunks, nc = slab % p.n_chunks;
+    const int64_t total_steps = (p.rows + DW_KSTEP - 1) / DW_KSTEP;
+    const int64_t s0 = total_steps * split / p.splits, s1 = total_steps * (split + 1) / p.splits;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmap_a);
+        tc::tma_prefetch_desc(&tmap_b);
+        for (int i = 0; i < p.stages; ++i) {
+            tc::mbar_init(&full[i], 1);
+            tc::mbar_init(&empty[i], 1);
+        }
+        tc::mbar_init(acc_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    if (warp == 3) {      // the tile of ones behind the bias gradient
+        uint32_t* o = reinterpret_cast<uint32_t*>(ones);
+        for (int i = lane; i < DW_ONES_BYTES / 4; i += 32) o[i] = 0x3F803F80u;      // bf16 1.0 | 1.0
+        tc::fence_proxy_async_smem();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t st = s0; st < s1; ++st, ++it) {
+                const uint32_t s = it % p.stages, use = it / p.stages;
+                tc::mbar_wait(&empty[s], (use & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+                uint8_t* sA = smem + (size_t)s * stage_bytes;
+                uint8_t* sB = sA + DW_A_BYTES;
+                const int r = (int)(st * DW_KSTEP);
+                if (p.a_cm) {
+                    tc::tma_load_2d(sA, &tmap_a, &full[s], r, mb * 128);                       // box {64 rows, 128 ch}
+                } else {
+                    tc::tma_load_2d(sA, &tmap_a, &full[s], mb * 128, r);                       // box {64 ch, 64 rows}
+                    tc::tma_load_2d(sA + 8192, &tmap_a, &full[s], mb * 128 + 64, r);
+                }
+                if (p.b_cm) {
+                    for (int j = 0; j * 128 < p.n_chunk; ++j)
+                        tc::tma_load_2d(sB + j * 16384, &tmap_b, &full[s], r, nc * p.n_chunk + j * 128);
+                } else {
+                    for (int j = 0; j * 64 < p.n_chunk; ++j)
+                        tc::tma_load_2d(sB + j * 8192, &tmap_b, &full[s], nc * p.n_chunk + j * 64, r);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(128, p.n_chunk, p.a_cm ? 0 : 1, p.b_cm ? 0 : 1);
+            const uint32_t idesc_b = tc::make_idesc_bf16(128, DW_BIAS_COLS, p.a_cm ? 0 : 1, 0);
+            const uint64_t ones_desc = tc::make_desc_k_sw128(tc::smem_u32(ones));
+            uint32_t it = 0;
+            for (int64_t st = s0; st < s1; ++st, ++it) {
+                const uint32_t s = it % p.stages, use = it / p.stages;
+                tc::mbar_wait(&full[s], use & 1);
+                tc::tc_fence_after();
+                const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + DW_A_BYTES;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {          // 4 x (K = 16 rows)
+                    const uint64_t a_desc = p.a_cm ? tc::make_desc_k_sw128(a_addr) + (uint64_t)(k4 * 2)
+                                                   : tc::make_desc_mn_sw128(a_addr + k4 * 2048, 8192);
+                    const uint64_t b_desc = p.b_cm ? tc::make_desc_k_sw128(b_addr) + (uint64_t)(k4 * 2)
+                                                   : tc::make_desc_mn_sw128(b_addr + k4 * 2048, 8192);
+                    const uint32_t accum = (it | (uint32_t)k4) != 0;
+                    tc::mma_bf16_ss(tmem_base, a_desc, b_desc, idesc, accum);
+                    tc::mma_bf16_ss(tmem_base + p.n_chunk, a_desc, ones_desc + (uint64_t)(k4 * 2), idesc_b, accum);
+                }
+                tc::mma_commit(&empty[s]);
+            }
+            tc::mma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int TW = p.n_chunk + DW_BIAS_COLS;
+        float* out = p.ws + ((size_t)(split * gridDim.y + slab) * 128 + q * 32 + lane) * TW;
+        const bool have = s1 > s0;
+        if (have) {
+            tc::mbar_wait(acc_full, 0);
+            tc::tc_fence_after();
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < TW; c += 16) {
+            float v[16];
+            if (have) {
+                tc::tmem_ld_32x16(taddr + c, v);
+                tc::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(out + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// out[m, n] = sum over splits (in order) of the slab partials; db[m] from the bias column of the nc = 0 slabs.
+__global__ void k_dw_reduce(const float* __restrict__ ws, int splits, int slabs, int n_chunk, int n_chunks, int M, int N,
+                            float* __restrict__ out, int ldo, float* __restrict__ db, int accumulate) {
+    const int TW = n_chunk + DW_BIAS_COLS;
+    const int64_t total = (int64_t)M * (N + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / (N + 1)), n = (int)(i % (N + 1));
+        const bool bias = n == N;
+        if (bias && !db) continue;
+        const int mb = m >> 7, nc = bias ? 0 : n / n_chunk, col = bias ? n_chunk : n % n_chunk;
+        const int slab = mb * n_chunks + nc;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[((size_t)(s * slabs + slab) * 128 + (m & 127)) * TW + col];
+        if (bias) db[m] = accumulate ? db[m] + acc : acc;
+        else out[(int64_t)m * ldo + n] = accumulate ? out[(int64_t)m * ldo + n] + acc : acc;
+    }
+}
+
+struct DwPlan {
+    int n_chunk, n_chunks, m_blocks, slabs, splits, stages;
+    size_t ws_bytes, smem;
+};
+
+inline DwPlan dw_plan(int64_t rows, int M, int N, int b_cm) {
+    DwPlan d;
+    const int unit = b_cm ? 128 : 64;          // B channels per TMA box
+    const int npad = (N + unit - 1) / unit * unit;
+    d.n_chunks = (npad + 255) / 256;
+    d.n_chunk = ((npad / unit + d.n_chunks - 1) / d.n_chunks) * unit;
+    d.m_blocks = (M + 127) / 128;
+    d.slabs = d.m_blocks * d.n_chunks;
+    const int64_t steps = (rows + DW_KSTEP - 1) / DW_KSTEP;
+    int splits = GSATB_NUM_SMS / d.slabs;
+    if (splits < 1) splits = 1;
+    if ((int64_t)splits > steps) splits = steps > 0 ? (int)steps : 1;
+    d.splits = splits;
+    const int stage_bytes = DW_A_BYTES + d.n_chunk * 128;
+    int stages = (227 * 1024 - 1024 - DW_ONES_BYTES - 256) / stage_bytes;
+    d.stages = stages > 8 ? 8 : stages;
+    d.smem = (size_t)d.stages * stage_bytes + DW_ONES_BYTES + 256 + 1024;
+    d.ws_bytes = (size_t)d.splits * d.slabs * 128 * (d.n_chunk + DW_BIAS_COLS) * sizeof(float);
+    return d;
+}
+
+// operand tensor map: channel-major [C, rows] -> boxes {64 rows, 128 ch}; row-major [rows, C] -> boxes {64 ch, 64 rows}
+inline int make_dw_tmap(CUtensorMap* tm, const void* x, int64_t rows, int C, int64_t ld, int cm) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (!fn) return GSATB_ELAUNCH;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0 || (ld % 8) != 0) return GSATB_EALIGN;
+    cuuint64_t gdim[2], gstride[1];
+    cuuint32_t box[2], estr[2] = {1, 1};
+    if (cm) {
+        gdim[0] = (cuuint64_t)rows, gdim[1] = (cuuint64_t)C;
+        box[0] = 64, box[1] = 128;
+    } else {
+        gdim[0] = (cuuint64_t)C, gdim[1] = (cuuint64_t)rows;
+        box[0] = 64, box[1] = 64;
+    }
+    gstride[0] = (cuuint64_t)ld * 2;
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GSATB_OK : GSATB_EINVAL;
+}
+
+}  // namespace
+
+extern "C" size_t gsatb_tc_dw_workspace(int64_t rows, int M, int N) {
+    if (rows < 0 || M <= 0 || N <= 0) return 0;
+    const size_t a = dw_plan(rows, M, N, 0).ws_bytes, b = dw_plan(rows, M, N, 1).ws_bytes;
+    return a > b ? a : b;
+}
+
+extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda, const void* b_bf16, int b_channel_major,
+                           int64_t ldb, int64_t rows, int M, int N, float* dW, int ldo, float* db, int accumulate,
+                           void* workspace, size_t ws_bytes, gsatb_stream_t stream) {
+    if (rows < 0 || M <= 0 || N <= 0 || ldo < N) return GSATB_EINVAL;
+    if (!dW) return GSATB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        if (!accumulate) {
+            for (int m = 0; m < M; ++m)
+                if (cudaMemsetAsync(dW + (size_t)m * ldo, 0, (size_t)N * 4, st) != cudaSuccess) return GSATB_ELAUNCH;
+            if (db && cudaMemsetAsync(db, 0, (size_t)M * 4, st) != cudaSuccess) return GSATB_ELAUNCH;
+        }
+        return GSATB_OK;
+    }
+    if (!a_bf16 || !b_bf16 || !workspace) return GSATB_EINVAL;
+    const DwPlan d = dw_plan(rows, M, N, b_channel_major ? 1 : 0);
+    if (ws_bytes < d.ws_bytes) return GSATB_EWS_TOO_SMALL;
+    if (d.stages < 2) return GSATB_ESHAPE;
+    CUtensorMap ta, tb;
+    int rc = make_dw_tmap(&ta, a_bf16, rows, M, lda, a_channel_major);
+    if (rc != GSATB_OK) return rc;
+    rc = make_dw_tmap(&tb, b_bf16, rows, N, ldb, b_channel_major);
+    if (rc != GSATB_OK) return rc;
+    DwParams p{rows, M, N, a_channel_major ? 1 : 0, b_channel_major ? 1 : 0, d.n_chunk, d.n_chunks, d.splits, d.stages,
+               (float*)workspace};
+    if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return GSATB_ELAUNCH;
+    k_tc_dw<<<dim3(d.splits, d.slabs), DW_THREADS, d.smem, st>>>(ta, tb, p);
+    GSATB_CHECK_LAUNCH();
+    const int64_t total = (int64_t)M * (N + 1);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 4 * GSATB_NUM_SMS) grid = 4 * GSATB_NUM_SMS;
+    k_dw_reduce<<<grid, 256, 0, st>>>((const float*)workspace, d.splits, d.slabs, d.n_chunk, d.n_chunks, M, N, dW, ldo, db,
+                                      accumulate);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}

@@ -73,7 +73,7 @@ def reorder_like(from_edge_index, to_edge_index, values):
                ptr(g_from.src), ptr(g_from.dst), ptr(mp), ptr(mism), E, stream())
     if int(mism.item()) != 0:
         raise ValueError(msg)
-    return ops.gather_reverse(values, mp)
+    return ops.gather_reverse(values, mp, involution=False)
 
 
 def get_r(decay_interval, decay_r, current_epoch, init_r=0.9, final_r=0.5):

@@ -262,29 +262,41 @@ def sample_avg_info(logit, *, training: bool, rev: Optional[torch.Tensor], avera
 
 class _GatherRev(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, v, rev):
+    def forward(ctx, v, rev, involution):
         vc = _f32c(v)
         E = vc.shape[0]
         C = vc.numel() // max(E, 1)
         out = torch.empty_like(vc)
         lib().call('gsatb_gather_rev', ptr(vc), ptr(rev), ptr(out), E, max(C, 1), stream())
         ctx.save_for_backward(rev)
+        ctx.involution = bool(involution)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (rev,) = ctx.saved_tensors      # rev is an involution on symmetric edge sets, so the adjoint is the same gather
+        (rev,) = ctx.saved_tensors
         gc = _f32c(g)
         E = gc.shape[0]
         C = gc.numel() // max(E, 1)
-        out = torch.empty_like(gc)
-        lib().call('gsatb_gather_rev', ptr(gc), ptr(rev), ptr(out), E, max(C, 1), stream())
-        return out, None
+        if ctx.involution:
+            # the reverse-edge map of a symmetric edge set is its own inverse: the adjoint is the same gather
+            out = torch.empty_like(gc)
+            lib().call('gsatb_gather_rev', ptr(gc), ptr(rev), ptr(out), E, max(C, 1), stream())
+            return out, None, None
+        # general matching permutation (reorder_like between two arbitrary orders; -1 = no partner, forward wrote 0):
+        # out[i] = v[rev[i]]  =>  dv[rev[i]] += g[i]
+        ok = rev >= 0
+        idx = torch.where(ok, rev, torch.zeros_like(rev)).long()
+        g2 = gc.reshape(E, max(C, 1)) * ok.view(-1, 1).to(gc.dtype)
+        dv = torch.zeros_like(g2).index_add_(0, idx, g2)
+        return dv.view_as(gc), None, None
 
 
-def gather_reverse(values, rev):
-    """values[rev] == reorder_like(transpose(edge_index, values), edge_index, values) on a symmetric edge set."""
-    return _GatherRev.apply(values, rev)
+def gather_reverse(values, rev, involution: bool = True):
+    """values[rev] == reorder_like(transpose(edge_index, values), edge_index, values) on a symmetric edge set.
+    ``involution=False``: ``rev`` is an arbitrary matching permutation (general reorder_like); the backward then
+    scatters through it instead of re-using the gather."""
+    return _GatherRev.apply(values, rev, involution)
 
 
 class _Lift(torch.autograd.Function):

@@ -80,6 +80,13 @@ class TrainStep:
         self.group = group
         if sync_bn and dist.is_available() and dist.is_initialized():
             enable_sync_batchnorm(gsat.clf, group)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            # every rank draws its own noise / dropout streams: the sampler's Philox stream and the dropout hashes are
+            # indexed by LOCAL edge / row ids, so identical seeds would give every shard the same draws
+            r = dist.get_rank(group)
+            for m in (gsat, gsat.clf, gsat.extractor):
+                if hasattr(m, 'seed'):
+                    m.seed = int(m.seed) + 1000003 * (r + 1)
         params = list(gsat.extractor.parameters()) + list(gsat.clf.parameters())   # order of src/run_gsat.py:1007
         self.bucket = FlatGradBucket(params)
         if fused_adam is None:
@@ -87,22 +94,31 @@ class TrainStep:
         # capturable: the step count lives on the device, so the optimizer step can sit inside a CUDA graph
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused_adam,
                                           capturable=bool(fused_adam))
-        self._counts = {}
         self.graph = None            # torch.cuda.CUDAGraph of one whole step (enable_cuda_graph)
         self._graph_key = None
         self._graph_out = None
         self.launches_per_step = None
 
     def set_shard_weights(self, data):
-        key = (int(data.edge_index.shape[1]), int(data.batch.numel()), int(data.y.shape[0]))
-        if key not in self._counts:
-            learn = getattr(self.gsat, 'learn_edge_att', True)
-            n_att = data.edge_index.shape[1] if learn or getattr(self.gsat, 'info_on', 'att') == 'edge_att' \
-                else data.batch.numel()
-            n_g = int(data.y.shape[0])
-            eg, gg = global_counts(n_att, n_g, data.x.device, self.group)
-            self._counts[key] = (n_att / max(eg, 1), n_g / max(gg, 1))
-        self.gsat.info_scale, self.gsat.pred_scale = self._counts[key]
+        """Weights of the local loss terms (E_local/E_global, G_local/G_global).  The global counts cost one tiny
+        all-reduce; the result is cached ON THE BATCH OBJECT, so the hit / miss decision is a property of the batch
+        object the (SPMD) training loop hands to every rank at the same step -- never of local counts that two
+        different batches can share on one rank and not on another (which would leave ranks issuing different
+        collectives)."""
+        cache = getattr(data, '_cache', None)
+        key = ('shard_weights', id(self))
+        if cache is not None and key in cache:
+            self.gsat.info_scale, self.gsat.pred_scale = cache[key]
+            return
+        learn = getattr(self.gsat, 'learn_edge_att', True)
+        n_att = data.edge_index.shape[1] if learn or getattr(self.gsat, 'info_on', 'att') == 'edge_att' \
+            else data.batch.numel()
+        n_g = int(data.y.shape[0])
+        eg, gg = global_counts(n_att, n_g, data.x.device, self.group)
+        w = (n_att / max(eg, 1), n_g / max(gg, 1))
+        if cache is not None:
+            cache[key] = w
+        self.gsat.info_scale, self.gsat.pred_scale = w
 
     @staticmethod
     def _key(data, epoch):

@@ -253,8 +253,20 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     return h, (z1, a1, mean, rstd, scale, shift, p, posmask)
 
 
+def _dropout_scale(p: float, injected_mask: bool) -> float:
+    """The scale the forward kernels apply to kept values (tc_ops_common.cuh make_dropout): with an injected mask the
+    reference's 1/(1-p); with the in-kernel word scheme p is quantised to thr8 = round(256 p)/256 and the kept values
+    are scaled by the exact keep rate 256/(256 - thr8).  Backward must use the SAME number."""
+    if p <= 0:
+        return 1.0
+    if injected_mask:
+        return 1.0 / (1.0 - p)
+    thr8 = min(256, int(p * 256.0 + 0.5))
+    return 256.0 / (256 - thr8) if thr8 < 256 else 1.0 / (1.0 - p)
+
+
 def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, shift, training, p, posmask=None,
-                      sync_group=None):
+                      sync_group=None, injected_mask: bool = False):
     """-> (d agg fp32 [N, K], dW1, db1, dgamma, dbeta, dW2, db2).  With ``sync_group`` the BatchNorm backward sums span
     the group (the returned dgamma / dbeta stay the LOCAL sums: the step's gradient all-reduce adds them up)."""
     N, Kin = agg16.shape
@@ -270,7 +282,7 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     # before the call is made -- harmless with the stream-ordered caching allocator, but not something to lean on)
     w2t = prep_weight(w2, transpose=True)
     L.call('gsatb_tc_gin_bwd2', ptr(dh), None if posmask is not None else ptr(h), ptr(posmask),
-           ctypes.c_float(1.0 / (1.0 - p) if p > 0 else 1.0),
+           ctypes.c_float(_dropout_scale(p, injected_mask)),
            ptr(w2t), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
            ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
     dbeta, dgamma = stats[:H1], stats[H1:]
@@ -313,15 +325,16 @@ class _GinMlpFused(torch.autograd.Function):
             agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
             drop_seed, drop_mask, sync_group=sync_group)
         ctx.save_for_backward(agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
-        ctx.cfg = (bool(training), p, sync_group)
+        ctx.cfg = (bool(training), p, sync_group, drop_mask is not None)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        training, p, sync_group = ctx.cfg
+        training, p, sync_group, injected = ctx.cfg
         dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p, posmask, sync_group)
+                                                                    scale, shift, training, p, posmask, sync_group,
+                                                                    injected)
         return (dagg, dW1, db1, dgamma, dbeta, dW2, db2) + (None,) * 10
 
 
@@ -353,15 +366,17 @@ class _GinLayerFused(torch.autograd.Function):
             agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
             drop_seed, drop_mask, sync_group=sync_group)
         ctx.save_for_backward(x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift)
-        ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape, sync_group)
+        ctx.cfg = (bool(training), p, gi, float(conv_eps), None if att is None else att.shape, sync_group,
+                   drop_mask is not None)
         return h
 
     @staticmethod
     def backward(ctx, dh):
         x, att_flat, agg16, z1, a1, posmask, w1, w2, gamma, mean, rstd, scale, shift = ctx.saved_tensors
-        training, p, gi, conv_eps, att_shape, sync_group = ctx.cfg
+        training, p, gi, conv_eps, att_shape, sync_group, injected = ctx.cfg
         dagg, dW1, db1, dgamma, dbeta, dW2, db2 = _gin_mlp_backward(dh, agg16, None, w1, w2, gamma, z1, a1, mean, rstd,
-                                                                    scale, shift, training, p, posmask, sync_group)
+                                                                    scale, shift, training, p, posmask, sync_group,
+                                                                    injected)
         N, K = x.shape
         need_att = att_flat is not None and ctx.needs_input_grad[1]
         dx = torch.empty_like(x)

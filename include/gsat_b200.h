@@ -364,6 +364,19 @@ int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed,
 int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* dst, void* f12, int64_t rows, int H,
                           gsatb_stream_t stream);
 
+/* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
+ * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through
+ * loss.backward() at src/run_gsat.py:634; round 1 ran them as library GEMMs).  A and B are bf16 activations, each either
+ * row-major [rows, C] (ld = elements per row) or channel-major [C, rows] (ld = elements per channel): TMA loads them as
+ * MN-major / K-major SWIZZLE_128B operand tiles, so no transposed copy is made.  Split-K over the rows with a
+ * fixed-order reduction of the per-CTA partials: run-to-run deterministic.  dW is row-major [M, ldo] fp32 (the layout of
+ * nn.Linear.weight.grad for A = dz, B = layer input); db [M] nullable; accumulate != 0 adds to dW / db in place.
+ * workspace: gsatb_tc_dw_workspace(rows, M, N) bytes. */
+size_t gsatb_tc_dw_workspace(int64_t rows, int M, int N);
+int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda, const void* b_bf16, int b_channel_major,
+                int64_t ldb, int64_t rows, int M, int N, float* dW, int ldo, float* db /* [nullable] */, int accumulate,
+                void* workspace, size_t ws_bytes, gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * the step BEFORE the path -- feature encoders and batch collate on the device.
  *

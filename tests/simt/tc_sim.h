@@ -114,22 +114,34 @@ inline float bf16_at(const uint8_t* base, uint32_t off) {
     std::memcpy(&f, &u, 4);
     return f;
 }
-// D[tmem lane m][column n] (+)= sum_k A[m][k] * B[n][k]; M, N from the instruction descriptor, K = 16 (kind::f16)
+// Byte address of element (i = M/N index, k) of an operand tile described by a shared-memory descriptor.
+//   K-major  SWIZZLE_128B: 128-byte rows of 64 K elements, row i at (i / 8) * SBO + (i % 8) * 128
+//   MN-major SWIZZLE_128B: for every k a 128-byte row of 64 consecutive M/N elements; 8 k-rows per 1024-byte atom, the
+//                          next 8 k at + SBO, the next 64 M/N elements at + LBO (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO))
+//                          in 16-byte units)
+inline uint32_t operand_addr(uint64_t desc, bool mn_major, int i, int k) {
+    const uint32_t a0 = (uint32_t)(desc & 0x3fff) << 4, lbo = (uint32_t)((desc >> 16) & 0x3fff) << 4,
+                   sbo = (uint32_t)((desc >> 32) & 0x3fff) << 4;
+    if (!mn_major) return swizzle128(a0 + (uint32_t)(i >> 3) * sbo + (uint32_t)(i & 7) * 128 + (uint32_t)k * 2);
+    return swizzle128(a0 + (uint32_t)(i >> 6) * lbo + (uint32_t)(k >> 3) * sbo + (uint32_t)(k & 7) * 128 + (uint32_t)(i & 63) * 2);
+}
+// D[tmem lane m][column n] (+)= sum_k A[m][k] * B[n][k]; M, N, operand majors from the instruction descriptor,
+// K = 16 (kind::f16)
 inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     const int M = (int)((idesc >> 24) & 0x1f) << 4, N = (int)((idesc >> 17) & 0x3f) << 3;
+    const bool a_mn = (idesc >> 15) & 1u, b_mn = (idesc >> 16) & 1u;
     if (M != 128) simt::fail("only the M = 128 accumulator layout (row m -> TMEM lane m) is modelled");
-    if (((desc_a >> 61) & 7) != 2 || ((desc_b >> 61) & 7) != 2) simt::fail("only SWIZZLE_128B K-major operands are modelled");
+    if (N < 16 || N > 256 || (N & 15)) simt::fail("tcgen05.mma: N must be a multiple of 16 in [16, 256] for M = 128");
+    if (((desc_a >> 61) & 7) != 2 || ((desc_b >> 61) & 7) != 2) simt::fail("only SWIZZLE_128B operands are modelled");
     const uint8_t* base = simt::dyn_smem();
-    const uint32_t a0 = (uint32_t)(desc_a & 0x3fff) << 4, sa = (uint32_t)((desc_a >> 32) & 0x3fff) << 4;
-    const uint32_t b0 = (uint32_t)(desc_b & 0x3fff) << 4, sb = (uint32_t)((desc_b >> 32) & 0x3fff) << 4;
     float* tm = simt::tmem();
     const uint32_t col0 = tmem_d & 0xffff;
     if ((tmem_d >> 16) != 0 || col0 + N > simt::kTmemCols) simt::fail("MMA accumulator outside the allocated TMEM");
     float a[16], bcol[16];
     for (int n = 0; n < N; ++n) {
-        for (int k = 0; k < 16; ++k) bcol[k] = bf16_at(base, swizzle128(b0 + (n >> 3) * sb + (n & 7) * 128 + k * 2));
+        for (int k = 0; k < 16; ++k) bcol[k] = bf16_at(base, operand_addr(desc_b, b_mn, n, k));
         for (int m = 0; m < M; ++m) {
-            for (int k = 0; k < 16; ++k) a[k] = bf16_at(base, swizzle128(a0 + (m >> 3) * sa + (m & 7) * 128 + k * 2));
+            for (int k = 0; k < 16; ++k) a[k] = bf16_at(base, operand_addr(desc_a, a_mn, m, k));
             float acc = accumulate ? tm[m * simt::kTmemCols + col0 + n] : 0.f;
             for (int k = 0; k < 16; ++k) acc += a[k] * bcol[k];
             tm[m * simt::kTmemCols + col0 + n] = acc;
@@ -143,6 +155,38 @@ inline void tmem_ld_32x32(uint32_t taddr, float* v) {
     const float* row = simt::tmem() + (size_t)(lane0 + simt::lane_id()) * simt::kTmemCols + col;
     for (int j = 0; j < 32; ++j) v[j] = row[j];
 }
+inline void tmem_ld_cols(uint32_t taddr, float* v, int ncols) {
+    const uint32_t lane0 = taddr >> 16, col = taddr & 0xffff;
+    if (lane0 != 32u * ((uint32_t)(simt::S().cur >> 5) & 3u)) simt::fail("tcgen05.ld: a warp may only read its own TMEM lane quarter");
+    if (col + ncols > (uint32_t)simt::kTmemCols) simt::fail("tcgen05.ld beyond the TMEM columns");
+    const float* row = simt::tmem() + (size_t)(lane0 + simt::lane_id()) * simt::kTmemCols + col;
+    for (int j = 0; j < ncols; ++j) v[j] = row[j];
+}
+inline void tmem_ld_32x16(uint32_t taddr, float* v) { tmem_ld_cols(taddr, v, 16); }
+inline void tmem_ld_32x8(uint32_t taddr, float* v) { tmem_ld_cols(taddr, v, 8); }
 inline void tmem_ld_wait() {}
+
+// TMA store: shared-memory box (same layout rules as the load) -> global tensor; out-of-bounds elements are dropped
+inline void tma_store_2d(const void* desc, const void* smem_src, int crd0, int crd1) {
+    const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);
+    const uint8_t* base = simt::dyn_smem();
+    const uint32_t src = smem_u32(smem_src);
+    if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B && (src & 1023u)) simt::fail("SWIZZLE_128B box not 1024-byte aligned");
+    const uint32_t row_bytes = tm.box[0] * tm.elem_bytes;
+    for (uint32_t r = 0; r < tm.box[1]; ++r)
+        for (uint32_t c = 0; c < tm.box[0]; ++c) {
+            const int64_t gr = (int64_t)crd1 + r, gc = (int64_t)crd0 + c;
+            if (gr < 0 || gc < 0 || (uint64_t)gr >= tm.dim[1] || (uint64_t)gc >= tm.dim[0]) continue;
+            uint32_t off = src + r * row_bytes + c * 2;
+            if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) off = swizzle128(off);
+            *reinterpret_cast<uint16_t*>(const_cast<uint8_t*>(tm.base) + (uint64_t)gr * tm.row_stride + (uint64_t)gc * 2) =
+                *reinterpret_cast<const uint16_t*>(base + off);
+        }
+}
+inline void tma_store_commit() {}
+template <int N>
+inline void tma_store_wait_read() {}
+template <int N>
+inline void tma_store_wait_all() {}
 
 }  // namespace tc
