@@ -364,6 +364,32 @@ int gsatb_tc_ext_make_h1(const void* xhat1, const uint8_t* mask1, uint64_t seed,
 int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* dst, void* f12, int64_t rows, int H,
                           gsatb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K1 fused: the whole extractor MLP of src/run_gsat.py:909-927 (ExtractorMLP.forward: f12 = cat(emb[col], emb[row]),
+ * col, row = edge_index) + src/utils/get_model.py:57-68 (Linear -> InstanceNorm -> ReLU -> Dropout, twice, then
+ * Linear(H, 1)) as ONE persistent tcgen05 kernel per direction; no [rows, 4H] or [rows, 2H] tensor reaches HBM in the
+ * forward pass.
+ *
+ * gsatb_ext_tile_plan: packs consecutive graphs into tiles of <= 128 slots (every graph padded to a multiple of 8
+ *   slots) and <= 16 graphs, on the device.  seg_ptr = edge_ptr (edge mode) or node_ptr (node mode) of the GraphIndex;
+ *   tile_seg needs G + 1 entries; out2[0] = number of tiles T, out2[1] = graphs with more than 128 rows (the fused
+ *   kernels must not be run on such a batch: the caller takes the unfused tensor-core path).
+ * gsatb_ext_fused_fwd: logit[r] for every row (edge, or node when src == dst == NULL).  w1 / w2 come from
+ *   gsatb_tc_prep_weight.  The per-graph mean is removed from the gathered rows in fp32 BEFORE the bf16 rounding (the
+ *   Linear biases in front of an InstanceNorm cancel exactly, so b1 / b2 are not read).  mask1 [rows, C1] / mask2
+ *   [rows, H] inject dropout masks (parity tests); otherwise masks come from (seed, step counter, row, channel) and the
+ *   effective seeds are written to seed_out[2] for the backward pass.  xhat2t (nullable): the InstanceNorm-2 output as
+ *   bf16 in SLOT space [H, ld_slots], tile t owning columns [128 t, 128 t + 128) -- what the backward needs of the
+ *   forward besides the logits.  max_tiles >= T bounds the grid (pass G).  H % 8 == 0, H <= 128. */
+int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int32_t* tile_seg, int32_t* out2, gsatb_stream_t stream);
+int gsatb_ext_fused_fwd(const float* emb, const int32_t* src /* [nullable] */, const int32_t* dst /* [nullable] */,
+                        const int32_t* seg_ptr, const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles,
+                        const void* w1_bf16_padded, const void* w2_bf16_padded, const float* w3,
+                        const float* b3 /* [nullable] */, const uint8_t* mask1 /* [nullable] */,
+                        const uint8_t* mask2 /* [nullable] */, uint64_t seed, float pdrop, int training, float* logit,
+                        void* xhat2t /* [nullable] */, int64_t ld_slots, uint32_t* seed_out /* [nullable] */,
+                        int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
+
 /* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
  * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through
  * loss.backward() at src/run_gsat.py:634; round 1 ran them as library GEMMs).  A and B are bf16 activations, each either
