@@ -16,8 +16,10 @@
 //     logit per row; optionally x^2 = InstanceNorm-2 output as bf16 in slot space [H, tiles * 128] for the backward.
 // Weights stream from L2 through a ring of [128 x 64] TMA bricks in the order the MMA issuer consumes them.
 //
-// Roles (20 warps): 0 weight TMA, 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue 1 (two warpgroups, one per GEMM1
-// accumulator), 12-15 epilogue 2, 16-19 gather producers.
+// Roles (16 warps): 0 weight TMA, 1 MMA issuer, 2 TMEM allocator, 4-11 two epilogue warpgroups (one per GEMM1
+// accumulator; they take the tiles' GEMM2 epilogue in turns), 12-15 gather producers.  setmaxnreg hands the epilogue
+// threads 176 registers: a whole <= 64-slot graph of a channel stays in registers between the statistics sweep and the
+// emitting sweep (one tcgen05.wait per graph instead of one per 8-column piece).
 #include "ext_fused.cuh"
 
 namespace {
@@ -25,9 +27,7 @@ namespace {
 using namespace extf;
 
 struct FwdParams {
-    const float* emb;
-    const int32_t* src;          // null: node mode (row r = node r, K = H)
-    const int32_t* dst;
+    GatherArgs ga;               // emb, src / dst (null: node mode), node_ptr, degree pointers, H, Kin, KB1
     const int32_t* seg_ptr;      // [G + 1] rows of every graph
     const int32_t* tile_seg;     // [T + 1] first graph of every tile
     const int32_t* num_tiles;    // [1] device
@@ -37,22 +37,25 @@ struct FwdParams {
     float* logit;                // [rows]
     uint16_t* xhat2t;            // bf16 [H, ld_slots] (slot space: tile t owns columns [128 t, 128 t + 128)), nullable
     int64_t ld_slots;
+    float* rstd2;                // [G, H] InstanceNorm-2 reciprocal standard deviations (for the backward), nullable
     uint32_t* seed_out;          // [2] effective dropout seeds of this launch (for the backward), nullable
     int H, Kin, C1, KB1, NCB, NXB, NW;
+    int xkb;                     // bytes of one K-block of the x tile: max slots per tile * 128
     float eps;
+    long long* dbg;              // optional per-CTA cycle counters [grid][16] (gsatb_tc_set_profile_buffer)
 };
 
 struct Smem {
     uint32_t ring, x, h1, red, scr, bars, total;
 };
-__host__ __device__ inline Smem smem_plan(int KB1, int NXB, int NW) {
+__host__ __device__ inline Smem smem_plan(int KB1, int NXB, int NW, int xkb) {
     Smem s;
     s.ring = 0;
     s.x = s.ring + (uint32_t)NW * BRICK;
-    s.h1 = s.x + (uint32_t)NXB * KB1 * BRICK;
+    s.h1 = s.x + (uint32_t)NXB * KB1 * xkb;
     s.red = s.h1 + 2 * BRICK;
     s.scr = s.red + 2 * 4 * 128 * 4;          // epilogue-2 reduction scratch, double buffered
-    s.bars = s.scr + 4096 + 1024;             // producer scratch: partial column sums + the segment mean
+    s.bars = s.scr + GATHER_SCRATCH;          // producer scratch: slot -> node table, partial column sums, segment mean
     s.total = s.bars + 256 + 1024;            // + slack for the manual 1024-byte alignment
     return s;
 }
@@ -72,7 +75,135 @@ __device__ __forceinline__ int k2_blocks(int C1, int cb) {      // 64-channel K 
     return left >= 128 ? 2 : (left > 0 ? 1 : 0);
 }
 
-constexpr int BAR_EPI1 = 2, BAR_EPI2 = 4, BAR_PRO = 5;      // named barriers: BAR_EPI1 + e, BAR_EPI2, BAR_PRO (+8: waits)
+// run CALL with a compile-time NB = nb (1..MAXNB)
+#define EXT_DISPATCH_NB8(nb, CALL)                          \
+    switch (nb) {                                           \
+        case 1: { constexpr int NB = 1; CALL; } break;      \
+        case 2: { constexpr int NB = 2; CALL; } break;      \
+        case 3: { constexpr int NB = 3; CALL; } break;      \
+        case 4: { constexpr int NB = 4; CALL; } break;      \
+        case 5: { constexpr int NB = 5; CALL; } break;      \
+        case 6: { constexpr int NB = 6; CALL; } break;      \
+        case 7: { constexpr int NB = 7; CALL; } break;      \
+        default: { constexpr int NB = 8; CALL; } break;     \
+    }
+#define EXT_DISPATCH_NB4(nb, CALL)                          \
+    switch (nb) {                                           \
+        case 1: { constexpr int NB = 1; CALL; } break;      \
+        case 2: { constexpr int NB = 2; CALL; } break;      \
+        case 3: { constexpr int NB = 3; CALL; } break;      \
+        default: { constexpr int NB = 4; CALL; } break;     \
+    }
+
+struct Epi1Ctx {
+    uint32_t taddr;      // TMEM address of this warp's lane quarter of the accumulator
+    uint32_t h1_s;       // shared address of the h1 tile
+    int ch, gtid;
+    bool ch_ok;
+    float eps, dscale;
+};
+// Epilogue 1 of one graph of NB <= 8 blocks, register resident: one TMEM wait, statistics and emission from registers.
+template <int NB, class WaitH1>
+__device__ __forceinline__ void epi1_graph(const Epi1Ctx& c, const DropCtx& dc, int n, int row0, int slot0, WaitH1 wait_h1) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot0, v);
+    tc::tmem_ld_wait();
+    const float rs = c.dscale / sqrtf(sumsq_blocks<NB>(v) / (float)n + c.eps);
+    wait_h1();
+    const uint32_t k0 = keep_bits32(dc, c.ch, c.ch_ok, row0, n);
+    uint32_t k1 = 0xffffffffu;
+    if (NB > 4) k1 = keep_bits32(dc, c.ch, c.ch_ok, row0 + 32, n - 32);
+    const int blk0 = slot0 >> 3;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+        emit_h1_blk(&v[8 * b], rs, b < 4 ? k0 >> (8 * b) : k1 >> (8 * (b - 4)), c.h1_s + mn_tile_offset_blk(c.gtid, blk0 + b));
+}
+// larger graphs, in chunks of <= 4 blocks: statistics pass, then emitting pass (the accumulator is read twice)
+template <int NB>
+__device__ __forceinline__ float epi1_chunk_sumsq(const Epi1Ctx& c, int slot) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot, v);
+    tc::tmem_ld_wait();
+    return sumsq_blocks<NB>(v);
+}
+template <int NB>
+__device__ __forceinline__ void epi1_chunk_emit(const Epi1Ctx& c, const DropCtx& dc, float rs, int nleft, int row, int slot) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot, v);
+    const uint32_t k0 = keep_bits32(dc, c.ch, c.ch_ok, row, nleft);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) emit_h1_blk(&v[8 * b], rs, k0 >> (8 * b), c.h1_s + mn_tile_offset_blk(c.gtid, (slot >> 3) + b));
+}
+
+struct Epi2Ctx {
+    uint32_t taddr;
+    uint32_t redq_s;     // shared address of this warp's row of the reduction scratch [4][128] floats
+    uint16_t* xrow;      // xhat2t row of this channel at the tile's first slot, or null
+    float* rs_out;       // rstd2 + channel (stride H per graph), or null
+    int ch, lane;
+    bool ch_ok;
+    float eps, w3s;      // w3s = dropout scale * w3[ch]
+};
+// Epilogue 2, 8 slots of one channel: xhat = (z - mu) * rstd (stored as bf16 in slot space when xrow is given), then
+// Dropout(ReLU(xhat)) * scale * w3 reduced over the warp's 32 channels; lanes 0-7 leave the 8 partial dots in redq.
+template <bool LAST>
+__device__ __forceinline__ void out2_blk(const Epi2Ctx& c, float* v, int nv, float r, float nmr, uint32_t bits, int slot) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float xh = fmaf(v[j], r, nmr);
+        if (LAST) xh = j < nv ? xh : 0.f;
+        v[j] = xh;
+        const float h = ((bits >> j) & 1u) ? fmaxf(xh, 0.f) : 0.f;
+        a[j] = h * c.w3s;
+    }
+    if (c.xrow)
+        *reinterpret_cast<uint4*>(c.xrow + slot) = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]),
+                                                              tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
+    const float tot = transpose_reduce<8>(a, c.lane);
+    if (c.lane < 8) tc::sts_f32(c.redq_s + 4 * (slot + c.lane), tot);
+}
+template <int NB>
+__device__ __forceinline__ void epi2_graph(const Epi2Ctx& c, const DropCtx& dc, int n, int row0, int slot0, float* rs_out) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot0, v);
+    tc::tmem_ld_wait();
+    const float Ksh = v[0], inv_n = 1.f / (float)n;
+    float s1 = 0.f, s2 = 0.f;
+    shifted_stats<NB>(v, n - 8 * (NB - 1), Ksh, s1, s2);
+    const float md = s1 * inv_n;
+    const float r = 1.f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + c.eps), nmr = -(Ksh + md) * r;
+    if (rs_out) *rs_out = r;
+    const uint32_t k0 = keep_bits32(dc, c.ch, c.ch_ok, row0, n);
+    uint32_t k1 = 0xffffffffu;
+    if (NB > 4) k1 = keep_bits32(dc, c.ch, c.ch_ok, row0 + 32, n - 32);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t bits = b < 4 ? k0 >> (8 * b) : k1 >> (8 * (b - 4));
+        if (b == NB - 1) out2_blk<true>(c, &v[8 * b], n - 8 * b, r, nmr, bits, slot0 + 8 * b);
+        else out2_blk<false>(c, &v[8 * b], 8, r, nmr, bits, slot0 + 8 * b);
+    }
+}
+template <int NB>
+__device__ __forceinline__ void epi2_chunk_stats(const Epi2Ctx& c, int slot, int nv_last, bool first, float& Ksh, float& s1, float& s2) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot, v);
+    tc::tmem_ld_wait();
+    if (first) Ksh = v[0];
+    shifted_stats<NB>(v, nv_last, Ksh, s1, s2);
+}
+template <int NB>
+__device__ __forceinline__ void epi2_chunk_out(const Epi2Ctx& c, const DropCtx& dc, float r, float nmr, int nleft, int row, int slot) {
+    float v[8 * NB];
+    tmem_ld_blocks<NB>(c.taddr + slot, v);
+    const uint32_t k0 = keep_bits32(dc, c.ch, c.ch_ok, row, nleft);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) out2_blk<true>(c, &v[8 * b], nleft - 8 * b, r, nmr, k0 >> (8 * b), slot + 8 * b);
+}
+
+constexpr int BAR_EPI1 = 2, BAR_PRO = 5;      // named barriers: BAR_EPI1 + e (+ 8), BAR_PRO (+ 8)
 
 __global__ void __launch_bounds__(EXT_THREADS, 1)
 k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2, const FwdParams p) {
@@ -82,7 +213,7 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
 #endif
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const Smem L = smem_plan(p.KB1, p.NXB, p.NW);
+    const Smem L = smem_plan(p.KB1, p.NXB, p.NW, p.xkb);
     uint8_t* ring = smem + L.ring;
     uint8_t* xt = smem + L.x;
     uint8_t* h1 = smem + L.h1;
@@ -135,7 +266,7 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        tc::reg_dec<CTL_REGS>();
+        tc::reg_dec<EXT_CTL_REGS>();
         if (warp == 0) {
             // ===================== weight bricks (TMA), in MMA consumption order =====================
             if (lane == 0) {
@@ -161,26 +292,35 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
             // ===================== MMA issuer =====================
             if (lane == 0) {
                 uint32_t cw = 0, n1 = 0, nh = 0, ti = 0;
+                long long wx = 0, wa1 = 0, ww = 0, wh = 0, wa2 = 0, t0, t_all = clock64();
                 for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
                     int N = pad16(tile_total_slots(p.tile_seg, p.seg_ptr, tile));
                     if (N < 16) N = 16;
                     const uint32_t idesc1 = tc::make_idesc_bf16(128, N, 0, 0), idesc2 = tc::make_idesc_bf16(128, N, 0, 1);
                     const uint32_t xb = ti % p.NXB, xuse = ti / p.NXB, b2 = ti & 1, use2 = ti >> 1;
-                    const uint32_t x_addr = tc::smem_u32(xt + (size_t)xb * p.KB1 * BRICK);
+                    const uint32_t x_addr = tc::smem_u32(xt) + xb * p.KB1 * p.xkb;
                     const uint32_t h1_addr = tc::smem_u32(h1);
                     schedule(p.NCB, [&](bool g1, int cb) {
                         if (g1) {
                             const uint32_t buf = n1 & 1, use = n1 >> 1;
+                            t0 = clock64();
                             tc::mbar_wait(&acc1_empty[buf], (use & 1) ^ 1);
-                            if (cb == 0) tc::mbar_wait(&x_full[xb], xuse & 1);
+                            wa1 += clock64() - t0;
+                            if (cb == 0) {
+                                t0 = clock64();
+                                tc::mbar_wait(&x_full[xb], xuse & 1);
+                                wx += clock64() - t0;
+                            }
                             tc::tc_fence_after();
                             const uint32_t d = tmem_base + buf * 128;
                             for (int kb = 0; kb < p.KB1; ++kb, ++cw) {
                                 const uint32_t s = cw % p.NW, usew = cw / p.NW;
+                                t0 = clock64();
                                 tc::mbar_wait(&w_full[s], usew & 1);
+                                ww += clock64() - t0;
                                 tc::tc_fence_after();
                                 const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(ring + s * BRICK));
-                                const uint64_t b_desc = tc::make_desc_k_sw128(x_addr + kb * BRICK);
+                                const uint64_t b_desc = tc::make_desc_k_sw128(x_addr + kb * p.xkb);
 #pragma unroll
                                 for (int k4 = 0; k4 < 4; ++k4)
                                     tc::mma_bf16_ss(d, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc1,
@@ -191,14 +331,22 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                             if (cb == p.NCB - 1) tc::mma_commit(&x_empty[xb]);
                             ++n1;
                         } else {
+                            t0 = clock64();
                             tc::mbar_wait(h1_full, nh & 1);
-                            if (cb == 0) tc::mbar_wait(&acc2_empty[b2], (use2 & 1) ^ 1);
+                            wh += clock64() - t0;
+                            if (cb == 0) {
+                                t0 = clock64();
+                                tc::mbar_wait(&acc2_empty[b2], (use2 & 1) ^ 1);
+                                wa2 += clock64() - t0;
+                            }
                             tc::tc_fence_after();
                             const uint32_t d = tmem_base + 256 + b2 * 128;
                             const int nk = k2_blocks(p.C1, cb);
                             for (int kb = 0; kb < nk; ++kb, ++cw) {
                                 const uint32_t s = cw % p.NW, usew = cw / p.NW;
+                                t0 = clock64();
                                 tc::mbar_wait(&w_full[s], usew & 1);
+                                ww += clock64() - t0;
                                 tc::tc_fence_after();
                                 const uint64_t a_desc = tc::make_desc_k_sw128(tc::smem_u32(ring + s * BRICK));
 #pragma unroll
@@ -214,164 +362,122 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                         }
                     });
                 }
+                if (p.dbg) {
+                    long long* d = p.dbg + (size_t)blockIdx.x * 16;
+                    d[0] = clock64() - t_all, d[1] = wx, d[2] = wa1, d[3] = ww, d[4] = wh, d[5] = wa2;
+                }
             }
         }
     } else if (warp < 12) {
-        // ===================== epilogue 1: InstanceNorm 1 -> ReLU -> Dropout -> h1 tile (B operand of GEMM2) ==========
-        tc::reg_inc<EPI4_REGS>();
+        // ===================== epilogue warpgroups ====================================================================
+        //   epilogue 1 (per channel block): InstanceNorm 1 -> ReLU -> Dropout -> h1 tile (B operand of GEMM2)
+        //   epilogue 2 (per tile, warpgroup ti % 2): InstanceNorm 2 -> ReLU -> Dropout -> w3 dot -> logit
+        tc::reg_inc<EXT_EPI_REGS>();
         const int e = (warp - 4) >> 2, q = warp & 3, gtid = q * 32 + lane;
-        DropCtx dc;
-        dc.d = p.drop1;
-        dc.seed = dropout_seed(p.drop1);
-        dc.on = p.drop1.enabled != 0;
-        dc.use_mask = dc.on && p.drop1.mask != nullptr;
-        dc.C = p.C1;
-        const float dscale = p.drop1.scale;
-        uint32_t n1 = 0;
-        for (int tile = blockIdx.x; tile < T; tile += gridDim.x) {
+        const float w3 = gtid < p.H ? __ldg(p.w3 + gtid) : 0.f;
+        const float b3 = p.b3 ? __ldg(p.b3) : 0.f;
+        uint32_t n1 = 0, ti = 0;
+        long long w_acc = 0, w_h1 = 0, t_work = 0, w_acc2 = 0, t_work2 = 0, t0;
+        for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
             const SegTable tb = load_seg_table(p.tile_seg, p.seg_ptr, tile, lane);
             for (int cb = 0; cb < p.NCB; ++cb, ++n1) {
                 if ((int)(n1 & 1) != e) continue;
+                const DropCtx dc = make_drop_ctx(p.drop1, dropout_seed(p.drop1), p.C1);
+                const float dscale = p.drop1.scale;
                 const uint32_t use = n1 >> 1;
                 const int ch = cb * 128 + gtid;
                 const bool ch_ok = ch < p.C1;
+                t0 = clock64();
                 tc::group_mbar_wait(gtid == 0, &acc1_full[e], use & 1, BAR_EPI1 + e, 128);
+                w_acc += clock64() - t0;
                 tc::tc_fence_after();
+                const long long t_begin = clock64();
                 const uint32_t taddr = tmem_base + e * 128 + ((uint32_t)(q * 32) << 16);
+                const uint32_t h1_s = tc::smem_u32(h1);
                 bool h1_ready = false;
+                auto wait_h1 = [&]() {      // the single h1 tile: GEMM2 of the previous channel block has read it
+                    if (!h1_ready) {
+                        t0 = clock64();
+                        tc::group_mbar_wait(gtid == 0, h1_empty, (n1 & 1) ^ 1, BAR_EPI1 + 8 + e, 128);
+                        w_h1 += clock64() - t0;
+                        h1_ready = true;
+                    }
+                };
+                Epi1Ctx c1;
+                c1.taddr = taddr, c1.h1_s = h1_s, c1.ch = ch, c1.gtid = gtid, c1.ch_ok = ch_ok, c1.eps = p.eps, c1.dscale = dscale;
                 for (int s = 0; s < tb.nseg; ++s) {
                     const int n = __shfl_sync(0xffffffffu, tb.n, s);
                     if (n == 0) continue;
-                    const int npad = pad8(n);
+                    const int nblk = pad8(n) >> 3;
                     const int slot0 = __shfl_sync(0xffffffffu, tb.slot0, s), row0 = __shfl_sync(0xffffffffu, tb.row0, s);
-                    float qa = 0.f, qb = 0.f;
-                    for_pieces(npad, [&](auto Wt, int off) {
-                        constexpr int W = decltype(Wt)::value;
-                        float v[W];
-                        tmem_ld_cols<W>(taddr + slot0 + off, v);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < W; j += 2) {
-                            qa = fmaf(v[j], v[j], qa);
-                            qb = fmaf(v[j + 1], v[j + 1], qb);
+                    if (nblk <= 8) {
+                        EXT_DISPATCH_NB8(nblk, (epi1_graph<NB>(c1, dc, n, row0, slot0, wait_h1)));
+                    } else {
+                        float q = 0.f;
+                        for (int cb4 = 0; cb4 < nblk; cb4 += 4) {
+                            const int nbk = nblk - cb4 < 4 ? nblk - cb4 : 4;
+                            EXT_DISPATCH_NB4(nbk, (q += epi1_chunk_sumsq<NB>(c1, slot0 + 8 * cb4)));
                         }
-                    });
-                    const float rs = dscale / sqrtf((qa + qb) / (float)n + p.eps);
-                    if (!h1_ready) {      // the single h1 tile: GEMM2 of the previous channel block has read it
-                        tc::group_mbar_wait(gtid == 0, h1_empty, (n1 & 1) ^ 1, BAR_EPI1 + 8 + e, 128);
-                        h1_ready = true;
+                        const float rs = dscale / sqrtf(q / (float)n + p.eps);
+                        wait_h1();
+                        for (int cb4 = 0; cb4 < nblk; cb4 += 4) {
+                            const int nbk = nblk - cb4 < 4 ? nblk - cb4 : 4;
+                            EXT_DISPATCH_NB4(nbk, (epi1_chunk_emit<NB>(c1, dc, rs, n - 8 * cb4, row0 + 8 * cb4, slot0 + 8 * cb4)));
+                        }
                     }
-                    uint32_t kw = 0xffffffffu;
-                    for_pieces(npad, [&](auto Wt, int off) {
-                        constexpr int W = decltype(Wt)::value;
-                        if (dc.on && !dc.use_mask && (off & 31) == 0) kw = keep_word32(dc, (uint32_t)(row0 + off), ch, lane);
-                        const uint32_t bits = !dc.on ? 0xffffffffu
-                                              : dc.use_mask ? keep_bits_mask<W>(dc, row0 + off, n - off, ch, ch_ok)
-                                                            : (kw >> (off & 31));
-                        float v[W];
-                        tmem_ld_cols<W>(taddr + slot0 + off, v);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < W; j += 8) {
-                            uint32_t o[4];
-#pragma unroll
-                            for (int i = 0; i < 8; i += 2) {
-                                float a = fmaxf(v[j + i], 0.f) * rs, b = fmaxf(v[j + i + 1], 0.f) * rs;
-                                a = ((bits >> (j + i)) & 1u) ? a : 0.f;
-                                b = ((bits >> (j + i + 1)) & 1u) ? b : 0.f;
-                                o[i >> 1] = tc::pack_bf16(a, b);
-                            }
-                            *reinterpret_cast<uint4*>(h1 + mn_tile_offset(gtid, slot0 + off + j)) = make_uint4(o[0], o[1], o[2], o[3]);
-                        }
-                    });
                 }
-                if (!h1_ready) tc::group_mbar_wait(gtid == 0, h1_empty, (n1 & 1) ^ 1, BAR_EPI1 + 8 + e, 128);
+                wait_h1();
                 tc::fence_proxy_async_smem();
                 tc::tc_fence_before();
                 tc::mbar_arrive(&acc1_empty[e]);
                 tc::mbar_arrive(h1_full);
+                t_work += clock64() - t_begin;
             }
-        }
-    } else if (warp < 16) {
-        // ===================== epilogue 2: InstanceNorm 2 -> ReLU -> Dropout -> w3 dot -> logit =====================
-        tc::reg_inc<EPI4_REGS>();
-        const int q = warp & 3, gtid = q * 32 + lane;
-        const int ch = gtid;
-        const bool ch_ok = ch < p.H;
-        const float w3 = ch_ok ? __ldg(p.w3 + ch) : 0.f;
-        const float b3 = p.b3 ? __ldg(p.b3) : 0.f;
-        DropCtx dc;
-        dc.d = p.drop2;
-        dc.seed = dropout_seed(p.drop2);
-        dc.on = p.drop2.enabled != 0;
-        dc.use_mask = dc.on && p.drop2.mask != nullptr;
-        dc.C = p.H;
-        const float dscale = p.drop2.scale;
-        uint32_t ti = 0;
-        for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
+            if ((int)(ti & 1) != e) continue;
+            // ---------- epilogue 2 of this tile ----------
             const uint32_t b2 = ti & 1, use2 = ti >> 1;
-            const SegTable tb = load_seg_table(p.tile_seg, p.seg_ptr, tile, lane);
-            float* red = reinterpret_cast<float*>(smem + L.red) + b2 * 512;
-            tc::group_mbar_wait(gtid == 0, &acc2_full[b2], use2 & 1, BAR_EPI2, 128);
+            const int ch = gtid;
+            const bool ch_ok = ch < p.H;
+            const DropCtx dc = make_drop_ctx(p.drop2, dropout_seed(p.drop2), p.H);
+            const float dscale = p.drop2.scale;
+            const uint32_t red_s = tc::smem_u32(smem + L.red) + b2 * 2048;
+            t0 = clock64();
+            tc::group_mbar_wait(gtid == 0, &acc2_full[b2], use2 & 1, BAR_EPI1 + e, 128);
+            w_acc2 += clock64() - t0;
+            t0 = clock64();
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + 256 + b2 * 128 + ((uint32_t)(q * 32) << 16);
             uint16_t* xrow = p.xhat2t && ch_ok ? p.xhat2t + (int64_t)ch * p.ld_slots + (int64_t)tile * TILE_SLOTS : nullptr;
+            Epi2Ctx c2;
+            c2.taddr = taddr, c2.redq_s = red_s + 4 * (q * 128), c2.xrow = xrow, c2.ch = ch, c2.lane = lane, c2.ch_ok = ch_ok;
+            c2.eps = p.eps, c2.w3s = dscale * w3;
             for (int s = 0; s < tb.nseg; ++s) {
                 const int n = __shfl_sync(0xffffffffu, tb.n, s);
                 if (n == 0) continue;
-                const int npad = pad8(n);
+                const int nblk = pad8(n) >> 3;
                 const int slot0 = __shfl_sync(0xffffffffu, tb.slot0, s), row0 = __shfl_sync(0xffffffffu, tb.row0, s);
-                // sweep 1: sums of d = z - K and d^2 around a shift K close to the mean (the graph's first row)
-                float s1 = 0.f, s2 = 0.f, Ksh = 0.f;
-                for_pieces(npad, [&](auto Wt, int off) {
-                    constexpr int W = decltype(Wt)::value;
-                    float v[W];
-                    tmem_ld_cols<W>(taddr + slot0 + off, v);
-                    tc::tmem_ld_wait();
-                    if (off == 0) Ksh = v[0];
-                    const int nv = n - off;
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const float d = j < nv ? v[j] - Ksh : 0.f;
-                        s1 += d;
-                        s2 = fmaf(d, d, s2);
+                float* rs_out = p.rstd2 && ch_ok ? p.rstd2 + (int64_t)(tb.g0 + s) * p.H + ch : nullptr;
+                if (nblk <= 8) {
+                    EXT_DISPATCH_NB8(nblk, (epi2_graph<NB>(c2, dc, n, row0, slot0, rs_out)));
+                } else {
+                    float Ksh = 0.f, s1 = 0.f, s2 = 0.f;
+                    for (int cb4 = 0; cb4 < nblk; cb4 += 4) {
+                        const int nbk = nblk - cb4 < 4 ? nblk - cb4 : 4;
+                        const int nvl = cb4 + 4 >= nblk ? n - 8 * (nblk - 1) : 8;
+                        EXT_DISPATCH_NB4(nbk, (epi2_chunk_stats<NB>(c2, slot0 + 8 * cb4, nvl, cb4 == 0, Ksh, s1, s2)));
                     }
-                });
-                const float inv_n = 1.f / (float)n, md = s1 * inv_n;
-                const float var = fmaxf(s2 * inv_n - md * md, 0.f);
-                const float r = 1.f / sqrtf(var + p.eps), mu = Ksh + md;
-                uint32_t kw = 0xffffffffu;
-                for_pieces(npad, [&](auto Wt, int off) {
-                    constexpr int W = decltype(Wt)::value;
-                    if (dc.on && !dc.use_mask && (off & 31) == 0) kw = keep_word32(dc, (uint32_t)(row0 + off), ch, lane);
-                    const uint32_t bits = !dc.on ? 0xffffffffu
-                                          : dc.use_mask ? keep_bits_mask<W>(dc, row0 + off, n - off, ch, ch_ok)
-                                                        : (kw >> (off & 31));
-                    float v[W], a[W];
-                    tmem_ld_cols<W>(taddr + slot0 + off, v);
-                    tc::tmem_ld_wait();
-                    const int nv = n - off;
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const float xh = j < nv ? (v[j] - mu) * r : 0.f;
-                        v[j] = xh;
-                        const float h = ((bits >> j) & 1u) ? fmaxf(xh, 0.f) : 0.f;
-                        a[j] = h * (dscale * w3);
+                    const float inv_n = 1.f / (float)n, md = s1 * inv_n;
+                    const float r = 1.f / sqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + p.eps), nmr = -(Ksh + md) * r;
+                    if (rs_out) *rs_out = r;
+                    for (int cb4 = 0; cb4 < nblk; cb4 += 4) {
+                        const int nbk = nblk - cb4 < 4 ? nblk - cb4 : 4;
+                        EXT_DISPATCH_NB4(nbk, (epi2_chunk_out<NB>(c2, dc, r, nmr, n - 8 * cb4, row0 + 8 * cb4, slot0 + 8 * cb4)));
                     }
-                    if (xrow) {
-#pragma unroll
-                        for (int j = 0; j < W; j += 8)
-                            *reinterpret_cast<uint4*>(xrow + slot0 + off + j) =
-                                make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]),
-                                           tc::pack_bf16(v[j + 4], v[j + 5]), tc::pack_bf16(v[j + 6], v[j + 7]));
-                    }
-                    const float tot = transpose_reduce<W>(a, lane);
-                    if (lane < W) red[q * 128 + slot0 + off + lane] = tot;
-                });
+                }
             }
             tc::tc_fence_before();
             tc::mbar_arrive(&acc2_empty[b2]);
-            tc::named_bar_sync(BAR_EPI2 + 8, 128);
+            tc::named_bar_sync(BAR_EPI1 + 8 + e, 128);
             // one logit per valid slot: the four lane quarters' partial dots + b3
             {
                 const int slot = gtid;
@@ -381,98 +487,38 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                               r0 = __shfl_sync(0xffffffffu, tb.row0, s);
                     if (slot >= sl0 && slot < sl0 + n) row = r0 + slot - sl0;
                 }
-                if (row >= 0) p.logit[row] = red[slot] + red[128 + slot] + red[256 + slot] + red[384 + slot] + b3;
+                if (row >= 0)
+                    p.logit[row] = tc::lds_f32(red_s + 4 * slot) + tc::lds_f32(red_s + 4 * (128 + slot)) +
+                                   tc::lds_f32(red_s + 4 * (256 + slot)) + tc::lds_f32(red_s + 4 * (384 + slot)) + b3;
             }
+            t_work2 += clock64() - t0;
+        }
+        if (p.dbg && gtid == 0) {
+            long long* d = p.dbg + (size_t)blockIdx.x * 16 + 6 + e * 4;
+            d[0] = w_acc, d[1] = t_work, d[2] = w_acc2, d[3] = t_work2;        // t_work includes the h1_empty waits
         }
     } else {
         // ===================== gather producers: centred bf16 rows of f12 -> swizzled B tile of GEMM1 ================
-        tc::reg_inc<PRO_REGS>();
-        const int pt = threadIdx.x - 16 * 32;                  // 0..127
-        const int nck = p.Kin >> 3;                            // 8-element chunks per row
-        const int RP = 128 / nck > 0 ? 128 / nck : 1;          // rows processed in parallel
-        const int ck = pt % nck, rl = pt / nck;
-        const bool active = rl < RP && pt < RP * nck;
-        const int k0 = ck * 8;
-        const bool second = p.src != nullptr && k0 >= p.H;    // dst half of the concatenation
-        const int kk = second ? k0 - p.H : k0;
-        const int32_t* idx = p.src == nullptr ? nullptr : (second ? p.dst : p.src);
-        float* part = reinterpret_cast<float*>(smem + L.scr);           // [RP][Kin] partial column sums
-        float* mean = part + 1024;                                       // [Kin]
-        const int kb = k0 >> 6, kin = k0 & 63;
+        tc::reg_dec<EXT_PRO_REGS>();
+        const int pt = threadIdx.x - 12 * 32;                  // 0..127
         uint32_t ti = 0;
+        long long w_x = 0, t_work = 0, t0;
         for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
             const uint32_t xb = ti % p.NXB, xuse = ti / p.NXB;
             const SegTable tb = load_seg_table(p.tile_seg, p.seg_ptr, tile, lane);
+            t0 = clock64();
             tc::group_mbar_wait(pt == 0, &x_empty[xb], (xuse & 1) ^ 1, BAR_PRO + 8, 128);
-            uint8_t* xbuf = xt + (size_t)xb * p.KB1 * BRICK + (size_t)kb * BRICK;
-            for (int s = 0; s < tb.nseg; ++s) {
-                const int n = __shfl_sync(0xffffffffu, tb.n, s);
-                if (n == 0) continue;
-                const int npad = pad8(n);
-                const int slot0 = __shfl_sync(0xffffffffu, tb.slot0, s), row0 = __shfl_sync(0xffffffffu, tb.row0, s);
-                // pass 1: column sums of the graph's gathered rows
-                float acc[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                if (active) {
-#pragma unroll 4
-                    for (int r = rl; r < n; r += RP) {
-                        const int64_t node = idx ? __ldg(idx + row0 + r) : row0 + r;
-                        float v[8];
-                        load8_f32(p.emb + node * p.H, kk, p.H, v);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] += v[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) part[rl * p.Kin + k0 + i] = acc[i];
-                }
-                tc::named_bar_sync(BAR_PRO, 128);
-                if (active && rl == 0) {
-                    const float inv_n = 1.f / (float)n;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float t = 0.f;
-                        for (int j = 0; j < RP; ++j) t += part[j * p.Kin + k0 + i];
-                        mean[k0 + i] = t * inv_n;
-                    }
-                }
-                tc::named_bar_sync(BAR_PRO, 128);
-                // pass 2: centre, round to bf16, store swizzled; padding slots of the graph are zero rows
-                if (active) {
-                    float mu[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) mu[i] = mean[k0 + i];
-#pragma unroll 4
-                    for (int r = rl; r < npad; r += RP) {
-                        uint32_t o[4] = {0u, 0u, 0u, 0u};
-                        if (r < n) {
-                            const int64_t node = idx ? __ldg(idx + row0 + r) : row0 + r;
-                            float v[8];
-                            load8_f32(p.emb + node * p.H, kk, p.H, v);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] -= mu[i];
-                            pack8(v, o);
-                        }
-                        *reinterpret_cast<uint4*>(xbuf + tc::sw128_offset(slot0 + r, kin)) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-            }
-            // slots between the last graph and the MMA width, and the K padding up to the 64-block, are zero
-            {
-                int N = pad16(tb.total);
-                if (N < 16) N = 16;
-                if (active)
-                    for (int r = tb.total + rl; r < N; r += RP)
-                        *reinterpret_cast<uint4*>(xbuf + tc::sw128_offset(r, kin)) = make_uint4(0u, 0u, 0u, 0u);
-                const int kpad = p.KB1 * 64 - p.Kin;         // < 64, multiple of 8
-                for (int i = pt; i < (kpad >> 3) * N; i += 128) {
-                    const int r = i / (kpad >> 3), c = p.Kin + (i % (kpad >> 3)) * 8;
-                    *reinterpret_cast<uint4*>(xt + (size_t)xb * p.KB1 * BRICK + (size_t)(c >> 6) * BRICK +
-                                              tc::sw128_offset(r, c & 63)) = make_uint4(0u, 0u, 0u, 0u);
-                }
-            }
+            w_x += clock64() - t0;
+            t0 = clock64();
+            prefetch_next_tile(p.ga, p.tile_seg, p.seg_ptr, tile + (int)gridDim.x, T, pt);
+            produce_x_tile(p.ga, tb, tc::smem_u32(xt) + xb * p.KB1 * p.xkb, p.xkb, tc::smem_u32(smem + L.scr), pt, lane, BAR_PRO);
             tc::fence_proxy_async_smem();
             tc::mbar_arrive(&x_full[xb]);
+            t_work += clock64() - t0;
+        }
+        if (p.dbg && pt == 0) {
+            long long* d = p.dbg + (size_t)blockIdx.x * 16 + 14;
+            d[0] = w_x, d[1] = t_work;
         }
     }
     tc::tc_fence_before();
@@ -488,15 +534,15 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
 constexpr int PLAN_CHUNK = 256, PLAN_THREADS = 1024;
 
 template <class F>
-__device__ __forceinline__ int plan_chunk(const int32_t* __restrict__ seg_ptr, int64_t g_lo, int64_t g_hi, int& oversize, F emit) {
+__device__ __forceinline__ int plan_chunk(const int32_t* __restrict__ seg_ptr, int64_t g_lo, int64_t g_hi, int cap, int& oversize, F emit) {
     int cnt = 0, used = 0, nsg = 0;
     int prev = g_lo < g_hi ? __ldg(seg_ptr + g_lo) : 0;
     for (int64_t g = g_lo; g < g_hi; ++g) {
         const int nx = __ldg(seg_ptr + g + 1);
         const int len = nx - prev, np = pad8(len);
         prev = nx;
-        if (len > TILE_SLOTS) ++oversize;
-        if (nsg > 0 && (used + np > TILE_SLOTS || nsg == MAX_TSEG)) {
+        if (np > cap) ++oversize;
+        if (nsg > 0 && (used + np > cap || nsg == MAX_TSEG)) {
             ++cnt;
             used = 0;
             nsg = 0;
@@ -509,7 +555,7 @@ __device__ __forceinline__ int plan_chunk(const int32_t* __restrict__ seg_ptr, i
 }
 
 __global__ void __launch_bounds__(PLAN_THREADS, 1)
-k_ext_tile_plan(const int32_t* __restrict__ seg_ptr, int64_t G, int32_t* __restrict__ tile_seg, int32_t* __restrict__ out) {
+k_ext_tile_plan(const int32_t* __restrict__ seg_ptr, int64_t G, int cap, int32_t* __restrict__ tile_seg, int32_t* __restrict__ out) {
     __shared__ int scan[PLAN_THREADS];
     __shared__ int base, over;
     if (threadIdx.x == 0) base = 0, over = 0;
@@ -519,7 +565,7 @@ k_ext_tile_plan(const int32_t* __restrict__ seg_ptr, int64_t G, int32_t* __restr
         const int64_t c = c0 + threadIdx.x;
         const int64_t g_lo = c * PLAN_CHUNK < G ? c * PLAN_CHUNK : G, g_hi = (c + 1) * PLAN_CHUNK < G ? (c + 1) * PLAN_CHUNK : G;
         int oversize = 0;
-        const int cnt = plan_chunk(seg_ptr, g_lo, g_hi, oversize, [](int, int32_t) {});
+        const int cnt = plan_chunk(seg_ptr, g_lo, g_hi, cap, oversize, [](int, int32_t) {});
         if (oversize) atomicAdd(&over, oversize);
         scan[threadIdx.x] = cnt;
         __syncthreads();
@@ -531,7 +577,7 @@ k_ext_tile_plan(const int32_t* __restrict__ seg_ptr, int64_t G, int32_t* __restr
         }
         const int my0 = base + scan[threadIdx.x] - cnt;
         int dummy = 0;
-        plan_chunk(seg_ptr, g_lo, g_hi, dummy, [&](int k, int32_t g) { tile_seg[my0 + k] = g; });
+        plan_chunk(seg_ptr, g_lo, g_hi, cap, dummy, [&](int k, int32_t g) { tile_seg[my0 + k] = g; });
         __syncthreads();
         if (threadIdx.x == PLAN_THREADS - 1) base += scan[PLAN_THREADS - 1];
         __syncthreads();
@@ -545,41 +591,55 @@ k_ext_tile_plan(const int32_t* __restrict__ seg_ptr, int64_t G, int32_t* __restr
 
 }  // namespace
 
-extern "C" int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int32_t* tile_seg, int32_t* out2,
+// Slots per tile for hidden width H: 112 when the GEMM1 operand tile is wider than two 64-blocks (two x buffers of
+// 4 x 14 KiB fit beside the weight ring; 112 = two 56-slot graphs of the BA-2Motifs shape), else 128.
+extern "C" int gsatb_ext_tile_slots(int H, int edge_mode) {
+    const int Kin = edge_mode ? 2 * H : H;
+    return Kin > 128 ? 112 : 128;
+}
+
+extern "C" int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int max_slots, int32_t* tile_seg, int32_t* out2,
                                    gsatb_stream_t stream) {
     if (G < 0 || !tile_seg || !out2 || (G > 0 && !seg_ptr)) return GSATB_EINVAL;
-    GSATB_LAUNCH(k_ext_tile_plan, 1, PLAN_THREADS, (cudaStream_t)stream, seg_ptr, G, tile_seg, out2);
+    if (max_slots < 8 || max_slots > TILE_SLOTS || max_slots % 8 != 0) return GSATB_EINVAL;
+    GSATB_LAUNCH(k_ext_tile_plan, 1, PLAN_THREADS, (cudaStream_t)stream, seg_ptr, G, max_slots, tile_seg, out2);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }
 
-extern "C" int gsatb_ext_fused_fwd(const float* emb, const int32_t* src, const int32_t* dst, const int32_t* seg_ptr,
-                                   const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles,
+extern "C" int gsatb_ext_fused_fwd(const float* emb, const int32_t* src, const int32_t* dst, const int32_t* node_ptr,
+                                   const int32_t* rowptr_src, const int32_t* rowptr_dst, const int32_t* seg_ptr,
+                                   const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles, int max_slots,
                                    const void* w1_bf16_padded, const void* w2_bf16_padded, const float* w3,
                                    const float* b3, const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop,
-                                   int training, float* logit, void* xhat2t, int64_t ld_slots, uint32_t* seed_out,
+                                   int training, float* logit, void* xhat2t, int64_t ld_slots, float* rstd2, uint32_t* seed_out,
                                    int64_t rows, int H, int C1, float eps, gsatb_stream_t stream) {
     if (rows < 0 || H <= 0 || C1 <= 0 || max_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || max_tiles == 0) return GSATB_OK;
     if (!emb || !seg_ptr || !tile_seg || !num_tiles_dev || !w1_bf16_padded || !w2_bf16_padded || !w3 || !logit)
         return GSATB_EINVAL;
     if ((src == nullptr) != (dst == nullptr)) return GSATB_EINVAL;
+    if (src && (!node_ptr || !rowptr_src || !rowptr_dst)) return GSATB_EINVAL;
     const int Kin = src ? 2 * H : H;
     if (H % 8 != 0 || H > 128 || Kin > 256 || C1 > 512) return GSATB_ESHAPE;
     if (!gsatb_aligned16(emb) || (xhat2t && (!gsatb_aligned16(xhat2t) || ld_slots % 8 != 0))) return GSATB_EALIGN;
     FwdParams p;
-    p.emb = emb, p.src = src, p.dst = dst, p.seg_ptr = seg_ptr, p.tile_seg = tile_seg, p.num_tiles = num_tiles_dev;
+    p.ga = GatherArgs{emb, src, dst, node_ptr, rowptr_src, rowptr_dst, H, Kin, (Kin + 63) / 64};
+    p.seg_ptr = seg_ptr, p.tile_seg = tile_seg, p.num_tiles = num_tiles_dev;
     p.w3 = w3, p.b3 = b3;
     p.drop1 = make_dropout(mask1, seed * 2 + 1, pdrop, training, 1);
     p.drop2 = make_dropout(mask2, seed * 2 + 2, pdrop, training, 1);
-    p.logit = logit, p.xhat2t = (uint16_t*)xhat2t, p.ld_slots = ld_slots, p.seed_out = seed_out;
+    p.logit = logit, p.xhat2t = (uint16_t*)xhat2t, p.ld_slots = ld_slots, p.rstd2 = rstd2, p.seed_out = seed_out;
     p.H = H, p.Kin = Kin, p.C1 = C1, p.KB1 = (Kin + 63) / 64, p.NCB = (C1 + 127) / 128;
-    p.NXB = p.KB1 <= 2 ? 2 : 1;
+    if (max_slots != gsatb_ext_tile_slots(H, src != nullptr)) return GSATB_EINVAL;      // the plan was built for another width
+    p.NXB = 2;
+    p.xkb = max_slots * 128;
     p.eps = eps;
+    p.dbg = profile_buffer();
     int nw = 8;
-    while (nw > 2 && smem_plan(p.KB1, p.NXB, nw).total > 227 * 1024) --nw;
+    while (nw > 2 && smem_plan(p.KB1, p.NXB, nw, p.xkb).total > 227 * 1024) --nw;
     p.NW = nw;
-    const Smem L = smem_plan(p.KB1, p.NXB, p.NW);
+    const Smem L = smem_plan(p.KB1, p.NXB, p.NW, p.xkb);
     if (L.total > 227 * 1024) return GSATB_ESHAPE;
     CUtensorMap tm1, tm2;
     int rc = make_weight_tmap(&tm1, w1_bf16_padded, p.NCB * 128, p.KB1 * 64);

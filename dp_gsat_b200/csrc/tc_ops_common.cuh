@@ -99,6 +99,33 @@ __device__ __forceinline__ uint32_t dropout_word(const Dropout& d, uint32_t row,
     }
     return d.thr8 >= 256u ? 0u : ~lt;      // keep = not (U < thr8)
 }
+// "Channel word" scheme (fused extractor kernels, whose threads own a CHANNEL and walk rows): ONE call yields the keep
+// bits of the 32 rows 32 g .. 32 g + 31 of channel ch (bit b = keep(32 g + b, ch)), thread-local, no warp transpose.
+// Same estimator as dropout_word: p = 0.5 is one hash, any other p an 8-bit uniform held bit-sliced in 8 hashes.
+__device__ __forceinline__ uint32_t dropout_chan_word(const Dropout& d, uint32_t ch, uint32_t g, uint32_t seed) {
+    const uint32_t base = g * 0x9E3779B1u + ch * 0x7FEB352Du + seed;
+    if (d.thr8 == 128u) return mix32(base);
+    uint32_t lt = 0u, eq = 0xffffffffu;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        const uint32_t h = mix32(base + (uint32_t)(i + 1) * 0x632BE5ABu);
+        if ((d.thr8 >> i) & 1u) {
+            lt |= eq & ~h;
+            eq &= h;
+        } else {
+            eq &= ~h;
+        }
+    }
+    return d.thr8 >= 256u ? 0u : ~lt;
+}
+// keep bits of rows row0 .. row0 + 31 (bit j = keep(row0 + j, ch)) for any row0
+__device__ __forceinline__ uint32_t dropout_chan_bits32(const Dropout& d, uint32_t ch, uint32_t row0, uint32_t seed) {
+    const uint32_t g = row0 >> 5, sh = row0 & 31u;
+    const uint32_t w0 = dropout_chan_word(d, ch, g, seed);
+    if (sh == 0) return w0;
+    return tc::funnel_r(w0, dropout_chan_word(d, ch, g + 1, seed), sh);
+}
+
 // 32 x 32 bit-matrix transpose across a warp: in: lane r holds word r (bit c = element (r, c)); out: lane c holds the
 // bits of column c (bit r = element (r, c)).  Five shuffle / mask steps.
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {

@@ -125,12 +125,12 @@ class GraphIndex:
                 plans[key] = (tr[:T + 1].to(self.device), ts[:T + 1].to(self.device), T)
         return plans[key]
 
-    def ext_plan(self, by: str = 'edge'):
+    def ext_plan(self, by: str = 'edge', max_slots: int = 128):
         """Slot-space tile plan of the fused extractor kernels (gsatb_ext_tile_plan, built on the device): whole
         graphs packed into tiles of <= 128 slots, every graph padded to a multiple of 8 slots.  Returns a dict with
         ``tile_seg`` (int32 [G+1], device), ``out2`` (int32 [2] device: tiles, oversize graphs), and the host copies
         ``T`` / ``oversize`` (ONE 8-byte D2H read per batch, cached with the index)."""
-        key = ('ext', by)
+        key = ('ext', by, int(max_slots))
         plans = self._plans
         if plans is None:
             plans = self._plans = {}
@@ -140,10 +140,10 @@ class GraphIndex:
             tile_seg = torch.empty(self.G + 2, dtype=torch.int32, device=self.device)
             out2 = torch.zeros(2, dtype=torch.int32, device=self.device)
             with device_guard(self.device):
-                lib().call('gsatb_ext_tile_plan', ptr(seg_ptr), self.G, ptr(tile_seg), ptr(out2), stream())
+                lib().call('gsatb_ext_tile_plan', ptr(seg_ptr), self.G, int(max_slots), ptr(tile_seg), ptr(out2), stream())
             T, over = (int(v) for v in out2.cpu().tolist())
             plans[key] = dict(tile_seg=tile_seg, out2=out2, T=T, oversize=over, seg_ptr=seg_ptr,
-                              rows=self.E if by == 'edge' else self.N)
+                              rows=self.E if by == 'edge' else self.N, max_slots=int(max_slots))
         return plans[key]
 
     def require_graph_contiguous(self):

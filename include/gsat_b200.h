@@ -370,25 +370,50 @@ int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* d
  * Linear(H, 1)) as ONE persistent tcgen05 kernel per direction; no [rows, 4H] or [rows, 2H] tensor reaches HBM in the
  * forward pass.
  *
- * gsatb_ext_tile_plan: packs consecutive graphs into tiles of <= 128 slots (every graph padded to a multiple of 8
- *   slots) and <= 16 graphs, on the device.  seg_ptr = edge_ptr (edge mode) or node_ptr (node mode) of the GraphIndex;
- *   tile_seg needs G + 1 entries; out2[0] = number of tiles T, out2[1] = graphs with more than 128 rows (the fused
+ * gsatb_ext_tile_plan: packs consecutive graphs into tiles of <= max_slots = gsatb_ext_tile_slots(H, edge_mode) slots
+ *   (128, or 112 when 2H > 128; every graph padded to a multiple of 8 slots) and <= 16 graphs, on the device.  seg_ptr = edge_ptr (edge mode) or node_ptr (node mode) of the GraphIndex;
+ *   tile_seg needs G + 1 entries; out2[0] = number of tiles T, out2[1] = graphs with more than max_slots rows (the fused
  *   kernels must not be run on such a batch: the caller takes the unfused tensor-core path).
  * gsatb_ext_fused_fwd: logit[r] for every row (edge, or node when src == dst == NULL).  w1 / w2 come from
  *   gsatb_tc_prep_weight.  The per-graph mean is removed from the gathered rows in fp32 BEFORE the bf16 rounding (the
- *   Linear biases in front of an InstanceNorm cancel exactly, so b1 / b2 are not read).  mask1 [rows, C1] / mask2
+ *   Linear biases in front of an InstanceNorm cancel exactly, so b1 / b2 are not read); the mean comes from the graph's
+ *   contiguous node rows weighted by out- / in-degree (node_ptr, rowptr_src, rowptr_dst of the GraphIndex).  mask1 [rows, C1] / mask2
  *   [rows, H] inject dropout masks (parity tests); otherwise masks come from (seed, step counter, row, channel) and the
  *   effective seeds are written to seed_out[2] for the backward pass.  xhat2t (nullable): the InstanceNorm-2 output as
  *   bf16 in SLOT space [H, ld_slots], tile t owning columns [128 t, 128 t + 128) -- what the backward needs of the
  *   forward besides the logits.  max_tiles >= T bounds the grid (pass G).  H % 8 == 0, H <= 128. */
-int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int32_t* tile_seg, int32_t* out2, gsatb_stream_t stream);
+int gsatb_ext_tile_slots(int H, int edge_mode);
+int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int max_slots, int32_t* tile_seg, int32_t* out2,
+                        gsatb_stream_t stream);
 int gsatb_ext_fused_fwd(const float* emb, const int32_t* src /* [nullable] */, const int32_t* dst /* [nullable] */,
-                        const int32_t* seg_ptr, const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles,
+                        const int32_t* node_ptr /* [nullable: node mode] */, const int32_t* rowptr_src /* [nullable: node mode] */,
+                        const int32_t* rowptr_dst /* [nullable: node mode] */, const int32_t* seg_ptr,
+                        const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles, int max_slots,
                         const void* w1_bf16_padded, const void* w2_bf16_padded, const float* w3,
                         const float* b3 /* [nullable] */, const uint8_t* mask1 /* [nullable] */,
                         const uint8_t* mask2 /* [nullable] */, uint64_t seed, float pdrop, int training, float* logit,
-                        void* xhat2t /* [nullable] */, int64_t ld_slots, uint32_t* seed_out /* [nullable] */,
-                        int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
+                        void* xhat2t /* [nullable] */, int64_t ld_slots, float* rstd2 /* [G, H], [nullable] */,
+                        uint32_t* seed_out /* [nullable] */, int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
+
+/* gsatb_ext_fused_bwd: backward of gsatb_ext_fused_fwd over the same tile plan (autograd of src/run_gsat.py:909-927 +
+ *   src/utils/get_model.py:57-68 at loss.backward(), src/run_gsat.py:634).  GEMM1 is recomputed per tile; inputs besides
+ *   the forward's own are d logit [rows], xhat2t / rstd2 / seeds as the forward wrote them, W2^T and W1^T from
+ *   gsatb_tc_prep_weight(transpose = 1).  Outputs: d f12 [rows, Kin] fp32 (Kin = 2H, or H in node mode: then it IS d emb;
+ *   edge mode: reduce with gsatb_gather_concat_bwd), dw3_part [min(max_tiles, 148) * 2, H] partial sums of d w3 (add
+ *   them up), and the bf16 operands of the weight-gradient products in slot space (ld_slots = T * 128 columns / rows):
+ *   dz2t [H, ld_slots], dz1t [C1, ld_slots], h1t [C1, ld_slots] channel-major and xs [ld_slots, ldx = pad64(Kin)] row-major,
+ *   so that dW2 = gsatb_tc_dw(dz2t, h1t) and dW1 = gsatb_tc_dw(dz1t, xs) with rows = ld_slots (padding slots are zero
+ *   in dz1t / dz2t).  d b1 = d b2 = 0 exactly (the biases cancel in the InstanceNorms); d b3 = sum(d logit). */
+int gsatb_ext_fused_bwd(const float* emb, const int32_t* src /* [nullable] */, const int32_t* dst /* [nullable] */,
+                        const int32_t* node_ptr /* [nullable: node mode] */, const int32_t* rowptr_src /* [nullable: node mode] */,
+                        const int32_t* rowptr_dst /* [nullable: node mode] */, const int32_t* seg_ptr,
+                        const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles, int max_slots,
+                        const void* w1_bf16_padded, const void* w2t_bf16_padded, const void* w1t_bf16_padded,
+                        const float* w3, const float* dlogit, const void* xhat2t, const float* rstd2,
+                        const uint8_t* mask1 /* [nullable] */, const uint8_t* mask2 /* [nullable] */,
+                        const uint32_t* seeds /* [nullable] */, float pdrop, int training, void* dz2t, void* dz1t, void* h1t,
+                        void* xs, int ldx, float* df12, float* dw3_part, int64_t ld_slots, int64_t rows, int H, int C1,
+                        float eps, gsatb_stream_t stream);
 
 /* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
  * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through

@@ -77,6 +77,24 @@ inline void reg_dec() {}
 template <int N>
 inline void reg_inc() {}
 
+// ---- explicit shared-space accesses on 32-bit shared addresses (= offsets into the block's dynamic shared memory) ----
+inline void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    if (saddr & 15u) simt::fail("st.shared.v4 not 16-byte aligned");
+    uint32_t* q = reinterpret_cast<uint32_t*>(simt::dyn_smem() + saddr);
+    q[0] = a, q[1] = b, q[2] = c, q[3] = d;
+}
+inline void sts32(uint32_t saddr, uint32_t a) { *reinterpret_cast<uint32_t*>(simt::dyn_smem() + saddr) = a; }
+inline void sts_f32(uint32_t saddr, float a) { *reinterpret_cast<float*>(simt::dyn_smem() + saddr) = a; }
+inline uint32_t lds32(uint32_t saddr) { return *reinterpret_cast<const uint32_t*>(simt::dyn_smem() + saddr); }
+inline float lds_f32(uint32_t saddr) { return *reinterpret_cast<const float*>(simt::dyn_smem() + saddr); }
+inline uint4 lds128(uint32_t saddr) {
+    if (saddr & 15u) simt::fail("ld.shared.v4 not 16-byte aligned");
+    return *reinterpret_cast<const uint4*>(simt::dyn_smem() + saddr);
+}
+inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u));
+}
+
 // ---- TMA -------------------------------------------------------------------------------------------------------
 inline void tma_prefetch_desc(const void*) {}
 inline uint32_t swizzle128(uint32_t byte_addr) { return byte_addr ^ (((byte_addr >> 7) & 7u) << 4); }
