@@ -38,6 +38,7 @@ struct FwdParams {
     uint16_t* xhat2t;            // bf16 [H, ld_slots] (slot space: tile t owns columns [128 t, 128 t + 128)), nullable
     int64_t ld_slots;
     float* rstd2;                // [G, H] InstanceNorm-2 reciprocal standard deviations (for the backward), nullable
+    int dump_xs;                 // store every centred bf16 input tile to xs [tiles * 128, pad64(Kin)] (TMA), for the backward
     uint32_t* seed_out;          // [2] effective dropout seeds of this launch (for the backward), nullable
     int H, Kin, C1, KB1, NCB, NXB, NW;
     int xkb;                     // bytes of one K-block of the x tile: max slots per tile * 128
@@ -206,7 +207,8 @@ __device__ __forceinline__ void epi2_chunk_out(const Epi2Ctx& c, const DropCtx& 
 constexpr int BAR_EPI1 = 2, BAR_PRO = 5;      // named barriers: BAR_EPI1 + e (+ 8), BAR_PRO (+ 8)
 
 __global__ void __launch_bounds__(EXT_THREADS, 1)
-k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2, const FwdParams p) {
+k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                const __grid_constant__ CUtensorMap tm_xs, const FwdParams p) {
 #ifdef GSATB_HOST_SIM
     uint8_t* smem_raw = simt::dyn_smem();
 #else
@@ -503,16 +505,28 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
         const int pt = threadIdx.x - 12 * 32;                  // 0..127
         uint32_t ti = 0;
         long long w_x = 0, t_work = 0, t0;
+        if (p.dump_xs)      // whole tiles are stored: rows past a tile's MMA width must hold finite values (0 * NaN = NaN in dW1)
+            for (uint32_t o = (uint32_t)pt * 16; o < (uint32_t)(p.NXB * p.KB1) * p.xkb; o += 128 * 16)
+                tc::sts128(tc::smem_u32(xt) + o, 0u, 0u, 0u, 0u);
         for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
             const uint32_t xb = ti % p.NXB, xuse = ti / p.NXB;
             const SegTable tb = load_seg_table(p.tile_seg, p.seg_ptr, tile, lane);
             t0 = clock64();
+            if (p.dump_xs && pt == 0) tc::tma_store_wait_read<0>();      // earlier xs stores have read their x buffer
             tc::group_mbar_wait(pt == 0, &x_empty[xb], (xuse & 1) ^ 1, BAR_PRO + 8, 128);
             w_x += clock64() - t0;
             t0 = clock64();
             prefetch_next_tile(p.ga, p.tile_seg, p.seg_ptr, tile + (int)gridDim.x, T, pt);
             produce_x_tile(p.ga, tb, tc::smem_u32(xt) + xb * p.KB1 * p.xkb, p.xkb, tc::smem_u32(smem + L.scr), pt, lane, BAR_PRO);
             tc::fence_proxy_async_smem();
+            if (p.dump_xs) {
+                tc::named_bar_sync(BAR_PRO, 128);
+                if (pt == 0) {
+                    for (int kb = 0; kb < p.KB1; ++kb)
+                        tc::tma_store_2d(&tm_xs, xt + ((size_t)xb * p.KB1 + kb) * p.xkb, kb * 64, tile * TILE_SLOTS);
+                    tc::tma_store_commit();
+                }
+            }
             tc::mbar_arrive(&x_full[xb]);
             t_work += clock64() - t0;
         }
@@ -521,6 +535,7 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
             d[0] = w_x, d[1] = t_work;
         }
     }
+    if (p.dump_xs && warp == 12 && lane == 0) tc::tma_store_wait_all<0>();
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
@@ -612,7 +627,7 @@ extern "C" int gsatb_ext_fused_fwd(const float* emb, const int32_t* src, const i
                                    const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles, int max_slots,
                                    const void* w1_bf16_padded, const void* w2_bf16_padded, const float* w3,
                                    const float* b3, const uint8_t* mask1, const uint8_t* mask2, uint64_t seed, float pdrop,
-                                   int training, float* logit, void* xhat2t, int64_t ld_slots, float* rstd2, uint32_t* seed_out,
+                                   int training, float* logit, void* xhat2t, int64_t ld_slots, float* rstd2, void* xs, uint32_t* seed_out,
                                    int64_t rows, int H, int C1, float eps, gsatb_stream_t stream) {
     if (rows < 0 || H <= 0 || C1 <= 0 || max_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || max_tiles == 0) return GSATB_OK;
@@ -646,10 +661,24 @@ extern "C" int gsatb_ext_fused_fwd(const float* emb, const int32_t* src, const i
     if (rc != GSATB_OK) return rc;
     rc = make_weight_tmap(&tm2, w2_bf16_padded, 128, ((C1 + 63) / 64) * 64);
     if (rc != GSATB_OK) return rc;
+    CUtensorMap txs = tm1;
+    p.dump_xs = xs != nullptr;
+    if (xs) {      // xs [ld_slots, pad64(Kin)] row-major: boxes of 64 input channels x max_slots rows
+        if (!gsatb_aligned16(xs) || ld_slots <= 0) return GSATB_EALIGN;
+        PFN_tmapEncodeTiled fn = get_encode_fn();
+        if (!fn) return GSATB_ELAUNCH;
+        const int ldx = p.KB1 * 64;
+        cuuint64_t gdim[2] = {(cuuint64_t)ldx, (cuuint64_t)ld_slots};
+        cuuint64_t gstride[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)max_slots}, estr[2] = {1, 1};
+        if (fn(&txs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return GSATB_EINVAL;
+    }
     if (cudaFuncSetAttribute(k_ext_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return GSATB_ELAUNCH;
     const int grid = max_tiles < GSATB_NUM_SMS ? max_tiles : GSATB_NUM_SMS;
-    k_ext_fused_fwd<<<grid, EXT_THREADS, L.total, (cudaStream_t)stream>>>(tm1, tm2, p);
+    k_ext_fused_fwd<<<grid, EXT_THREADS, L.total, (cudaStream_t)stream>>>(tm1, tm2, txs, p);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }

@@ -393,27 +393,26 @@ int gsatb_ext_fused_fwd(const float* emb, const int32_t* src /* [nullable] */, c
                         const float* b3 /* [nullable] */, const uint8_t* mask1 /* [nullable] */,
                         const uint8_t* mask2 /* [nullable] */, uint64_t seed, float pdrop, int training, float* logit,
                         void* xhat2t /* [nullable] */, int64_t ld_slots, float* rstd2 /* [G, H], [nullable] */,
-                        uint32_t* seed_out /* [nullable] */, int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
+                        void* xs /* [ld_slots, pad64(Kin)] bf16, [nullable] */, uint32_t* seed_out /* [nullable] */, int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
 
 /* gsatb_ext_fused_bwd: backward of gsatb_ext_fused_fwd over the same tile plan (autograd of src/run_gsat.py:909-927 +
- *   src/utils/get_model.py:57-68 at loss.backward(), src/run_gsat.py:634).  GEMM1 is recomputed per tile; inputs besides
- *   the forward's own are d logit [rows], xhat2t / rstd2 / seeds as the forward wrote them, W2^T and W1^T from
+ *   src/utils/get_model.py:57-68 at loss.backward(), src/run_gsat.py:634).  GEMM1 is recomputed per tile from xs, the
+ *   centred bf16 input tiles the forward stored (TMA) in slot space [ld_slots = T * 128, pad64(Kin)]; the other inputs are
+ *   d logit [rows], xhat2t / rstd2 / seeds as the forward wrote them, W2^T and W1^T from
  *   gsatb_tc_prep_weight(transpose = 1).  Outputs: d f12 [rows, Kin] fp32 (Kin = 2H, or H in node mode: then it IS d emb;
  *   edge mode: reduce with gsatb_gather_concat_bwd), dw3_part [min(max_tiles, 148) * 2, H] partial sums of d w3 (add
- *   them up), and the bf16 operands of the weight-gradient products in slot space (ld_slots = T * 128 columns / rows):
- *   dz2t [H, ld_slots], dz1t [C1, ld_slots], h1t [C1, ld_slots] channel-major and xs [ld_slots, ldx = pad64(Kin)] row-major,
- *   so that dW2 = gsatb_tc_dw(dz2t, h1t) and dW1 = gsatb_tc_dw(dz1t, xs) with rows = ld_slots (padding slots are zero
- *   in dz1t / dz2t).  d b1 = d b2 = 0 exactly (the biases cancel in the InstanceNorms); d b3 = sum(d logit). */
-int gsatb_ext_fused_bwd(const float* emb, const int32_t* src /* [nullable] */, const int32_t* dst /* [nullable] */,
-                        const int32_t* node_ptr /* [nullable: node mode] */, const int32_t* rowptr_src /* [nullable: node mode] */,
-                        const int32_t* rowptr_dst /* [nullable: node mode] */, const int32_t* seg_ptr,
-                        const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles, int max_slots,
-                        const void* w1_bf16_padded, const void* w2t_bf16_padded, const void* w1t_bf16_padded,
-                        const float* w3, const float* dlogit, const void* xhat2t, const float* rstd2,
-                        const uint8_t* mask1 /* [nullable] */, const uint8_t* mask2 /* [nullable] */,
-                        const uint32_t* seeds /* [nullable] */, float pdrop, int training, void* dz2t, void* dz1t, void* h1t,
-                        void* xs, int ldx, float* df12, float* dw3_part, int64_t ld_slots, int64_t rows, int H, int C1,
-                        float eps, gsatb_stream_t stream);
+ *   them up), and the bf16 operands of the weight-gradient products in channel-major slot space, written with TMA stores:
+ *   dz2t [H, ld_slots], dz1t [C1, ld_slots], h1t [C1, ld_slots], so that dW2 = gsatb_tc_dw(dz2t, h1t) and
+ *   dW1 = gsatb_tc_dw(dz1t, xs) with rows = ld_slots (slots outside the graphs are zero in dz1t / dz2t / h1t; xs must have
+ *   been allocated zero-filled: rows [128 t + max_slots, 128 t + 128) are never written).  d b1 = d b2 = 0 exactly (the
+ *   biases cancel in the InstanceNorms); d b3 = sum(d logit). */
+int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_seg, const int32_t* num_tiles_dev, int max_tiles,
+                        int max_slots, int edge_mode, const void* w1_bf16_padded, const void* w2t_bf16_padded,
+                        const void* w1t_bf16_padded, const float* w3, const float* dlogit, const void* xhat2t,
+                        const float* rstd2, const void* xs, const uint8_t* mask1 /* [nullable] */,
+                        const uint8_t* mask2 /* [nullable] */, const uint32_t* seeds /* [nullable] */, float pdrop, int training,
+                        void* dz2t, void* dz1t, void* h1t, float* df12, float* dw3_part, int64_t ld_slots, int64_t rows, int H,
+                        int C1, float eps, gsatb_stream_t stream);
 
 /* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
  * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through

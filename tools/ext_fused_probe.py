@@ -25,7 +25,7 @@ def fwd(emb, gi, w1, w2, w3, b3, edge, m1=None, m2=None, pdrop=0.0, training=0, 
            ptr(gi.node_ptr) if edge else None, ptr(gi.rowptr_src) if edge else None, ptr(gi.rowptr_dst) if edge else None,
            ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, ptr(w1p), ptr(w2p), ptr(w3),
            ptr(b3), ptr(m1), ptr(m2), ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(logit), ptr(xh2t),
-           T * 128, None, ptr(seeds), rows, H, C1, ctypes.c_float(1e-5), stream())
+           T * 128, None, None, ptr(seeds), rows, H, C1, ctypes.c_float(1e-5), stream())
     return logit, xh2t
 
 
@@ -89,7 +89,7 @@ def timing(n_graphs=196000, H=128):
         print(f'fused extractor fwd (training={tr}) E={gi.E} H={H}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s', flush=True)
 
 
-if __name__ == '__main__' and not (len(sys.argv) > 1 and sys.argv[1] in ('roles', 'bwd')):
+if __name__ == '__main__' and not (len(sys.argv) > 1 and sys.argv[1] in ('roles', 'bwd', 'roles_bwd')):
     ok = True
     ok &= check(64, 40)
     ok &= check(64, 40, masks=True)
@@ -136,24 +136,36 @@ if len(sys.argv) > 1 and sys.argv[1] == 'roles':
     roles()
 
 
-def bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds, edge, m1=None, m2=None, pdrop=0.0, training=0):
+def bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds_xs, edge, m1=None, m2=None, pdrop=0.0, training=0):
+    seeds, xs = seeds_xs
     H, C1 = emb.shape[1], w1.shape[0]
     Kin = 2 * H if edge else H
     ms = int(L.cdll.gsatb_ext_tile_slots(H, int(edge)))
     plan = gi.ext_plan('edge' if edge else 'node', ms)
     rows, T = plan['rows'], plan['T']
-    ld, ldx = T * 128, (Kin + 63) // 64 * 64
+    ld = T * 128
     bf = dict(dtype=torch.bfloat16, device=dev)
-    dz2t, dz1t, h1t, xs = torch.empty(H, ld, **bf), torch.empty(C1, ld, **bf), torch.empty(C1, ld, **bf), torch.empty(ld, ldx, **bf)
+    dz2t, dz1t, h1t = torch.empty(H, ld, **bf), torch.empty(C1, ld, **bf), torch.empty(C1, ld, **bf)
     df12 = torch.empty(rows, Kin, device=dev)
     dw3p = torch.zeros(min(max(gi.G, 1), 148) * 2, H, device=dev)
     w1p, w2t, w1t = tc.prep_weight(w1), tc.prep_weight(w2, transpose=True), tc.prep_weight(w1, transpose=True)
-    L.call('gsatb_ext_fused_bwd', ptr(emb), ptr(gi.src) if edge else None, ptr(gi.dst) if edge else None,
-           ptr(gi.node_ptr) if edge else None, ptr(gi.rowptr_src) if edge else None, ptr(gi.rowptr_dst) if edge else None,
-           ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, ptr(w1p), ptr(w2t), ptr(w1t),
-           ptr(w3), ptr(dlogit), ptr(xh2t), ptr(rstd2), ptr(m1), ptr(m2), ptr(seeds), ctypes.c_float(pdrop), int(training),
-           ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(xs), ldx, ptr(df12), ptr(dw3p), ld, rows, H, C1, ctypes.c_float(1e-5), stream())
+    L.call('gsatb_ext_fused_bwd', ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, int(edge),
+           ptr(w1p), ptr(w2t), ptr(w1t), ptr(w3), ptr(dlogit), ptr(xh2t), ptr(rstd2), ptr(xs), ptr(m1), ptr(m2), ptr(seeds),
+           ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), ptr(dw3p), ld, rows, H, C1,
+           ctypes.c_float(1e-5), stream())
     return dz2t, dz1t, h1t, xs, df12, dw3p
+
+
+_XS = {}
+
+
+def _xs_buffer(rows, ldx):
+    """zero-filled once, re-used: rows [128 t + max_slots, 128 t + 128) are never written by the kernels"""
+    key = (rows, ldx)
+    if key not in _XS:
+        _XS.clear()
+        _XS[key] = torch.zeros(rows, ldx, dtype=torch.bfloat16, device=dev)
+    return _XS[key]
 
 
 def fwd_full(emb, gi, w1, w2, w3, b3, edge, m1, m2, pdrop, training, seed=3):
@@ -165,13 +177,15 @@ def fwd_full(emb, gi, w1, w2, w3, b3, edge, m1, m2, pdrop, training, seed=3):
     xh2t = torch.empty(H, T * 128, dtype=torch.bfloat16, device=dev)
     rstd2 = torch.empty(max(gi.G, 1), H, device=dev)
     seeds = torch.zeros(2, dtype=torch.int32, device=dev)
+    Kin = 2 * H if edge else H
+    xs = _xs_buffer(T * 128, (Kin + 63) // 64 * 64)
     w1p, w2p = tc.prep_weight(w1), tc.prep_weight(w2)
     L.call('gsatb_ext_fused_fwd', ptr(emb), ptr(gi.src) if edge else None, ptr(gi.dst) if edge else None,
            ptr(gi.node_ptr) if edge else None, ptr(gi.rowptr_src) if edge else None, ptr(gi.rowptr_dst) if edge else None,
            ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, ptr(w1p), ptr(w2p), ptr(w3),
            ptr(b3), ptr(m1), ptr(m2), ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training), ptr(logit), ptr(xh2t),
-           T * 128, ptr(rstd2), ptr(seeds), rows, H, C1, ctypes.c_float(1e-5), stream())
-    return logit, xh2t, rstd2, seeds
+           T * 128, ptr(rstd2), ptr(xs), ptr(seeds), rows, H, C1, ctypes.c_float(1e-5), stream())
+    return logit, xh2t, rstd2, (seeds, xs)
 
 
 def check_bwd(H, n_graphs, edge=True, masks=False, gen='ba'):
@@ -247,3 +261,33 @@ if len(sys.argv) > 1 and sys.argv[1] == 'bwd':
     print('BWD ALL OK' if ok else 'BWD SOME FAILED', flush=True)
     if ok:
         timing_bwd()
+
+
+def roles_bwd(n_graphs=40000, H=128):
+    from dp_gsat_b200.data import ba2motifs_batch
+    b = ba2motifs_batch(n_graphs, seed=0).to(dev)
+    gi = G.get_graph_index(b.edge_index, b.batch)
+    emb = torch.randn(b.num_nodes, H, device=dev)
+    w1 = torch.randn(4 * H, 2 * H, device=dev) / 16
+    w2 = torch.randn(H, 4 * H, device=dev) / 22
+    w3 = torch.randn(H, device=dev) / 11
+    b3 = torch.zeros(1, device=dev)
+    dlogit = torch.randn(gi.E, device=dev)
+    logit, xh2t, rstd2, seeds = fwd_full(emb, gi, w1, w2, w3, b3, True, None, None, 0.5, 1)
+    bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds, True, None, None, 0.5, 1)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    L.cdll.gsatb_tc_set_profile_buffer(ctypes.c_void_p(buf.data_ptr()))
+    bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds, True, None, None, 0.5, 1)
+    torch.cuda.synchronize()
+    L.cdll.gsatb_tc_set_profile_buffer(None)
+    d = buf.view(148, 16).double()
+    tiles = gi.ext_plan('edge', int(L.cdll.gsatb_ext_tile_slots(H, 1)))['T'] / 148.0
+    names = ['mma_total', 'mma_wait_inputs', 'mma_wait_acc_empty', 'mma_wait_w', 'mma_wait_dz1', 'mma_wait_dx_empty',
+             'epi_wait_head', 'epi_head', 'epi_wait_cb', 'epi_cb(all 4)', 'epi_wait_dx', 'epi_dxout']
+    print(f'bwd roles: tiles/CTA {tiles:.1f}; cycles per tile (mean over CTAs)')
+    for i, nme in enumerate(names):
+        print(f'  {nme:22s} {d[:, i].mean().item() / tiles:10.0f}')
+
+
+if len(sys.argv) > 1 and sys.argv[1] == 'roles_bwd':
+    roles_bwd()
