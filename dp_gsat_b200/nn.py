@@ -514,11 +514,13 @@ class ExtractorMLP(tnn.Module):
         mlp = getattr(self, self._name)
         gi = get_graph_index(edge_index, batch)
         gi.require_graph_contiguous()
-        if self.precision == 'bf16' and emb.shape[1] % 8 == 0 and emb.shape[1] <= 128 \
-                and gi.tile_plan('edge' if self.learn_edge_att else 'node') is not None:
-            # fused tensor-core path (tcgen05, bf16 operands): K1 of the design.  Falls through to the fp32 path when
-            # a graph exceeds one 128-row tile or the width is unsupported -- same math, different precision mode.
+        if self.precision == 'bf16':
+            # fused tensor-core path (tcgen05, bf16 operands): K1 of the design, one persistent kernel per direction
             from . import tc
+            if not tc.fused_extractor_supported(emb, gi, self.learn_edge_att):
+                raise ValueError("precision='bf16': the fused extractor needs hidden_size % 8 == 0, hidden_size <= 128 and "
+                                 "every graph within one tile (<= 128 rows, <= 112 when 2 * hidden_size > 128); use "
+                                 "precision='fp32' for this batch")
             lin = [m for m in mlp if isinstance(m, tnn.Linear)]
             p = next(m.p for m in mlp if isinstance(m, tnn.Dropout))
             rows_n = gi.E if self.learn_edge_att else gi.N
@@ -527,9 +529,9 @@ class ExtractorMLP(tnn.Module):
                 m1 = self.masks.get('ext.0', (rows_n, lin[0].weight.shape[0]), p).to(device=emb.device, dtype=torch.uint8)
                 m2 = self.masks.get('ext.1', (rows_n, lin[1].weight.shape[0]), p).to(device=emb.device, dtype=torch.uint8)
             self._calls += 1
-            return tc.fused_extractor(emb, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
-                                      lin[2].bias, gi, edge_mode=self.learn_edge_att, pdrop=p, training=self.training,
-                                      seed=self.seed * 1000003 + self._calls, mask1=m1, mask2=m2)
+            return tc.fused_extractor_v2(emb, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
+                                         lin[2].bias, gi, edge_mode=self.learn_edge_att, pdrop=p, training=self.training,
+                                         seed=self.seed * 1000003 + self._calls, mask1=m1, mask2=m2)
         if self.learn_edge_att:
             f12 = ops.gather_concat(emb, gi)      # cat(emb[col], emb[row]) with col, row = edge_index
             rows, seg_all = f12, (gi.edge_ptr, gi.G)

@@ -162,7 +162,7 @@ class _FusedExtractor(torch.autograd.Function):
             h1 = torch.empty((rows, C1), dtype=torch.bfloat16, device=dev)
             L.call('gsatb_tc_ext_make_h1', ptr(sv['xhat1']), ptr(mask1), ctypes.c_uint64(seed), ctypes.c_float(pdrop),
                    int(training), ptr(h1), rows, C1, stream())
-        dW2 = _mm_f32(dz2.t(), h1)
+        dW2, _ = weight_grad(dz2, False, h1, False, rows, H, C1)
         del h1
         sv['h1'] = None
         f12 = sv.get('f12')
@@ -170,7 +170,7 @@ class _FusedExtractor(torch.autograd.Function):
             f12 = torch.empty((rows, Kin), dtype=torch.bfloat16, device=dev)
             L.call('gsatb_tc_ext_make_f12', ptr(emb), ptr(gi.src) if edge_mode else None,
                    ptr(gi.dst) if edge_mode else None, ptr(f12), rows, H, stream())
-        dW1 = _mm_f32(dz1.t(), f12)
+        dW1, _ = weight_grad(dz1, False, f12, False, rows, C1, Kin)
         del f12
         sv['f12'] = None
         # input gradient: d f12 = dz1 W1, then the deterministic scatter back to the nodes
@@ -190,12 +190,132 @@ class _FusedExtractor(torch.autograd.Function):
         return (demb, dW1, db1, dW2, db2, dw3, db3, None, None, None, None, None, None, None, None)
 
 
-def _mm_f32(a_bf16: torch.Tensor, b_bf16: torch.Tensor) -> torch.Tensor:
-    """Plain library GEMM (cuBLAS) of bf16 operands with an fp32 result."""
-    try:
-        return torch.mm(a_bf16, b_bf16, out_dtype=torch.float32)
-    except TypeError:
-        return torch.mm(a_bf16, b_bf16).float()
+def weight_grad(a16: torch.Tensor, a_channel_major: bool, b16: torch.Tensor, b_channel_major: bool, rows: int, M: int,
+                N: int, want_bias: bool = False):
+    """dW [M, N] = sum_r A[r, m] B[r, n] (and db [M] = sum_r A[r, m]) on the tensor cores (gsatb_tc_dw: split-K tcgen05
+    GEMM with a fixed-order reduction).  A / B are bf16, row-major [rows, C] or channel-major [C, rows]; the leading
+    dimension is the tensor's stride(0)."""
+    dev = a16.device
+    dW = torch.empty((M, N), dtype=torch.float32, device=dev)
+    db = torch.empty(M, dtype=torch.float32, device=dev) if want_bias else None
+    nb = int(lib().cdll.gsatb_tc_dw_workspace(rows, M, N))
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+    lib().call('gsatb_tc_dw', ptr(a16), int(a_channel_major), int(a16.stride(0)), ptr(b16), int(b_channel_major),
+               int(b16.stride(0)), rows, M, N, ptr(dW), N, ptr(db), 0, ptr(ws), ctypes.c_size_t(nb), stream())
+    return dW, db
+
+
+def ext_tile_slots(H: int, edge_mode: bool) -> int:
+    return int(lib().cdll.gsatb_ext_tile_slots(int(H), int(edge_mode)))
+
+
+def fused_extractor_supported(emb: torch.Tensor, gi: GraphIndex, edge_mode: bool) -> bool:
+    """The fused tcgen05 extractor takes hidden widths H % 8 == 0, H <= 128 and batches whose graphs fit one tile
+    (<= 128 rows, <= 112 when 2H > 128)."""
+    H = emb.shape[1]
+    if H % 8 != 0 or H > 128:
+        return False
+    return gi.ext_plan('edge' if edge_mode else 'node', ext_tile_slots(H, edge_mode))['oversize'] == 0
+
+
+class _FusedExtractorV2(torch.autograd.Function):
+    """The whole extractor MLP as ONE persistent tcgen05 kernel per direction (csrc/ext_fused_fwd.cu, ext_fused_bwd.cu):
+    forward keeps nothing of width 4H in HBM (saved for backward: the logits' inputs xhat2 [H, slots] bf16, rstd2, the
+    centred input tiles xs and the effective dropout seeds); backward recomputes GEMM1, leaves the bf16 operands of the
+    weight-gradient products in channel-major slot space and gsatb_tc_dw turns them into dW1 / dW2; the node gradient is
+    the deterministic CSR reduction of d f12.  b1 / b2 sit in front of an InstanceNorm and get exact zeros."""
+
+    @staticmethod
+    def forward(ctx, emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps):
+        emb = emb.contiguous()
+        N, H = emb.shape
+        C1 = w1.shape[0]
+        ms = ext_tile_slots(H, edge_mode)
+        plan = gi.ext_plan('edge' if edge_mode else 'node', ms)
+        if plan['oversize']:
+            raise ValueError(f"{plan['oversize']} graph(s) exceed one {ms}-row tile of the fused extractor")
+        rows, T = plan['rows'], plan['T']
+        dev = emb.device
+        need_grad = any(ctx.needs_input_grad[:7])
+        ld = T * 128
+        Kin = 2 * H if edge_mode else H
+        logit = torch.empty((rows, 1), dtype=torch.float32, device=dev)
+        xh2t = torch.empty((H, ld), dtype=torch.bfloat16, device=dev) if need_grad else None
+        rstd2 = torch.empty((max(gi.G, 1), H), dtype=torch.float32, device=dev) if need_grad else None
+        xs = _xs_buffer(plan, ld, _pad(Kin, 64), dev) if need_grad else None
+        token = object()
+        if need_grad:
+            plan['xs_token'] = token      # the dump is per batch: a second forward on it invalidates this one's backward
+        seeds = torch.zeros(2, dtype=torch.int32, device=dev)
+        w1p, w2p = prep_weight(w1), prep_weight(w2)
+        w3f = w3.detach().reshape(-1).contiguous()
+        e = bool(edge_mode)
+        lib().call('gsatb_ext_fused_fwd', ptr(emb), ptr(gi.src) if e else None, ptr(gi.dst) if e else None,
+                   ptr(gi.node_ptr) if e else None, ptr(gi.rowptr_src) if e else None, ptr(gi.rowptr_dst) if e else None,
+                   ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, ptr(w1p), ptr(w2p),
+                   ptr(w3f), ptr(b3), ptr(mask1), ptr(mask2), ctypes.c_uint64(seed), ctypes.c_float(pdrop), int(training),
+                   ptr(logit), ptr(xh2t), ld, ptr(rstd2), ptr(xs), ptr(seeds), rows, H, C1, ctypes.c_float(eps), stream())
+        ctx.cfg = (gi, e, float(pdrop), bool(training), mask1, mask2, float(eps), plan, ms, token)
+        ctx.save_for_backward(w1, w2, w3f, xh2t, rstd2, xs, seeds)
+        ctx.has_b = (b1 is not None, b2 is not None, b3 is not None)
+        ctx.emb_shape = (N, H)
+        return logit
+
+    @staticmethod
+    def backward(ctx, dlogit):
+        w1, w2, w3f, xh2t, rstd2, xs, seeds = ctx.saved_tensors
+        gi, e, pdrop, training, mask1, mask2, eps, plan, ms, token = ctx.cfg
+        if plan.get('xs_token') is not token:
+            raise RuntimeError('the fused extractor ran forward again on this batch before this backward: its saved input '
+                               'tiles (one buffer per batch) were overwritten')
+        N, H = ctx.emb_shape
+        C1, Kin = w1.shape
+        rows, T = plan['rows'], plan['T']
+        ld = T * 128
+        dev = dlogit.device
+        L = lib()
+        dl = dlogit.contiguous().view(-1).float()
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        dz2t, dz1t, h1t = torch.empty((H, ld), **bf), torch.empty((C1, ld), **bf), torch.empty((C1, ld), **bf)
+        df12 = torch.empty((rows, Kin), dtype=torch.float32, device=dev)
+        nslab = 2 * min(max(gi.G, 1), 148)
+        dw3p = torch.zeros((nslab, H), dtype=torch.float32, device=dev)
+        w1p, w2t, w1t = prep_weight(w1), prep_weight(w2, transpose=True), prep_weight(w1, transpose=True)
+        L.call('gsatb_ext_fused_bwd', ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, int(e),
+               ptr(w1p), ptr(w2t), ptr(w1t), ptr(w3f), ptr(dl), ptr(xh2t), ptr(rstd2), ptr(xs), ptr(mask1), ptr(mask2),
+               ptr(seeds), ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), ptr(dw3p), ld, rows,
+               H, C1, ctypes.c_float(eps), stream())
+        dW2, _ = weight_grad(dz2t, True, h1t, True, ld, H, C1)
+        dW1, _ = weight_grad(dz1t, True, xs, False, ld, C1, Kin)
+        del dz1t, h1t, dz2t
+        if e:
+            demb = torch.empty((N, H), dtype=torch.float32, device=dev)
+            L.call('gsatb_gather_concat_bwd', ptr(df12), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst),
+                   ptr(gi.eid_by_dst), ptr(demb), N, H, stream())
+        else:
+            demb = df12
+        dw3 = dw3p.sum(0).view(1, H)
+        db3 = dl.sum().view(1) if ctx.has_b[2] else None
+        db1 = torch.zeros(C1, device=dev) if ctx.has_b[0] else None
+        db2 = torch.zeros(H, device=dev) if ctx.has_b[1] else None
+        return (demb, dW1, db1, dW2, db2, dw3, db3, None, None, None, None, None, None, None, None)
+
+
+def _xs_buffer(plan: dict, rows: int, ldx: int, dev) -> torch.Tensor:
+    """The centred-input dump of the fused forward, [tiles * 128, pad64(Kin)] bf16, cached with the tile plan: it is
+    allocated ZERO-FILLED once (rows [128 t + max_slots, 128 t + 128) are never written and meet zero columns of dz1t in
+    dW1) and re-used by every step on this batch."""
+    key = ('xs', ldx)
+    buf = plan.get(key)
+    if buf is None or buf.shape[0] != rows or buf.device != dev:
+        buf = torch.zeros((rows, ldx), dtype=torch.bfloat16, device=dev)
+        plan[key] = buf
+    return buf
+
+
+def fused_extractor_v2(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: float, training: bool, seed: int,
+                       mask1=None, mask2=None, eps: float = 1e-5):
+    return _FusedExtractorV2.apply(emb, w1, b1, w2, b2, w3, b3, gi, edge_mode, pdrop, training, seed, mask1, mask2, eps)
 
 
 def fused_extractor(emb, w1, b1, w2, b2, w3, b3, gi, *, edge_mode: bool, pdrop: float, training: bool, seed: int,
@@ -304,11 +424,8 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     cA, cB, cC, w1t = cA.contiguous(), cB.contiguous(), cC.contiguous(), prep_weight(w1, transpose=True)
     L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, Kin,
            stream())
-    ones = torch.ones((1, N), dtype=torch.bfloat16, device=dev)
-    dW2 = _mm_f32(d2.t(), a1)
-    db2 = _mm_f32(ones, d2).view(-1)
-    dW1 = _mm_f32(dz1.t(), agg16)
-    db1 = _mm_f32(ones, dz1).view(-1)
+    dW2, db2 = weight_grad(d2, False, a1, False, N, H, H1, want_bias=True)
+    dW1, db1 = weight_grad(dz1, False, agg16, False, N, H1, Kin, want_bias=True)
     return dagg, dW1, db1, dgamma.clone(), dbeta.clone(), dW2, db2
 
 

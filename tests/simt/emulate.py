@@ -93,7 +93,6 @@ def patch_product(setattr_fn) -> EmulatedLib:
     tc = importlib.import_module('dp_gsat_b200.tc')
     setattr_fn(tc, 'lib', lambda: emu)
     setattr_fn(tc, 'stream', lambda: None)
-    setattr_fn(tc, '_mm_f32', lambda a, b: a.float() @ b.float())      # torch.mm(out_dtype=) exists on CUDA only
     index = importlib.import_module('dp_gsat_b200.index')
     index.clear_index_cache()
     return emu
