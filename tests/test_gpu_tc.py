@@ -80,19 +80,27 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize('case', ['ba_edge_H64', 'ba_edge_H128', 'mol_node_H64', 'mol_edge_H80_p03', 'eval_mode'])
+@pytest.mark.parametrize('case', ['ba_edge_H64', 'ba_edge_H128', 'mol_node_H64', 'mol_edge_H80_p03', 'eval_mode',
+                                  'ba_node_H128'])
 def test_fused_extractor_fwd_bwd(G, case):
-    """Two bars.  (1) Kernel correctness: against an fp32 autograd restatement with the SAME rounding points (bf16
-    operands / bf16-stored activations), relative L2 error <= 2.5e-2 on logits and every gradient (the kernels round
-    the gradient tensors dz2 / dz1 / h1 / f12 to bf16 as well, ~4e-3 each).  (2) Precision mode: against the pure fp32
-    oracle, logits within 3e-2 of max and gradients within 0.25 relative L2 (observed 0.05-0.17) -- ReLU gates of near-zero activations flip
-    under bf16 operand rounding and InstanceNorm backward amplifies it; the emulation shows the same 5-7 %."""
+    """The fused extractor (gsatb_ext_fused_fwd / _bwd + gsatb_tc_dw), two bars.
+    (1) Kernel correctness: against a restatement with bf16 rounding at exactly the kernels' rounding points
+    (tests/helpers/ext_ref.py: centred input rows, weights, h1, the saved xhat2, dz2, dz1), relative L2 <= 1e-2 on the
+    logits and every gradient (observed 1e-4 .. 4e-3).
+    (2) Precision mode: against the pure fp32 oracle, logits <= 1e-2 relative L2 and gradients <= 0.2 (observed 4e-2 ..
+    7e-2 on the BA-2Motifs batches, 0.16 on the molhiv-shaped batch with graphs of a handful of rows).  The gradient
+    figure is the floor of ANY single-pass bf16 forward GEMM in front of a ReLU: operand rounding (2^-9 per element)
+    flips the gates of the ~0.3 % of activations closest to zero, which is 4.5-6e-2 in relative L2 of dW / d emb; the
+    backward pass's own rounding points contribute 3e-3 (tools/ext_rounding_budget.py, profiles/r2_ext_rounding_budget.txt).
+    precision='fp32' (split-bf16 x3 on the same tensor-core kernels) is the mode held to rtol 1e-5."""
     from dp_gsat_b200 import tc
     from dp_gsat_b200.data import ba2motifs_batch, molhiv_like_batch
+    from tests.helpers.ext_ref import extractor_forward, extractor_backward_emulated
     edge_mode, p, training, H = True, 0.5, True, 64
     if case.startswith('ba'):
         b = ba2motifs_batch(40, seed=3)
         H = 128 if case.endswith('128') else 64
+        edge_mode = 'node' not in case
     elif case == 'eval_mode':
         b, training = ba2motifs_batch(24, seed=5), False
     else:
@@ -116,17 +124,14 @@ def test_fused_extractor_fwd_bwd(G, case):
     m1f = ms.get('ext.0', (rows, C1), p) if training else None
     m2f = ms.get('ext.1', (rows, H), p) if training else None
 
-    def grads_of(fn):
-        for l in lin:
-            l.weight.grad = l.bias.grad = None
-        e = emb.clone().requires_grad_(True)
-        out = fn(e)
-        (out * wt).sum().backward()
-        return [out.detach(), e.grad, lin[0].weight.grad.clone(), lin[1].weight.grad.clone(),
-                lin[2].weight.grad.clone(), lin[2].bias.grad.clone()]
-    ref32 = grads_of(lambda e: ext_o(e, b.edge_index, b.batch))
+    for l in lin:
+        l.weight.grad = l.bias.grad = None
+    e = emb.clone().requires_grad_(True)
+    out = ext_o(e, b.edge_index, b.batch)
+    (out * wt).sum().backward()
+    ref32 = [out.detach(), e.grad, lin[0].weight.grad.clone(), lin[1].weight.grad.clone(), lin[2].weight.grad.clone(),
+             lin[2].bias.grad.clone()]
     b1_grad_o = lin[0].bias.grad.clone()
-    emu = grads_of(lambda e: _emulated_bf16_extractor(e, b.edge_index, b.batch, lin, edge_mode, p, training, m1f, m2f))
 
     gi = G.get_graph_index(b.edge_index.cuda(), b.batch.cuda(), b.num_graphs)
     params = [t.detach().clone().cuda().requires_grad_(True) for t in
@@ -134,14 +139,34 @@ def test_fused_extractor_fwd_bwd(G, case):
     m1 = m1f.to(torch.uint8).cuda() if training else None
     m2 = m2f.to(torch.uint8).cuda() if training else None
     emb_g = emb.clone().cuda().requires_grad_(True)
-    out_g = tc.fused_extractor(emb_g, *params, gi, edge_mode=edge_mode, pdrop=p, training=training, seed=3,
-                               mask1=m1, mask2=m2)
+    if not tc.fused_extractor_supported(emb_g, gi, edge_mode):
+        with pytest.raises(ValueError):                     # loud, never a silent change of precision mode
+            tc.fused_extractor_v2(emb_g, *params, gi, edge_mode=edge_mode, pdrop=p, training=training, seed=3)
+        pytest.skip('a graph of this batch exceeds one tile of the fused extractor')
+    out_g = tc.fused_extractor_v2(emb_g, *params, gi, edge_mode=edge_mode, pdrop=p, training=training, seed=3,
+                                  mask1=m1, mask2=m2)
     (out_g * wt.cuda()).sum().backward()
     got = [out_g, emb_g.grad, params[0].grad, params[2].grad, params[4].grad, params[5].grad]
+
+    # same-rounding restatement (host, fp32 arithmetic)
+    src, dst = (b.edge_index[0], b.edge_index[1]) if edge_mode else (None, None)
+    seg_ids = b.batch[src] if edge_mode else b.batch
+    seg = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(seg_ids, minlength=b.num_graphs).cumsum(0)])
+    w1, w2, w3, b3 = lin[0].weight.detach(), lin[1].weight.detach(), lin[2].weight.detach().reshape(-1), lin[2].bias.detach()
+    pe = p if training else 0.0
+    e_logit = extractor_forward(emb, src, dst, seg, w1, w2, w3, b3, m1f, m2f, pe, rounding='bf16')
+    e_df, e_dW1, e_dW2, e_dw3 = extractor_backward_emulated(emb, src, dst, seg, w1, w2, w3, wt.view(-1), m1f, m2f, pe)
+    if edge_mode:
+        e_demb = torch.zeros_like(emb).index_add_(0, src, e_df[:, :H]).index_add_(0, dst, e_df[:, H:])
+    else:
+        e_demb = e_df
+    emu = [e_logit, e_demb, e_dW1, e_dW2, e_dw3.view(1, -1), wt.sum().view(1)]
     names = ['logits', 'd emb', 'dW1', 'dW2', 'dw3', 'db3']
     for n, a, e_, r_ in zip(names, got, emu, ref32):
-        assert rel_l2(a, e_) <= 2.5e-2, f'{n}: rel L2 vs bf16-emulated reference {rel_l2(a, e_):.3e}'
-        assert rel_l2(a, r_) <= 0.25, f'{n}: rel L2 vs fp32 oracle {rel_l2(a, r_):.3e}'
+        print(f'{case} {n}: rel L2 vs same-rounding restatement {rel_l2(a, e_):.3e}, vs fp32 oracle {rel_l2(a, r_):.3e}')
+    for n, a, e_, r_ in zip(names, got, emu, ref32):
+        assert rel_l2(a, e_) <= 1e-2, f'{n}: rel L2 vs same-rounding restatement {rel_l2(a, e_):.3e}'
+        assert rel_l2(a, r_) <= (1e-2 if n in ('logits', 'db3') else 0.2), f'{n}: rel L2 vs fp32 oracle {rel_l2(a, r_):.3e}'
     assert_bf16_close(out_g, ref32[0], 'logits vs fp32 oracle')
     assert float(params[1].grad.abs().max()) == 0.0 and float(params[3].grad.abs().max()) == 0.0   # exact zeros
     assert float(b1_grad_o.abs().max()) < 1e-4 * max(1.0, float(ref32[2].abs().max()))            # oracle: ~0 too
@@ -238,6 +263,87 @@ def test_gsat_step_bf16_mode_tracks_oracle(G):
     cos = float(torch.dot(go_flat, gg_flat) / (go_flat.norm() * gg_flat.norm()))
     assert cos > 0.97, cos
     assert torch.isfinite(gg_flat).all()
+
+
+def _step_models(G, H, L, dt=torch.float32):
+    cfg = {'model_name': 'GIN', 'hidden_size': H, 'n_layers': L, 'dropout_p': 0.3, 'use_edge_attr': False}
+    shared = {'learn_edge_att': True, 'extractor_dropout_p': 0.5}
+    torch.manual_seed(0)
+    clf_o, ext_o = O.get_model(10, 0, 2, False, cfg), O.ExtractorMLP(H, shared)
+    return cfg, shared, clf_o, ext_o
+
+
+def test_gsat_step_bf16_benched_shape_per_tensor_bounds(G):
+    """The BENCHED shape class (bench.py: H = 128, 2 layers, BA-2Motifs graphs, learn_edge_att) as a whole training step
+    in precision='bf16' -- 2048 graphs / ~104 k edges, non-constant node features, injected noise and dropout masks --
+    against the fp32 oracle AND the fp64 oracle (ground truth), tensor by tensor:
+
+      loss                      |d| <= 2e-2 * max(1, |loss|)
+      edge attention            rel. L2 <= 3e-2
+      clf logits                rel. L2 <= 5e-2
+      GIN / classifier gradients   rel. L2 <= 6e-2 and cosine >= 0.998 vs fp64   (observed 6e-5 .. 3.9e-2)
+      extractor W1 / W2 gradients  rel. L2 <= 0.2 and cosine >= 0.98             (observed 0.135 / 0.105: ReLU gate flips
+                                   under bf16 operand rounding, see test_fused_extractor_fwd_bwd; w3 / b3: 2.5e-3 / 4e-4)
+      all gradients together       rel. L2 <= 1e-2                               (observed 4.4e-3)
+
+    The fp32 oracle's own distance to fp64 is printed beside each line."""
+    from dp_gsat_b200.data import ba2motifs_batch
+    H, L = 128, 2
+    b = ba2motifs_batch(2048, seed=7)
+    b.x = torch.rand(b.x.shape, generator=torch.Generator().manual_seed(5))
+    cfg, shared, clf_o, ext_o = _step_models(G, H, L)
+    import copy
+    clf_d, ext_d = copy.deepcopy(clf_o).double(), copy.deepcopy(ext_o).double()
+    clf_g, ext_g = G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(H, shared).cuda()
+    clf_g.load_state_dict(clf_o.state_dict())
+    ext_g.load_state_dict(ext_o.state_dict())
+    clf_g.precision = ext_g.precision = 'bf16'
+    ms = O.MaskSource(2)
+    for m in (clf_o, ext_o, clf_d, ext_d, clf_g, ext_g):
+        m.masks = ms
+    u = torch.rand(b.num_edges, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
+
+    def run(mod, clf, ext, batch, noise):
+        g = mod.GSAT(clf, ext, mod.Criterion(2, False), learn_edge_att=True, final_r=0.5)
+        g.train()
+        ea, loss, _, logits = g.forward_pass(batch, 3, True, noise_u=noise)
+        loss.backward()
+        return ea.detach(), loss.detach(), logits.detach()
+    ea_o, loss_o, lg_o = run(O, clf_o, ext_o, b, u)
+    bd = copy.copy(b)
+    bd.x = b.x.double()
+    ea_d, loss_d, lg_d = run(O, clf_d, ext_d, bd, u.double())
+    ea_g, loss_g, lg_g = run(G, clf_g, ext_g, b.to('cuda'), u.cuda())
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - float(loss_d)) <= 2e-2 * max(1.0, abs(float(loss_d)))
+    print(f'loss: product {float(loss_g):.6f}  fp32 oracle {float(loss_o):.6f}  fp64 oracle {float(loss_d):.6f}')
+    print(f'edge_att rel L2 vs fp64: product {rel_l2(ea_g, ea_d):.3e}, fp32 oracle {rel_l2(ea_o, ea_d):.3e}')
+    print(f'clf logits rel L2 vs fp64: product {rel_l2(lg_g, lg_d):.3e}, fp32 oracle {rel_l2(lg_o, lg_d):.3e}')
+    assert rel_l2(ea_g, ea_d) <= 3e-2
+    assert rel_l2(lg_g, lg_d) <= 5e-2
+    bad, allg, alld = [], [], []
+    named_o = dict(list(('clf.' + n, p) for n, p in clf_o.named_parameters()) + list(('ext.' + n, p) for n, p in ext_o.named_parameters()))
+    named_d = dict(list(('clf.' + n, p) for n, p in clf_d.named_parameters()) + list(('ext.' + n, p) for n, p in ext_d.named_parameters()))
+    named_g = dict(list(('clf.' + n, p) for n, p in clf_g.named_parameters()) + list(('ext.' + n, p) for n, p in ext_g.named_parameters()))
+    gmax = max(float(p.grad.abs().max()) for p in named_d.values() if p.grad is not None)
+    for n, pd in named_d.items():
+        if pd.grad is None:
+            continue
+        gd, go, gg = pd.grad, named_o[n].grad, named_g[n].grad
+        if float(gd.abs().max()) < 1e-6 * gmax:             # analytically zero (biases in front of a norm layer)
+            assert float(gg.abs().max()) <= 1e-4 * gmax, n
+            continue
+        cos = float(torch.dot(gg.double().cpu().flatten(), gd.flatten()) / (gg.double().norm().cpu() * gd.norm()))
+        print(f'{n:40s} rel L2 vs fp64: product {rel_l2(gg, gd):.3e} (cos {cos:.5f}), fp32 oracle {rel_l2(go, gd):.3e}')
+        allg.append(gg.double().cpu().flatten())
+        alld.append(gd.flatten())
+        loose = n in ('ext.feature_extractor.0.weight', 'ext.feature_extractor.4.weight')
+        if rel_l2(gg, gd) > (0.2 if loose else 6e-2) or cos < (0.98 if loose else 0.998):
+            bad.append((n, rel_l2(gg, gd), cos))
+    tot = rel_l2(torch.cat(allg), torch.cat(alld))
+    print(f'all gradients: rel L2 vs fp64 {tot:.3e}')
+    assert not bad, bad
+    assert tot <= 1e-2, tot
 
 
 @pytest.mark.parametrize('p', [0.5, 0.3, 0.1])
