@@ -289,7 +289,7 @@ extern "C" int gsatb_tc_linear_bf16_fwd(const void* x_bf16, int ldx, const void*
     if (rows == 0) return GSATB_OK;
     if (!x_bf16 || !w_bf16 || !out) return GSATB_EINVAL;
     if (stat_partials && (OUT > 128 || !stats)) return GSATB_ESHAPE;
-    if (K > 512 || K % 8 != 0 || ldx % 8 != 0) return GSATB_ESHAPE;
+    if (K % 8 != 0 || ldx % 8 != 0) return GSATB_ESHAPE;      // any K: the K loop streams 64-column blocks of both operands
     cudaStream_t st = (cudaStream_t)stream;
     Tiling tl = uniform_tiling(rows);
     if (stat_partials)

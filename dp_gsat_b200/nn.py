@@ -10,8 +10,9 @@ state_dict keys), backed by the sm_100a kernels of libgsat_b200.so.
   torch_geometric InstanceNorm / global_add_pool / global_mean_pool        -> InstanceNorm / ops.global_*_pool
   src/run_gsat.py:888-927, example/gsat.py:120-139  ExtractorMLP           -> ExtractorMLP
 
-Dense Linear / BatchNorm1d layers are (for now) PyTorch library calls; every gather / scatter / segment / sampling
-op is a kernel of this repo.  Dropout masks can be injected (``masks``) for parity tests; otherwise F.dropout.
+Dense Linear / BatchNorm1d layers run on this repo's tcgen05 GEMM and streaming kernels in both precision modes
+(dense.py: 'fp32' = split-bf16 x3 strict mode, 'bf16' = single pass); every gather / scatter / segment / sampling op is a
+kernel of this repo.  Dropout masks can be injected (``masks``) for parity tests; otherwise F.dropout.
 """
 from __future__ import annotations
 
@@ -21,7 +22,8 @@ import torch
 import torch.nn as tnn
 import torch.nn.functional as F
 
-from . import ops
+from . import dense, ops
+from .dense import Linear, PrecisionMixin
 from .index import GraphIndex, get_graph_index
 
 
@@ -86,7 +88,7 @@ class MLP(BatchSequential):
     def __init__(self, channels: Sequence[int], dropout: float, bias: bool = True):
         m = []
         for i in range(1, len(channels)):
-            m.append(tnn.Linear(channels[i - 1], channels[i], bias))
+            m.append(Linear(channels[i - 1], channels[i], bias))
             if i < len(channels) - 1:
                 m.append(InstanceNorm(channels[i]))
                 m.append(tnn.ReLU())
@@ -174,7 +176,13 @@ class BatchNorm1d(tnn.BatchNorm1d):
 
     def forward(self, x):
         if self.sync_group is None or not self.training:
-            return super().forward(x)
+            training = self.training or self.running_mean is None
+            if training and self.momentum is None:
+                raise NotImplementedError('BatchNorm1d(momentum=None) (cumulative average) is not used by the reference')
+            if training and self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return dense.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, training,
+                                    self.momentum if self.momentum is not None else 0.1, self.eps)
         return _SyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var,
                                       self.num_batches_tracked, self.momentum if self.momentum is not None else 0.1,
                                       self.eps, self.sync_group)
@@ -225,7 +233,7 @@ class GINEConv(tnn.Module):
         if edge_dim is not None:
             first = nn[0] if isinstance(nn, tnn.Sequential) else nn
             in_channels = first.in_features if hasattr(first, 'in_features') else first.in_channels
-            self.lin = tnn.Linear(edge_dim, in_channels)
+            self.lin = Linear(edge_dim, in_channels)
         else:
             self.lin = None
 
@@ -248,16 +256,16 @@ class LEConv(tnn.Module):
     def __init__(self, in_channels: int, out_channels: int, bias: bool = True):
         super().__init__()
         self.in_channels, self.out_channels = in_channels, out_channels
-        self.lin1 = tnn.Linear(in_channels, out_channels, bias=bias)
-        self.lin2 = tnn.Linear(in_channels, out_channels, bias=False)
-        self.lin3 = tnn.Linear(in_channels, out_channels, bias=bias)
+        self.lin1 = Linear(in_channels, out_channels, bias=bias)
+        self.lin2 = Linear(in_channels, out_channels, bias=False)
+        self.lin3 = Linear(in_channels, out_channels, bias=bias)
 
     def forward(self, x, edge_index, edge_weight=None, edge_atten=None, _index: Optional[GraphIndex] = None):
         gi = _index if _index is not None else get_graph_index(edge_index, None, num_nodes=x.shape[0])
         return ops.le_aggregate(self.lin1(x), self.lin2(x), edge_weight, edge_atten, gi, add=self.lin3(x))
 
 
-class SPMotifNet(tnn.Module):
+class SPMotifNet(PrecisionMixin, tnn.Module):
     """src/models/spmotif_gnn.py:9-87 (same attribute names, state_dict keys and method signatures)."""
 
     def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
@@ -265,17 +273,17 @@ class SPMotifNet(tnn.Module):
         self.n_layers = model_config['n_layers']
         hidden_size = model_config['hidden_size']
         self.edge_attr_dim = edge_attr_dim
-        self.node_emb = tnn.Linear(x_dim, hidden_size)
+        self.node_emb = Linear(x_dim, hidden_size)
         self.convs = tnn.ModuleList()
         self.relus = tnn.ModuleList()
         for _ in range(self.n_layers):
             self.convs.append(LEConv(in_channels=hidden_size, out_channels=hidden_size))
             self.relus.append(tnn.ReLU())
-        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
-                                     tnn.Linear(2 * hidden_size, num_class))
-        self.conf_mlp = tnn.Sequential(tnn.Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
-                                       tnn.Linear(2 * hidden_size, 3))
-        self.cq = tnn.Linear(3, 3)
+        self.fc_out = tnn.Sequential(Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
+                                     Linear(2 * hidden_size, num_class))
+        self.conf_mlp = tnn.Sequential(Linear(hidden_size, 2 * hidden_size), tnn.ReLU(),
+                                       Linear(2 * hidden_size, 3))
+        self.cq = Linear(3, 3)
         self.conf_fw = tnn.Sequential(self.conf_mlp, self.cq)
 
     def pool(self, x, batch, _index: Optional[GraphIndex] = None):
@@ -320,7 +328,7 @@ class SPMotifNet(tnn.Module):
                 param.uniform_(-1.0, 1.0)
 
 
-class GIN(tnn.Module):
+class GIN(PrecisionMixin, tnn.Module):
     """src/models/gin.py:12-81."""
 
     def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
@@ -336,9 +344,9 @@ class GIN(tnn.Module):
             if self.with_edges:
                 self.edge_encoder = BondEncoder(emb_dim=hidden_size)
         else:
-            self.node_encoder = tnn.Linear(x_dim, hidden_size)
+            self.node_encoder = Linear(x_dim, hidden_size)
             if self.with_edges:
-                self.edge_encoder = tnn.Linear(edge_attr_dim, hidden_size)
+                self.edge_encoder = Linear(edge_attr_dim, hidden_size)
         self.convs = tnn.ModuleList()
         self.relu = tnn.ReLU()
         for _ in range(self.n_layers):
@@ -346,16 +354,16 @@ class GIN(tnn.Module):
                 self.convs.append(GINEConv(GIN.MLP(hidden_size, hidden_size), edge_dim=hidden_size))
             else:
                 self.convs.append(GINConv(GIN.MLP(hidden_size, hidden_size)))
-        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
+        self.fc_out = tnn.Sequential(Linear(hidden_size, 1 if num_class == 2 and not multi_label else num_class))
         self.masks = None     # parity tests inject dropout masks here
-        self.precision = 'fp32'   # 'bf16': node MLPs on tcgen05 (tc.gin_mlp_relu); 'fp32': strict library path
+        self.precision = 'fp32'   # 'bf16': fused node MLPs on tcgen05 (tc.gin_layer); 'fp32': strict split-bf16 x3 path
         self.seed = 0
         self._calls = 0
 
     @staticmethod
     def MLP(in_channels: int, out_channels: int):
-        return tnn.Sequential(tnn.Linear(in_channels, out_channels), BatchNorm1d(out_channels),
-                              tnn.ReLU(inplace=True), tnn.Linear(out_channels, out_channels))
+        return tnn.Sequential(Linear(in_channels, out_channels), BatchNorm1d(out_channels),
+                              tnn.ReLU(inplace=True), Linear(out_channels, out_channels))
 
     def pool(self, x, batch, _index: Optional[GraphIndex] = None):
         gi = _index if _index is not None else get_graph_index(_no_edges(batch.device), batch)
@@ -481,7 +489,7 @@ class BondEncoder(_SumEmbeddingEncoder):
             self.bond_embedding_list.append(emb)
 
 
-class ExtractorMLP(tnn.Module):
+class ExtractorMLP(PrecisionMixin, tnn.Module):
     """Upstream form  ExtractorMLP(hidden_size, learn_edge_att).forward(emb, edge_index, batch)
     (example/gsat.py:120-139) and fork form  ExtractorMLP(hidden_size, shared_config, type).forward(emb, edge_index,
     batch, type)  (src/run_gsat.py:888-927; parameters live under '<type>_feature_extractor')."""
@@ -503,8 +511,8 @@ class ExtractorMLP(tnn.Module):
         setattr(self, self._name, mlp)
         self.masks = None
         self.chunk_rows = 1 << 21      # rows per graph-aligned chunk (0 = never chunk)
-        self.precision = 'fp32'        # 'fp32': strict path (library sgemm + segment-norm kernels, rtol 1e-5 parity);
-        #                                'bf16': fused tcgen05 kernels (tc.fused_extractor), documented bf16 tolerance
+        self.precision = 'fp32'        # 'fp32': strict path (split-bf16 x3 tcgen05 GEMMs + segment-norm kernels, rtol 1e-5
+        #                                parity); 'bf16': fused tcgen05 kernels (tc.fused_extractor_v2), bf16 tolerance
         self.seed = 0
         self._calls = 0
 
@@ -514,13 +522,12 @@ class ExtractorMLP(tnn.Module):
         mlp = getattr(self, self._name)
         gi = get_graph_index(edge_index, batch)
         gi.require_graph_contiguous()
-        if self.precision == 'bf16':
-            # fused tensor-core path (tcgen05, bf16 operands): K1 of the design, one persistent kernel per direction
-            from . import tc
-            if not tc.fused_extractor_supported(emb, gi, self.learn_edge_att):
-                raise ValueError("precision='bf16': the fused extractor needs hidden_size % 8 == 0, hidden_size <= 128 and "
-                                 "every graph within one tile (<= 128 rows, <= 112 when 2 * hidden_size > 128); use "
-                                 "precision='fp32' for this batch")
+        from . import tc
+        if self.precision == 'bf16' and tc.fused_extractor_supported(emb, gi, self.learn_edge_att):
+            # K1 of the design: the whole MLP as one persistent tcgen05 kernel per direction (bf16 operands).  Batches it
+            # cannot tile -- a graph with more rows than one accumulator tile (mutag-dual: up to 406 dual edges), or
+            # hidden_size > 128 / not a multiple of 8 (the H = 300 sweep) -- take the layer-by-layer path below in the
+            # SAME precision mode and on the same tensor-core GEMM kernels (dense.Linear + the segment-norm kernels).
             lin = [m for m in mlp if isinstance(m, tnn.Linear)]
             p = next(m.p for m in mlp if isinstance(m, tnn.Dropout))
             rows_n = gi.E if self.learn_edge_att else gi.N

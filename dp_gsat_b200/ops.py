@@ -413,14 +413,16 @@ def pna_aggregate(x, edge_feat, edge_atten, gi: GraphIndex, aggregators):
 # node encoder Linear(x_dim, H) with a small x_dim  (reference src/models/gin.py:22-25, pna.py:20-25)
 # ------------------------------------------------------------------------------------------------------------
 class _SmallLinear(torch.autograd.Function):
-    """y = x W^T + b for a narrow x [N, F] (F < 16).  Forward is the library GEMM; the weight / bias gradient (a K = N
-    reduction the library runs as a slow large-K sgemm) is gsatb_linear_small_dw."""
+    """y = x W^T + b for a narrow x [N, F] (F < 16): the node encoder.  Forward is the strict (split-bf16 x3) tcgen05
+    GEMM of dense.py in BOTH precision modes (the raw input features are never rounded to bf16; K' = 6 F <= 96 costs
+    nothing); the weight / bias gradient -- a K = N reduction -- is gsatb_linear_small_dw (exact fp32 FMA)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
+        from .dense import linear_forward
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+        return linear_forward(_f32c(x), _f32c(weight.detach()), None if bias is None else _f32c(bias.detach()), True)
 
     @staticmethod
     def backward(ctx, g):
@@ -436,7 +438,10 @@ class _SmallLinear(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
         L.call('gsatb_linear_small_dw', ptr(g), ptr(xc), ptr(dW), ptr(db), N, H, F_, ptr(ws), ctypes.c_size_t(ws_bytes),
                stream())
-        dx = g @ weight if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            from .dense import linear_forward
+            dx = linear_forward(g, _f32c(weight.detach().t()), None, True)
         return dx, dW, db
 
 

@@ -9,6 +9,7 @@ import torch.nn as tnn
 import torch.nn.functional as F
 
 from . import ops
+from .dense import Linear, PrecisionMixin
 from .index import GraphIndex, get_graph_index
 from .nn import AtomEncoder, BatchNorm, BondEncoder, _dropout, _encode_once
 
@@ -54,9 +55,9 @@ class PNAConvSimple(tnn.Module):
         degf = deg.to(torch.float)
         self.avg_deg: Dict[str, float] = {'lin': degf.mean().item(), 'log': (degf + 1).log().mean().item(),
                                           'exp': degf.exp().mean().item()}
-        modules = [tnn.Linear(len(aggregators) * len(scalers) * in_channels, out_channels)]
+        modules = [Linear(len(aggregators) * len(scalers) * in_channels, out_channels)]
         for _ in range(post_layers - 1):
-            modules += [tnn.ReLU(), tnn.Linear(out_channels, out_channels)]
+            modules += [tnn.ReLU(), Linear(out_channels, out_channels)]
         self.post_nn = tnn.Sequential(*modules)
 
     def forward(self, x, edge_index, edge_attr=None, edge_atten=None, _index: Optional[GraphIndex] = None):
@@ -68,7 +69,7 @@ class PNAConvSimple(tnn.Module):
         return self.post_nn(out)
 
 
-class PNA(tnn.Module):
+class PNA(PrecisionMixin, tnn.Module):
     """pna.py:12-78."""
 
     def __init__(self, x_dim, edge_attr_dim, num_class, multi_label, model_config):
@@ -83,9 +84,9 @@ class PNA(tnn.Module):
             if edge_attr_dim != 0 and use_ea:
                 self.edge_encoder = BondEncoder(emb_dim=hidden_size)
         else:
-            self.node_encoder = tnn.Linear(x_dim, hidden_size)
+            self.node_encoder = Linear(x_dim, hidden_size)
             if edge_attr_dim != 0 and use_ea:
-                self.edge_encoder = tnn.Linear(edge_attr_dim, hidden_size)
+                self.edge_encoder = Linear(edge_attr_dim, hidden_size)
         aggregators = model_config['aggregators']
         scalers = ['identity', 'amplification', 'attenuation'] if model_config['scalers'] else ['identity']
         deg = model_config['deg']
@@ -99,10 +100,11 @@ class PNA(tnn.Module):
             self.convs.append(PNAConvSimple(in_channels=in_channels, out_channels=hidden_size, aggregators=aggregators,
                                             scalers=scalers, deg=deg, post_layers=1))
             self.batch_norms.append(BatchNorm(hidden_size))
-        self.fc_out = tnn.Sequential(tnn.Linear(hidden_size, hidden_size // 2), tnn.ReLU(),
-                                     tnn.Linear(hidden_size // 2, hidden_size // 4), tnn.ReLU(),
-                                     tnn.Linear(hidden_size // 4, 1 if num_class == 2 and not multi_label else num_class))
+        self.fc_out = tnn.Sequential(Linear(hidden_size, hidden_size // 2), tnn.ReLU(),
+                                     Linear(hidden_size // 2, hidden_size // 4), tnn.ReLU(),
+                                     Linear(hidden_size // 4, 1 if num_class == 2 and not multi_label else num_class))
         self.masks = None
+        self.precision = 'fp32'
 
     def pool(self, x, batch, gi=None):
         gi = gi if gi is not None else get_graph_index(torch.zeros((2, 0), dtype=torch.int64, device=batch.device), batch)

@@ -427,6 +427,43 @@ int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda, const void
                 int64_t ldb, int64_t rows, int M, int N, float* dW, int ldo, float* db /* [nullable] */, int accumulate,
                 void* workspace, size_t ws_bytes, gsatb_stream_t stream);
 
+/* Dense-layer helpers around the tcgen05 GEMM kernels (csrc/dense.cu): every nn.Linear / BatchNorm1d of the path --
+ * src/models/gin.py:22-25 (encoders), :55-62 (node MLP), :42 (fc_out); src/models/pna.py:20-50; src/utils/get_model.py:57-68;
+ * src/models/conv_layers.py:49,77-79,149 (GINE / LE / PNA post_nn Linears) -- runs on this library's kernels in both
+ * precision modes, forward and backward (autograd of F.linear / F.batch_norm at src/run_gsat.py:634).
+ *
+ * gsatb_split_bf16: fp32 x [rows, C] (ldx floats per row) -> bf16 GEMM operand.  nseg == 1: plain round-to-nearest
+ * (precision 'bf16').  nseg == 6: strict mode (precision 'fp32'): x = h + m + l exactly with three bf16 parts, laid out as
+ * six K-segments so that ONE bf16 GEMM with fp32 accumulation sums the six significant partial products (A side
+ * pattern l,m,h,m,h,h; B side h,m,l,h,m,h -- smallest products first; pattern = 2 bits per segment, 0 = h, 1 = m, 2 = l, segment 0 in the low bits).
+ * layout 0: out [rows, ld_out], segments along the feature axis (columns >= nseg*C zero-filled); layout 1: out
+ * [nseg*rows, ld_out], segments stacked along the row axis (columns >= C zero-filled).  ld_out % 8 == 0. */
+int gsatb_split_bf16(const float* x, int64_t rows, int C, int64_t ldx, int nseg, int pattern, int layout, void* out_bf16,
+                     int64_t ld_out, gsatb_stream_t stream);
+/* workspace bytes of the column reductions below */
+size_t gsatb_col_workspace(int64_t rows, int C);
+/* out[c] = sum_r x[r, c] (bias gradient of a Linear), fp64 accumulation in a fixed order */
+int gsatb_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* workspace, size_t ws_bytes,
+                 gsatb_stream_t stream);
+/* BatchNorm1d (src/models/gin.py:59, pna.py:45) training-mode batch statistics of x [rows, C]: mean [C], rstd [C] =
+ * 1/sqrt(biased var + eps); running_mean / running_var [nullable, both or neither] updated in place with `momentum` and
+ * the unbiased variance as torch does; sums64 [nullable, 2C doubles] receives sum(x - x[0]), sum((x - x[0])^2). */
+int gsatb_bn_stats(const float* x, int64_t rows, int C, float eps, float momentum, float* running_mean /* [nullable] */,
+                   float* running_var /* [nullable] */, float* mean, float* rstd, double* sums64 /* [nullable] */,
+                   void* workspace, size_t ws_bytes, gsatb_stream_t stream);
+/* y = (x - mean) * rstd * gamma + beta, optionally followed by ReLU (gamma / beta nullable = 1 / 0) */
+int gsatb_bn_apply(const float* x, const float* mean, const float* rstd, const float* gamma /* [nullable] */,
+                   const float* beta /* [nullable] */, int relu, float* y, int64_t rows, int C, gsatb_stream_t stream);
+/* dbeta[c] = sum_r g, dgamma[c] = sum_r g * xhat with g = dy (zeroed where y_relu <= 0 when y_relu is given) */
+int gsatb_bn_bwd_stats(const float* dy, const float* x, const float* y_relu /* [nullable] */, const float* mean,
+                       const float* rstd, int64_t rows, int C, float* dbeta, float* dgamma, double* sums64 /* [nullable] */,
+                       void* workspace, size_t ws_bytes, gsatb_stream_t stream);
+/* dx = gamma * rstd * (g - sum_g * inv_n - xhat * sum_gx * inv_n) in training mode, gamma * rstd * g in eval mode */
+int gsatb_bn_bwd_apply(const float* dy, const float* x, const float* y_relu /* [nullable] */, const float* mean,
+                       const float* rstd, const float* gamma /* [nullable] */, const float* sum_g /* [nullable] */,
+                       const float* sum_gx /* [nullable] */, float inv_n, int training, float* dx, int64_t rows, int C,
+                       gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * the step BEFORE the path -- feature encoders and batch collate on the device.
  *

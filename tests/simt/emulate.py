@@ -21,7 +21,7 @@ import torch
 
 from .simlib import sim
 
-_PRODUCT_MODULES = ('_lib', 'ops', 'index', 'gsat', 'loader', 'dual', 'metrics', 'nn', 'pna')
+_PRODUCT_MODULES = ('_lib', 'ops', 'index', 'gsat', 'loader', 'dual', 'metrics', 'nn', 'pna', 'dense')
 
 
 class EmulatedLib:
