@@ -38,10 +38,17 @@ def parse():
     ap.add_argument('--layers', type=int, default=2)
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'],
-                    help='bf16: tcgen05 MLPs (bf16 operands, fp32 accumulate); fp32: strict library-sgemm path')
+                    help='bf16: tcgen05 MLPs (bf16 operands, fp32 accumulate); fp32: strict mode, the same tcgen05 GEMM '
+                         'kernels on split-bf16 x3 operands (fp32-accurate products, the rtol-1e-5 parity mode)')
     ap.add_argument('--cuda-graph', default='auto', choices=['auto', 'on', 'off'],
                     help='replay the whole step (fwd + bwd + all-reduce + Adam) as ONE CUDA graph in the timed region; '
-                         'auto = when the per-rank shard is small enough for host launch overhead to matter (N > 1)')
+                         'auto = on at every N (the same launch mode for the whole scaling run), eager if capture fails')
+    ap.add_argument('--sync-bn', action='store_true',
+                    help='exact multi-GPU mode: BatchNorm batch statistics span all ranks (the N-GPU step then computes '
+                         'the single-GPU step); default = shard-local statistics (DDP semantics)')
+    ap.add_argument('--strict-steps', type=int, default=2,
+                    help='N = 1, bf16 run only: also time this many steps of the strict fp32 mode on the same workload '
+                         '(reported under "strict_mode"; 0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-graphs', type=int, default=0, help='0 = size automatically (~10-30 s of CPU work)')
     return ap.parse_args()
@@ -206,6 +213,10 @@ def kernel_models(N, E, G, H):
     written once; the bf16 intermediates a kernel reads / writes are part of ITS contract."""
     C1 = 4 * H
     return {
+        # the fused extractor, SURVEY section 8d's contract figures: bytes = emb + indices + logits (fwd), 2x emb + 12E
+        # (bwd); flops = GEMM1 (2H x 4H) + GEMM2 (4H x H) forward, recomputed GEMM1 + dh1 + d f12 backward
+        'gsatb_ext_fused_fwd': (4.0 * N * H + 12.0 * E, E * (24.0 * H * H + 2.0 * H)),
+        'gsatb_ext_fused_bwd': (8.0 * N * H + 12.0 * E, E * 40.0 * H * H),
         'gsatb_gin_aggregate_fwd:att': (8.0 * N * H + 8.0 * E + 4.0 * N, 2.0 * E * H),
         'gsatb_gin_aggregate_fwd:noatt': (8.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
         'gsatb_gin_aggregate_bwd:att': (12.0 * N * H + 16.0 * E, 4.0 * E * H),
@@ -234,7 +245,7 @@ def kernel_models(N, E, G, H):
     }
 
 
-def build_roofline(timer, N, E, G, H, steps, ms_step):
+def build_roofline(timer, N, E, G, H, steps, ms_step, unmodelled=()):
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -253,6 +264,11 @@ def build_roofline(timer, N, E, G, H, steps, ms_step):
             tot = sum(ms)
             row = {'kernel': key, 'launches_per_step': len(ms) / steps, 'avg_launch_ms': tot / len(ms),
                    'share_of_step': tot / steps / ms_step}
+            if name in unmodelled:
+                models.pop(key, None)
+            elif name == 'gsatb_tc_dw' and tag:          # tag = 'rows x M x N' of the product dW[M, N] = A[rows, M]^T B[rows, N]
+                r_, m_, n_ = (float(v) for v in tag.split('x'))
+                models[key] = (2.0 * r_ * (m_ + n_) + 4.0 * m_ * n_, 2.0 * r_ * m_ * n_)
             if key in models:
                 nbytes, flops = models[key]
                 t_hbm, t_tc = nbytes / (hbm * 1e9), flops / (tc * 1e12)
@@ -273,7 +289,7 @@ def build_roofline(timer, N, E, G, H, steps, ms_step):
     # dram__bytes_read + write per launch from the committed ncu --set full captures (same shapes), where one exists
     traffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_ncu_traffic.json')))
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
     except Exception:
         pass
     for r in rows:
@@ -323,7 +339,7 @@ def run_b200(a):
     clf.precision = ext.precision = a.precision
     gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5, lazy_metrics=True)
     gsat.train()
-    step = TrainStep(gsat, lr=1e-3)
+    step = TrainStep(gsat, lr=1e-3, sync_bn=a.sync_bn)
     data = shard_host.to(dev)
     N_loc, E_loc, H = data.num_nodes, data.num_edges, a.hidden
 
@@ -332,7 +348,7 @@ def run_b200(a):
     barrier()
 
     L = lib()
-    use_graph = a.cuda_graph == 'on' or (a.cuda_graph == 'auto' and world > 1)
+    use_graph = a.cuda_graph in ('on', 'auto')
     graphed = step.enable_cuda_graph(data, 0, warmup=2) if use_graph else False
     if world > 1:                                            # every rank must take the same path
         flag = torch.tensor([1 if graphed else 0], device=dev)
@@ -371,6 +387,8 @@ def run_b200(a):
             return 'att' if args[2] is not None else 'noatt'
         if name == 'gsatb_tc_linear_bf16_fwd':
             return 'bf16' if args[5] else 'fp32'
+        if name == 'gsatb_tc_dw':
+            return f'{int(args[6])}x{int(args[7])}x{int(args[8])}'
         return ''
     L.timer_tag = tag
     clocks = Clocks(local)
@@ -394,7 +412,9 @@ def run_b200(a):
     launches = L.launches - launches0
     timer, L.timer, L.timer_all, L.timer_tag = L.timer, None, False, None
     ms_step = float(ms.item()) / a.steps
-    roofline = build_roofline(timer, N_loc, E_loc, data.num_graphs, H, a.steps, ms_step)
+    # (strict mode runs the GEMM entry points on 6x wider split operands: their bf16-mode byte models do not apply)
+    roofline = build_roofline(timer, N_loc, E_loc, data.num_graphs, H, a.steps, ms_step,
+                              unmodelled=('gsatb_tc_linear_bf16_fwd', 'gsatb_tc_dw') if a.precision == 'fp32' else ())
     if graphed:
         roofline['timed_in'] = (f'{a.steps} instrumented eager steps ({ms_step:.3f} ms/step) run right after the timed '
                                 'CUDA-graph replays: per-kernel events cannot be taken inside a graph replay')
@@ -439,6 +459,31 @@ def run_b200(a):
            'last_loss': loss_host,
            'how': 'pinned host batch -> H2D (copy stream, prefetched one step ahead) -> K0 index build -> step -> loss.item()'}
 
+    # strict-mode figure beside the bf16 one (N = 1): the same workload, model and step with precision='fp32' -- the
+    # mode the rtol-1e-5 parity tests hold to the fp32 oracle (same tcgen05 GEMM kernels, split-bf16 x3 operands)
+    strict = None
+    if world == 1 and a.precision == 'bf16' and a.strict_steps > 0:
+        try:
+            step.disable_cuda_graph()
+            G.clear_index_cache()
+            torch.cuda.empty_cache()
+            clf.precision = ext.precision = 'fp32'
+            step(data, 0)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(a.strict_steps):
+                step(data, 0)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_strict = ev0.elapsed_time(ev1) / a.strict_steps
+            strict = {'value': E_global / (ms_strict * 1e-3), 'unit': UNIT, 'ms_per_step': ms_strict, 'steps': a.strict_steps,
+                      'warmup': 1, 'dtype': 'f32 (split-bf16 x3 tensor-core products)', 'step_launch': 'eager launches'}
+        except Exception as exc:                          # an extra figure must never cost the bench line
+            strict = {'error': repr(exc)}
+        finally:
+            clf.precision = ext.precision = a.precision
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -464,8 +509,10 @@ def run_b200(a):
                 'config': {'workload': workload_name(a), 'precision': a.precision + (' tensor-core MLP operands, fp32 accumulate / gather / scatter / sampler' if a.precision == 'bf16' else ''), 'global_edges': E_global, 'global_nodes': a.graphs * 25,
                            'hidden': a.hidden, 'layers': a.layers, 'parallelism': f'graph-sharded dp{world}',
                            'step_launch': 'one CUDA graph replay per step' if graphed else 'eager launches',
+                           'batchnorm': 'statistics over all ranks (exact: equals the single-GPU step)' if a.sync_bn
+                           else ('shard-local statistics (DDP semantics)' if world > 1 else 'single device'),
                            'l2_policy': 'inputs larger than L2 (per-rank activations >> 126 MB)'},
-                'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': launches,
+                'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'strict_mode': strict, 'gpu_launches': launches,
                 'clocks': clk}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -18,7 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'gsat_b200.h')
 
 _CTYPES = {
     'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64, 'size_t': ctypes.c_size_t,
-    'float': ctypes.c_float, 'gsatb_stream_t': ctypes.c_void_p, 'void': None,
+    'float': ctypes.c_float, 'double': ctypes.c_double, 'gsatb_stream_t': ctypes.c_void_p, 'void': None,
 }
 
 

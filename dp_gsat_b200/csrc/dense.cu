@@ -322,3 +322,89 @@ extern "C" int gsatb_bn_bwd_apply(const float* dy, const float* x, const float* 
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }
+
+// ---- BatchNorm folding for the tensor-core GIN layer (tc.py): one launch instead of ~15 elementwise library launches ----
+namespace {
+
+__global__ void k_bn_fold_fwd(const double* __restrict__ stats, double n_host, const double* __restrict__ n_dev,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                              long long* __restrict__ nbt, int training, float* __restrict__ mean, float* __restrict__ rstd,
+                              float* __restrict__ scale, float* __restrict__ shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && training && nbt) *nbt += 1;
+    if (c >= C) return;
+    float mu, var;
+    if (training) {
+        const double n = n_dev ? *n_dev : n_host;
+        const double m = stats[c] / n;
+        double v = stats[C + c] / n - m * m;                  // biased variance, from the fp32 accumulators' fp64 sums
+        if (v < 0.0) v = 0.0;
+        mu = (float)m;
+        var = (float)v;
+        if (running_mean) {
+            const double nm1 = n - 1.0 > 1.0 ? n - 1.0 : 1.0;
+            const float unb = (float)(n / nm1);
+            running_mean[c] = running_mean[c] * (1.f - momentum) + momentum * mu;
+            running_var[c] = running_var[c] * (1.f - momentum) + momentum * (var * unb);
+        }
+    } else {
+        mu = running_mean[c];
+        var = running_var[c];
+    }
+    const float rs = 1.f / sqrtf(var + eps);
+    const float sc = (gamma ? gamma[c] : 1.f) * rs;
+    mean[c] = mu;
+    rstd[c] = rs;
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - mu * sc;
+}
+
+// dz1 = cA * g + cB * z1 + cC  with  coef = gamma * rstd:  training: cA = coef, cB = -coef rstd mean(g xhat),
+// cC = -coef mean(g) - cB mean;   eval (running statistics are constants): cA = coef, cB = cC = 0
+__global__ void k_bn_fold_bwd(const float* __restrict__ sum_g, const float* __restrict__ sum_gx, double n_host,
+                              const double* __restrict__ n_dev, const float* __restrict__ gamma,
+                              const float* __restrict__ mean, const float* __restrict__ rstd, int training,
+                              float* __restrict__ cA, float* __restrict__ cB, float* __restrict__ cC, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float coef = (gamma ? gamma[c] : 1.f) * rstd[c];
+    float b = 0.f, cc = 0.f;
+    if (training) {
+        const float inv_n = (float)(1.0 / (n_dev ? *n_dev : n_host));
+        b = -coef * rstd[c] * (sum_gx[c] * inv_n);
+        cc = -coef * (sum_g[c] * inv_n) - b * mean[c];
+    }
+    cA[c] = coef;
+    cB[c] = b;
+    cC[c] = cc;
+}
+
+}  // namespace
+
+extern "C" int gsatb_bn_fold_fwd(const double* stats, double n_host, const double* n_dev, const float* gamma, const float* beta,
+                                 float eps, float momentum, float* running_mean, float* running_var,
+                                 int64_t* num_batches_tracked, int training, float* mean, float* rstd, float* scale,
+                                 float* shift, int C, gsatb_stream_t stream) {
+    if (C <= 0 || !mean || !rstd || !scale || !shift) return GSATB_EINVAL;
+    if (training && (!stats || (!n_dev && !(n_host > 0.0)))) return GSATB_EINVAL;
+    if (!training && (!running_mean || !running_var)) return GSATB_EINVAL;
+    if ((running_mean == nullptr) != (running_var == nullptr)) return GSATB_EINVAL;
+    k_bn_fold_fwd<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n_host, n_dev, gamma, beta, eps, momentum,
+                                                                     running_mean, running_var,
+                                                                     (long long*)num_batches_tracked, training, mean, rstd,
+                                                                     scale, shift, C);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_bn_fold_bwd(const float* sum_g, const float* sum_gx, double n_host, const double* n_dev,
+                                 const float* gamma, const float* mean, const float* rstd, int training, float* cA, float* cB,
+                                 float* cC, int C, gsatb_stream_t stream) {
+    if (C <= 0 || !rstd || !cA || !cB || !cC) return GSATB_EINVAL;
+    if (training && (!sum_g || !sum_gx || !mean || (!n_dev && !(n_host > 0.0)))) return GSATB_EINVAL;
+    k_bn_fold_bwd<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum_g, sum_gx, n_host, n_dev, gamma, mean, rstd, training,
+                                                                     cA, cB, cC, C);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}

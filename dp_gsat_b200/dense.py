@@ -168,7 +168,10 @@ class Linear(tnn.Linear):
     precision = 'fp32'
 
     def forward(self, x):
-        return linear(x, self.weight, self.bias, self.precision)
+        # raw input features (encoders, K < 16) and final logits (OUT < 8) are never rounded to bf16: those layers are a
+        # negligible share of the FLOPs and always take the strict product
+        narrow = self.in_features < 16 or self.out_features < 8
+        return linear(x, self.weight, self.bias, 'fp32' if narrow else self.precision)
 
 
 def set_precision(module: tnn.Module, precision: str) -> None:

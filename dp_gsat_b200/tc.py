@@ -345,24 +345,22 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     BatchNorm + ReLU are folded into Linear2's operand load, the outer ReLU and the dropout into its epilogue."""
     N = agg16.shape[0]
     H1, H = w1.shape[0], w2.shape[0]
+    dev = agg16.device
     w1p, w2p = prep_weight(w1), prep_weight(w2)
+    mean, rstd, scale, shift = (torch.empty(H1, dtype=torch.float32, device=dev) for _ in range(4))
     if training:
         z1, stats = linear_bf16(agg16, w1p, b1, H1, want_stats=True)
         n_rows = _allreduce_stats(stats, N, sync_group)          # python int, or the group-wide count on the device
-        mean64 = stats[:H1] / n_rows
-        var64 = (stats[H1:] / n_rows - mean64 * mean64).clamp_min(0.0)
-        mean, var = mean64.float(), var64.float()
-        unbias = N / max(N - 1, 1) if sync_group is None else (n_rows / (n_rows - 1).clamp_min(1)).float()
-        with torch.no_grad():
-            running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-            running_var.mul_(1 - momentum).add_(var * unbias, alpha=momentum)
-            nbt.add_(1)
+        n_dev = n_rows if torch.is_tensor(n_rows) else None
+        # batch statistics -> (mean, rstd, scale, shift) + running-statistics update, one launch (gsatb_bn_fold_fwd)
+        lib().call('gsatb_bn_fold_fwd', ptr(stats), ctypes.c_double(float(N)), ptr(n_dev), ptr(gamma), ptr(beta),
+                   ctypes.c_float(eps), ctypes.c_float(momentum), ptr(running_mean), ptr(running_var), ptr(nbt), 1, ptr(mean),
+                   ptr(rstd), ptr(scale), ptr(shift), H1, stream())
     else:
         z1 = linear_bf16(agg16, w1p, b1, H1)
-        mean, var = running_mean.clone(), running_var.clone()
-    rstd = torch.rsqrt(var + eps)
-    scale = (gamma * rstd).contiguous()
-    shift = (beta - mean * scale).contiguous()
+        lib().call('gsatb_bn_fold_fwd', None, ctypes.c_double(1.0), None, ptr(gamma), ptr(beta), ctypes.c_float(eps),
+                   ctypes.c_float(momentum), ptr(running_mean), ptr(running_var), None, 0, ptr(mean), ptr(rstd), ptr(scale),
+                   ptr(shift), H1, stream())
     p = float(pdrop) if training else 0.0
     a1 = torch.empty_like(z1)
     lib().call('gsatb_bn_relu_bf16', ptr(z1), ptr(scale), ptr(shift), ptr(a1), N, H1, stream())
@@ -406,27 +404,22 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
            ptr(w2t), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
            ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
     dbeta, dgamma = stats[:H1], stats[H1:]
-    coef = gamma * rstd
-    if training:      # dz1 = coef * (g - dbeta/N - xhat * dgamma/N),  xhat = (z1 - mean) * rstd
-        if sync_group is not None:                   # sums and row count over every rank's rows
-            dbeta, dgamma = dbeta.clone(), dgamma.clone()                       # local sums -> parameter gradients
-            n_glob = _allreduce_stats(stats, N, sync_group)
-            m_dbeta, m_dgamma = (stats[:H1] / n_glob).float(), (stats[H1:] / n_glob).float()
-        else:
-            m_dbeta, m_dgamma = dbeta / N, dgamma / N
-        cA = coef
-        cB = -coef * rstd * m_dgamma
-        cC = -coef * m_dbeta - cB * mean
-    else:             # running statistics are constants: dz1 = coef * g
-        cA, cB, cC = coef, torch.zeros_like(coef), torch.zeros_like(coef)
+    n_glob = None
+    if training and sync_group is not None:              # sums and row count over every rank's rows
+        dbeta, dgamma = dbeta.clone(), dgamma.clone()                           # local sums -> parameter gradients
+        n_glob = _allreduce_stats(stats, N, sync_group)
+    # dz1 = cA * g + cB * z1 + cC (BatchNorm backward folded into three per-channel vectors), one launch
+    cA, cB, cC = (torch.empty(H1, dtype=torch.float32, device=dev) for _ in range(3))
+    L.call('gsatb_bn_fold_bwd', ptr(stats[:H1]), ptr(stats[H1:]), ctypes.c_double(float(max(N, 1))), ptr(n_glob), ptr(gamma),
+           ptr(mean), ptr(rstd), int(bool(training)), ptr(cA), ptr(cB), ptr(cC), H1, stream())
     dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
     dagg = torch.empty((N, Kin), dtype=torch.float32, device=dev)
-    cA, cB, cC, w1t = cA.contiguous(), cB.contiguous(), cC.contiguous(), prep_weight(w1, transpose=True)
+    w1t = prep_weight(w1, transpose=True)
     L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, Kin,
            stream())
     dW2, db2 = weight_grad(d2, False, a1, False, N, H, H1, want_bias=True)
     dW1, db1 = weight_grad(dz1, False, agg16, False, N, H1, Kin, want_bias=True)
-    return dagg, dW1, db1, dgamma.clone(), dbeta.clone(), dW2, db2
+    return dagg, dW1, db1, dgamma, dbeta, dW2, db2
 
 
 class _GinMlpFused(torch.autograd.Function):

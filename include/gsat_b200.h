@@ -464,6 +464,23 @@ int gsatb_bn_bwd_apply(const float* dy, const float* x, const float* y_relu /* [
                        const float* sum_gx /* [nullable] */, float inv_n, int training, float* dx, int64_t rows, int C,
                        gsatb_stream_t stream);
 
+/* BatchNorm1d folding for the tensor-core GIN layer (src/models/gin.py:59 inside the node MLP of :55-62): one launch each way
+ * instead of a chain of elementwise library kernels.  n = rows the statistics span: n_dev (device double, e.g. the
+ * all-reduced count of the data-parallel group) when given, else n_host.
+ * fwd: stats = [sum z, sum z^2] (2C doubles, from gsatb_tc_linear_bf16_fwd) -> mean, rstd, scale = gamma * rstd,
+ *      shift = beta - mean * scale; training != 0 also updates running_mean / running_var (momentum, unbiased variance)
+ *      and num_batches_tracked += 1; training == 0 folds the running statistics (stats unused).
+ * bwd: dz1 = cA * g + cB * z1 + cC from sum_g = sum g, sum_gx = sum g * xhat (C floats each). */
+int gsatb_bn_fold_fwd(const double* stats /* [nullable] */, double n_host, const double* n_dev /* [nullable] */,
+                      const float* gamma /* [nullable] */, const float* beta /* [nullable] */, float eps, float momentum,
+                      float* running_mean /* [nullable] */, float* running_var /* [nullable] */,
+                      int64_t* num_batches_tracked /* [nullable] */, int training, float* mean, float* rstd, float* scale,
+                      float* shift, int C, gsatb_stream_t stream);
+int gsatb_bn_fold_bwd(const float* sum_g /* [nullable] */, const float* sum_gx /* [nullable] */, double n_host,
+                      const double* n_dev /* [nullable] */, const float* gamma /* [nullable] */,
+                      const float* mean /* [nullable] */, const float* rstd, int training, float* cA, float* cB, float* cC,
+                      int C, gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * the step BEFORE the path -- feature encoders and batch collate on the device.
  *

@@ -106,7 +106,7 @@ def build(force: bool = False) -> str:
         with open(g, 'w') as f:
             f.write(f'#line 1 "{s}"\n' + rewrite_launches(open(s).read()))
         o = os.path.join(OUT_DIR, base + '.o')
-        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O1', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE'] + FMA_FLAGS + ['-I', HERE, '-I', gen, '-I', CSRC,
+        cmd = ['g++', '-x', 'c++', '-std=c++17', '-O2', '-g', '-fPIC', '-DGSATB_HOST_SIM', '-U_FORTIFY_SOURCE'] + FMA_FLAGS + ['-I', HERE, '-I', gen, '-I', CSRC,
                '-Wno-attributes', '-Wno-unused', '-Wno-unknown-pragmas', '-c', g, '-o', o]
         procs.append((s, o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []

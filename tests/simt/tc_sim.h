@@ -155,14 +155,18 @@ inline void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
     float* tm = simt::tmem();
     const uint32_t col0 = tmem_d & 0xffff;
     if ((tmem_d >> 16) != 0 || col0 + N > simt::kTmemCols) simt::fail("MMA accumulator outside the allocated TMEM");
-    float a[16], bcol[16];
-    for (int n = 0; n < N; ++n) {
-        for (int k = 0; k < 16; ++k) bcol[k] = bf16_at(base, operand_addr(desc_b, b_mn, n, k));
-        for (int m = 0; m < M; ++m) {
-            for (int k = 0; k < 16; ++k) a[k] = bf16_at(base, operand_addr(desc_a, a_mn, m, k));
-            float acc = accumulate ? tm[m * simt::kTmemCols + col0 + n] : 0.f;
-            for (int k = 0; k < 16; ++k) acc += a[k] * bcol[k];
-            tm[m * simt::kTmemCols + col0 + n] = acc;
+    // decode both operand tiles once (the address arithmetic of the descriptors is the expensive part), then accumulate
+    static thread_local float a[128][16], b[256][16];
+    for (int m = 0; m < M; ++m)
+        for (int k = 0; k < 16; ++k) a[m][k] = bf16_at(base, operand_addr(desc_a, a_mn, m, k));
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 16; ++k) b[n][k] = bf16_at(base, operand_addr(desc_b, b_mn, n, k));
+    for (int m = 0; m < M; ++m) {
+        float* row = tm + (size_t)m * simt::kTmemCols + col0;
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? row[n] : 0.f;
+            for (int k = 0; k < 16; ++k) acc += a[m][k] * b[n][k];
+            row[n] = acc;
         }
     }
 }
