@@ -223,8 +223,9 @@ __device__ __forceinline__ void epi3_emit_blk(const Epi3Ctx& c, const float* xh,
     tc::sts128(c.dz1_s + mn_tile_offset_blk(c.gtid, blk), o[0], o[1], o[2], o[3]);
     tc::sts128(c.h1_s + mn_tile_offset_blk(c.gtid, blk), hq[0], hq[1], hq[2], hq[3]);
 }
-template <int NB, class WaitTiles>
-__device__ __forceinline__ void epi3_graph(const Epi3Ctx& c, const DropCtx& dc, int n, int row0, int slot0, WaitTiles wait_tiles) {
+template <int NB, class WaitTiles, class Loaded>
+__device__ __forceinline__ void epi3_graph(const Epi3Ctx& c, const DropCtx& dc, int n, int row0, int slot0, WaitTiles wait_tiles,
+                                           Loaded loaded) {
     float z[8 * NB], d[8 * NB];
     tmem_ld_blocks<NB>(c.t1 + slot0, z);
     tmem_ld_blocks<NB>(c.t3 + slot0, d);
@@ -232,6 +233,7 @@ __device__ __forceinline__ void epi3_graph(const Epi3Ctx& c, const DropCtx& dc, 
     uint32_t k1 = 0xffffffffu;
     if (NB > 4) k1 = keep_bits32(dc, c.ch, c.ch_ok, row0 + 32, n - 32);
     tc::tmem_ld_wait();
+    loaded();      // both accumulators of this graph now live in registers: the caller may hand them back to the MMA issuer
     const float inv_n = 1.f / (float)n;
     const float r = 1.f / sqrtf(sumsq_blocks<NB>(z) * inv_n + c.eps);
     float s1 = 0.f, s2 = 0.f;
@@ -456,12 +458,8 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                     };
                     t0 = clock64();
                     tc::mbar_wait(x_full, ti & 1);
-                    tc::mbar_wait(dz2_ready, ti & 1);
                     w_in += clock64() - t0;
                     tc::tc_fence_after();
-                    tc::tma_store_2d(&tm_dz2, smem + L.dz2, tile * TILE_SLOTS, 0);
-                    tc::tma_store_2d(&tm_dz2, smem + L.dz2 + BRICK, tile * TILE_SLOTS + 64, 0);
-                    tc::tma_store_commit();
                     for (int cb = 0; cb < p.NCB; ++cb, ++n) {
                         t0 = clock64();
                         tc::mbar_wait(acc_empty, (n & 1) ^ 1);
@@ -475,6 +473,15 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                                 tc::mma_bf16_ss(tmem_base, a_desc + (uint64_t)(k4 * 2), b_desc + (uint64_t)(k4 * 2), idesc_k,
                                                 (kb | k4) != 0);
                             release();
+                        }
+                        if (cb == 0) {      // GEMM1 of the first block ran underneath the head epilogue; dh1 needs its dz2 tile
+                            t0 = clock64();
+                            tc::mbar_wait(dz2_ready, ti & 1);
+                            w_in += clock64() - t0;
+                            tc::tc_fence_after();
+                            tc::tma_store_2d(&tm_dz2, smem + L.dz2, tile * TILE_SLOTS, 0);
+                            tc::tma_store_2d(&tm_dz2, smem + L.dz2 + BRICK, tile * TILE_SLOTS + 64, 0);
+                            tc::tma_store_commit();
                         }
                         for (int kb = 0; kb < p.KBH; ++kb) {          // dh1 = W2^T[cb] dz2
                             const uint64_t a_desc = brick();
@@ -587,6 +594,9 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
             }
             // ---------- per channel block: InstanceNorm-1 backward (graphs s % 2 == e) ----------
             const DropCtx dc = make_drop_ctx(p.drop1, seed1, p.C1);
+            int last_s = -1;                   // this warpgroup's last non-empty graph of the tile
+            for (int s = e; s < tb.nseg; s += 2)
+                if (__shfl_sync(0xffffffffu, tb.n, s) != 0) last_s = s;
             for (int cb = 0; cb < p.NCB; ++cb, ++n) {
                 Epi3Ctx c3;
                 c3.t1 = tmem_base + ((uint32_t)(q * 32) << 16), c3.t3 = c3.t1 + 128;
@@ -605,13 +615,25 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                         tiles_ready = true;
                     }
                 };
+                // The accumulators go back to the MMA issuer as soon as this warpgroup's LAST graph of the block has been
+                // read into registers (not after its statistics / emitting sweeps): GEMM1 + dh1 of the next channel block
+                // then run underneath this block's epilogue arithmetic instead of after it.
+                bool acc_released = false;
                 for (int s = e; s < tb.nseg; s += 2) {
                     const int ns = __shfl_sync(0xffffffffu, tb.n, s);
                     if (ns == 0) continue;
                     const int nblk = pad8(ns) >> 3;
                     const int slot0 = __shfl_sync(0xffffffffu, tb.slot0, s), row0 = __shfl_sync(0xffffffffu, tb.row0, s);
                     if (nblk <= 7) {
-                        EXT_DISPATCH_NB7(nblk, (epi3_graph<NB>(c3, dc, ns, row0, slot0, wait_tiles)));
+                        const bool last = s == last_s;
+                        auto loaded = [&]() {
+                            if (last) {
+                                tc::tc_fence_before();
+                                tc::mbar_arrive(acc_empty);
+                                acc_released = true;
+                            }
+                        };
+                        EXT_DISPATCH_NB7(nblk, (epi3_graph<NB>(c3, dc, ns, row0, slot0, wait_tiles, loaded)));
                     } else {
                         float qs = 0.f;
                         for (int c4 = 0; c4 < nblk; c4 += 4) {
@@ -642,8 +664,10 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                     }
                 }
                 tc::fence_proxy_async_smem();
-                tc::tc_fence_before();
-                tc::mbar_arrive(acc_empty);
+                if (!acc_released) {      // (multi-pass path of a large last graph, or no graph at all for this warpgroup)
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(acc_empty);
+                }
                 tc::mbar_arrive(dz1_full);
                 t_cb += clock64() - t0;
             }

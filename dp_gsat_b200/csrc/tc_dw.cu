@@ -57,7 +57,10 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
     const int split = blockIdx.x, slab = blockIdx.y;
     const int mb = slab / p.n_chunks, nc = slab % p.n_chunks;
     const int64_t total_steps = (p.rows + DW_KSTEP - 1) / DW_KSTEP;
-    const int64_t s0 = total_steps * split / p.splits, s1 = total_steps * (split + 1) / p.splits;
+    // K-steps are dealt round-robin over the splits (split s takes steps s, s + splits, ...): at any moment the CTAs of a
+    // slab stream ADJACENT 64-row slices of the operands, so a channel-major operand ([C, rows]: one 128-byte piece per
+    // channel row and step) is read as long contiguous runs per DRAM page instead of 128-byte pieces ~rows/splits apart.
+    const int64_t s0 = split, s1 = total_steps, sstep = p.splits;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmap_a);
@@ -86,7 +89,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t st = s0; st < s1; ++st, ++it) {
+            for (int64_t st = s0; st < s1; st += sstep, ++it) {
                 const uint32_t s = it % p.stages, use = it / p.stages;
                 tc::mbar_wait(&empty[s], (use & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
@@ -114,7 +117,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
             const uint32_t idesc_b = tc::make_idesc_bf16(128, DW_BIAS_COLS, p.a_cm ? 0 : 1, 0);
             const uint64_t ones_desc = tc::make_desc_k_sw128(tc::smem_u32(ones));
             uint32_t it = 0;
-            for (int64_t st = s0; st < s1; ++st, ++it) {
+            for (int64_t st = s0; st < s1; st += sstep, ++it) {
                 const uint32_t s = it % p.stages, use = it / p.stages;
                 tc::mbar_wait(&full[s], use & 1);
                 tc::tc_fence_after();

@@ -198,33 +198,35 @@ def test_fused_extractor_hash_dropout_statistics(G):
     assert torch.allclose(h1.float()[kept], (s1['xhat1'].float()[kept] * 2).bfloat16().float())
 
 
-def test_gin_mlp_fused_matches_torch(G):
-    """Node MLP relu(Linear(relu(BN(Linear(x))))) on tcgen05 vs the same torch modules in fp32 on the device."""
+@pytest.mark.parametrize('H', [64, 128])
+def test_gin_mlp_fused_matches_torch(G, H):
+    """Node MLP relu(Linear(relu(BN(Linear(x))))) on tcgen05 vs the oracle's node MLP (oracle/gsat_oracle.py gin_mlp: the
+    reference's torch modules of src/models/gin.py:55-62 in fp32 on the CPU), at both benched widths."""
     from dp_gsat_b200 import tc
     torch.manual_seed(0)
-    H, N = 64, 5000
+    N = 5000
     seq = G.GIN.MLP(H, H).cuda()
-    ref = G.GIN.MLP(H, H).cuda()
+    ref = O.gin_mlp(H, H)
     ref.load_state_dict(seq.state_dict())
     x = torch.randn(N, H, device='cuda')
     w = torch.randn(N, H, device='cuda')
     for training in (True, False):
         seq.train(training)
         ref.train(training)
-        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        xa, xb = x.clone().requires_grad_(True), x.clone().cpu().requires_grad_(True)
         out = tc.gin_mlp_relu(xa, seq, training)
         exp = torch.relu(ref(xb))
         (out * w).sum().backward()
-        (exp * w).sum().backward()
+        (exp * w.cpu()).sum().backward()
         assert rel_l2(out, exp) < 1e-2
         assert rel_l2(xa.grad, xb.grad) < 0.1
         gscale = max(float(p.grad.abs().max()) for p in ref.parameters())
         for (n1, p1), (_, p2) in zip(seq.named_parameters(), ref.named_parameters()):
             # (the bias in front of BatchNorm has an analytically zero gradient: compare absolutely)
-            assert float((p1.grad - p2.grad).abs().max()) < 0.12 * gscale, n1   # bf16 operand rounding, see above
+            assert float((p1.grad.cpu() - p2.grad).abs().max()) < 0.12 * gscale, n1   # bf16 operand rounding, see above
             p1.grad = p2.grad = None
-        assert torch.allclose(seq[1].running_mean, ref[1].running_mean, rtol=1e-2, atol=1e-3)
-        assert torch.allclose(seq[1].running_var, ref[1].running_var, rtol=1e-2, atol=1e-3)
+        assert torch.allclose(seq[1].running_mean.cpu(), ref[1].running_mean, rtol=1e-2, atol=1e-3)
+        assert torch.allclose(seq[1].running_var.cpu(), ref[1].running_var, rtol=1e-2, atol=1e-3)
         assert int(seq[1].num_batches_tracked) == int(ref[1].num_batches_tracked)
 
 
@@ -344,6 +346,109 @@ def test_gsat_step_bf16_benched_shape_per_tensor_bounds(G):
     print(f'all gradients: rel L2 vs fp64 {tot:.3e}')
     assert not bad, bad
     assert tot <= 1e-2, tot
+
+
+def _bf16_step_vs_oracle(G, b, cfg, shared, x_dim, ea_dim, final_r=0.5, min_cos=0.97):
+    """One precision='bf16' training step against the fp32 oracle on the same weights / noise / masks: loss within 3e-2,
+    attention within 5e-2 relative L2, all gradients together: cosine >= min_cos; returns the kernel names launched."""
+    from torch.profiler import profile, ProfilerActivity
+    learn = shared['learn_edge_att']
+    H = cfg['hidden_size']
+    torch.manual_seed(0)
+    clf_o, ext_o = O.get_model(x_dim, ea_dim, 2, False, cfg), O.ExtractorMLP(H, shared)
+    clf_g, ext_g = G.get_model(x_dim, ea_dim, 2, False, cfg, 'cuda'), G.ExtractorMLP(H, shared).cuda()
+    clf_g.load_state_dict(clf_o.state_dict())
+    ext_g.load_state_dict(ext_o.state_dict())
+    clf_g.precision = ext_g.precision = 'bf16'
+    ms = O.MaskSource(2)
+    for m in (clf_o, ext_o, clf_g, ext_g):
+        m.masks = ms
+    go = O.GSAT(clf_o, ext_o, O.Criterion(2, False), learn_edge_att=learn, final_r=final_r)
+    gg = G.GSAT(clf_g, ext_g, G.Criterion(2, False), learn_edge_att=learn, final_r=final_r)
+    go.train()
+    gg.train()
+    n_noise = b.num_edges if learn else b.num_nodes
+    u = torch.rand(n_noise, 1, generator=torch.Generator().manual_seed(1)).clamp(1e-10, 1 - 1e-10)
+    ea_o, loss_o, _, _ = go.forward_pass(b, 3, True, noise_u=u)
+    loss_o.backward()
+    bd = b.to('cuda')
+    if bd.x.is_cuda:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            ea_g, loss_g, _, _ = gg.forward_pass(bd, 3, True, noise_u=u.cuda())
+            loss_g.backward()
+            torch.cuda.synchronize()
+        names = {e.key for e in prof.key_averages()}
+    else:                                  # the host-emulator dry run of this test body: no kernel names to look at
+        ea_g, loss_g, _, _ = gg.forward_pass(bd, 3, True, noise_u=u.cuda())
+        loss_g.backward()
+        names = None
+    assert abs(float(loss_g.detach()) - float(loss_o.detach())) < 3e-2 * max(1.0, abs(float(loss_o.detach())))
+    assert rel_l2(ea_g, ea_o) < 5e-2, rel_l2(ea_g, ea_o)
+    po = list(clf_o.parameters()) + list(ext_o.parameters())
+    pg = list(clf_g.parameters()) + list(ext_g.parameters())
+    go_flat = torch.cat([p.grad.flatten() for p in po if p.grad is not None])
+    gg_flat = torch.cat([q.grad.flatten().cpu() for p, q in zip(po, pg) if p.grad is not None])
+    assert torch.isfinite(gg_flat).all()
+    cos = float(torch.dot(go_flat, gg_flat) / (go_flat.norm() * gg_flat.norm()))
+    assert cos >= min_cos, cos
+    print(f'loss {float(loss_g.detach()):.5f} / {float(loss_o.detach()):.5f}, edge_att rel L2 {rel_l2(ea_g, ea_o):.3e}, gradient cosine {cos:.5f}')
+    if names is not None:
+        banned = [n for n in names if not any(o in n for o in ('k_tc_gemm', 'k_ext_fused', 'k_tc_dw')) and
+                  any(t in n.lower() for t in ('gemm', 'nvjet', 'cutlass', 'cublas', 'batch_norm', 'splitkreduce', 'gemv'))]
+        assert not banned, banned
+    return names
+
+
+@pytest.mark.parametrize('case', ['mutag_dual_big_graphs', 'ba_H300', 'ba_H80_node_att'])
+def test_bf16_mode_layer_by_layer_path(G, case):
+    """precision='bf16' on batches the fused extractor kernel cannot tile -- BASELINE config 2 (mutag-dual line graphs
+    with up to 400 dual edges per graph: more rows than one 128-row accumulator tile) and the hidden-300 width of the
+    config-5 sweep -- runs layer by layer on the SAME tensor-core GEMM kernels in the same precision mode (no library
+    GEMM, no change of precision): whole step against the oracle at the documented bf16 bound."""
+    import os
+    from dp_gsat_b200 import tc
+    from dp_gsat_b200.data import (ba2motifs_batch, load_mutag_fixture, line_graph_dual, graph_contiguous_relabel,
+                                   batch_from_edge_list)
+    H, learn = 64, True
+    if case == 'mutag_dual_big_graphs':
+        golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'mutag_slice.npz')
+        src, dst, ng = load_mutag_fixture(golden)
+        keep = ng[src] < 128
+        ds, dd, dng = line_graph_dual(src[keep], dst[keep], ng)
+        ds, dd = graph_contiguous_relabel(ds, dd, dng)
+        b = batch_from_edge_list(ds, dd, dng, x_dim=31, seed=0)
+    else:
+        b = ba2motifs_batch(48, seed=4)
+        b.x = torch.rand(b.x.shape, generator=torch.Generator().manual_seed(5))
+        H, learn = (300, True) if case == 'ba_H300' else (80, False)
+    cfg = {'model_name': 'GIN', 'hidden_size': H, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    shared = {'learn_edge_att': learn, 'extractor_dropout_p': 0.5}
+    gi = G.get_graph_index(b.edge_index.cuda(), b.batch.cuda(), b.num_graphs)
+    emb_probe = torch.zeros(b.num_nodes, H, device='cuda')
+    fused_ok = tc.fused_extractor_supported(emb_probe, gi, learn)
+    names = _bf16_step_vs_oracle(G, b, cfg, shared, b.x.shape[1], 0)
+    assert fused_ok == (case == 'ba_H80_node_att')
+    if names is None:
+        return
+    if fused_ok:
+        assert any('k_ext_fused' in n for n in names)
+    else:
+        assert not any('k_ext_fused' in n for n in names)                                       # the layer-by-layer path ran ...
+        assert any('k_tc_gemm' in n for n in names) and any('k_tc_dw' in n for n in names)     # ... on tcgen05
+
+
+@pytest.mark.parametrize('use_edge_attr', [False, True])
+def test_gsat_pna_step_bf16_mode(G, use_edge_attr):
+    """BASELINE config 3 in precision='bf16': PNA's post_nn Linear(A * F -> H, K = 640 / 960), BatchNorm and fc_out run on
+    this library's kernels (tcgen05 GEMMs on bf16 operands, gsatb_bn_*); whole step within the documented bf16 bound."""
+    from dp_gsat_b200.data import molhiv_like_batch, in_degree_histogram
+    b = molhiv_like_batch(64, seed=3, with_edge_attr=use_edge_attr)
+    cfg = {'model_name': 'PNA', 'hidden_size': 80, 'n_layers': 4, 'dropout_p': 0.3, 'atom_encoder': True,
+           'use_edge_attr': use_edge_attr, 'aggregators': ['mean', 'min', 'max', 'std'], 'scalers': False,
+           'deg': in_degree_histogram(b)}
+    shared = {'learn_edge_att': False, 'extractor_dropout_p': 0.5}
+    names = _bf16_step_vs_oracle(G, b, cfg, shared, 9, 3 if use_edge_attr else 0, final_r=0.7, min_cos=0.95)
+    assert names is None or any('k_tc_gemm' in n for n in names)
 
 
 @pytest.mark.parametrize('p', [0.5, 0.3, 0.1])

@@ -82,9 +82,10 @@ CASES = [
     _case(T.test_fused_extractor_fwd_bwd, case='mol_node_H64'),
     _case(T.test_fused_extractor_fwd_bwd, case='mol_edge_H80_p03'),
     _case(T.test_fused_extractor_fwd_bwd, case='eval_mode'),
-    _case(T.test_gin_mlp_fused_matches_torch),
+    _case(T.test_gin_mlp_fused_matches_torch, H=64),
     _case(T.test_gsat_step_bf16_mode_tracks_oracle),
     _case(T.test_word_dropout_rate_and_scale, p=0.3),
+    _case(T.test_bf16_mode_layer_by_layer_path, case='mutag_dual_big_graphs'),
     # SURVEY 8f rows built after the GPU budget was spent: emulator runs are all they have had so far
     _case(Z.test_le_aggregate_fwd_bwd, H=32, with_w=True, with_att=True),
     _case(Z.test_le_aggregate_fwd_bwd, H=300, with_w=True, with_att=True),
