@@ -31,6 +31,9 @@ _PARTS_A = (2, 1, 0, 1, 0, 0)      # the activation-side operand
 _PARTS_B = (0, 1, 2, 0, 1, 0)      # the other operand
 PATTERN_A = sum(p << (2 * i) for i, p in enumerate(_PARTS_A))
 PATTERN_B = sum(p << (2 * i) for i, p in enumerate(_PARTS_B))
+# 'bf16x2': two bf16 parts per operand (16 mantissa bits), three K-segments  m h + h m + h h  -- for layers whose
+# gradients are small residuals of large cancelling terms (PNA post_nn in front of BatchNorm, see pna.py)
+_MODES = {'bf16': (1, 0, 0), 'bf16x2': (3, 1 | (0 << 2) | (0 << 4), 0 | (1 << 2) | (0 << 4)), 'fp32': (6, PATTERN_A, PATTERN_B)}
 _CHUNK_BYTES = 1 << 29             # operand bytes staged per row chunk (bounds the 6x expansion of the strict mode)
 OUT_BLOCK = 512                    # output channels per GEMM launch (four 128-lane accumulators)
 
@@ -48,17 +51,18 @@ def split_bf16(x: torch.Tensor, nseg: int, pattern: int, layout: int, out: Optio
         ld_out = _pad(nseg * C if layout == 0 else C, 8)
     if out is None:
         out = torch.empty((rows if layout == 0 else nseg * rows, ld_out), dtype=torch.bfloat16, device=x.device)
-    lib().call('gsatb_split_bf16', ptr(x), rows, C, int(x.stride(0)), nseg, pattern, layout, ptr(out), ld_out, stream())
+    ldx = int(x.stride(0)) if rows > 1 else C          # (a one-row view may carry any stride in its size-1 dimension)
+    lib().call('gsatb_split_bf16', ptr(x), rows, C, ldx, nseg, pattern, layout, ptr(out), ld_out, stream())
     return out
 
 
-def _weight_operand(w: torch.Tensor, nseg: int):
+def _weight_operand(w: torch.Tensor, nseg: int, pattern: int):
     """fp32 [OUT, K] -> (zero-padded bf16 [pad128(OUT), pad64(Kc)] in the TMA box layout of the GEMM's A operand, Kc)."""
     OUT, K = w.shape
     Kc = _pad(nseg * K, 8)
     ldw = _pad(Kc, 64)
     wp = torch.zeros((_pad(OUT, 128), ldw), dtype=torch.bfloat16, device=w.device)
-    split_bf16(w, nseg, PATTERN_B if nseg > 1 else 0, 0, out=wp, ld_out=ldw)
+    split_bf16(w, nseg, pattern, 0, out=wp, ld_out=ldw)
     return wp, Kc
 
 
@@ -86,24 +90,32 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def linear_forward(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], strict: bool) -> torch.Tensor:
+def _mode(strict) -> tuple:
+    """(segments, activation-side pattern, other-side pattern) of a precision mode ('bf16' | 'bf16x2' | 'fp32'; a bool
+    means strict 'fp32' / plain 'bf16')."""
+    if isinstance(strict, bool):
+        strict = 'fp32' if strict else 'bf16'
+    return _MODES[strict]
+
+
+def linear_forward(x2: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], strict) -> torch.Tensor:
     """x2 [rows, K] fp32 (unit column stride), w [OUT, K] fp32 contiguous -> x2 w^T + b, no autograd bookkeeping."""
     rows, K = x2.shape
     OUT = w.shape[0]
-    nseg = 6 if strict else 1
+    nseg, pat_a, pat_b = _mode(strict)
     out = torch.empty((rows, OUT), dtype=torch.float32, device=x2.device)
     if rows > 0:
-        wp, Kc = _weight_operand(w, nseg)
+        wp, Kc = _weight_operand(w, nseg, pat_b)
         step = _row_chunk(rows, K, nseg)
         for r0 in range(0, rows, step):
-            xs = split_bf16(x2[r0:r0 + step], nseg, PATTERN_A if strict else 0, 0)
+            xs = split_bf16(x2[r0:r0 + step], nseg, pat_a, 0)
             _gemm(xs, Kc, wp, b, out[r0:r0 + step], OUT)
     return out
 
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, strict: bool):
+    def forward(ctx, x, weight, bias, strict):
         OUT, K = weight.shape
         lead = x.shape[:-1]
         x2 = x.reshape(-1, K)
@@ -125,16 +137,16 @@ class _LinearFn(torch.autograd.Function):
         dy2 = dy.reshape(-1, OUT)
         if dy2.dtype != torch.float32 or not dy2.is_contiguous():
             dy2 = dy2.float().contiguous()
-        nseg = 6 if strict else 1
+        nseg, pat_a, pat_b = _mode(strict)
         dev = dy2.device
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((rows, K), dtype=torch.float32, device=dev)
             if rows > 0:
-                wtp, Oc = _weight_operand(w.t().contiguous(), nseg)
+                wtp, Oc = _weight_operand(w.t().contiguous(), nseg, pat_b)
                 step = _row_chunk(rows, OUT, nseg)
                 for r0 in range(0, rows, step):
-                    ds = split_bf16(dy2[r0:r0 + step], nseg, PATTERN_A if strict else 0, 0)
+                    ds = split_bf16(dy2[r0:r0 + step], nseg, pat_a, 0)
                     _gemm(ds, Oc, wtp, None, dx[r0:r0 + step], K)
             dx = dx.view(*lead, K)
         if ctx.needs_input_grad[1]:
@@ -146,8 +158,8 @@ class _LinearFn(torch.autograd.Function):
             if rows == 0:
                 dW.zero_()
             for i, r0 in enumerate(range(0, rows, step)):
-                a = split_bf16(dy2[r0:r0 + step], nseg, PATTERN_A if strict else 0, 1)        # [nseg * n, pad8(OUT)]
-                bq = split_bf16(x2[r0:r0 + step], nseg, PATTERN_B if strict else 0, 1)        # [nseg * n, pad8(K)]
+                a = split_bf16(dy2[r0:r0 + step], nseg, pat_a, 1)        # [nseg * n, pad8(OUT)]
+                bq = split_bf16(x2[r0:r0 + step], nseg, pat_b, 1)        # [nseg * n, pad8(K)]
                 L.call('gsatb_tc_dw', ptr(a), 0, int(a.stride(0)), ptr(bq), 0, int(bq.stride(0)), a.shape[0], OUT, K, ptr(dW),
                        K, None, int(i > 0), ptr(ws), ctypes.c_size_t(nb), stream())
         if has_bias and ctx.needs_input_grad[2]:
@@ -156,22 +168,25 @@ class _LinearFn(torch.autograd.Function):
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], precision: str = 'fp32') -> torch.Tensor:
-    """F.linear(x, weight, bias) on the tcgen05 kernels; precision 'fp32' = split-bf16 x3 strict mode, 'bf16' = one pass."""
-    if precision not in ('fp32', 'bf16'):
+    """F.linear(x, weight, bias) on the tcgen05 kernels; precision 'fp32' = split-bf16 x3 strict mode, 'bf16' = one pass,
+    'bf16x2' = two bf16 parts per operand (three passes, 16 mantissa bits)."""
+    if precision not in _MODES:
         raise ValueError(f'unknown precision {precision!r}')
-    return _LinearFn.apply(x, weight, bias, precision == 'fp32')
+    return _LinearFn.apply(x, weight, bias, precision)
 
 
 class Linear(tnn.Linear):
     """torch.nn.Linear with the same parameters, initialisation and state_dict keys, computed by this library's kernels
     in the precision mode of its owner model (``precision``: 'fp32' strict / 'bf16')."""
     precision = 'fp32'
+    bf16_mode = 'bf16'       # what precision 'bf16' means for THIS layer: 'bf16' (one pass) or 'bf16x2' (see pna.py)
 
     def forward(self, x):
         # raw input features (encoders, K < 16) and final logits (OUT < 8) are never rounded to bf16: those layers are a
         # negligible share of the FLOPs and always take the strict product
         narrow = self.in_features < 16 or self.out_features < 8
-        return linear(x, self.weight, self.bias, 'fp32' if narrow else self.precision)
+        mode = 'fp32' if (narrow or self.precision == 'fp32') else self.bf16_mode
+        return linear(x, self.weight, self.bias, mode)
 
 
 def set_precision(module: tnn.Module, precision: str) -> None:

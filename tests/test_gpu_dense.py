@@ -72,6 +72,23 @@ def test_bf16_linear_within_documented_bound(G, rows, K, OUT):
         assert float((a.cpu() - r).abs().max()) <= 3e-2 * float(r.abs().max())
 
 
+@pytest.mark.parametrize('rows,K,OUT', [(1000, 960, 80), (513, 640, 80)])
+def test_bf16x2_linear(G, rows, K, OUT):
+    """'bf16x2' (two bf16 parts per operand, three K-segments; PNA post_nn in precision 'bf16'): 1e-4 of max."""
+    from dp_gsat_b200 import dense
+    g = torch.Generator().manual_seed(K)
+    x, w, b = torch.randn(rows, K, generator=g), torch.randn(OUT, K, generator=g) / K ** 0.5, torch.randn(OUT, generator=g)
+    dy = torch.randn(rows, OUT, generator=g)
+    ref = [t.clone().requires_grad_(True) for t in (x, w, b)]
+    y_r = torch.nn.functional.linear(*ref)
+    y_r.backward(dy)
+    got = [t.clone().cuda().requires_grad_(True) for t in (x, w, b)]
+    y = dense.linear(got[0], got[1], got[2], 'bf16x2')
+    y.backward(dy.cuda())
+    for a, r in zip([y, got[0].grad, got[1].grad, got[2].grad], [y_r, ref[0].grad, ref[1].grad, ref[2].grad]):
+        assert float((a.detach().cpu() - r.detach()).abs().max()) <= 1e-4 * float(r.detach().abs().max())
+
+
 @pytest.mark.parametrize('rows,C,relu', [(1000, 80, False), (5000, 128, True), (37, 64, False), (2, 16, True)])
 def test_batch_norm_matches_torch(G, rows, C, relu):
     from dp_gsat_b200 import dense

@@ -16,6 +16,7 @@ import pytest
 import tests.test_gpu_parity as P
 import tests.test_gpu_tc as T
 import tests.test_gpu_z_next_rows as Z
+import tests.test_gpu_dense as D
 
 
 @pytest.fixture
@@ -86,6 +87,12 @@ CASES = [
     _case(T.test_gsat_step_bf16_mode_tracks_oracle),
     _case(T.test_word_dropout_rate_and_scale, p=0.3),
     _case(T.test_bf16_mode_layer_by_layer_path, case='mutag_dual_big_graphs'),
+    _case(T.test_gsat_pna_step_bf16_mode, use_edge_attr=True),
+    _case(D.test_bf16x2_linear, rows=513, K=640, OUT=80),
+    _case(D.test_strict_linear_matches_fp32, rows=513, K=10, OUT=64),
+    _case(D.test_strict_linear_matches_fp32, rows=129, K=3, OUT=3),
+    _case(D.test_batch_norm_matches_torch, rows=1000, C=80, relu=False),
+    _case(D.test_batch_norm_matches_torch, rows=2, C=16, relu=True),
     # SURVEY 8f rows built after the GPU budget was spent: emulator runs are all they have had so far
     _case(Z.test_le_aggregate_fwd_bwd, H=32, with_w=True, with_att=True),
     _case(Z.test_le_aggregate_fwd_bwd, H=300, with_w=True, with_att=True),
