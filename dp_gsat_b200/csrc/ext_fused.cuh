@@ -28,6 +28,7 @@ constexpr int EXT_CTL_REGS = 56, EXT_PRO_REGS = 96, EXT_EPI_REGS = 176;      // 
 
 __host__ __device__ inline int pad8(int n) { return (n + 7) & ~7; }
 __host__ __device__ inline int pad16(int n) { return (n + 15) & ~15; }
+__host__ __device__ inline int pad128(int n) { return (n + 127) & ~127; }
 
 // Per-warp view of a tile's segments, held in registers: lane s < nseg owns segment s.
 struct SegTable {

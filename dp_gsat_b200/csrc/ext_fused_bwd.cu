@@ -34,14 +34,15 @@ struct BwdParams {
     const float* rstd2;          // [G, H]
     Dropout drop1, drop2;
     const uint32_t* seeds;       // [2] effective seeds written by the forward (null: injected masks / no dropout)
-    uint16_t* dz2t;              // bf16 [H, ld_slots]
-    uint16_t* dz1t;              // bf16 [C1, ld_slots]
-    uint16_t* h1t;               // bf16 [C1, ld_slots]
+    uint16_t* dz2t;              // bf16 slot space, tile-major [tiles][pad128(H)][128]
+    uint16_t* dz1t;              // bf16 [tiles][pad128(C1)][128]
+    uint16_t* h1t;               // bf16 [tiles][pad128(C1)][128]
     float* df12;                 // [rows, Kin]
     float* dw3_part;             // [grid, H]
     int64_t ld_slots;
     int ldx;
     int H, Kin, C1, KB1, KBH, NCB, KM, NW;
+    int HP, C1P;                 // pad128(H), pad128(C1): channel rows per tile block of the slot-space tensors
     int xkb;
     float eps;
     long long* dbg;
@@ -438,8 +439,8 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                         w_dx += clock64() - t0;
                         tc::tc_fence_after();
                         for (int sl = 0; sl < 2; ++sl) {              // channel-major slot-space operands of dW1 / dW2
-                            tc::tma_store_2d(&tm_dz1, smem + L.dz1 + sl * BRICK, tile * TILE_SLOTS + sl * 64, cb * 128);
-                            tc::tma_store_2d(&tm_h1, smem + L.h1 + sl * BRICK, tile * TILE_SLOTS + sl * 64, cb * 128);
+                            tc::tma_store_2d(&tm_dz1, smem + L.dz1 + sl * BRICK, sl * 64, tile * p.C1P + cb * 128);
+                            tc::tma_store_2d(&tm_h1, smem + L.h1 + sl * BRICK, sl * 64, tile * p.C1P + cb * 128);
                         }
                         tc::tma_store_commit();
                         const int nk = kblocks_in_cb(p.C1, cb);
@@ -479,8 +480,8 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                             tc::mbar_wait(dz2_ready, ti & 1);
                             w_in += clock64() - t0;
                             tc::tc_fence_after();
-                            tc::tma_store_2d(&tm_dz2, smem + L.dz2, tile * TILE_SLOTS, 0);
-                            tc::tma_store_2d(&tm_dz2, smem + L.dz2 + BRICK, tile * TILE_SLOTS + 64, 0);
+                            tc::tma_store_2d(&tm_dz2, smem + L.dz2, 0, tile * p.HP);
+                            tc::tma_store_2d(&tm_dz2, smem + L.dz2 + BRICK, 64, tile * p.HP);
                             tc::tma_store_commit();
                         }
                         for (int kb = 0; kb < p.KBH; ++kb) {          // dh1 = W2^T[cb] dz2
@@ -522,8 +523,8 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                     (void)cap;
                     tc::mbar_wait(dz2_empty, (ti & 1) ^ 1);
                     tc::mbar_arrive_expect_tx(x2_full, 2 * BRICK);
-                    tc::tma_load_2d(smem + L.dz2, &tm_x2, x2_full, tile * TILE_SLOTS, 0);
-                    tc::tma_load_2d(smem + L.dz2 + BRICK, &tm_x2, x2_full, tile * TILE_SLOTS + 64, 0);
+                    tc::tma_load_2d(smem + L.dz2, &tm_x2, x2_full, 0, tile * p.HP);
+                    tc::tma_load_2d(smem + L.dz2 + BRICK, &tm_x2, x2_full, 64, tile * p.HP);
                 }
             }
         }
@@ -536,6 +537,35 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
         float dw3 = 0.f;
         uint32_t n = 0, ti = 0;
         long long w_head = 0, t_head = 0, w_cb = 0, t_cb = 0, w_dxf = 0, t_dx = 0, t0;
+        // d f12^T -> d f12 rows of one tile (warpgroup e takes the 128-channel blocks mb % 2 == e).  Deferred: it runs AFTER the
+        // head of the NEXT tile, so the wait for the tile's last dx GEMM overlaps that head instead of stalling the epilogue.
+        auto dx_out = [&](const SegTable& tq, uint32_t tiq) {
+            t0 = clock64();
+            tc::group_mbar_wait(gtid == 0, dx_full, tiq & 1, BAR_EPI + e, 128);
+            w_dxf += clock64() - t0;
+            t0 = clock64();
+            tc::tc_fence_after();
+            for (int mb = e; mb < p.KM; mb += 2) {
+                const int k = mb * 128 + gtid;
+                const uint32_t taddr = tmem_base + 256 + mb * 128 + ((uint32_t)(q * 32) << 16);
+                for (int s = 0; s < tq.nseg; ++s) {
+                    const int ns = __shfl_sync(0xffffffffu, tq.n, s);
+                    if (ns == 0) continue;
+                    const int nblk = pad8(ns) >> 3;
+                    const int slot0 = __shfl_sync(0xffffffffu, tq.slot0, s), row0 = __shfl_sync(0xffffffffu, tq.row0, s);
+                    for (int c4 = 0; c4 < nblk; c4 += 4) {
+                        const int nbk = nblk - c4 < 4 ? nblk - c4 : 4;
+                        float* out = k < p.Kin ? p.df12 + (int64_t)(row0 + 8 * c4) * p.Kin + k : nullptr;
+                        EXT_DISPATCH_NB4(nbk, (dx_chunk_out<NB>(taddr + slot0 + 8 * c4, out, p.Kin, ns - 8 * c4)));
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(dx_empty);
+            t_dx += clock64() - t0;
+        };
+        SegTable tb_prev;
+        bool have_prev = false;
         for (int tile = blockIdx.x; tile < T; tile += gridDim.x, ++ti) {
             const SegTable tb = load_seg_table(p.tile_seg, p.seg_ptr, tile, lane);
             // ---------- head: x^2, d logit -> dz2 (graphs s % 2 == e) ----------
@@ -592,6 +622,7 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                 tc::mbar_arrive(dz2_ready);
                 t_head += clock64() - t0;
             }
+            if (have_prev) dx_out(tb_prev, ti - 1);      // the previous tile's input gradient (see dx_out)
             // ---------- per channel block: InstanceNorm-1 backward (graphs s % 2 == e) ----------
             const DropCtx dc = make_drop_ctx(p.drop1, seed1, p.C1);
             int last_s = -1;                   // this warpgroup's last non-empty graph of the tile
@@ -671,31 +702,10 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                 tc::mbar_arrive(dz1_full);
                 t_cb += clock64() - t0;
             }
-            // ---------- d f12^T -> d f12 rows (warpgroup e takes the 128-channel blocks mb % 2 == e) ----------
-            t0 = clock64();
-            tc::group_mbar_wait(gtid == 0, dx_full, ti & 1, BAR_EPI + e, 128);
-            w_dxf += clock64() - t0;
-            t0 = clock64();
-            tc::tc_fence_after();
-            for (int mb = e; mb < p.KM; mb += 2) {
-                const int k = mb * 128 + gtid;
-                const uint32_t taddr = tmem_base + 256 + mb * 128 + ((uint32_t)(q * 32) << 16);
-                for (int s = 0; s < tb.nseg; ++s) {
-                    const int ns = __shfl_sync(0xffffffffu, tb.n, s);
-                    if (ns == 0) continue;
-                    const int nblk = pad8(ns) >> 3;
-                    const int slot0 = __shfl_sync(0xffffffffu, tb.slot0, s), row0 = __shfl_sync(0xffffffffu, tb.row0, s);
-                    for (int c4 = 0; c4 < nblk; c4 += 4) {
-                        const int nbk = nblk - c4 < 4 ? nblk - c4 : 4;
-                        float* out = k < p.Kin ? p.df12 + (int64_t)(row0 + 8 * c4) * p.Kin + k : nullptr;
-                        EXT_DISPATCH_NB4(nbk, (dx_chunk_out<NB>(taddr + slot0 + 8 * c4, out, p.Kin, ns - 8 * c4)));
-                    }
-                }
-            }
-            tc::tc_fence_before();
-            tc::mbar_arrive(dx_empty);
-            t_dx += clock64() - t0;
+            tb_prev = tb;
+            have_prev = true;
         }
+        if (have_prev) dx_out(tb_prev, ti - 1);
         if (p.dbg && gtid == 0 && e == 0) {
             long long* d = p.dbg + (size_t)blockIdx.x * 16 + 6;
             d[0] = w_head, d[1] = t_head, d[2] = w_cb, d[3] = t_cb, d[4] = w_dxf, d[5] = t_dx;
@@ -726,7 +736,7 @@ extern "C" int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_s
     const int Kin = edge_mode ? 2 * H : H;
     if (H % 8 != 0 || H > 128 || Kin > 256 || C1 > 512) return GSATB_ESHAPE;
     if (max_slots != gsatb_ext_tile_slots(H, edge_mode)) return GSATB_EINVAL;
-    if (ld_slots % 8 != 0) return GSATB_EINVAL;
+    if (ld_slots % TILE_SLOTS != 0) return GSATB_EINVAL;
     if (!gsatb_aligned16(xhat2t) || !gsatb_aligned16(dz2t) || !gsatb_aligned16(dz1t) || !gsatb_aligned16(h1t) || !gsatb_aligned16(xs))
         return GSATB_EALIGN;
     BwdParams p;
@@ -741,6 +751,7 @@ extern "C" int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_s
     p.df12 = df12, p.dw3_part = dw3_part, p.ld_slots = ld_slots;
     p.H = H, p.Kin = Kin, p.C1 = C1, p.KB1 = (Kin + 63) / 64, p.KBH = (H + 63) / 64, p.NCB = (C1 + 127) / 128;
     p.KM = (Kin + 127) / 128;
+    p.HP = pad128(H), p.C1P = pad128(C1);
     p.ldx = p.KB1 * 64;
     p.xkb = max_slots * 128;
     p.eps = eps;
@@ -759,11 +770,15 @@ extern "C" int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_s
     rc = make_weight_tmap(&tm1t, w1t_bf16_padded, p.KM * 128, ((C1 + 63) / 64) * 64);  // W1^T [Kin, C1]
     if (rc != GSATB_OK) return rc;
     CUtensorMap tdz2, tdz1, th1, txs;
-    auto slot_map = [&](CUtensorMap* tm, const void* base, int C) -> int {      // channel-major slot space [C, ld_slots]
+    // slot-space tensors are TILE-major [tiles][pad128(C)][128 slots]: one contiguous block per tile, so the [128 channels x
+    // 64 slots] boxes the kernels move are 128-byte pieces 256 bytes apart inside one 32 KiB run (not 128-byte pieces
+    // ld_slots * 2 bytes apart).  As a 2-D map: rows = tile * pad128(C) + channel, 128 columns.
+    const int64_t tiles = ld_slots / TILE_SLOTS;
+    auto slot_map = [&](CUtensorMap* tm, const void* base, int C) -> int {
         PFN_tmapEncodeTiled fn = get_encode_fn();
         if (!fn) return GSATB_ELAUNCH;
-        cuuint64_t gdim[2] = {(cuuint64_t)ld_slots, (cuuint64_t)C};
-        cuuint64_t gstride[1] = {(cuuint64_t)ld_slots * 2};
+        cuuint64_t gdim[2] = {(cuuint64_t)TILE_SLOTS, (cuuint64_t)(tiles * pad128(C))};
+        cuuint64_t gstride[1] = {(cuuint64_t)TILE_SLOTS * 2};
         cuuint32_t box[2] = {64, 128}, estr[2] = {1, 1};
         return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

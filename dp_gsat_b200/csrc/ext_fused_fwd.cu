@@ -35,7 +35,7 @@ struct FwdParams {
     const float* b3;             // nullable
     Dropout drop1, drop2;
     float* logit;                // [rows]
-    uint16_t* xhat2t;            // bf16 [H, ld_slots] (slot space: tile t owns columns [128 t, 128 t + 128)), nullable
+    uint16_t* xhat2t;            // bf16 slot space, TILE-major [tiles][pad128(H)][128 slots] (one contiguous block per tile), nullable
     int64_t ld_slots;
     float* rstd2;                // [G, H] InstanceNorm-2 reciprocal standard deviations (for the backward), nullable
     int dump_xs;                 // store every centred bf16 input tile to xs [tiles * 128, pad64(Kin)] (TMA), for the backward
@@ -449,7 +449,7 @@ k_ext_fused_fwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
             t0 = clock64();
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + 256 + b2 * 128 + ((uint32_t)(q * 32) << 16);
-            uint16_t* xrow = p.xhat2t && ch_ok ? p.xhat2t + (int64_t)ch * p.ld_slots + (int64_t)tile * TILE_SLOTS : nullptr;
+            uint16_t* xrow = p.xhat2t && ch_ok ? p.xhat2t + ((int64_t)tile * pad128(p.H) + ch) * TILE_SLOTS : nullptr;
             Epi2Ctx c2;
             c2.taddr = taddr, c2.redq_s = red_s + 4 * (q * 128), c2.xrow = xrow, c2.ch = ch, c2.lane = lane, c2.ch_ok = ch_ok;
             c2.eps = p.eps, c2.w3s = dscale * w3;

@@ -7,6 +7,8 @@
 //   row-major     [rows, C]  (ld = elements per row)      -> TMA boxes of 64 channels x 64 rows = an MN-major
 //                                                            SWIZZLE_128B operand tile (K = rows runs across smem rows)
 //   channel-major [C, rows]  (ld = elements per channel)  -> TMA boxes of 64 rows x 128 channels = the usual K-major tile
+//   tile-major    [rows / 128][ld channels][128 rows]       -> the same boxes out of one contiguous block per 128 rows (the
+//                                                            slot space of the fused extractor kernels, layout code 2)
 // so no transposed copy of an activation is ever made.
 //
 // Split-K over the rows: grid = (splits, slabs); a slab is one 128-channel block of A times up to 256 channels of B
@@ -28,7 +30,8 @@ constexpr int DW_BIAS_COLS = 16;
 struct DwParams {
     int64_t rows;
     int M, N;            // channels of A (output rows of D) and of B (output columns of D)
-    int a_cm, b_cm;      // 1: channel-major operand
+    int a_cm, b_cm;      // 1: channel-major operand, 2: tile-major (channel-major inside blocks of 128 rows)
+    int lda, ldb;        // tile-major operands: channel rows per 128-row block
     int n_chunk;         // B channels per slab: multiple of 64, <= 256
     int n_chunks;        // slabs per A block
     int splits;
@@ -96,13 +99,18 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
                 uint8_t* sA = smem + (size_t)s * stage_bytes;
                 uint8_t* sB = sA + DW_A_BYTES;
                 const int r = (int)(st * DW_KSTEP);
-                if (p.a_cm) {
+                if (p.a_cm == 2) {
+                    tc::tma_load_2d(sA, &tmap_a, &full[s], r & 127, (r >> 7) * p.lda + mb * 128);
+                } else if (p.a_cm) {
                     tc::tma_load_2d(sA, &tmap_a, &full[s], r, mb * 128);                       // box {64 rows, 128 ch}
                 } else {
                     tc::tma_load_2d(sA, &tmap_a, &full[s], mb * 128, r);                       // box {64 ch, 64 rows}
                     tc::tma_load_2d(sA + 8192, &tmap_a, &full[s], mb * 128 + 64, r);
                 }
-                if (p.b_cm) {
+                if (p.b_cm == 2) {
+                    for (int j = 0; j * 128 < p.n_chunk; ++j)
+                        tc::tma_load_2d(sB + j * 16384, &tmap_b, &full[s], r & 127, (r >> 7) * p.ldb + nc * p.n_chunk + j * 128);
+                } else if (p.b_cm) {
                     for (int j = 0; j * 128 < p.n_chunk; ++j)
                         tc::tma_load_2d(sB + j * 16384, &tmap_b, &full[s], r, nc * p.n_chunk + j * 128);
                 } else {
@@ -217,7 +225,12 @@ inline int make_dw_tmap(CUtensorMap* tm, const void* x, int64_t rows, int C, int
     if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0 || (ld % 8) != 0) return GSATB_EALIGN;
     cuuint64_t gdim[2], gstride[1];
     cuuint32_t box[2], estr[2] = {1, 1};
-    if (cm) {
+    if (cm == 2) {      // [rows / 128][ld][128]: rows of the map = block * ld + channel, 128 columns
+        if (rows % 128 != 0 || ld % 128 != 0 || ld < C) return GSATB_ESHAPE;
+        gdim[0] = 128, gdim[1] = (cuuint64_t)(rows / 128) * (cuuint64_t)ld;
+        box[0] = 64, box[1] = 128;
+        ld = 128;
+    } else if (cm) {
         gdim[0] = (cuuint64_t)rows, gdim[1] = (cuuint64_t)C;
         box[0] = 64, box[1] = 128;
     } else {
@@ -254,6 +267,7 @@ extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda,
         return GSATB_OK;
     }
     if (!a_bf16 || !b_bf16 || !workspace) return GSATB_EINVAL;
+    if (a_channel_major < 0 || a_channel_major > 2 || b_channel_major < 0 || b_channel_major > 2) return GSATB_EINVAL;
     const DwPlan d = dw_plan(rows, M, N, b_channel_major ? 1 : 0);
     if (ws_bytes < d.ws_bytes) return GSATB_EWS_TOO_SMALL;
     if (d.stages < 2) return GSATB_ESHAPE;
@@ -262,7 +276,7 @@ extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda,
     if (rc != GSATB_OK) return rc;
     rc = make_dw_tmap(&tb, b_bf16, rows, N, ldb, b_channel_major);
     if (rc != GSATB_OK) return rc;
-    DwParams p{rows, M, N, a_channel_major ? 1 : 0, b_channel_major ? 1 : 0, d.n_chunk, d.n_chunks, d.splits, d.stages,
+    DwParams p{rows, M, N, a_channel_major, b_channel_major, (int)lda, (int)ldb, d.n_chunk, d.n_chunks, d.splits, d.stages,
                (float*)workspace};
     if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return GSATB_ELAUNCH;

@@ -190,18 +190,19 @@ class _FusedExtractor(torch.autograd.Function):
         return (demb, dW1, db1, dW2, db2, dw3, db3, None, None, None, None, None, None, None, None)
 
 
-def weight_grad(a16: torch.Tensor, a_channel_major: bool, b16: torch.Tensor, b_channel_major: bool, rows: int, M: int,
-                N: int, want_bias: bool = False):
+def weight_grad(a16: torch.Tensor, a_layout, b16: torch.Tensor, b_layout, rows: int, M: int, N: int,
+                want_bias: bool = False):
     """dW [M, N] = sum_r A[r, m] B[r, n] (and db [M] = sum_r A[r, m]) on the tensor cores (gsatb_tc_dw: split-K tcgen05
-    GEMM with a fixed-order reduction).  A / B are bf16, row-major [rows, C] or channel-major [C, rows]; the leading
-    dimension is the tensor's stride(0)."""
+    GEMM with a fixed-order reduction).  A / B are bf16 in layout 0 = row-major [rows, C], 1 = channel-major [C, rows]
+    (leading dimension = stride(0)) or 2 = tile-major [rows / 128, Cpad, 128] (leading dimension = Cpad)."""
     dev = a16.device
     dW = torch.empty((M, N), dtype=torch.float32, device=dev)
     db = torch.empty(M, dtype=torch.float32, device=dev) if want_bias else None
     nb = int(lib().cdll.gsatb_tc_dw_workspace(rows, M, N))
     ws = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
-    lib().call('gsatb_tc_dw', ptr(a16), int(a_channel_major), int(a16.stride(0)), ptr(b16), int(b_channel_major),
-               int(b16.stride(0)), rows, M, N, ptr(dW), N, ptr(db), 0, ptr(ws), ctypes.c_size_t(nb), stream())
+    ld = lambda t, lay: int(t.shape[1]) if int(lay) == 2 else int(t.stride(0))
+    lib().call('gsatb_tc_dw', ptr(a16), int(a_layout), ld(a16, a_layout), ptr(b16), int(b_layout), ld(b16, b_layout), rows, M, N,
+               ptr(dW), N, ptr(db), 0, ptr(ws), ctypes.c_size_t(nb), stream())
     return dW, db
 
 
@@ -220,9 +221,9 @@ def fused_extractor_supported(emb: torch.Tensor, gi: GraphIndex, edge_mode: bool
 
 class _FusedExtractorV2(torch.autograd.Function):
     """The whole extractor MLP as ONE persistent tcgen05 kernel per direction (csrc/ext_fused_fwd.cu, ext_fused_bwd.cu):
-    forward keeps nothing of width 4H in HBM (saved for backward: the logits' inputs xhat2 [H, slots] bf16, rstd2, the
+    forward keeps nothing of width 4H in HBM (saved for backward: the logits' inputs xhat2 (bf16, tile-major slot space), rstd2, the
     centred input tiles xs and the effective dropout seeds); backward recomputes GEMM1, leaves the bf16 operands of the
-    weight-gradient products in channel-major slot space and gsatb_tc_dw turns them into dW1 / dW2; the node gradient is
+    weight-gradient products in tile-major slot space ([tiles, channels, 128 slots]) and gsatb_tc_dw turns them into dW1 / dW2; the node gradient is
     the deterministic CSR reduction of d f12.  b1 / b2 sit in front of an InstanceNorm and get exact zeros."""
 
     @staticmethod
@@ -240,7 +241,10 @@ class _FusedExtractorV2(torch.autograd.Function):
         ld = T * 128
         Kin = 2 * H if edge_mode else H
         logit = torch.empty((rows, 1), dtype=torch.float32, device=dev)
-        xh2t = torch.empty((H, ld), dtype=torch.bfloat16, device=dev) if need_grad else None
+        # tile-major slot space; the kernel writes channels < H only, and the backward's TMA boxes cover all pad128(H)
+        # channel rows of a block: the padding rows must read as zero (they meet zero weight columns in dh1 = W2^T dz2)
+        xh2t = (torch.empty if H % 128 == 0 else torch.zeros)((T, _pad(H, 128), 128), dtype=torch.bfloat16, device=dev) \
+            if need_grad else None
         rstd2 = torch.empty((max(gi.G, 1), H), dtype=torch.float32, device=dev) if need_grad else None
         xs = _xs_buffer(plan, ld, _pad(Kin, 64), dev) if need_grad else None
         token = object()
@@ -276,7 +280,8 @@ class _FusedExtractorV2(torch.autograd.Function):
         L = lib()
         dl = dlogit.contiguous().view(-1).float()
         bf = dict(dtype=torch.bfloat16, device=dev)
-        dz2t, dz1t, h1t = torch.empty((H, ld), **bf), torch.empty((C1, ld), **bf), torch.empty((C1, ld), **bf)
+        HP, C1P = _pad(H, 128), _pad(C1, 128)
+        dz2t, dz1t, h1t = torch.empty((T, HP, 128), **bf), torch.empty((T, C1P, 128), **bf), torch.empty((T, C1P, 128), **bf)
         df12 = torch.empty((rows, Kin), dtype=torch.float32, device=dev)
         nslab = 2 * min(max(gi.G, 1), 148)
         dw3p = torch.zeros((nslab, H), dtype=torch.float32, device=dev)
@@ -285,8 +290,8 @@ class _FusedExtractorV2(torch.autograd.Function):
                ptr(w1p), ptr(w2t), ptr(w1t), ptr(w3f), ptr(dl), ptr(xh2t), ptr(rstd2), ptr(xs), ptr(mask1), ptr(mask2),
                ptr(seeds), ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), ptr(dw3p), ld, rows,
                H, C1, ctypes.c_float(eps), stream())
-        dW2, _ = weight_grad(dz2t, True, h1t, True, ld, H, C1)
-        dW1, _ = weight_grad(dz1t, True, xs, False, ld, C1, Kin)
+        dW2, _ = weight_grad(dz2t, 2, h1t, 2, ld, H, C1)
+        dW1, _ = weight_grad(dz1t, 2, xs, 0, ld, C1, Kin)
         del dz1t, h1t, dz2t
         if e:
             demb = torch.empty((N, H), dtype=torch.float32, device=dev)

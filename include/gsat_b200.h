@@ -380,7 +380,8 @@ int gsatb_tc_ext_make_f12(const float* emb, const int32_t* src, const int32_t* d
  *   contiguous node rows weighted by out- / in-degree (node_ptr, rowptr_src, rowptr_dst of the GraphIndex).  mask1 [rows, C1] / mask2
  *   [rows, H] inject dropout masks (parity tests); otherwise masks come from (seed, step counter, row, channel) and the
  *   effective seeds are written to seed_out[2] for the backward pass.  xhat2t (nullable): the InstanceNorm-2 output as
- *   bf16 in SLOT space [H, ld_slots], tile t owning columns [128 t, 128 t + 128) -- what the backward needs of the
+ *   bf16 in SLOT space, tile-major [ld_slots / 128 tiles][pad128(H) channels][128 slots] (one contiguous block per tile;
+ *   channel rows >= H must be zero-initialised by the caller when H % 128 != 0) -- what the backward needs of the
  *   forward besides the logits.  max_tiles >= T bounds the grid (pass G).  H % 8 == 0, H <= 128. */
 int gsatb_ext_tile_slots(int H, int edge_mode);
 int gsatb_ext_tile_plan(const int32_t* seg_ptr, int64_t G, int max_slots, int32_t* tile_seg, int32_t* out2,
@@ -401,8 +402,9 @@ int gsatb_ext_fused_fwd(const float* emb, const int32_t* src /* [nullable] */, c
  *   d logit [rows], xhat2t / rstd2 / seeds as the forward wrote them, W2^T and W1^T from
  *   gsatb_tc_prep_weight(transpose = 1).  Outputs: d f12 [rows, Kin] fp32 (Kin = 2H, or H in node mode: then it IS d emb;
  *   edge mode: reduce with gsatb_gather_concat_bwd), dw3_part [min(max_tiles, 148) * 2, H] partial sums of d w3 (add
- *   them up), and the bf16 operands of the weight-gradient products in channel-major slot space, written with TMA stores:
- *   dz2t [H, ld_slots], dz1t [C1, ld_slots], h1t [C1, ld_slots], so that dW2 = gsatb_tc_dw(dz2t, h1t) and
+ *   them up), and the bf16 operands of the weight-gradient products in tile-major slot space, written with TMA stores:
+ *   dz2t [tiles][pad128(H)][128], dz1t and h1t [tiles][pad128(C1)][128] (layout code 2 of gsatb_tc_dw: every 128-channel x
+ *   64-slot box is a 32 KiB-local access instead of 128-byte pieces a whole row apart), so that dW2 = gsatb_tc_dw(dz2t, h1t) and
  *   dW1 = gsatb_tc_dw(dz1t, xs) with rows = ld_slots (slots outside the graphs are zero in dz1t / dz2t / h1t; xs must have
  *   been allocated zero-filled: rows [128 t + max_slots, 128 t + 128) are never written).  d b1 = d b2 = 0 exactly (the
  *   biases cancel in the InstanceNorms); d b3 = sum(d logit). */
@@ -417,7 +419,8 @@ int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_seg, const i
 /* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
  * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through
  * loss.backward() at src/run_gsat.py:634; round 1 ran them as library GEMMs).  A and B are bf16 activations, each either
- * row-major [rows, C] (ld = elements per row) or channel-major [C, rows] (ld = elements per channel): TMA loads them as
+ * row-major [rows, C] (layout 0, ld = elements per row), channel-major [C, rows] (layout 1, ld = elements per channel) or
+ * tile-major [rows / 128][ld channels][128 rows] (layout 2, ld = channel rows per block, a multiple of 128): TMA loads them as
  * MN-major / K-major SWIZZLE_128B operand tiles, so no transposed copy is made.  Split-K over the rows with a
  * fixed-order reduction of the per-CTA partials: run-to-run deterministic.  dW is row-major [M, ldo] fp32 (the layout of
  * nn.Linear.weight.grad for A = dz, B = layer input); db [M] nullable; accumulate != 0 adds to dW / db in place.

@@ -18,7 +18,7 @@ def fwd(emb, gi, w1, w2, w3, b3, edge, m1=None, m2=None, pdrop=0.0, training=0, 
     plan = gi.ext_plan('edge' if edge else 'node', ms)
     rows, T = plan['rows'], plan['T']
     logit = torch.empty(rows, device=dev)
-    xh2t = torch.empty(H, T * 128, dtype=torch.bfloat16, device=dev) if want_x else None
+    xh2t = torch.zeros(T, (H + 127) // 128 * 128, 128, dtype=torch.bfloat16, device=dev) if want_x else None      # tile-major
     seeds = torch.zeros(2, dtype=torch.int32, device=dev)
     w1p, w2p = tc.prep_weight(w1), tc.prep_weight(w2)
     L.call('gsatb_ext_fused_fwd', ptr(emb), ptr(gi.src) if edge else None, ptr(gi.dst) if edge else None,
@@ -145,7 +145,8 @@ def bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds_xs, edge, m1=None, m2=No
     rows, T = plan['rows'], plan['T']
     ld = T * 128
     bf = dict(dtype=torch.bfloat16, device=dev)
-    dz2t, dz1t, h1t = torch.empty(H, ld, **bf), torch.empty(C1, ld, **bf), torch.empty(C1, ld, **bf)
+    HP, C1P = (H + 127) // 128 * 128, (C1 + 127) // 128 * 128
+    dz2t, dz1t, h1t = torch.empty(T, HP, 128, **bf), torch.empty(T, C1P, 128, **bf), torch.empty(T, C1P, 128, **bf)
     df12 = torch.empty(rows, Kin, device=dev)
     dw3p = torch.zeros(min(max(gi.G, 1), 148) * 2, H, device=dev)
     w1p, w2t, w1t = tc.prep_weight(w1), tc.prep_weight(w2, transpose=True), tc.prep_weight(w1, transpose=True)
@@ -174,7 +175,7 @@ def fwd_full(emb, gi, w1, w2, w3, b3, edge, m1, m2, pdrop, training, seed=3):
     plan = gi.ext_plan('edge' if edge else 'node', ms)
     rows, T = plan['rows'], plan['T']
     logit = torch.empty(rows, device=dev)
-    xh2t = torch.empty(H, T * 128, dtype=torch.bfloat16, device=dev)
+    xh2t = torch.zeros(T, (H + 127) // 128 * 128, 128, dtype=torch.bfloat16, device=dev)
     rstd2 = torch.empty(max(gi.G, 1), H, device=dev)
     seeds = torch.zeros(2, dtype=torch.int32, device=dev)
     Kin = 2 * H if edge else H
@@ -217,8 +218,9 @@ def check_bwd(H, n_graphs, edge=True, masks=False, gen='ba'):
     src, dst = (gi.src.long(), gi.dst.long()) if edge else (None, None)
     e_df, e_dW1, e_dW2, e_dw3 = extractor_backward_emulated(emb, src, dst, seg, w1, w2, w3, dlogit, m1, m2, pd if masks else 0.0)
     rel = lambda a, c: ((a.double() - c.double()).norm() / c.double().norm().clamp_min(1e-30)).item()
-    dW2 = dz2t.float() @ h1t.float().t()
-    dW1 = dz1t.float() @ xs.float()[:, :Kin]
+    cm = lambda t, C: t.float().permute(1, 0, 2).reshape(t.shape[1], -1)[:C]      # tile-major -> [C, slots]
+    dW2 = cm(dz2t, H) @ cm(h1t, C1).t()
+    dW1 = cm(dz1t, C1) @ xs.float()[:, :Kin]
     errs = [rel(df12, e_df), rel(dW1, e_dW1), rel(dW2, e_dW2), rel(dw3p.sum(0), e_dw3)]
     ok = all(e < 5e-3 for e in errs)
     print(f'bwd H={H} graphs={n_graphs} rows={rows} edge={edge} masks={masks}: vs same-rounding emulation df12 {errs[0]:.2e} '
