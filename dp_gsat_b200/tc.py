@@ -307,13 +307,17 @@ class _FusedExtractorV2(torch.autograd.Function):
 
 
 def _xs_buffer(plan: dict, rows: int, ldx: int, dev) -> torch.Tensor:
-    """The centred-input dump of the fused forward, [tiles * 128, pad64(Kin)] bf16, cached with the tile plan: it is
-    allocated ZERO-FILLED once (rows [128 t + max_slots, 128 t + 128) are never written and meet zero columns of dz1t in
-    dW1) and re-used by every step on this batch."""
+    """The centred-input dump of the fused forward, [tiles * 128, pad64(Kin)] bf16, cached with the tile plan and re-used by
+    every step on this batch.  The kernel writes rows [128 t, 128 t + max_slots) of every tile; the remaining rows of a
+    tile are never written and meet zero columns of dz1 in dW1, so they only have to be finite: they are zeroed ONCE here
+    (a strided fill of 128 - max_slots rows per tile, not a memset of the whole buffer)."""
     key = ('xs', ldx)
     buf = plan.get(key)
     if buf is None or buf.shape[0] != rows or buf.device != dev:
-        buf = torch.zeros((rows, ldx), dtype=torch.bfloat16, device=dev)
+        buf = torch.empty((rows, ldx), dtype=torch.bfloat16, device=dev)
+        ms = int(plan['max_slots'])
+        if ms < 128:
+            buf.view(rows // 128, 128, ldx)[:, ms:, :].zero_()
         plan[key] = buf
     return buf
 
