@@ -38,7 +38,56 @@ __device__ __forceinline__ uint16_t split_part(float v, int part) {
     return bf16_bits(r1 - bf16_val(m));
 }
 
-// one thread = 8 consecutive output elements of one output row (one 16-byte store)
+// Fast path (C % 8 == 0, 16-byte aligned rows): one thread = 8 consecutive INPUT elements of a row -- two 128-bit loads,
+// the three parts computed once, one 128-bit store per segment.  Every input element is read once however many segments
+// are written (the generic path below re-reads and re-splits it per segment and divides by C per element).
+__global__ void __launch_bounds__(256)
+k_split_bf16_vec(const float* __restrict__ x, int64_t rows, int C, int64_t ldx, int nseg, uint32_t pattern, int layout,
+                 uint16_t* __restrict__ out, int64_t ld_out) {
+    const int cpr = C >> 3;                                  // 8-element chunks per input row
+    const int64_t total = rows * cpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cpr;
+        const int c0 = (int)(i - r * cpr) << 3;
+        const float4 a = *reinterpret_cast<const float4*>(x + r * ldx + c0);
+        const float4 b = *reinterpret_cast<const float4*>(x + r * ldx + c0 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint16_t part[3][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint16_t h = bf16_bits(v[k]);
+            const float r1 = v[k] - bf16_val(h);
+            const uint16_t m = bf16_bits(r1);
+            part[0][k] = h;
+            part[1][k] = m;
+            part[2][k] = bf16_bits(r1 - bf16_val(m));
+        }
+        for (int s = 0; s < nseg; ++s) {
+            const int ps = (int)((pattern >> (2 * s)) & 3u);
+            const uint16_t* o = ps == 0 ? part[0] : (ps == 1 ? part[1] : part[2]);
+            uint4 q;
+            q.x = (uint32_t)o[0] | ((uint32_t)o[1] << 16);
+            q.y = (uint32_t)o[2] | ((uint32_t)o[3] << 16);
+            q.z = (uint32_t)o[4] | ((uint32_t)o[5] << 16);
+            q.w = (uint32_t)o[6] | ((uint32_t)o[7] << 16);
+            uint16_t* dst = layout == 0 ? out + r * ld_out + (int64_t)s * C + c0 : out + ((int64_t)s * rows + r) * ld_out + c0;
+            *reinterpret_cast<uint4*>(dst) = q;
+        }
+    }
+}
+// zero the padding columns [width, ld_out) of every output row (fast path only; width % 8 == 0)
+__global__ void __launch_bounds__(256)
+k_split_pad_zero(uint16_t* __restrict__ out, int64_t out_rows, int width, int64_t ld_out) {
+    const int cpr = (int)((ld_out - width) >> 3);
+    const int64_t total = out_rows * cpr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cpr;
+        const int c0 = width + ((int)(i - r * cpr) << 3);
+        *reinterpret_cast<uint4*>(out + r * ld_out + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// generic path: one thread = 8 consecutive output elements of one output row (one 16-byte store)
 __global__ void __launch_bounds__(256)
 k_split_bf16(const float* __restrict__ x, int64_t rows, int C, int64_t ldx, int nseg, uint32_t pattern, int layout,
              uint16_t* __restrict__ out, int64_t ld_out) {
@@ -258,9 +307,22 @@ extern "C" int gsatb_split_bf16(const float* x, int64_t rows, int C, int64_t ldx
     if (!gsatb_aligned16(out_bf16)) return GSATB_EALIGN;
     for (int s = 0; s < nseg; ++s)
         if ((((uint32_t)pattern >> (2 * s)) & 3u) > 2u) return GSATB_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C % 8 == 0 && ldx % 4 == 0 && gsatb_aligned16(x)) {
+        const int64_t out_rows = layout == 0 ? rows : rows * nseg;
+        k_split_bf16_vec<<<stream_grid(rows * (C / 8)), 256, 0, st>>>(x, rows, C, ldx, nseg, (uint32_t)pattern, layout,
+                                                                    (uint16_t*)out_bf16, ld_out);
+        GSATB_CHECK_LAUNCH();
+        if (ld_out > width) {
+            k_split_pad_zero<<<stream_grid(out_rows * ((ld_out - width) / 8)), 256, 0, st>>>((uint16_t*)out_bf16, out_rows,
+                                                                                            (int)width, ld_out);
+            GSATB_CHECK_LAUNCH();
+        }
+        return GSATB_OK;
+    }
     const int64_t total = (layout == 0 ? rows : rows * nseg) * (ld_out / 8);
-    k_split_bf16<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(x, rows, C, ldx, nseg, (uint32_t)pattern, layout,
-                                                                       (uint16_t*)out_bf16, ld_out);
+    k_split_bf16<<<stream_grid(total), 256, 0, st>>>(x, rows, C, ldx, nseg, (uint32_t)pattern, layout,
+                                                     (uint16_t*)out_bf16, ld_out);
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }

@@ -34,7 +34,7 @@ PATTERN_B = sum(p << (2 * i) for i, p in enumerate(_PARTS_B))
 # 'bf16x2': two bf16 parts per operand (16 mantissa bits), three K-segments  m h + h m + h h  -- for layers whose
 # gradients are small residuals of large cancelling terms (PNA post_nn in front of BatchNorm, see pna.py)
 _MODES = {'bf16': (1, 0, 0), 'bf16x2': (3, 1 | (0 << 2) | (0 << 4), 0 | (1 << 2) | (0 << 4)), 'fp32': (6, PATTERN_A, PATTERN_B)}
-_CHUNK_BYTES = 1 << 29             # operand bytes staged per row chunk (bounds the 6x expansion of the strict mode)
+_CHUNK_BYTES = 1 << 31             # operand bytes staged per row chunk (bounds the 6x expansion of the strict mode)
 OUT_BLOCK = 512                    # output channels per GEMM launch (four 128-lane accumulators)
 
 

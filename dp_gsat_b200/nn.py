@@ -443,12 +443,11 @@ BOND_FEATURE_DIMS = [5, 6, 2]
 class _SumEmbeddingEncoder(tnn.Module):
     """Sum of one embedding table per integer feature column (ogb 1.3.2 AtomEncoder / BondEncoder).
 
-    ``fused = True`` runs the whole encoder as ONE gather-sum kernel forward and one deterministic backward into the
-    tables (csrc/encoders.cu, SURVEY section 8f row 4) instead of K embedding lookups + K-1 adds and K scatter-adds;
-    results are bit-identical forward (same addition order).  It is opt-in this round: the kernels were written after
-    the round's GPU time was spent and have so far only run on the host SIMT emulator and in tests/test_gpu_z_next_rows.py
-    (``fused = False`` keeps the library embedding lookups the earlier GPU parity runs used)."""
-    fused = False
+    ``fused = True`` (default) runs the whole encoder as ONE gather-sum kernel forward and one deterministic backward into
+    the tables (csrc/encoders.cu) instead of K embedding lookups + K-1 adds and K scatter-adds
+    (sorts + atomics) backward; results are bit-identical forward (same addition order).  ``fused = False`` keeps the library
+    embedding lookups."""
+    fused = True
     _list_name = ''
 
     def _tables(self):

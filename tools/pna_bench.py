@@ -26,19 +26,23 @@ gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=False, final_r=0.7
 gsat.train()
 data = b.to(dev)
 step = TrainStep(gsat, lr=1e-3)
-for _ in range(3):
-    step(data, 0)
-torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-n = 5
-for _ in range(n):
-    step(data, 0)
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / n
-print(f'GSAT-PNA (molhiv-shaped, fp32 strict path): graphs={ng} N={data.num_nodes} E={data.num_edges} H=80 L=4: '
-      f'{ms:.2f} ms/step = {data.num_edges / ms / 1e3:.2f} M edges/s')
+for precision in ('bf16', 'fp32'):
+    clf.precision = ext.precision = precision
+    for _ in range(3):
+        step(data, 0)
+    torch.cuda.synchronize()
+    e0.record()
+    n = 5
+    for _ in range(n):
+        step(data, 0)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    what = {'bf16': "bf16 mode: post_nn as 'bf16x2' tcgen05 GEMM, fc_out / extractor on tcgen05",
+            'fp32': 'fp32 strict mode: split-bf16 x3 tcgen05 GEMMs'}[precision]
+    print(f'GSAT-PNA (molhiv-shaped, {what}): graphs={ng} N={data.num_nodes} E={data.num_edges} H=80 L=4: '
+          f'{ms:.2f} ms/step = {data.num_edges / ms / 1e3:.2f} M edges/s', flush=True)
 gi = G.get_graph_index(data.edge_index, data.batch, data.num_graphs)
 N, E, H = gi.N, gi.E, 80
 x = torch.randn(N, H, device=dev)

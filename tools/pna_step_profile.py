@@ -17,6 +17,7 @@ clf = G.get_model(9, 0, 2, False, cfg, dev)
 ext = G.ExtractorMLP(80, shared).to(dev)
 gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=False, final_r=0.7, lazy_metrics=True)
 gsat.train()
+clf.precision = ext.precision = (sys.argv[2] if len(sys.argv) > 2 else 'bf16')
 data = b.to(dev)
 step = TrainStep(gsat, lr=1e-3)
 for _ in range(3):
@@ -29,5 +30,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 ev = prof.key_averages()
 tot = sum(e.device_time_total for e in ev) / 2
 print(f'# PNA graphs={ng} N={data.num_nodes} E={data.num_edges}: {tot / 1e3:.2f} ms of kernel time per step')
-for e in sorted(ev, key=lambda e: -e.device_time_total)[:22]:
+for e in sorted(ev, key=lambda e: -e.device_time_total)[:30]:
     print(f'{e.device_time_total / 2e3:9.3f} ms {100 * e.device_time_total / 2 / tot:5.1f}% x{e.count // 2:4d}  {e.key[:110]}')
