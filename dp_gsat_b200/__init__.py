@@ -23,10 +23,11 @@ from .pna import PNA, PNAConvSimple  # noqa: E402
 from .dual import line_graph_dual, line_graph_dual_dense, dense_dual_node_features  # noqa: E402
 from .metrics import get_precision_at_k, get_delta_kl  # noqa: E402
 from .loader import Graph, PackedDataset, DeviceLoader  # noqa: E402
-from . import ops  # noqa: E402
+from . import ops, dense  # noqa: E402
+from .dense import Linear  # noqa: E402
 
 __all__ = ['Batch', 'GraphIndex', 'get_graph_index', 'clear_index_cache', 'set_index_cache_capacity', 'GIN', 'GINConv', 'GINEConv', 'LEConv', 'SPMotifNet', 'ExtractorMLP', 'MLP',
            'BatchSequential', 'InstanceNorm', 'Criterion', 'get_model', 'get_preds', 'AtomEncoder', 'BondEncoder',
            'GSAT', 'DualGSAT', 'is_undirected', 'transpose', 'reorder_like', 'get_r', 'concrete_sample',
            'lift_node_att_to_edge_att', 'gumbel_sigmoid', 'f1_sparsity_loss', 'info_loss', 'ops', 'PNA', 'PNAConvSimple', 'line_graph_dual', 'line_graph_dual_dense', 'dense_dual_node_features', 'get_precision_at_k', 'get_delta_kl',
-           'Graph', 'PackedDataset', 'DeviceLoader']
+           'Graph', 'PackedDataset', 'DeviceLoader', 'Linear', 'dense']
