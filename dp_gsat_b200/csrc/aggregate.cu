@@ -14,6 +14,7 @@
 //
 // HBM bound.  Algorithmic bytes / launch: fwd 8NH + 8E + 4N, bwd 12NH + 16E.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -411,6 +412,20 @@ k_gin_aggregate_bwd(const float4* __restrict__ g, const float4* __restrict__ x, 
     }
 }
 
+// Rows of 16 / 32 float4 (H = 64 / 128) can be walked by half as many lanes carrying two columns each: twice the rows per
+// warp instruction, i.e. half the per-entry instruction overhead per byte (H = 64 was issue bound at 16 lanes per row).
+// Development switch GSATB_K3_WIDE: 0 = off, 1 = H = 64 only, 2 = H = 64 and 128 (default; measured on the B200 at
+// N = 4.9 M: H = 64 fwd 0.717 -> 0.688 ms, H = 128 fwd 1.057 -> 1.022 ms, backward within 2 %).
+inline int k3_wide_lanes(int HV) {
+    static const int mode = [] {
+        const char* e = getenv("GSATB_K3_WIDE");
+        return e ? atoi(e) : 2;
+    }();
+    if (HV == 16 && mode >= 1) return 8;
+    if (HV == 32 && mode >= 2) return 16;
+    return 0;
+}
+
 inline int pick_lpr(int HV) {
     int l = 1;
     while (l < HV && l < 32) l <<= 1;
@@ -438,13 +453,17 @@ inline unsigned agg_tile_grid(int64_t N, int per_sm) {
 template <bool HAS_ATT, bool OUT_BF16>
 int launch_fwd(const float* x, const float* att, const int32_t* rowptr, const int32_t* eid, const int32_t* nbr,
                float self_scale, void* out, int64_t N, int HV, cudaStream_t st) {
-    const int lpr = pick_lpr(HV);
-    const int nv = (HV + lpr - 1) / lpr;
+    int lpr = pick_lpr(HV);
+    int nv = (HV + lpr - 1) / lpr;
     const unsigned grid = agg_tile_grid(N, 3);
+    const int wide = k3_wide_lanes(HV);      // narrow rows: fewer lanes per row, two float4 columns per lane
+    if (wide) lpr = wide, nv = 2;
 #define FWD_CASE(L, V)                                                                                       \
     k_gin_aggregate_fwd<L, V, HAS_ATT, OUT_BF16><<<grid, K3_THREADS, 0, st>>>((const float4*)x, att, rowptr, eid, nbr, \
                                                                                self_scale, out, N, HV)
-    if (nv == 1) {
+    if (wide == 8) FWD_CASE(8, 2);
+    else if (wide == 16) FWD_CASE(16, 2);
+    else if (nv == 1) {
         switch (lpr) {
             case 1: FWD_CASE(1, 1); break;
             case 2: FWD_CASE(2, 1); break;
@@ -464,13 +483,17 @@ int launch_fwd(const float* x, const float* att, const int32_t* rowptr, const in
 template <bool HAS_ATT, bool WANT_DATT>
 int launch_bwd(const float* g, const float* x, const float* att, const int32_t* rowptr, const int32_t* eid,
                const int32_t* nbr, float self_scale, float* dx, float* datt, int64_t N, int HV, cudaStream_t st) {
-    const int lpr = pick_lpr(HV);
-    const int nv = (HV + lpr - 1) / lpr;
+    int lpr = pick_lpr(HV);
+    int nv = (HV + lpr - 1) / lpr;
     const unsigned grid = agg_tile_grid(N, 3);
+    const int wide = k3_wide_lanes(HV);
+    if (wide) lpr = wide, nv = 2;
 #define BWD_CASE(L, V)                                                                                  \
     k_gin_aggregate_bwd<L, V, HAS_ATT, WANT_DATT><<<grid, K3_THREADS, 0, st>>>(                         \
         (const float4*)g, (const float4*)x, att, rowptr, eid, nbr, self_scale, (float4*)dx, datt, N, HV)
-    if (nv == 1) {
+    if (wide == 8) BWD_CASE(8, 2);
+    else if (wide == 16) BWD_CASE(16, 2);
+    else if (nv == 1) {
         switch (lpr) {
             case 1: BWD_CASE(1, 1); break;
             case 2: BWD_CASE(2, 1); break;
