@@ -347,6 +347,26 @@ def _allreduce_stats(stats: torch.Tensor, n_local: int, group):
     return buf[-1].clone()
 
 
+def _rows_path(K: int, H1: int, H: int) -> bool:
+    """The row-owner kernels of csrc/gin_rows.cu serve the node MLP when all three widths are equal and 64 or 128 (every
+    GIN layer of the reference, src/models/gin.py:28-35); other shapes take the channel-owner skeleton kernels."""
+    return bool(lib().cdll.gsatb_gin_rows_supported(int(K), int(H1), int(H)))
+
+
+def _rows_lin1(agg16, w1p, b1, H1: int, want_stats: bool):
+    N = agg16.shape[0]
+    dev = agg16.device
+    z1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
+    L = lib()
+    if not want_stats:
+        L.call('gsatb_gin_rows_lin1', ptr(agg16), ptr(w1p), ptr(b1), ptr(z1), None, None, N, H1, stream())
+        return z1
+    part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
+    stats = torch.empty(2 * H1, dtype=torch.float64, device=dev)
+    L.call('gsatb_gin_rows_lin1', ptr(agg16), ptr(w1p), ptr(b1), ptr(z1), ptr(part), ptr(stats), N, H1, stream())
+    return z1, stats
+
+
 def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_var, nbt, training, momentum, eps, pdrop,
                      drop_seed, drop_mask, keep_sign: bool = True, sync_group=None):
     """Dropout(ReLU(Linear2(ReLU(BatchNorm1d(Linear1(agg)))))) on bf16 ``agg16`` [N, K].  Linear1 is a TMA-fed tcgen05
@@ -357,8 +377,9 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
     dev = agg16.device
     w1p, w2p = prep_weight(w1), prep_weight(w2)
     mean, rstd, scale, shift = (torch.empty(H1, dtype=torch.float32, device=dev) for _ in range(4))
+    rows_path = _rows_path(agg16.shape[1], H1, H)
     if training:
-        z1, stats = linear_bf16(agg16, w1p, b1, H1, want_stats=True)
+        z1, stats = _rows_lin1(agg16, w1p, b1, H1, True) if rows_path else linear_bf16(agg16, w1p, b1, H1, want_stats=True)
         n_rows = _allreduce_stats(stats, N, sync_group)          # python int, or the group-wide count on the device
         n_dev = n_rows if torch.is_tensor(n_rows) else None
         # batch statistics -> (mean, rstd, scale, shift) + running-statistics update, one launch (gsatb_bn_fold_fwd)
@@ -366,15 +387,23 @@ def _gin_mlp_forward(agg16, w1, b1, gamma, beta, w2, b2, running_mean, running_v
                    ctypes.c_float(eps), ctypes.c_float(momentum), ptr(running_mean), ptr(running_var), ptr(nbt), 1, ptr(mean),
                    ptr(rstd), ptr(scale), ptr(shift), H1, stream())
     else:
-        z1 = linear_bf16(agg16, w1p, b1, H1)
+        z1 = _rows_lin1(agg16, w1p, b1, H1, False) if rows_path else linear_bf16(agg16, w1p, b1, H1)
         lib().call('gsatb_bn_fold_fwd', None, ctypes.c_double(1.0), None, ptr(gamma), ptr(beta), ctypes.c_float(eps),
                    ctypes.c_float(momentum), ptr(running_mean), ptr(running_var), None, 0, ptr(mean), ptr(rstd), ptr(scale),
                    ptr(shift), H1, stream())
     p = float(pdrop) if training else 0.0
     a1 = torch.empty_like(z1)
-    lib().call('gsatb_bn_relu_bf16', ptr(z1), ptr(scale), ptr(shift), ptr(a1), N, H1, stream())
     # sign bits of h: all the backward pass needs of the layer output (4 bytes per 32 channels instead of 128)
     posmask = torch.empty((N, (H + 31) // 32), dtype=torch.int32, device=agg16.device) if keep_sign else None
+    if rows_path:
+        # BatchNorm + ReLU are applied to the z1 tile in shared memory on its way into the second GEMM; a1 leaves as the
+        # bf16 operand of dW2 from the same tile
+        h = torch.empty((N, H), dtype=torch.float32, device=dev)
+        mk = None if drop_mask is None else drop_mask.to(torch.uint8).contiguous()
+        lib().call('gsatb_gin_rows_lin2', ptr(z1), ptr(scale), ptr(shift), ptr(w2p), ptr(b2), ptr(a1), ptr(h), ptr(posmask),
+                   ptr(mk), ctypes.c_uint64(int(drop_seed) & (2 ** 64 - 1)), ctypes.c_float(p), N, H, stream())
+        return h, (z1, a1, mean, rstd, scale, shift, p, posmask)
+    lib().call('gsatb_bn_relu_bf16', ptr(z1), ptr(scale), ptr(shift), ptr(a1), N, H1, stream())
     h = linear_bf16(a1, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=p, drop_seed=drop_seed, drop_mask=drop_mask,
                     posmask=posmask)
     return h, (z1, a1, mean, rstd, scale, shift, p, posmask)
@@ -424,8 +453,11 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     dz1 = torch.empty((N, H1), dtype=torch.bfloat16, device=dev)
     dagg = torch.empty((N, Kin), dtype=torch.float32, device=dev)
     w1t = prep_weight(w1, transpose=True)
-    L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, Kin,
-           stream())
+    if _rows_path(Kin, H1, H):
+        L.call('gsatb_gin_rows_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, stream())
+    else:
+        L.call('gsatb_tc_gin_bwd1', ptr(g), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz1), ptr(dagg), N, H1, Kin,
+               stream())
     dW2, db2 = weight_grad(d2, False, a1, False, N, H, H1, want_bias=True)
     dW1, db1 = weight_grad(dz1, False, agg16, False, N, H1, Kin, want_bias=True)
     return dagg, dW1, db1, dgamma, dbeta, dW2, db2

@@ -312,6 +312,29 @@ int gsatb_tc_gin_bwd1(const void* g, const void* z1, const float* cA, const floa
                       const void* w1t_bf16_padded, void* dz1, float* dx, int64_t N, int H1, int Kin,
                       gsatb_stream_t stream);
 
+/* GIN node MLP in the row-owner orientation (csrc/gin_rows.cu) for K = H1 = H in {64, 128} -- the shape of every GIN
+ * layer of the reference (src/models/gin.py:28-35: MLP(hidden, hidden)).  Same contracts as the entries above, one
+ * kernel per GEMM with every tile moved by TMA in both directions:
+ *   gin_rows_lin1: z1 = x W1^T + b1 (bf16 [rows,H]) + BatchNorm batch statistics stats[0:H] = sum z, stats[H:2H] = sum z^2
+ *                  from the fp32 accumulators (stat_partials: gsatb_tc_stat_partials_elems(H) floats; both nullable)
+ *   gin_rows_lin2: a1 = ReLU(z1*scale + shift) formed in shared memory (stored as bf16 [rows,H] when a1_bf16 is given:
+ *                  the operand of dW2), h = Dropout(ReLU(a1 W2^T + b2)) fp32 [rows,H], posmask_out as in
+ *                  gsatb_tc_linear_bf16_fwd (same dropout word stream: identical masks for identical seeds)
+ *   gin_rows_bwd1: dz1 = cA*g + cB*z1 + cC formed in shared memory (stored as bf16 when dz1_bf16 is given), dx = dz1 W1
+ *                  fp32 [rows,H]   (autograd of gin.py:55-62; replaces gsatb_tc_gin_bwd1 at these shapes)
+ * gsatb_gin_rows_supported -> 1 when the three widths qualify. */
+int gsatb_gin_rows_supported(int K, int H1, int H);
+int gsatb_gin_rows_lin1(const void* x_bf16, const void* w1_bf16_padded, const float* bias /* [nullable] */, void* z1_bf16,
+                        float* stat_partials /* [nullable] */, double* stats /* [nullable] */, int64_t rows, int H,
+                        gsatb_stream_t stream);
+int gsatb_gin_rows_lin2(const void* z1_bf16, const float* bn_scale, const float* bn_shift, const void* w2_bf16_padded,
+                        const float* bias /* [nullable] */, void* a1_bf16 /* [nullable] */, float* h,
+                        uint32_t* posmask_out /* [nullable] */, const uint8_t* drop_mask /* [nullable] */,
+                        uint64_t drop_seed, float pdrop, int64_t rows, int H, gsatb_stream_t stream);
+int gsatb_gin_rows_bwd1(const void* g_bf16, const void* z1_bf16, const float* cA, const float* cB, const float* cC,
+                        const void* w1t_bf16_padded, void* dz1_bf16 /* [nullable] */, float* dx, int64_t rows, int H,
+                        gsatb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * K1  extractor MLP forward, fused on the tensor cores.  Replaces ExtractorMLP.forward (src/run_gsat.py:909-927,
  * example/gsat.py:131-139) and the MLP/InstanceNorm stack of src/utils/get_model.py:47-68.

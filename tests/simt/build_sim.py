@@ -16,7 +16,7 @@ LIB = os.path.join(OUT_DIR, 'libgsat_sim.so')
 # every kernel source without tcgen05 / TMA / mbarrier PTX: the fp32 path of the step, K0, the line-graph builder, metrics
 SIM_SOURCES = ['aggregate.cu', 'gine.cu', 'leconv.cu', 'pna.cu', 'index_build.cu', 'line_graph.cu', 'sampler.cu',
                'segnorm.cu', 'small_ops.cu', 'metrics.cu', 'encoders.cu', 'collate.cu', 'api.cu',
-               'tc_ops.cu', 'tc_gin.cu', 'tc_extractor.cu', 'tc_extractor_bwd.cu', 'tc_dw.cu', 'ext_fused_fwd.cu', 'ext_fused_bwd.cu', 'dense.cu']
+               'tc_ops.cu', 'tc_gin.cu', 'tc_extractor.cu', 'tc_extractor_bwd.cu', 'tc_dw.cu', 'ext_fused_fwd.cu', 'ext_fused_bwd.cu', 'dense.cu', 'gin_rows.cu']
 
 def _host_has_fma() -> bool:
     try:

@@ -107,12 +107,13 @@ inline void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int crd
     for (uint32_t r = 0; r < tm.box[1]; ++r)
         for (uint32_t c = 0; c < tm.box[0]; ++c) {
             const int64_t gr = (int64_t)crd1 + r, gc = (int64_t)crd0 + c;
-            uint16_t v = 0;                                            // out-of-bounds elements read as zero
+            const uint32_t es = tm.elem_bytes;
+            uint8_t v[4] = {0, 0, 0, 0};                               // out-of-bounds elements read as zero
             if (gr >= 0 && gc >= 0 && (uint64_t)gr < tm.dim[1] && (uint64_t)gc < tm.dim[0])
-                v = *reinterpret_cast<const uint16_t*>(tm.base + (uint64_t)gr * tm.row_stride + (uint64_t)gc * 2);
-            uint32_t off = dst + r * row_bytes + c * 2;
+                memcpy(v, tm.base + (uint64_t)gr * tm.row_stride + (uint64_t)gc * es, es);
+            uint32_t off = dst + r * row_bytes + c * es;
             if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) off = swizzle128(off);
-            *reinterpret_cast<uint16_t*>(base + off) = v;
+            memcpy(base + off, v, es);
         }
     mbar_complete_tx(bar, tm.box[1] * row_bytes);
 }
@@ -199,10 +200,10 @@ inline void tma_store_2d(const void* desc, const void* smem_src, int crd0, int c
         for (uint32_t c = 0; c < tm.box[0]; ++c) {
             const int64_t gr = (int64_t)crd1 + r, gc = (int64_t)crd0 + c;
             if (gr < 0 || gc < 0 || (uint64_t)gr >= tm.dim[1] || (uint64_t)gc >= tm.dim[0]) continue;
-            uint32_t off = src + r * row_bytes + c * 2;
+            const uint32_t es = tm.elem_bytes;
+            uint32_t off = src + r * row_bytes + c * es;
             if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) off = swizzle128(off);
-            *reinterpret_cast<uint16_t*>(const_cast<uint8_t*>(tm.base) + (uint64_t)gr * tm.row_stride + (uint64_t)gc * 2) =
-                *reinterpret_cast<const uint16_t*>(base + off);
+            memcpy(const_cast<uint8_t*>(tm.base) + (uint64_t)gr * tm.row_stride + (uint64_t)gc * es, base + off, es);
         }
 }
 inline void tma_store_commit() {}

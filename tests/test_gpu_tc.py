@@ -473,3 +473,68 @@ def test_word_dropout_rate_and_scale(G, p):
     assert float((kept.float().mean(0) - keep_rate).abs().max()) < 0.05
     assert float((kept.float().mean(1) - keep_rate).abs().max()) < 0.27      # 128 samples per row: 6 sigma
     assert abs(float(out.mean()) - 1.0) < 1e-2          # unbiased
+
+
+@pytest.mark.parametrize('H', [64, 128])
+@pytest.mark.parametrize('N', [777, 4096 + 40])
+def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N):
+    """The row-owner node-MLP kernels (csrc/gin_rows.cu: TMA in / TMA out, BatchNorm + ReLU and the BatchNorm backward
+    applied to the operand tile in shared memory, statistics from the swapped product) against the channel-owner
+    skeleton kernels they replace at H = 64 / 128 -- same contracts (src/models/gin.py:55-62 forward and autograd), same
+    rounding points, same dropout word stream: outputs agree to accumulation order, masks and sign bits exactly."""
+    import ctypes
+    from dp_gsat_b200 import tc
+    from dp_gsat_b200._lib import lib, ptr, stream
+    L = lib()
+    assert L.cdll.gsatb_gin_rows_supported(H, H, H) == 1 and L.cdll.gsatb_gin_rows_supported(H, H, 2 * H) == 0
+    torch.manual_seed(N + H)
+    dev = 'cuda'
+    x16 = torch.randn(N, H, device=dev).bfloat16()
+    w1, w2 = torch.randn(H, H, device=dev) / H ** 0.5, torch.randn(H, H, device=dev) / H ** 0.5
+    b1, b2 = torch.randn(H, device=dev), torch.randn(H, device=dev) * 0.3
+    w1p, w2p, w1t = tc.prep_weight(w1), tc.prep_weight(w2), tc.prep_weight(w1, transpose=True)
+    # --- first Linear + batch statistics
+    z_old, st_old = tc.linear_bf16(x16, w1p, b1, H, want_stats=True)
+    z_new, st_new = tc._rows_lin1(x16, w1p, b1, H, True)
+    assert torch.equal(z_new.view(torch.int16), z_old.view(torch.int16))
+    assert torch.allclose(st_new, st_old, rtol=1e-5, atol=1e-3)
+    assert torch.equal(tc._rows_lin1(x16, w1p, None, H, False).view(torch.int16), tc.linear_bf16(x16, w1p, None, H).view(torch.int16))
+    # --- BatchNorm + ReLU folded into the second Linear, hash dropout / injected mask / eval
+    scale, shift = torch.rand(H, device=dev) + 0.5, torch.randn(H, device=dev) * 0.2
+    a_old = torch.empty_like(z_old)
+    L.call('gsatb_bn_relu_bf16', ptr(z_old), ptr(scale), ptr(shift), ptr(a_old), N, H, stream())
+    inj = (torch.rand(N, H, device=dev) > 0.3).to(torch.uint8)
+    for pdrop, mask in ((0.3, None), (0.5, None), (0.3, inj), (0.0, None)):
+        pm_old = torch.zeros((N, H // 32), dtype=torch.int32, device=dev)
+        pm_new = torch.zeros_like(pm_old)
+        h_old = tc.linear_bf16(a_old, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=pdrop, drop_seed=5, drop_mask=mask, posmask=pm_old)
+        a_new = torch.zeros_like(z_old)
+        h_new = torch.full((N, H), float('nan'), device=dev)
+        L.call('gsatb_gin_rows_lin2', ptr(z_old), ptr(scale), ptr(shift), ptr(w2p), ptr(b2), ptr(a_new), ptr(h_new), ptr(pm_new),
+               ptr(mask), ctypes.c_uint64(5), ctypes.c_float(pdrop), N, H, stream())
+        assert torch.equal(a_new.view(torch.int16), a_old.view(torch.int16))
+        assert torch.equal(h_new != 0, h_old != 0)                     # same dropout decisions
+        assert torch.allclose(h_new, h_old, rtol=1e-5, atol=1e-5)
+        assert torch.equal(pm_new, pm_old)
+        assert torch.equal(h_new > 0, tc_unpack_bits(pm_new, H))
+    # a1 not wanted (eval): nothing is written through the operand store
+    h_eval = torch.empty((N, H), device=dev)
+    L.call('gsatb_gin_rows_lin2', ptr(z_old), ptr(scale), ptr(shift), ptr(w2p), ptr(b2), None, ptr(h_eval), None, None,
+           ctypes.c_uint64(0), ctypes.c_float(0.0), N, H, stream())
+    assert torch.allclose(h_eval, tc.linear_bf16(a_old, w2p, b2, H, out_bf16=False, relu_out=True), rtol=1e-5, atol=1e-5)
+    # --- BatchNorm backward folded into the dX product of the first Linear
+    g16 = torch.randn(N, H, device=dev).bfloat16()
+    cA, cB, cC = torch.randn(H, device=dev), torch.randn(H, device=dev) * 0.1, torch.randn(H, device=dev) * 0.01
+    dz_old, dz_new = torch.empty_like(g16), torch.zeros_like(g16)
+    dx_old, dx_new = torch.empty((N, H), device=dev), torch.full((N, H), float('nan'), device=dev)
+    L.call('gsatb_tc_gin_bwd1', ptr(g16), ptr(z_old), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz_old), ptr(dx_old), N, H, H, stream())
+    L.call('gsatb_gin_rows_bwd1', ptr(g16), ptr(z_old), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz_new), ptr(dx_new), N, H, stream())
+    assert torch.equal(dz_new.view(torch.int16), dz_old.view(torch.int16))
+    assert torch.allclose(dx_new, dx_old, rtol=1e-5, atol=1e-5)
+
+
+def tc_unpack_bits(words: torch.Tensor, H: int) -> torch.Tensor:
+    """[rows, ceil(H/32)] int32 sign-bit words -> bool [rows, H] (bit c % 32 of word c // 32)"""
+    sh = torch.arange(32, device=words.device, dtype=torch.int64)
+    bits = ((words.to(torch.int64).unsqueeze(-1) >> sh) & 1).bool()
+    return bits.reshape(words.shape[0], -1)[:, :H]
