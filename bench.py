@@ -225,6 +225,13 @@ def kernel_models(N, E, G, H):
         'gsatb_gin_aggregate_fwd_bf16:noatt': (6.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
         'gsatb_tc_linear_bf16_fwd:bf16': (4.0 * N * H, 2.0 * N * H * H),              # bf16 agg in, bf16 z1 out
         'gsatb_tc_linear_bf16_fwd:fp32': (6.0 * N * H, 2.0 * N * H * H),              # bf16 a1 in, fp32 h out
+        # row-owner node-MLP kernels (csrc/gin_rows.cu): lin1 = bf16 agg in, bf16 z1 out; lin2 = bf16 z1 in, bf16 a1 +
+        # fp32 h + sign bits out; bwd1 = bf16 g, z1 in, bf16 dz1 + fp32 dx out; bwd2 = fp32 dh, sign bits, bf16 z1 in,
+        # bf16 d2, g out
+        'gsatb_gin_rows_lin1': (4.0 * N * H, 2.0 * N * H * H),
+        'gsatb_gin_rows_lin2': (N * (2.0 * H + 2 * H + 4 * H + H / 8.0), 2.0 * N * H * H),
+        'gsatb_gin_rows_bwd1': (N * (2.0 * H + 2 * H + 2 * H + 4 * H), 2.0 * N * H * H),
+        'gsatb_gin_rows_bwd2': (N * (4.0 * H + H / 8.0 + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),
         'gsatb_bn_relu_bf16': (4.0 * N * H, 0.0),
         'gsatb_tc_linear_fwd': (8.0 * N * H, 2.0 * N * H * H),
         'gsatb_tc_gin_bwd2': (N * (4.0 * H + H / 8.0 + 2 * H + 2 * H + 2 * H), 2.0 * N * H * H),   # dh, sign bits, z1 in; d2, g out

@@ -534,6 +534,362 @@ k_rows(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtenso
     if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// gin_bwd2 in the row-owner orientation:  d2 = dh * (h > 0) * drop_scale (sign bits from the forward);  da1 = d2 W2;
+// g = da1 * (ReLU(BN(z1)) > 0);  BatchNorm-backward statistics sum(g), sum(g * xhat) per channel.
+//   warp 0       TMA loads: W2^T once, then the fp32 dh tile of every tile as [128 rows x 32 fp32] SWIZZLE_128B boxes
+//   warps 16-19  transform, thread = row: per 64-channel block the row's 256 bytes of dh are read from two boxes, masked,
+//                scaled, rounded to bf16 and written IN PLACE over the first of the two boxes, which thereby becomes the
+//                [128 x 64] bf16 K-block of the A operand (a thread only ever overwrites bytes it has itself consumed)
+//   warp 1       MMA issuer;  warp 2: TMEM allocator + TMA store of the d2 K-blocks (operand of dW2)
+//   warps 4-11   two epilogue groups, per [32 rows x 64 channels] block of the warp: row phase (lane = row: accumulator ->
+//                bf16 in the staging buffer), then channel phase (lane = channel pair: gate from z1, statistics, in place),
+//                then one TMA store
+// ------------------------------------------------------------------------------------------------------------------
+struct RowsBwd2Params {
+    const uint32_t* posmask;    // [rows, H / 32]
+    float drop_scale;
+    const uint16_t* z1;         // bf16 [rows, H]
+    const float* sc;            // BatchNorm folded: a1 = relu(z1 * sc + sf)
+    const float* sf;
+    const float* mu;
+    float* stat_partials;       // [gridDim * 8 epilogue warps][2][H]: sum g, sum g * (z1 - mu)
+};
+constexpr int RW2_NACC = 2;             // accumulators = epilogue groups (warps 4-11; three groups with one staging buffer
+                                        // each measured slower: 1.50 vs 1.36 ms at 4.9 M x 128)
+constexpr int RW2_ROW_WARPS = 4 * RW2_NACC;
+constexpr int RW2_STG = 8192;       // per epilogue warp: two [32 rows x 128 bytes] staging buffers
+
+struct Rows2Smem {
+    uint32_t in_off, stage_bytes, stg_off, bar_off, total;
+};
+__host__ __device__ inline Rows2Smem rows2_smem(const RowsShape& s) {
+    Rows2Smem l;
+    l.in_off = (uint32_t)s.KB * BLK_BYTES;
+    l.stage_bytes = (uint32_t)(s.H / 32) * BLK_BYTES;
+    l.stg_off = l.in_off + (uint32_t)s.NST * l.stage_bytes;
+    l.bar_off = l.stg_off + RW2_ROW_WARPS * RW2_STG;
+    l.total = l.bar_off + 512 + 1024;
+    return l;
+}
+
+__global__ void __launch_bounds__(RW_THREADS, 1)
+k_rows_bwd2(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_dh,
+            const __grid_constant__ CUtensorMap tm_d2, const __grid_constant__ CUtensorMap tm_g, const RowsShape sh,
+            const RowsBwd2Params p) {
+    constexpr int NACC = RW2_NACC;
+#ifdef GSATB_HOST_SIM
+    uint8_t* smem_raw = simt::dyn_smem();
+#else
+    extern __shared__ uint8_t smem_raw[];
+#endif
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const Rows2Smem L = rows2_smem(sh);
+    uint8_t* sW = smem;
+    uint8_t* sIn = smem + L.in_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+    uint64_t* w_full = bars;
+    uint64_t* in_full = bars + 1;             // [NST <= 6]
+    uint64_t* xf_done = bars + 7;
+    uint64_t* in_free = bars + 13;
+    uint64_t* acc_full = bars + 19;           // [3]
+    uint64_t* acc_empty = bars + 22;          // [3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = sh.H, KB = sh.KB, NB = sh.H >> 5;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tm_w);
+        tc::tma_prefetch_desc(&tm_dh);
+        tc::tma_prefetch_desc(&tm_d2);
+        tc::tma_prefetch_desc(&tm_g);
+        tc::mbar_init(w_full, 1);
+        for (int i = 0; i < sh.NST; ++i) {
+            tc::mbar_init(&in_full[i], 1);
+            tc::mbar_init(&xf_done[i], 128);
+            tc::mbar_init(&in_free[i], 2);
+        }
+        for (int i = 0; i < NACC; ++i) {
+            tc::mbar_init(&acc_full[i], 1);
+            tc::mbar_init(&acc_empty[i], 128);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) {
+        tc::tmem_alloc(tmem_slot, 512);
+        tc::tmem_relinquish();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        tc::reg_dec<CTL_REGS>();
+        if (warp == 0) {
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(w_full, (uint32_t)KB * BLK_BYTES);
+                for (int kb = 0; kb < KB; ++kb) tc::tma_load_2d(sW + kb * BLK_BYTES, &tm_w, w_full, kb * KBLK, 0);
+                uint32_t ti = 0;
+                for (int tile = blockIdx.x; tile < sh.num_tiles; tile += gridDim.x, ++ti) {
+                    const uint32_t s = ti % sh.NST, u = ti / sh.NST;
+                    tc::mbar_wait(&in_free[s], (u & 1) ^ 1);
+                    tc::mbar_arrive_expect_tx(&in_full[s], L.stage_bytes);
+                    uint8_t* st = sIn + (size_t)s * L.stage_bytes;
+                    for (int b = 0; b < NB; ++b) tc::tma_load_2d(st + b * BLK_BYTES, &tm_dh, &in_full[s], b * 32, tile * TILE_ROWS);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = tc::make_idesc_bf16(128, H);
+                long long w_in = 0, w_acc = 0, t_all = clock64(), t0;
+                tc::mbar_wait(w_full, 0);
+                uint32_t ti = 0;
+                for (int tile = blockIdx.x; tile < sh.num_tiles; tile += gridDim.x, ++ti) {
+                    const uint32_t s = ti % sh.NST, u = ti / sh.NST;
+                    const uint32_t a = ti % NACC, ua = ti / NACC;
+                    t0 = clock64();
+                    tc::mbar_wait(&xf_done[s], u & 1);
+                    w_in += clock64() - t0;
+                    t0 = clock64();
+                    tc::mbar_wait(&acc_empty[a], (ua & 1) ^ 1);
+                    w_acc += clock64() - t0;
+                    tc::tc_fence_after();
+                    const uint32_t x_base = tc::smem_u32(sIn + (size_t)s * L.stage_bytes);
+                    const uint32_t w_base = tc::smem_u32(sW);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint64_t xd = tc::make_desc_k_sw128(x_base + 2 * kb * BLK_BYTES);     // d2 K-block kb lies over dh box 2 kb
+                        const uint64_t wd = tc::make_desc_k_sw128(w_base + kb * BLK_BYTES);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            tc::mma_bf16_ss(tmem_base + a * 128, xd + (uint64_t)(k4 * 2), wd + (uint64_t)(k4 * 2), idesc,
+                                            (kb | k4) != 0);
+                    }
+                    tc::mma_commit(&in_free[s]);
+                    tc::mma_commit(&acc_full[a]);
+                }
+                if (sh.dbg) {
+                    long long* d = sh.dbg + (size_t)blockIdx.x * 16;
+                    d[0] = clock64() - t_all;
+                    d[1] = w_in;
+                    d[2] = w_acc;
+                }
+            }
+        } else if (warp == 2) {
+            if (lane == 0) {
+                uint32_t ti = 0;
+                for (int tile = blockIdx.x; tile < sh.num_tiles; tile += gridDim.x, ++ti) {
+                    const uint32_t s = ti % sh.NST, u = ti / sh.NST;
+                    tc::mbar_wait(&xf_done[s], u & 1);
+                    const uint8_t* st = sIn + (size_t)s * L.stage_bytes;
+                    for (int kb = 0; kb < KB; ++kb) tc::tma_store_2d(&tm_d2, st + 2 * kb * BLK_BYTES, kb * KBLK, tile * TILE_ROWS);
+                    tc::tma_store_commit();
+                    tc::tma_store_wait_read<0>();
+                    tc::mbar_arrive(&in_free[s]);
+                }
+                tc::tma_store_wait_all<0>();
+            }
+        }
+    } else {
+        tc::reg_inc<EPI4_REGS>();
+        const int q = warp & 3;
+        const int nchunk = H >> 5;
+        if (warp >= 16) {
+            // ===================== transform: fp32 dh boxes -> bf16 d2 K-blocks, in place =====================
+            const int row = threadIdx.x - 16 * 32;               // 0..127: thread = row, one 64-channel block after the other
+            const int pt = row;
+            const int W = H >> 5;
+            const uint32_t r7 = (uint32_t)(row & 7);
+            uint32_t ti = 0;
+            long long w_in = 0, t_work = 0, t0;
+            for (int tile = blockIdx.x; tile < sh.num_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t s = ti % sh.NST, u = ti / sh.NST;
+                const int64_t grow = (int64_t)tile * TILE_ROWS + row;
+                uint32_t mk[4] = {0u, 0u, 0u, 0u};
+                if (grow < sh.rows) {
+                    const uint32_t* pm = p.posmask + grow * W;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i < W) mk[i] = __ldg(pm + i);
+                }
+                t0 = clock64();
+                tc::group_mbar_wait(pt == 0, &in_full[s], u & 1, RW_BAR_XF, 128);
+                w_in += clock64() - t0;
+                t0 = clock64();
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+                if (kb < KB) {
+                    const uint32_t m0 = mk[2 * kb], m1 = mk[2 * kb + 1];
+                    const uint32_t b0 = tc::smem_u32(sIn + (size_t)s * L.stage_bytes) + (uint32_t)(2 * kb) * BLK_BYTES + (uint32_t)row * 128u;
+                    uint4 qv[16];
+#pragma unroll
+                    for (int jx = 0; jx < 8; ++jx) qv[jx] = tc::lds128(b0 + (((uint32_t)jx ^ r7) << 4));
+#pragma unroll
+                    for (int jx = 0; jx < 8; ++jx) qv[8 + jx] = tc::lds128(b0 + BLK_BYTES + (((uint32_t)jx ^ r7) << 4));
+                    // (every load of the row precedes every store: the asm statements are volatile and keep their order)
+#pragma unroll
+                    for (int jx = 0; jx < 8; ++jx) {          // output chunk jx = channels 8 jx .. 8 jx + 7 of the block
+                        const uint32_t mw = (jx < 4 ? m0 : m1) >> ((jx & 3) * 8);
+                        const uint4 x0 = qv[2 * jx], x1 = qv[2 * jx + 1];
+                        const float f[8] = {__uint_as_float(x0.x), __uint_as_float(x0.y), __uint_as_float(x0.z), __uint_as_float(x0.w),
+                                            __uint_as_float(x1.x), __uint_as_float(x1.y), __uint_as_float(x1.z), __uint_as_float(x1.w)};
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = ((mw >> i) & 1u) ? f[i] * p.drop_scale : 0.f;
+                        uint32_t o[4];
+                        pack8(v, o);
+                        tc::sts128(b0 + (((uint32_t)jx ^ r7) << 4), o[0], o[1], o[2], o[3]);
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                tc::mbar_arrive(&xf_done[s]);
+                t_work += clock64() - t0;
+            }
+            if (sh.dbg && pt == 0) {
+                long long* d = sh.dbg + (size_t)blockIdx.x * 16;
+                d[6] = w_in;
+                d[7] = t_work;
+            }
+        } else {
+            // ===================== epilogue groups: row-owner phase, then channel-pair phase, per 64-channel block ==========
+            // Row phase (lane = row): accumulator -> bf16 da1 in the warp's staging buffer.  Channel phase (lane = channel
+            // pair, the warp's 32 rows in order): z1 comes straight from global memory -- 128 contiguous bytes per row per
+            // warp, issued before the accumulator is awaited -- the gate is applied to the staged values in place, sum g
+            // and sum g (z1 - mu) accumulate in a fixed order (deterministic, no atomics), and the block leaves by TMA.
+            const int ew = warp - 4, grp = ew >> 2;
+            const int nblk = H >> 6;
+            uint8_t* stg = smem + L.stg_off + (size_t)ew * RW2_STG;
+            float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            uint32_t sb = 0, ti = 0;
+            long long w_acc = 0, t_work = 0, t0;
+            for (int tile = blockIdx.x; tile < sh.num_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t a = ti % NACC, ua = ti / NACC;
+                if ((int)a != grp) continue;
+                const int64_t r0 = (int64_t)tile * TILE_ROWS;
+                const int64_t left = sh.rows - r0;
+                const int cnt = left < TILE_ROWS ? (int)left : TILE_ROWS;
+                const int64_t rbase = r0 + q * 32;
+                const bool any_row = q * 32 < cnt;
+                uint32_t zz[32];
+                // rows past the end of the tensor re-read the last valid row (in bounds; masked in the channel phase)
+                const int64_t rfirst = rbase < sh.rows ? rbase : sh.rows - 1;
+                const int rmax = (int)((sh.rows - 1 - rfirst) < 31 ? (sh.rows - 1 - rfirst) : 31);
+                auto load_z = [&](int b) {
+                    const uint32_t* zp = reinterpret_cast<const uint32_t*>(p.z1 + rfirst * H + b * 64) + lane;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        zz[r] = __ldg(zp);
+                        if (r < rmax) zp += H >> 1;
+                    }
+                };
+                load_z(0);
+                {   // pull this warp's z1 rows of the group's NEXT tile towards L2 (lane = row)
+                    const int64_t nrow = rbase + (int64_t)NACC * gridDim.x * TILE_ROWS + lane;
+                    if (nrow < sh.rows) {
+                        tc::prefetch_l2(p.z1 + nrow * H);
+                        if (nblk > 1) tc::prefetch_l2(p.z1 + nrow * H + 64);
+                    }
+                }
+                t0 = clock64();
+                if (lane == 0) tc::mbar_wait(&acc_full[a], ua & 1);
+                __syncwarp();
+                w_acc += clock64() - t0;
+                tc::tc_fence_after();
+                t0 = clock64();
+                const uint32_t taddr = tmem_base + a * 128 + ((uint32_t)(q * 32) << 16);
+                // (one copy of the block body: unrolled over the blocks the kernel's hot code outgrew the instruction cache --
+                // stall_no_inst was the top stall reason in ncu)
+#pragma unroll 1
+                for (int b = 0; b < nblk; ++b) {
+                    {
+                        const int ch = b * 64 + 2 * lane;
+                        const float sc0 = __ldg(p.sc + ch), sc1 = __ldg(p.sc + ch + 1), sf0 = __ldg(p.sf + ch), sf1 = __ldg(p.sf + ch + 1);
+                        const float mu0 = __ldg(p.mu + ch), mu1 = __ldg(p.mu + ch + 1);
+                        float t1a = 0.f, t1b = 0.f, t2a = 0.f, t2b = 0.f;
+                        if (lane == 0) tc::tma_store_wait_read<1>();       // the store that last used this buffer has read it
+                        __syncwarp();
+                        uint8_t* buf = stg + (sb & 1u) * 4096u;
+                        const uint32_t rowa = tc::smem_u32(buf) + (uint32_t)lane * 128u;
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq) {           // 16 accumulator columns at a time (z1 of the block is live)
+                            float v[16];
+                            tc::tmem_ld_32x16(taddr + b * 64 + cq * 16, v);
+                            tc::tmem_ld_wait();
+                            if (b == nblk - 1 && cq == 3) {
+                                tc::tc_fence_before();
+                                tc::mbar_arrive(&acc_empty[a]);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 2; ++jj)
+                                tc::sts128(rowa + (uint32_t)(((cq * 2 + jj) ^ (lane & 7)) << 4), tc::pack_bf16(v[8 * jj], v[8 * jj + 1]),
+                                           tc::pack_bf16(v[8 * jj + 2], v[8 * jj + 3]), tc::pack_bf16(v[8 * jj + 4], v[8 * jj + 5]),
+                                           tc::pack_bf16(v[8 * jj + 6], v[8 * jj + 7]));
+                        }
+                        __syncwarp();
+                        const uint32_t ba = tc::smem_u32(buf) + (uint32_t)(lane & 3) * 4u;
+                        const uint32_t cb = (uint32_t)(lane >> 2);
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            const uint32_t ad = ba + (uint32_t)r * 128u + ((cb ^ (uint32_t)(r & 7)) << 4);
+                            const uint32_t w = tc::lds32(ad);
+                            const float z0 = __uint_as_float(zz[r] << 16), z1v = __uint_as_float(zz[r] & 0xFFFF0000u);
+                            const bool ok = q * 32 + r < cnt;
+                            // the same fma as the forward's a1 = relu(z1 * sc + sf)
+                            const uint32_t w0 = (ok && fmaf(z0, sc0, sf0) > 0.f) ? (w << 16) : 0u;
+                            const uint32_t w1 = (ok && fmaf(z1v, sc1, sf1) > 0.f) ? (w & 0xFFFF0000u) : 0u;
+                            tc::sts32(ad, (w0 >> 16) | w1);
+                            const float g0 = __uint_as_float(w0), g1 = __uint_as_float(w1);
+                            t1a += g0;
+                            t1b += g1;
+                            t2a = fmaf(g0, z0 - mu0, t2a);
+                            t2b = fmaf(g1, z1v - mu1, t2b);
+                        }
+                        if (b == 0) s1[0][0] += t1a, s1[0][1] += t1b, s2[0][0] += t2a, s2[0][1] += t2b;
+                        else s1[1][0] += t1a, s1[1][1] += t1b, s2[1][0] += t2a, s2[1][1] += t2b;
+                        if (b + 1 < nblk) load_z(b + 1);
+                        rows_stage_store(&tm_g, buf, lane, b * 64, (int)rbase, any_row);
+                        ++sb;
+                    }
+                }
+                t_work += clock64() - t0;
+            }
+            if (lane == 0) tc::tma_store_wait_all<0>();
+            if (p.stat_partials) {
+                const size_t part = (size_t)blockIdx.x * RW2_ROW_WARPS + ew;
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int ch = b * 64 + 2 * lane + i;
+                        if (ch < H) {
+                            p.stat_partials[(part * 2 + 0) * H + ch] = s1[b][i];
+                            p.stat_partials[(part * 2 + 1) * H + ch] = s2[b][i];
+                        }
+                    }
+            }
+            if (sh.dbg && ew == 0 && lane == 0) {
+                long long* d = sh.dbg + (size_t)blockIdx.x * 16;
+                d[4] = w_acc;
+                d[5] = t_work;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// stats[j] = sum over parts of s1; stats[H + j] = rstd[j] * sum over parts of s2   (fixed order, fp64)
+__global__ void k_rows_bwd2_reduce(const float* __restrict__ partials, int parts, int H, const float* __restrict__ rstd,
+                                   float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 2 * H) return;
+    double acc = 0.0;
+    for (int q = 0; q < parts; ++q) acc += (double)partials[(size_t)q * 2 * H + j];
+    out[j] = j < H ? (float)acc : (float)(acc * (double)rstd[j - H]);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 // [rows, cols] row-major tensor (ld elements per row) -> SWIZZLE_128B boxes of box_cols x box_rows elements
 inline int make_rows_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int es, const void* base, int64_t rows, int cols, int64_t ld,
@@ -606,7 +962,8 @@ int launch_rows(const void* w_bf16_padded, const void* in0, const void* in1, voi
             return GSATB_ELAUNCH;
         attr_set = true;
     }
-    const int grid = sh.num_tiles < GSATB_NUM_SMS ? sh.num_tiles : GSATB_NUM_SMS;
+    const int max_grid = rows_env("GSATB_ROWS_GRID", GSATB_NUM_SMS, 1, GSATB_NUM_SMS);      // (tests: many tiles per CTA at small sizes)
+    const int grid = sh.num_tiles < max_grid ? sh.num_tiles : max_grid;
     k_rows<Op><<<grid, RW_THREADS, L.total, st>>>(tw, t0, t1, tx, to, sh, p);
     if (cudaPeekAtLastError() != cudaSuccess) return GSATB_ELAUNCH;
     return GSATB_OK;
@@ -675,4 +1032,60 @@ extern "C" int gsatb_gin_rows_bwd1(const void* g_bf16, const void* z1_bf16, cons
     if (!gsatb_aligned16(cA) || !gsatb_aligned16(cB) || !gsatb_aligned16(cC)) return GSATB_EALIGN;
     OpRowsBwd1::Params p{cA, cB, cC, nullptr, 0, plain_epi()};
     return launch_rows<OpRowsBwd1>(w1t_bf16_padded, g_bf16, z1_bf16, dz1_bf16, dx, false, rows, H, p, (cudaStream_t)stream);
+}
+
+extern "C" size_t gsatb_gin_rows_stat_partials_elems(int H) { return (size_t)GSATB_NUM_SMS * RW2_ROW_WARPS * 2 * H; }
+
+extern "C" int gsatb_gin_rows_bwd2(const float* dh, const uint32_t* posmask, float drop_scale, const void* w2t_bf16_padded,
+                                   const void* z1_bf16, const float* bn_scale, const float* bn_shift, const float* mean,
+                                   const float* rstd, void* d2_bf16, void* g_bf16, float* stat_partials, float* stats,
+                                   int64_t rows, int H, gsatb_stream_t stream) {
+    if (rows < 0 || H <= 0) return GSATB_EINVAL;
+    if (rows == 0) return GSATB_OK;
+    if (!dh || !posmask || !w2t_bf16_padded || !z1_bf16 || !bn_scale || !bn_shift || !mean || !rstd || !d2_bf16 || !g_bf16 ||
+        !stat_partials || !stats)
+        return GSATB_EINVAL;
+    if (H != 64 && H != 128) return GSATB_ESHAPE;
+    if (rows > (int64_t)INT32_MAX - TILE_ROWS) return GSATB_ESHAPE;
+    if (!gsatb_aligned16(z1_bf16)) return GSATB_EALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    RowsShape sh;
+    sh.rows = rows;
+    sh.num_tiles = (int)((rows + TILE_ROWS - 1) / TILE_ROWS);
+    sh.H = H;
+    sh.KB = H / 64;
+    sh.NSB = 1;
+    sh.dbg = profile_buffer();
+    const int fixed = sh.KB * BLK_BYTES + RW2_ROW_WARPS * RW2_STG + 512 + 1024;
+    int nst = (227 * 1024 - fixed) / ((H / 32) * BLK_BYTES);
+    if (nst > 6) nst = 6;
+    nst = rows_env("GSATB_ROWS_NST", nst, 1, nst);
+    if (nst < 2) return GSATB_ESHAPE;
+    sh.NST = nst;
+    CUtensorMap tw, tdh, td2, tg;
+    int rc = make_weight_tmap(&tw, w2t_bf16_padded, 128, sh.KB * KBLK);
+    if (rc != GSATB_OK) return rc;
+    rc = make_rows_tmap(&tdh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dh, rows, H, H, 32, TILE_ROWS);
+    if (rc != GSATB_OK) return rc;
+    rc = make_act_tmap(&td2, d2_bf16, rows, H, H);
+    if (rc != GSATB_OK) return rc;
+    rc = make_rows_tmap(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_bf16, rows, H, H, 64, 32);
+    if (rc != GSATB_OK) return rc;
+    const Rows2Smem L = rows2_smem(sh);
+    if (L.total > 227 * 1024) return GSATB_ESHAPE;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_rows_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return GSATB_ELAUNCH;
+        attr_set = true;
+    }
+    cudaMemsetAsync(stat_partials, 0, gsatb_gin_rows_stat_partials_elems(H) * sizeof(float), st);
+    RowsBwd2Params p{posmask, drop_scale, (const uint16_t*)z1_bf16, bn_scale, bn_shift, mean, stat_partials};
+    const int max_grid = rows_env("GSATB_ROWS_GRID", GSATB_NUM_SMS, 1, GSATB_NUM_SMS);
+    const int grid = sh.num_tiles < max_grid ? sh.num_tiles : max_grid;
+    k_rows_bwd2<<<grid, RW_THREADS, L.total, st>>>(tw, tdh, td2, tg, sh, p);
+    if (cudaPeekAtLastError() != cudaSuccess) return GSATB_ELAUNCH;
+    k_rows_bwd2_reduce<<<(2 * H + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS * RW2_ROW_WARPS, H, rstd, stats);
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
 }

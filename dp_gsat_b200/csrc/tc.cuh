@@ -177,6 +177,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // TMA store: shared memory box -> global tensor (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int crd0, int crd1) {

@@ -437,10 +437,15 @@ def _gin_mlp_backward(dh, agg16, h, w1, w2, gamma, z1, a1, mean, rstd, scale, sh
     # (operands are held in locals until the launch has been enqueued: a temporary passed as ptr(f(x)) is released
     # before the call is made -- harmless with the stream-ordered caching allocator, but not something to lean on)
     w2t = prep_weight(w2, transpose=True)
-    L.call('gsatb_tc_gin_bwd2', ptr(dh), None if posmask is not None else ptr(h), ptr(posmask),
-           ctypes.c_float(_dropout_scale(p, injected_mask)),
-           ptr(w2t), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
-           ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
+    if posmask is not None and _rows_path(Kin, H1, H):
+        part = torch.empty(int(L.cdll.gsatb_gin_rows_stat_partials_elems(H1)), dtype=torch.float32, device=dev)
+        L.call('gsatb_gin_rows_bwd2', ptr(dh), ptr(posmask), ctypes.c_float(_dropout_scale(p, injected_mask)), ptr(w2t), ptr(z1),
+               ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2), ptr(g), ptr(part), ptr(stats), N, H, stream())
+    else:
+        L.call('gsatb_tc_gin_bwd2', ptr(dh), None if posmask is not None else ptr(h), ptr(posmask),
+               ctypes.c_float(_dropout_scale(p, injected_mask)),
+               ptr(w2t), ptr(z1), ptr(scale), ptr(shift), ptr(mean), ptr(rstd), ptr(d2),
+               ptr(g), None, ptr(part), ptr(stats), N, H, H1, stream())      # a1 was kept by the forward
     dbeta, dgamma = stats[:H1], stats[H1:]
     n_glob = None
     if training and sync_group is not None:              # sums and row count over every rank's rows

@@ -322,8 +322,18 @@ int gsatb_tc_gin_bwd1(const void* g, const void* z1, const float* cA, const floa
  *                  gsatb_tc_linear_bf16_fwd (same dropout word stream: identical masks for identical seeds)
  *   gin_rows_bwd1: dz1 = cA*g + cB*z1 + cC formed in shared memory (stored as bf16 when dz1_bf16 is given), dx = dz1 W1
  *                  fp32 [rows,H]   (autograd of gin.py:55-62; replaces gsatb_tc_gin_bwd1 at these shapes)
+ *   gin_rows_bwd2: d2 = dh*(h>0)*drop_scale (sign bits from posmask; formed in place in the TMA-loaded fp32 tile, stored
+ *                  as bf16 [rows,H]), da1 = d2 W2, g = da1*(ReLU(BN(z1))>0) as bf16 [rows,H]; stats[0:H] = sum_rows g,
+ *                  stats[H:2H] = sum_rows g*xhat, taken from the bf16-rounded g that is stored, with a fixed-order
+ *                  two-stage reduction (stat_partials: gsatb_gin_rows_stat_partials_elems(H) floats)   (replaces
+ *                  gsatb_tc_gin_bwd2 at these shapes)
  * gsatb_gin_rows_supported -> 1 when the three widths qualify. */
 int gsatb_gin_rows_supported(int K, int H1, int H);
+size_t gsatb_gin_rows_stat_partials_elems(int H);
+int gsatb_gin_rows_bwd2(const float* dh, const uint32_t* posmask, float drop_scale, const void* w2t_bf16_padded,
+                        const void* z1_bf16, const float* bn_scale, const float* bn_shift, const float* mean,
+                        const float* rstd, void* d2_bf16, void* g_bf16, float* stat_partials, float* stats, int64_t rows,
+                        int H, gsatb_stream_t stream);
 int gsatb_gin_rows_lin1(const void* x_bf16, const void* w1_bf16_padded, const float* bias /* [nullable] */, void* z1_bf16,
                         float* stat_partials /* [nullable] */, double* stats /* [nullable] */, int64_t rows, int H,
                         gsatb_stream_t stream);

@@ -97,6 +97,7 @@ inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 
 // ---- TMA -------------------------------------------------------------------------------------------------------
 inline void tma_prefetch_desc(const void*) {}
+inline void prefetch_l2(const void*) {}
 inline uint32_t swizzle128(uint32_t byte_addr) { return byte_addr ^ (((byte_addr >> 7) & 7u) << 4); }
 inline void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int crd0, int crd1) {
     const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);

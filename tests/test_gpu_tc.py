@@ -476,8 +476,8 @@ def test_word_dropout_rate_and_scale(G, p):
 
 
 @pytest.mark.parametrize('H', [64, 128])
-@pytest.mark.parametrize('N', [777, 4096 + 40])
-def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N):
+@pytest.mark.parametrize('N,grid', [(777, 148), (4096 + 40, 3)])
+def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeypatch):
     """The row-owner node-MLP kernels (csrc/gin_rows.cu: TMA in / TMA out, BatchNorm + ReLU and the BatchNorm backward
     applied to the operand tile in shared memory, statistics from the swapped product) against the channel-owner
     skeleton kernels they replace at H = 64 / 128 -- same contracts (src/models/gin.py:55-62 forward and autograd), same
@@ -487,6 +487,8 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N):
     from dp_gsat_b200._lib import lib, ptr, stream
     L = lib()
     assert L.cdll.gsatb_gin_rows_supported(H, H, H) == 1 and L.cdll.gsatb_gin_rows_supported(H, H, 2 * H) == 0
+    # grid = 3: eleven tiles per persistent CTA, so the stage rings, accumulator slots and staging buffers wrap
+    monkeypatch.setenv('GSATB_ROWS_GRID', str(grid))
     torch.manual_seed(N + H)
     dev = 'cuda'
     x16 = torch.randn(N, H, device=dev).bfloat16()
@@ -531,6 +533,35 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N):
     L.call('gsatb_gin_rows_bwd1', ptr(g16), ptr(z_old), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz_new), ptr(dx_new), N, H, stream())
     assert torch.equal(dz_new.view(torch.int16), dz_old.view(torch.int16))
     assert torch.allclose(dx_new, dx_old, rtol=1e-5, atol=1e-5)
+    # --- ReLU / dropout backward folded into the dX product of the second Linear, BatchNorm-backward statistics
+    dh = torch.randn(N, H, device=dev)
+    pm = torch.randint(-2 ** 31, 2 ** 31 - 1, (N, H // 32), dtype=torch.int64, device=dev).to(torch.int32)
+    mean, rstd = torch.randn(H, device=dev) * 0.3, torch.rand(H, device=dev) + 0.5
+    w2t = tc.prep_weight(w2, transpose=True)
+    outs = []
+    for name in ('gsatb_tc_gin_bwd2', 'gsatb_gin_rows_bwd2'):
+        d2, g = torch.zeros((N, H), dtype=torch.bfloat16, device=dev), torch.zeros((N, H), dtype=torch.bfloat16, device=dev)
+        stats = torch.empty(2 * H, device=dev)
+        if name == 'gsatb_tc_gin_bwd2':
+            part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H)), device=dev)
+            L.call(name, ptr(dh), None, ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
+                   ptr(rstd), ptr(d2), ptr(g), None, ptr(part), ptr(stats), N, H, H, stream())
+        else:
+            part = torch.empty(int(L.cdll.gsatb_gin_rows_stat_partials_elems(H)), device=dev)
+            L.call(name, ptr(dh), ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
+                   ptr(rstd), ptr(d2), ptr(g), ptr(part), ptr(stats), N, H, stream())
+        outs.append((d2, g, stats))
+    (d2_o, g_o, st_o), (d2_n, g_n, st_n) = outs
+    assert torch.equal(d2_n.view(torch.int16), d2_o.view(torch.int16))
+    assert torch.equal(g_n == 0, g_o == 0)                               # same gates
+    assert rel_l2(g_n.float(), g_o.float()) < 1e-3                       # (bf16 rounding of accumulators that differ in the last bit)
+    # (the row-owner kernel takes the sums from the bf16-rounded g it stores, the channel-owner one from the fp32 g)
+    sc_ = float(st_o.abs().max())
+    assert float((st_n - st_o).abs().max()) < 3e-3 * sc_ + 1e-3, (st_n - st_o).abs().max()
+    g64 = g_n.double()
+    xh = (z_old.double() - mean.double()) * rstd.double()
+    assert torch.allclose(st_n[:H].double(), g64.sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st_n[H:].double(), (g64 * xh).sum(0), rtol=1e-4, atol=1e-2)
 
 
 def tc_unpack_bits(words: torch.Tensor, H: int) -> torch.Tensor:

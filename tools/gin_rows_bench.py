@@ -58,12 +58,25 @@ for H in (128, 64):
          timed(lambda: L.call('gsatb_tc_gin_bwd1', ptr(g16), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz), ptr(dx), N, H, H, stream())), 10 * NH)
     line('new bwd1 (rows)',
          timed(lambda: L.call('gsatb_gin_rows_bwd1', ptr(g16), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz), ptr(dx), N, H, stream())), 10 * NH)
+    dh = torch.randn(N, H, device=dev)
+    mean, rstd = torch.randn(H, device=dev) * 0.3, torch.rand(H, device=dev) + 0.5
+    w2t = tc.prep_weight(w2, transpose=True)
+    d2, gg, stats = torch.empty_like(g16), torch.empty_like(g16), torch.empty(2 * H, device=dev)
+    part_o = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H)), device=dev)
+    part_n = torch.empty(int(L.cdll.gsatb_gin_rows_stat_partials_elems(H)), device=dev)
+    bwd2_old = lambda: L.call('gsatb_tc_gin_bwd2', ptr(dh), None, ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z1), ptr(scale), ptr(shift),
+                              ptr(mean), ptr(rstd), ptr(d2), ptr(gg), None, ptr(part_o), ptr(stats), N, H, H, stream())
+    bwd2_new = lambda: L.call('gsatb_gin_rows_bwd2', ptr(dh), ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z1), ptr(scale), ptr(shift),
+                              ptr(mean), ptr(rstd), ptr(d2), ptr(gg), ptr(part_n), ptr(stats), N, H, stream())
+    line('old bwd2 (skeleton, producer layout)', timed(bwd2_old), 10 * NH + N * H / 8 / 1e6)
+    line('new bwd2 (rows)', timed(bwd2_new), 10 * NH + N * H / 8 / 1e6)
     # role counters of the new kernels (MMA thread: total / wait input / wait accumulator; epilogue warp 4: wait / work;
     # transform warps: wait / work), cycles per tile of the CTA
     tiles = N / 128 / 148
     for name, fn in (('lin1', lambda: tc._rows_lin1(x16, w1p, b1, H, True)),
                      ('lin2', lambda: L.call('gsatb_gin_rows_lin2', ptr(z1), ptr(scale), ptr(shift), ptr(w2p), ptr(b2), ptr(a1), ptr(h), ptr(pm), None,
                                              ctypes.c_uint64(3), ctypes.c_float(0.3), N, H, stream())),
+                     ('bwd2', bwd2_new),
                      ('bwd1', lambda: L.call('gsatb_gin_rows_bwd1', ptr(g16), ptr(z1), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz), ptr(dx), N, H, stream()))):
         dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
         L.cdll.gsatb_tc_set_profile_buffer(ctypes.c_void_p(dbg.data_ptr()))
@@ -71,6 +84,6 @@ for H in (128, 64):
         L.cdll.gsatb_tc_set_profile_buffer(None)
         d = dbg.double().mean(0).cpu() / tiles
         print(f'    roles {name}: mma total {d[0]:.0f}, wait in {d[1]:.0f}, wait acc {d[2]:.0f}; epi(w4, own tiles only) wait {d[4]:.0f} work {d[5]:.0f}; '
-              f'xf wait {d[6]:.0f} work {d[7]:.0f}  cycles per CTA tile', flush=True)
-    del x16, z1, a1, h, g16, dz, dx, pm
+              f'xf wait {d[6]:.0f} work {d[7]:.0f}; gate/stat warp wait {d[8]:.0f} work {d[9]:.0f}  cycles per CTA tile', flush=True)
+    del x16, z1, a1, h, g16, dz, dx, pm, dh, d2, gg
     torch.cuda.empty_cache()
