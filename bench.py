@@ -223,8 +223,8 @@ def kernel_models(N, E, G, H):
         'gsatb_gin_aggregate_bwd:noatt': (8.0 * N * H + 8.0 * E, 1.0 * E * H),
         'gsatb_gin_aggregate_fwd_bf16:att': (6.0 * N * H + 8.0 * E + 4.0 * N, 2.0 * E * H),
         'gsatb_gin_aggregate_fwd_bf16:noatt': (6.0 * N * H + 4.0 * E + 4.0 * N, 1.0 * E * H),
-        'gsatb_tc_linear_bf16_fwd:bf16': (4.0 * N * H, 2.0 * N * H * H),              # bf16 agg in, bf16 z1 out
-        'gsatb_tc_linear_bf16_fwd:fp32': (6.0 * N * H, 2.0 * N * H * H),              # bf16 a1 in, fp32 h out
+        # (gsatb_tc_linear_bf16_fwd is not modelled: at H = 64 / 128 the node MLP runs on the row-owner kernels and the
+        # remaining calls are the small encoder / classifier Linears, whose shapes differ from call to call)
         # row-owner node-MLP kernels (csrc/gin_rows.cu): lin1 = bf16 agg in, bf16 z1 out; lin2 = bf16 z1 in, bf16 a1 +
         # fp32 h + sign bits out; bwd1 = bf16 g, z1 in, bf16 dz1 + fp32 dx out; bwd2 = fp32 dh, sign bits, bf16 z1 in,
         # bf16 d2, g out
@@ -436,14 +436,21 @@ def run_b200(a):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
 
+    from dp_gsat_b200 import tc as _tc
+    ext_plans = [('edge', _tc.ext_tile_slots(H, True))] if a.precision == 'bf16' else []
+
     def fetch():
         with torch.cuda.stream(copy_stream):
             d = shard_host.to(dev, non_blocking=True)                  # H2D of one step's inputs
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
         for t in (d.x, d.edge_index, d.batch, d.y, d.edge_attr, d.edge_label):
             if t is not None:
                 t.record_stream(main_stream)                           # allocated on the copy stream, used on the main one
+        # the loader's prefetch stage also builds the batch's index (K0 + tile plan) behind the copy, on the copy stream:
+        # ~40 short dependent launches that hide under the step the main stream is running
+        G.prefetch_graph_index(d.edge_index, d.batch, getattr(d, 'num_graphs', None), on_stream=copy_stream,
+                               for_stream=main_stream, ext_plans=ext_plans)
+        ev = torch.cuda.Event()
+        ev.record(copy_stream)
         return d, ev
 
     def e2e_loop(n):
@@ -452,11 +459,11 @@ def run_b200(a):
         for i in range(n):
             d, ev = nxt
             main_stream.wait_event(ev)
+            _, loss, _, _ = step(d, 0)                      # the step of batch i is enqueued (its index is already cached) ...
             if i + 1 < n:
-                nxt = fetch()
-            _, loss, _, _ = step(d, 0)                      # index build (K0) + step
+                nxt = fetch()                               # ... and runs while batch i + 1 is copied and indexed
             last = float(loss.item())                       # D2H of the step's result
-            G.clear_index_cache()                           # this batch is done: its index blocks go back to the allocator
+            G.evict_graph_index(d.edge_index, d.batch)      # this batch is done: its index blocks go back to the allocator
         return last
 
     # untimed warm-up of THIS loop (W >= 3 applies to it as well): the first passes grow the copy stream's allocator pool
@@ -472,7 +479,7 @@ def run_b200(a):
     e2e = {'value': E_global / float(t_e2e.item()), 'unit': UNIT, 'h2d_bytes_per_step': shard_host.nbytes() * world,
            'd2h_bytes_per_step': 4 * world, 'ms_per_step': float(t_e2e.item()) * 1e3, 'steps': e2e_steps,
            'last_loss': loss_host, 'warmup': 3,
-           'how': 'pinned host batch -> H2D (copy stream, prefetched one step ahead) -> K0 index build -> step -> loss.item()'}
+           'how': 'pinned host batch -> H2D + K0 index build on the copy stream, prefetched one step ahead -> step -> loss.item()'}
 
     # strict-mode figure beside the bf16 one (N = 1): the same workload, model and step with precision='fp32' -- the
     # mode the rtol-1e-5 parity tests hold to the fp32 oracle (same tcgen05 GEMM kernels, split-bf16 x3 operands)

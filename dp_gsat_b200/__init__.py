@@ -14,7 +14,7 @@ if 'dp_gsat_b200.build' not in getattr(_sys, 'orig_argv', []):     # `python -m 
     _lib()  # fail at import time if the CUDA library is missing or does not export the declared C ABI
 
 from .data import Batch  # noqa: E402
-from .index import GraphIndex, get_graph_index, clear_index_cache, set_index_cache_capacity  # noqa: E402
+from .index import GraphIndex, get_graph_index, prefetch_graph_index, evict_graph_index, clear_index_cache, set_index_cache_capacity  # noqa: E402
 from .nn import (GIN, GINConv, GINEConv, LEConv, SPMotifNet, ExtractorMLP, MLP, BatchSequential, InstanceNorm, Criterion, get_model,  # noqa: E402
                  get_preds, AtomEncoder, BondEncoder)
 from .gsat import (GSAT, DualGSAT, is_undirected, transpose, reorder_like, get_r, concrete_sample,  # noqa: E402
@@ -26,7 +26,7 @@ from .loader import Graph, PackedDataset, DeviceLoader  # noqa: E402
 from . import ops, dense  # noqa: E402
 from .dense import Linear  # noqa: E402
 
-__all__ = ['Batch', 'GraphIndex', 'get_graph_index', 'clear_index_cache', 'set_index_cache_capacity', 'GIN', 'GINConv', 'GINEConv', 'LEConv', 'SPMotifNet', 'ExtractorMLP', 'MLP',
+__all__ = ['Batch', 'GraphIndex', 'get_graph_index', 'prefetch_graph_index', 'evict_graph_index', 'clear_index_cache', 'set_index_cache_capacity', 'GIN', 'GINConv', 'GINEConv', 'LEConv', 'SPMotifNet', 'ExtractorMLP', 'MLP',
            'BatchSequential', 'InstanceNorm', 'Criterion', 'get_model', 'get_preds', 'AtomEncoder', 'BondEncoder',
            'GSAT', 'DualGSAT', 'is_undirected', 'transpose', 'reorder_like', 'get_r', 'concrete_sample',
            'lift_node_att_to_edge_att', 'gumbel_sigmoid', 'f1_sparsity_loss', 'info_loss', 'ops', 'PNA', 'PNAConvSimple', 'line_graph_dual', 'line_graph_dual_dense', 'dense_dual_node_features', 'get_precision_at_k', 'get_delta_kl',

@@ -185,6 +185,39 @@ def get_graph_index(edge_index: torch.Tensor, batch: Optional[torch.Tensor], num
     return hit[0]
 
 
+def prefetch_graph_index(edge_index: torch.Tensor, batch: torch.Tensor, num_graphs: Optional[int] = None, *,
+                         on_stream: "torch.cuda.Stream", for_stream: "torch.cuda.Stream", ext_plans=()) -> GraphIndex:
+    """Build (and cache) the index of a batch one step AHEAD of its use, as a data loader's prefetch stage would: K0,
+    the flag read-back and the fused extractor's tile plans (``ext_plans``: (by, max_slots) pairs) run on ``on_stream``
+    -- typically the copy stream that has just brought the batch in -- while the previous step computes on
+    ``for_stream``.  K0 at this size is ~40 short dependent launches (latency, not bandwidth), so it hides completely
+    under the running step; its two tiny D2H reads synchronise only ``on_stream``.  Every tensor of the bundle is
+    registered with ``for_stream`` (caching-allocator stream semantics), and ``for_stream`` must still wait on an event
+    recorded on ``on_stream`` after this call before it uses the batch."""
+    with torch.cuda.stream(on_stream):
+        gi = get_graph_index(edge_index, batch, num_graphs)
+        _ = gi.flags
+        for by, max_slots in ext_plans:
+            gi.ext_plan(by, max_slots)
+    for name in ('src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src', 'eid_by_src', 'dst_by_src',
+                 'node_ptr', 'edge_ptr', 'node_graph', 'edge_graph', 'flags_dev'):
+        getattr(gi, name).record_stream(for_stream)
+    for plan in (gi._plans or {}).values():
+        if isinstance(plan, dict):
+            for v in plan.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(for_stream)
+    return gi
+
+
+def evict_graph_index(edge_index: torch.Tensor, batch: torch.Tensor) -> bool:
+    """Drop the cached index of ONE batch (a loader that streams fresh batches calls this when a batch is done, so that
+    its index blocks go back to the allocator while the prefetched entry of the next batch stays)."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, batch.data_ptr(), int(batch.numel()),
+           batch._version, str(edge_index.device))
+    return _CACHE.pop(key, None) is not None
+
+
 def clear_index_cache():
     _CACHE.clear()
 

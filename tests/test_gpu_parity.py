@@ -74,6 +74,33 @@ def test_index_build_bit_exact(G, name):
     assert gi.graph_contiguous == ref['graph_contiguous']
 
 
+def test_prefetched_index_equals_the_index_built_in_the_step(G):
+    """prefetch_graph_index (the loader's prefetch stage: K0 + flags + extractor tile plan on a side stream, one batch
+    ahead) caches exactly the bundle a direct build produces, the consumer finds it under the same key, and
+    evict_graph_index drops that one entry only."""
+    from dp_gsat_b200 import tc
+    ei, batch = _cases()['ba2motifs']
+    ei_a, b_a, ei_b, b_b = ei.cuda(), batch.cuda(), ei.cuda(), batch.cuda()
+    ref = G.GraphIndex(ei_a, b_a)
+    G.clear_index_cache()
+    side, main = torch.cuda.Stream(), torch.cuda.current_stream()
+    slots = tc.ext_tile_slots(64, True)
+    gi = G.prefetch_graph_index(ei_b, b_b, 16, on_stream=side, for_stream=main, ext_plans=[('edge', slots)])
+    ev = torch.cuda.Event()
+    ev.record(side)
+    main.wait_event(ev)
+    assert G.get_graph_index(ei_b, b_b, 16) is gi                       # the step finds the prefetched entry
+    assert gi._flags_host is not None and ('ext', 'edge', slots) in gi._plans       # nothing left to read back in the step
+    for k in ('src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src', 'eid_by_src', 'dst_by_src',
+              'node_ptr', 'edge_ptr', 'node_graph', 'edge_graph'):
+        assert torch.equal(getattr(gi, k), getattr(ref, k)), k
+    assert gi.ext_plan('edge', slots)['T'] == ref.ext_plan('edge', slots)['T']
+    other = G.get_graph_index(ei_a, b_a)
+    assert G.evict_graph_index(ei_b, b_b) and not G.evict_graph_index(ei_b, b_b)
+    assert G.get_graph_index(ei_a, b_a) is other                        # the other batch's entry stayed
+    G.clear_index_cache()
+
+
 def test_mutag_reverse_is_xor1_on_gpu(G):
     ei, batch = _cases()['mutag']
     gi = G.GraphIndex(ei.cuda(), batch.cuda())
