@@ -95,6 +95,7 @@ class TrainStep:
         self.optimizer = torch.optim.Adam(self.bucket.params, lr=lr, weight_decay=weight_decay, fused=fused_adam,
                                           capturable=bool(fused_adam))
         self.graph = None            # torch.cuda.CUDAGraph of one whole step (enable_cuda_graph)
+        self._graph_data = self._graph_index = None
         self._graph_key = None
         self._graph_out = None
         self.launches_per_step = None
@@ -152,10 +153,57 @@ class TrainStep:
             return False
         self.launches_per_step = lib().launches - n0
         self.graph, self._graph_key, self._graph_out = graph, self._key(data, epoch), out
+        # the batch and the index bundle the graph reads (load_batch refreshes them in place)
+        from .index import get_graph_index
+        self._graph_data = data
+        self._graph_index = get_graph_index(data.edge_index, data.batch, getattr(data, 'num_graphs', None))
         return True
 
     def disable_cuda_graph(self):
         self.graph = self._graph_key = self._graph_out = None
+        self._graph_data = self._graph_index = None
+
+    _BATCH_FIELDS = ('x', 'edge_index', 'batch', 'y', 'edge_attr', 'edge_label', 'node_label')
+    _INDEX_FIELDS = ('src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src', 'eid_by_src',
+                     'dst_by_src', 'node_ptr', 'edge_ptr', 'node_graph', 'edge_graph', 'flags_dev')
+
+    def load_batch(self, batch, index=None) -> bool:
+        """Refresh the captured graph's RESIDENT batch with a fresh one of the same shape: a loader that streams new
+        batches (``data.to(device)`` every step, src/run_gsat.py:296) keeps the one-launch step by copying each batch --
+        and the index bundle K0 built for it, e.g. one step ahead with ``prefetch_graph_index`` -- into the static
+        buffers the graph reads (device-to-device, on the current stream), then calling the step on the resident batch.
+        Everything the capture baked in on the host is checked first: node / edge / graph counts, tensor shapes, the
+        index flags (symmetry, duplicates, contiguity) and the fused extractor's tile counts; returns False (nothing
+        copied) when the new batch does not fit, and the caller takes an eager step on it instead."""
+        if self.graph is None or getattr(self, '_graph_data', None) is None:
+            return False
+        from .index import get_graph_index
+        d, gi = self._graph_data, self._graph_index
+        if index is None:
+            index = get_graph_index(batch.edge_index, batch.batch, getattr(batch, 'num_graphs', None))
+        if (index.N, index.E, index.G) != (gi.N, gi.E, gi.G) or list(index.flags) != list(gi.flags):
+            return False
+        pairs = []
+        for name in self._BATCH_FIELDS:
+            a, b = getattr(d, name, None), getattr(batch, name, None)
+            if (a is None) != (b is None):
+                return False
+            if a is not None:
+                if a.shape != b.shape or a.dtype != b.dtype:
+                    return False
+                pairs.append((a, b))
+        for key, plan in (gi._plans or {}).items():
+            if not (isinstance(plan, dict) and key[0] == 'ext'):
+                return False                       # host-built plans are not refreshed
+            other = index.ext_plan(key[1], key[2])
+            if other['T'] != plan['T'] or other['oversize'] != plan['oversize']:
+                return False
+            pairs += [(plan['tile_seg'], other['tile_seg']), (plan['out2'], other['out2'])]
+        pairs += [(getattr(gi, n), getattr(index, n)) for n in self._INDEX_FIELDS]
+        with torch.no_grad():
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
+        return True
 
     def __call__(self, data, epoch: int, noise_u=None):
         if self.graph is not None and noise_u is None and self._key(data, epoch) == self._graph_key:

@@ -104,7 +104,8 @@ lib = ctypes.CDLL(m.LIB_PATH)
 bad = []
 for name, (restype, argtypes) in sorted(m.parse_header().items()):
     if restype is not ctypes.c_int or name in ('gsatb_version', 'gsatb_check_device', 'gsatb_set_step_counter',
-                                               'gsatb_tc_set_profile_buffer', 'gsatb_ext_tile_slots'):      # (the last one is a pure size query)
+                                               'gsatb_tc_set_profile_buffer', 'gsatb_ext_tile_slots',
+                                                   'gsatb_gin_rows_supported'):      # (the last two are pure shape queries)
         continue
     fn = getattr(lib, name); fn.restype, fn.argtypes = restype, argtypes
     args = [None if t is ctypes.c_void_p else (0.0 if t is ctypes.c_float else 1) for t in argtypes]

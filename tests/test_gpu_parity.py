@@ -611,6 +611,55 @@ def test_cuda_graph_training_step(G):
     assert np.isfinite(float(loss_e))
 
 
+def test_graph_step_load_batch_refreshes_the_resident_batch(G):
+    """TrainStep.load_batch: a fresh batch of the captured shape (here: other features, labels and edge order inside the
+    graphs) and the index K0 built for it are copied into the static buffers the step graph reads, so a streaming loader
+    keeps the one-launch step; a batch that does not fit is refused untouched."""
+    from dp_gsat_b200.data import ba2motifs_batch, Batch
+    from dp_gsat_b200.parallel import TrainStep
+    from dp_gsat_b200 import tc
+    b = ba2motifs_batch(64, seed=5).to('cuda')
+    cfg = {'model_name': 'GIN', 'hidden_size': 64, 'n_layers': 2, 'dropout_p': 0.3, 'use_edge_attr': False}
+    shared = {'learn_edge_att': True, 'extractor_dropout_p': 0.5}
+    torch.manual_seed(0)
+    clf, ext = G.get_model(10, 0, 2, False, cfg, 'cuda'), G.ExtractorMLP(64, shared).cuda()
+    clf.precision = ext.precision = 'bf16'
+    gsat = G.GSAT(clf, ext, G.Criterion(2, False), learn_edge_att=True, final_r=0.5, lazy_metrics=True)
+    gsat.train()
+    step = TrainStep(gsat, lr=1e-3)
+    assert step.load_batch(b) is False                                   # no graph yet
+    assert step.enable_cuda_graph(b, 0, warmup=2)
+    _, loss0, _, _ = step(b, 0)
+    loss0 = float(loss0)
+    # the same graphs with each graph's edge list reversed (still grouped by graph, still symmetric), new features / labels
+    gi0 = G.GraphIndex(b.edge_index.clone(), b.batch.clone(), b.num_graphs)
+    ep = gi0.edge_ptr.long()
+    e = torch.arange(b.num_edges, device='cuda')
+    g_of_e = gi0.edge_graph.long()
+    perm = ep[g_of_e] + (ep[g_of_e + 1] - 1 - e)
+    torch.manual_seed(1)
+    b2 = Batch(torch.randn_like(b.x), b.edge_index[:, perm].contiguous(), b.batch.clone(), 1 - b.y, None,
+               None if b.edge_label is None else b.edge_label[perm].contiguous(), b.num_graphs)
+    side = torch.cuda.Stream()
+    gi2 = G.prefetch_graph_index(b2.edge_index, b2.batch, b2.num_graphs, on_stream=side,
+                                 for_stream=torch.cuda.current_stream(), ext_plans=[('edge', tc.ext_tile_slots(64, True))])
+    torch.cuda.current_stream().wait_stream(side)
+    assert step.load_batch(b2, gi2) is True
+    assert torch.equal(b.x, b2.x) and torch.equal(b.edge_index, b2.edge_index) and torch.equal(b.y, b2.y)
+    ref = G.GraphIndex(b2.edge_index.clone(), b2.batch.clone(), b2.num_graphs)
+    for k in ('src', 'dst', 'rev', 'rowptr_dst', 'eid_by_dst', 'src_by_dst', 'rowptr_src', 'eid_by_src', 'dst_by_src',
+              'node_ptr', 'edge_ptr', 'node_graph', 'edge_graph'):
+        assert torch.equal(getattr(step._graph_index, k), getattr(ref, k)), k
+    edge_att, loss1, _, _ = step(b, 0)                                    # ONE replay, now on b2's contents
+    torch.cuda.synchronize()
+    assert np.isfinite(float(loss1)) and float(loss1) != loss0
+    assert torch.equal(edge_att.view(-1), edge_att.view(-1)[ref.rev.long()])          # symmetric under b2's reverse map
+    small = ba2motifs_batch(32, seed=5).to('cuda')
+    assert step.load_batch(small) is False                                # other counts: refused, nothing copied
+    assert torch.equal(b.x, b2.x)
+    step.disable_cuda_graph()
+
+
 @pytest.mark.parametrize('N,F_,H', [(1000, 10, 64), (33333, 14, 128), (777, 9, 80), (5, 1, 4)])
 def test_small_linear_weight_gradient(G, N, F_, H):
     """Node-encoder Linear (src/models/gin.py:22-25): own K = N weight / bias gradient kernel against autograd."""
