@@ -245,6 +245,7 @@ def kernel_models(N, E, G, H):
         'gsatb_tc_ext_make_h1': (4.0 * E * C1, 0.0),
         'gsatb_linear_small_dw': (4.0 * N * H + 40.0 * N, 2.0 * N * H * 11),
         'gsatb_gather_concat_bwd': (4.0 * E * 2 * H + 8.0 * E + 4.0 * N * H, 2.0 * E * H),
+        'gsatb_gather_concat_bwd_bf16': (2.0 * E * 2 * H + 8.0 * E + 4.0 * N * H, 2.0 * E * H),
         'gsatb_sample_avg_info_fwd': (20.0 * E, 0.0),
         'gsatb_sample_avg_info_bwd': (20.0 * E, 0.0),
         'gsatb_pool_fwd': (4.0 * N * H + 4.0 * G * H, 1.0 * N * H),

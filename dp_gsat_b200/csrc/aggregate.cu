@@ -705,6 +705,40 @@ k_gather_concat_bwd(const float4* __restrict__ g, const int32_t* __restrict__ ro
     }
 }
 
+// the same reduction over a bf16 g (d f12 as the fused extractor backward writes it in bf16 mode): half the bytes of the
+// step's largest intermediate; fp32 accumulation in the same order.  A lane owns 8 channels (one 16-byte load per edge).
+__device__ __forceinline__ void acc_bf16x8(float (&a)[8], const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[2 * i] += __uint_as_float(w[i] << 16);
+        a[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
+template <int LPR>
+__global__ void __launch_bounds__(AGG_THREADS)
+k_gather_concat_bwd_bf16(const uint4* __restrict__ g, const int32_t* __restrict__ rowptr_src,
+                         const int32_t* __restrict__ eid_by_src, const int32_t* __restrict__ rowptr_dst,
+                         const int32_t* __restrict__ eid_by_dst, float4* __restrict__ demb, int64_t N, int HV8) {
+    constexpr int ROWS_PER_WARP = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
+    const int64_t warp_global = (blockIdx.x * (int64_t)(AGG_THREADS / 32)) + (threadIdx.x >> 5);
+    const int64_t warps_total = (int64_t)gridDim.x * (AGG_THREADS / 32);
+    for (int64_t row0 = warp_global * ROWS_PER_WARP; row0 < N; row0 += warps_total * ROWS_PER_WARP) {
+        const int64_t row = row0 + sub;
+        if (row >= N) continue;
+        for (int c = sl; c < HV8; c += LPR) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int p = __ldg(rowptr_src + row), pe = __ldg(rowptr_src + row + 1); p < pe; ++p)
+                acc_bf16x8(acc, __ldg(g + (int64_t)__ldg(eid_by_src + p) * 2 * HV8 + c));
+            for (int p = __ldg(rowptr_dst + row), pe = __ldg(rowptr_dst + row + 1); p < pe; ++p)
+                acc_bf16x8(acc, __ldg(g + (int64_t)__ldg(eid_by_dst + p) * 2 * HV8 + HV8 + c));
+            demb[row * (2 * HV8) + 2 * c] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            demb[row * (2 * HV8) + 2 * c + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int gsatb_gather_concat_fwd(const float* emb, const int32_t* src, const int32_t* dst, float* out,
@@ -735,6 +769,32 @@ extern "C" int gsatb_gather_concat_bwd(const float* g, const int32_t* rowptr_src
     const int lpr = pick_lpr(HV);
     const unsigned grid = agg_grid(N, lpr);
 #define GC_CASE(L) k_gather_concat_bwd<L><<<grid, AGG_THREADS, 0, st>>>((const float4*)g, rowptr_src, eid_by_src, rowptr_dst, eid_by_dst, (float4*)demb, N, HV)
+    switch (lpr) {
+        case 1: GC_CASE(1); break;
+        case 2: GC_CASE(2); break;
+        case 4: GC_CASE(4); break;
+        case 8: GC_CASE(8); break;
+        case 16: GC_CASE(16); break;
+        default: GC_CASE(32); break;
+    }
+#undef GC_CASE
+    GSATB_CHECK_LAUNCH();
+    return GSATB_OK;
+}
+
+extern "C" int gsatb_gather_concat_bwd_bf16(const void* g_bf16, const int32_t* rowptr_src, const int32_t* eid_by_src,
+                                            const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N,
+                                            int H, gsatb_stream_t stream) {
+    if (N < 0 || H <= 0) return GSATB_EINVAL;
+    if (N == 0) return GSATB_OK;
+    if (!g_bf16 || !rowptr_src || !rowptr_dst || !demb) return GSATB_EINVAL;
+    if (H % 8 != 0) return GSATB_ESHAPE;
+    if (!gsatb_aligned16(g_bf16) || !gsatb_aligned16(demb)) return GSATB_EALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HV = H / 8;
+    const int lpr = pick_lpr(HV);
+    const unsigned grid = agg_grid(N, lpr);
+#define GC_CASE(L) k_gather_concat_bwd_bf16<L><<<grid, AGG_THREADS, 0, st>>>((const uint4*)g_bf16, rowptr_src, eid_by_src, rowptr_dst, eid_by_dst, (float4*)demb, N, HV)
     switch (lpr) {
         case 1: GC_CASE(1); break;
         case 2: GC_CASE(2); break;

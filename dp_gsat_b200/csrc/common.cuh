@@ -46,6 +46,16 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     return r;
 #endif
 }
+// 64-bit variant (four bf16)
+__device__ __forceinline__ uint2 ldg_stream_u2(const uint2* p) {
+#ifdef GSATB_HOST_SIM
+    return *p;
+#else
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+#endif
+}
 // 128-bit gather load through the read-only path, L1-allocating (neighbour rows are re-used inside a CTA).
 __device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
 

@@ -37,7 +37,8 @@ struct BwdParams {
     uint16_t* dz2t;              // bf16 slot space, tile-major [tiles][pad128(H)][128]
     uint16_t* dz1t;              // bf16 [tiles][pad128(C1)][128]
     uint16_t* h1t;               // bf16 [tiles][pad128(C1)][128]
-    float* df12;                 // [rows, Kin]
+    float* df12;                 // [rows, Kin] fp32, or bf16 when df12_bf16
+    int df12_bf16;
     float* dw3_part;             // [grid, H]
     int64_t ld_slots;
     int ldx;
@@ -302,7 +303,7 @@ __device__ __forceinline__ void epi3_chunk_emit(const Epi3Ctx& c, const DropCtx&
 
 // d f12 rows of one graph for one input channel: accumulator columns -> coalesced fp32 stores (lane = channel)
 template <int NB>
-__device__ __forceinline__ void dx_chunk_out(uint32_t taddr, float* out, int Kin, int nleft) {
+__device__ __forceinline__ void dx_chunk_out(uint32_t taddr, float* out, uint16_t* out16, int Kin, int nleft) {
     float v[8 * NB];
     tmem_ld_blocks<NB>(taddr, v);
     tc::tmem_ld_wait();
@@ -310,6 +311,10 @@ __device__ __forceinline__ void dx_chunk_out(uint32_t taddr, float* out, int Kin
 #pragma unroll
         for (int j = 0; j < 8 * NB; ++j)
             if (j < nleft) out[(int64_t)j * Kin] = v[j];
+    } else if (out16) {          // bf16 d f12 (edge mode of the bf16 precision mode: gsatb_gather_concat_bwd_bf16 reduces it)
+#pragma unroll
+        for (int j = 0; j < 8 * NB; ++j)
+            if (j < nleft) out16[(int64_t)j * Kin] = float_to_bf16_bits(v[j]);
     }
 }
 
@@ -555,8 +560,10 @@ k_ext_fused_bwd(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant
                     const int slot0 = __shfl_sync(0xffffffffu, tq.slot0, s), row0 = __shfl_sync(0xffffffffu, tq.row0, s);
                     for (int c4 = 0; c4 < nblk; c4 += 4) {
                         const int nbk = nblk - c4 < 4 ? nblk - c4 : 4;
-                        float* out = k < p.Kin ? p.df12 + (int64_t)(row0 + 8 * c4) * p.Kin + k : nullptr;
-                        EXT_DISPATCH_NB4(nbk, (dx_chunk_out<NB>(taddr + slot0 + 8 * c4, out, p.Kin, ns - 8 * c4)));
+                        const int64_t o = (int64_t)(row0 + 8 * c4) * p.Kin + k;
+                        float* out = (k < p.Kin && !p.df12_bf16) ? p.df12 + o : nullptr;
+                        uint16_t* out16 = (k < p.Kin && p.df12_bf16) ? reinterpret_cast<uint16_t*>(p.df12) + o : nullptr;
+                        EXT_DISPATCH_NB4(nbk, (dx_chunk_out<NB>(taddr + slot0 + 8 * c4, out, out16, p.Kin, ns - 8 * c4)));
                     }
                 }
             }
@@ -726,8 +733,8 @@ extern "C" int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_s
                                    const void* w1t_bf16_padded, const float* w3, const float* dlogit, const void* xhat2t,
                                    const float* rstd2, const void* xs, const uint8_t* mask1, const uint8_t* mask2,
                                    const uint32_t* seeds, float pdrop, int training, void* dz2t, void* dz1t, void* h1t,
-                                   float* df12, float* dw3_part, int64_t ld_slots, int64_t rows, int H, int C1, float eps,
-                                   gsatb_stream_t stream) {
+                                   void* df12, int df12_is_bf16, float* dw3_part, int64_t ld_slots, int64_t rows, int H, int C1,
+                                   float eps, gsatb_stream_t stream) {
     if (rows < 0 || H <= 0 || C1 <= 0 || max_tiles < 0) return GSATB_EINVAL;
     if (rows == 0 || max_tiles == 0) return GSATB_OK;
     if (!seg_ptr || !tile_seg || !num_tiles_dev || !w1_bf16_padded || !w2t_bf16_padded || !w1t_bf16_padded || !w3 || !dlogit ||
@@ -748,7 +755,7 @@ extern "C" int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_s
     p.drop1.step = nullptr, p.drop2.step = nullptr;
     p.seeds = seeds;
     p.dz2t = (uint16_t*)dz2t, p.dz1t = (uint16_t*)dz1t, p.h1t = (uint16_t*)h1t;
-    p.df12 = df12, p.dw3_part = dw3_part, p.ld_slots = ld_slots;
+    p.df12 = (float*)df12, p.df12_bf16 = df12_is_bf16 != 0, p.dw3_part = dw3_part, p.ld_slots = ld_slots;
     p.H = H, p.Kin = Kin, p.C1 = C1, p.KB1 = (Kin + 63) / 64, p.KBH = (H + 63) / 64, p.NCB = (C1 + 127) / 128;
     p.KM = (Kin + 127) / 128;
     p.HP = pad128(H), p.C1P = pad128(C1);

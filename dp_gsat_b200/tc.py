@@ -282,20 +282,22 @@ class _FusedExtractorV2(torch.autograd.Function):
         bf = dict(dtype=torch.bfloat16, device=dev)
         HP, C1P = _pad(H, 128), _pad(C1, 128)
         dz2t, dz1t, h1t = torch.empty((T, HP, 128), **bf), torch.empty((T, C1P, 128), **bf), torch.empty((T, C1P, 128), **bf)
-        df12 = torch.empty((rows, Kin), dtype=torch.float32, device=dev)
+        # edge mode: d f12 [E, 2H] is the step's largest intermediate (10 GB at cfg4 in fp32); it leaves the kernel in bf16
+        # and the CSR reduction into d emb accumulates it in fp32.  Node mode: d f12 IS d emb (fp32).
+        df12 = torch.empty((rows, Kin), dtype=torch.bfloat16 if e else torch.float32, device=dev)
         nslab = 2 * min(max(gi.G, 1), 148)
         dw3p = torch.zeros((nslab, H), dtype=torch.float32, device=dev)
         w1p, w2t, w1t = prep_weight(w1), prep_weight(w2, transpose=True), prep_weight(w1, transpose=True)
         L.call('gsatb_ext_fused_bwd', ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, int(e),
                ptr(w1p), ptr(w2t), ptr(w1t), ptr(w3f), ptr(dl), ptr(xh2t), ptr(rstd2), ptr(xs), ptr(mask1), ptr(mask2),
-               ptr(seeds), ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), ptr(dw3p), ld, rows,
-               H, C1, ctypes.c_float(eps), stream())
+               ptr(seeds), ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), int(bool(e)), ptr(dw3p),
+               ld, rows, H, C1, ctypes.c_float(eps), stream())
         dW2, _ = weight_grad(dz2t, 2, h1t, 2, ld, H, C1)
         dW1, _ = weight_grad(dz1t, 2, xs, 0, ld, C1, Kin)
         del dz1t, h1t, dz2t
         if e:
             demb = torch.empty((N, H), dtype=torch.float32, device=dev)
-            L.call('gsatb_gather_concat_bwd', ptr(df12), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst),
+            L.call('gsatb_gather_concat_bwd_bf16', ptr(df12), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst),
                    ptr(gi.eid_by_dst), ptr(demb), N, H, stream())
         else:
             demb = df12

@@ -154,6 +154,10 @@ int gsatb_gather_concat_fwd(const float* emb, const int32_t* src, const int32_t*
 int gsatb_gather_concat_bwd(const float* g, const int32_t* rowptr_src, const int32_t* eid_by_src,
                             const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N, int H,
                             gsatb_stream_t stream);
+/* the same reduction over a bf16 g (fp32 accumulation in the same order) */
+int gsatb_gather_concat_bwd_bf16(const void* g_bf16, const int32_t* rowptr_src, const int32_t* eid_by_src,
+                                 const int32_t* rowptr_dst, const int32_t* eid_by_dst, float* demb, int64_t N, int H,
+                                 gsatb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Line-graph ("dual") builder of the fork.  Replaces the Python dict loops of
@@ -434,7 +438,8 @@ int gsatb_ext_fused_fwd(const float* emb, const int32_t* src /* [nullable] */, c
  *   centred bf16 input tiles the forward stored (TMA) in slot space [ld_slots = T * 128, pad64(Kin)]; the other inputs are
  *   d logit [rows], xhat2t / rstd2 / seeds as the forward wrote them, W2^T and W1^T from
  *   gsatb_tc_prep_weight(transpose = 1).  Outputs: d f12 [rows, Kin] fp32 (Kin = 2H, or H in node mode: then it IS d emb;
- *   edge mode: reduce with gsatb_gather_concat_bwd), dw3_part [min(max_tiles, 148) * 2, H] partial sums of d w3 (add
+ *   edge mode: reduce with gsatb_gather_concat_bwd) -- or, with df12_is_bf16, the same tensor rounded to bf16 (edge mode of
+ *   the bf16 precision mode: half the bytes of the step's largest intermediate; reduce with gsatb_gather_concat_bwd_bf16), dw3_part [min(max_tiles, 148) * 2, H] partial sums of d w3 (add
  *   them up), and the bf16 operands of the weight-gradient products in tile-major slot space, written with TMA stores:
  *   dz2t [tiles][pad128(H)][128], dz1t and h1t [tiles][pad128(C1)][128] (layout code 2 of gsatb_tc_dw: every 128-channel x
  *   64-slot box is a 32 KiB-local access instead of 128-byte pieces a whole row apart), so that dW2 = gsatb_tc_dw(dz2t, h1t) and
@@ -446,8 +451,8 @@ int gsatb_ext_fused_bwd(const int32_t* seg_ptr, const int32_t* tile_seg, const i
                         const void* w1t_bf16_padded, const float* w3, const float* dlogit, const void* xhat2t,
                         const float* rstd2, const void* xs, const uint8_t* mask1 /* [nullable] */,
                         const uint8_t* mask2 /* [nullable] */, const uint32_t* seeds /* [nullable] */, float pdrop, int training,
-                        void* dz2t, void* dz1t, void* h1t, float* df12, float* dw3_part, int64_t ld_slots, int64_t rows, int H,
-                        int C1, float eps, gsatb_stream_t stream);
+                        void* dz2t, void* dz1t, void* h1t, void* df12, int df12_is_bf16, float* dw3_part, int64_t ld_slots,
+                        int64_t rows, int H, int C1, float eps, gsatb_stream_t stream);
 
 /* gsatb_tc_dw: weight / bias gradients on the tensor cores:  dW[m, n] = sum_r A[r, m] * B[r, n],  db[m] = sum_r A[r, m]
  * (autograd of the Linear layers of src/utils/get_model.py:57-68 and src/models/gin.py:55-62, reached through

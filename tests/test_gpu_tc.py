@@ -569,3 +569,27 @@ def tc_unpack_bits(words: torch.Tensor, H: int) -> torch.Tensor:
     sh = torch.arange(32, device=words.device, dtype=torch.int64)
     bits = ((words.to(torch.int64).unsqueeze(-1) >> sh) & 1).bool()
     return bits.reshape(words.shape[0], -1)[:, :H]
+
+
+@pytest.mark.parametrize('H', [8, 64, 128])
+def test_gather_concat_bwd_bf16_equals_the_fp32_reduction_of_the_same_values(G, H):
+    """d emb[j] = sum_{src(e)=j} g[e, :H] + sum_{dst(e)=j} g[e, H:] (backward of cat(emb[col], emb[row]),
+    src/run_gsat.py:917-920) over a bf16 g -- the form the fused extractor backward writes d f12 in -- accumulates in fp32
+    in the same CSR order as the fp32 kernel: bit-identical to it on the same (bf16-representable) values."""
+    from dp_gsat_b200.data import molhiv_like_batch
+    from dp_gsat_b200._lib import lib, ptr, stream
+    b = molhiv_like_batch(40, seed=H).to('cuda')
+    gi = G.get_graph_index(b.edge_index, b.batch)
+    torch.manual_seed(H)
+    g16 = torch.randn(gi.E, 2 * H, device='cuda').bfloat16()
+    g32 = g16.float()
+    out16, out32 = torch.full((gi.N, H), float('nan'), device='cuda'), torch.empty((gi.N, H), device='cuda')
+    L = lib()
+    L.call('gsatb_gather_concat_bwd_bf16', ptr(g16), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
+           ptr(out16), gi.N, H, stream())
+    L.call('gsatb_gather_concat_bwd', ptr(g32), ptr(gi.rowptr_src), ptr(gi.eid_by_src), ptr(gi.rowptr_dst), ptr(gi.eid_by_dst),
+           ptr(out32), gi.N, H, stream())
+    assert torch.equal(out16, out32)
+    src, dst = b.edge_index[0], b.edge_index[1]
+    ref = torch.zeros(gi.N, H, device='cuda', dtype=torch.float64).index_add_(0, src, g32[:, :H].double()).index_add_(0, dst, g32[:, H:].double())
+    assert torch.allclose(out16.double(), ref, rtol=1e-5, atol=1e-5)

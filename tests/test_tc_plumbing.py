@@ -21,6 +21,14 @@ class _StubLib:
         def gsatb_tc_dw_workspace(rows, m, n):
             return 16
 
+        @staticmethod
+        def gsatb_gin_rows_supported(k, h1, h):          # the row-owner kernels take hidden 64 / 128 (csrc/gin_rows.cu)
+            return int(k == h1 == h and h in (64, 128))
+
+        @staticmethod
+        def gsatb_gin_rows_stat_partials_elems(h):
+            return 8 * h
+
     def call(self, name, *args):
         self.launches += 1
         if name == 'gsatb_bn_fold_fwd' and args[10] and args[9] is not None and args[9].value:
@@ -68,9 +76,10 @@ def one_rank_group():
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('H', [16, 64])          # channel-owner skeleton kernels / row-owner kernels (hidden 64, 128)
 @pytest.mark.parametrize('sync', [False, True])
-def test_gin_layer_function_returns_one_gradient_per_input(tc, one_rank_group, sync):
-    N, E, H = 12, 30, 16
+def test_gin_layer_function_returns_one_gradient_per_input(tc, one_rank_group, sync, H):
+    N, E = 12, 30
     conv = _layer(H)
     bn = conv.nn[1]
     if sync:

@@ -152,7 +152,7 @@ def bwd(emb, gi, w1, w2, w3, dlogit, xh2t, rstd2, seeds_xs, edge, m1=None, m2=No
     w1p, w2t, w1t = tc.prep_weight(w1), tc.prep_weight(w2, transpose=True), tc.prep_weight(w1, transpose=True)
     L.call('gsatb_ext_fused_bwd', ptr(plan['seg_ptr']), ptr(plan['tile_seg']), ptr(plan['out2']), max(gi.G, 1), ms, int(edge),
            ptr(w1p), ptr(w2t), ptr(w1t), ptr(w3), ptr(dlogit), ptr(xh2t), ptr(rstd2), ptr(xs), ptr(m1), ptr(m2), ptr(seeds),
-           ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), ptr(dw3p), ld, rows, H, C1,
+           ctypes.c_float(pdrop), int(training), ptr(dz2t), ptr(dz1t), ptr(h1t), ptr(df12), 0, ptr(dw3p), ld, rows, H, C1,
            ctypes.c_float(1e-5), stream())
     return dz2t, dz1t, h1t, xs, df12, dw3p
 
