@@ -462,7 +462,7 @@ k_rows(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtenso
             }
             if constexpr (SWAP) {
                 if (p.stat_partials && ch_ok) {
-                    const size_t part = (size_t)blockIdx.x * MAX_GROUPS + grp;
+                    const size_t part = (size_t)blockIdx.x * 2 + grp;          // [gridDim][2 channel-owner groups]
                     p.stat_partials[(part * 2 + 0) * H + ch] = s1a + s1b;
                     p.stat_partials[(part * 2 + 1) * H + ch] = s2a + s2b;
                 }
@@ -553,12 +553,13 @@ struct RowsBwd2Params {
     const float* sc;            // BatchNorm folded: a1 = relu(z1 * sc + sf)
     const float* sf;
     const float* mu;
-    float* stat_partials;       // [gridDim * 8 epilogue warps][2][H]: sum g, sum g * (z1 - mu)
+    float* stat_partials;       // [gridDim][2][H]: sum g, sum g * (z1 - mu) over the CTA's tiles
 };
 constexpr int RW2_NACC = 2;             // accumulators = epilogue groups (warps 4-11; three groups with one staging buffer
                                         // each measured slower: 1.50 vs 1.36 ms at 4.9 M x 128)
 constexpr int RW2_ROW_WARPS = 4 * RW2_NACC;
 constexpr int RW2_STG = 8192;       // per epilogue warp: two [32 rows x 128 bytes] staging buffers
+constexpr int RW2_BAR_RED = 3;      // named barrier of the epilogue warps' final partial-sum exchange
 
 struct Rows2Smem {
     uint32_t in_off, stage_bytes, stg_off, bar_off, total;
@@ -694,7 +695,6 @@ k_rows_bwd2(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CU
     } else {
         tc::reg_inc<EPI4_REGS>();
         const int q = warp & 3;
-        const int nchunk = H >> 5;
         if (warp >= 16) {
             // ===================== transform: fp32 dh boxes -> bf16 d2 K-blocks, in place =====================
             const int row = threadIdx.x - 16 * 32;               // 0..127: thread = row, one 64-channel block after the other
@@ -751,7 +751,7 @@ k_rows_bwd2(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CU
                 d[6] = w_in;
                 d[7] = t_work;
             }
-        } else {
+        } else if (warp < 4 + RW2_ROW_WARPS) {       // (warps 12-15 have no role in this kernel)
             // ===================== epilogue groups: row-owner phase, then channel-pair phase, per 64-channel block ==========
             // Row phase (lane = row): accumulator -> bf16 da1 in the warp's staging buffer.  Channel phase (lane = channel
             // pair, the warp's 32 rows in order): z1 comes straight from global memory -- 128 contiguous bytes per row per
@@ -855,18 +855,25 @@ k_rows_bwd2(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CU
                 t_work += clock64() - t0;
             }
             if (lane == 0) tc::tma_store_wait_all<0>();
-            if (p.stat_partials) {
-                const size_t part = (size_t)blockIdx.x * RW2_ROW_WARPS + ew;
+            __syncwarp();
+            {   // the CTA's partial sums: the eight warps' values meet in their (now idle) staging buffers and are added in
+                // warp order -> one [2][H] row per CTA for the fixed-order reduction kernel
+                float* red = reinterpret_cast<float*>(stg);
 #pragma unroll
                 for (int b = 0; b < 2; ++b)
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int ch = b * 64 + 2 * lane + i;
-                        if (ch < H) {
-                            p.stat_partials[(part * 2 + 0) * H + ch] = s1[b][i];
-                            p.stat_partials[(part * 2 + 1) * H + ch] = s2[b][i];
-                        }
+                        if (ch < H) red[ch] = s1[b][i], red[H + ch] = s2[b][i];
                     }
+                tc::named_bar_sync(RW2_BAR_RED, RW2_ROW_WARPS * 32);
+                const int t = threadIdx.x - 4 * 32;
+                if (p.stat_partials && t < 2 * H) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int w = 0; w < RW2_ROW_WARPS; ++w) acc += reinterpret_cast<const float*>(smem + L.stg_off + (size_t)w * RW2_STG)[t];
+                    p.stat_partials[(size_t)blockIdx.x * 2 * H + t] = acc;
+                }
             }
             if (sh.dbg && ew == 0 && lane == 0) {
                 long long* d = sh.dbg + (size_t)blockIdx.x * 16;
@@ -904,6 +911,14 @@ inline int make_rows_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int es, const
     CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? GSATB_OK : GSATB_EINVAL;
+}
+
+inline int rows_env(const char* name, int dflt, int lo, int hi);
+// persistent grid of the row-owner kernels: one CTA per SM, fewer when there are fewer tiles
+inline int rows_grid(int64_t rows) {
+    const int64_t tiles = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    const int max_grid = rows_env("GSATB_ROWS_GRID", GSATB_NUM_SMS, 1, GSATB_NUM_SMS);      // (tests: many tiles per CTA at small sizes)
+    return (int)(tiles < max_grid ? tiles : max_grid);
 }
 
 inline int rows_env(const char* name, int dflt, int lo, int hi) {
@@ -962,8 +977,7 @@ int launch_rows(const void* w_bf16_padded, const void* in0, const void* in1, voi
             return GSATB_ELAUNCH;
         attr_set = true;
     }
-    const int max_grid = rows_env("GSATB_ROWS_GRID", GSATB_NUM_SMS, 1, GSATB_NUM_SMS);      // (tests: many tiles per CTA at small sizes)
-    const int grid = sh.num_tiles < max_grid ? sh.num_tiles : max_grid;
+    const int grid = rows_grid(rows);
     k_rows<Op><<<grid, RW_THREADS, L.total, st>>>(tw, t0, t1, tx, to, sh, p);
     if (cudaPeekAtLastError() != cudaSuccess) return GSATB_ELAUNCH;
     return GSATB_OK;
@@ -996,12 +1010,11 @@ extern "C" int gsatb_gin_rows_lin1(const void* x_bf16, const void* w1_bf16_padde
     if (!x_bf16 || !w1_bf16_padded || !z1_bf16) return GSATB_EINVAL;
     if (stat_partials && !stats) return GSATB_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (stat_partials) cudaMemsetAsync(stat_partials, 0, (size_t)GSATB_NUM_SMS * MAX_GROUPS * 2 * H * sizeof(float), st);
     OpRowsLin1::Params p{bias, stat_partials, 0, plain_epi()};
     int rc = launch_rows<OpRowsLin1>(w1_bf16_padded, x_bf16, nullptr, nullptr, z1_bf16, true, rows, H, p, st);
     if (rc != GSATB_OK) return rc;
-    if (stat_partials) {
-        k_rows_reduce_partials<<<(2 * H + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS * MAX_GROUPS, 2 * H, stats);
+    if (stat_partials) {       // every CTA of the launch wrote both of its partial rows: no memset, parts = 2 x grid
+        k_rows_reduce_partials<<<(2 * H + 63) / 64, 64, 0, st>>>(stat_partials, 2 * rows_grid(rows), 2 * H, stats);
         GSATB_CHECK_LAUNCH();
     }
     return GSATB_OK;
@@ -1034,7 +1047,7 @@ extern "C" int gsatb_gin_rows_bwd1(const void* g_bf16, const void* z1_bf16, cons
     return launch_rows<OpRowsBwd1>(w1t_bf16_padded, g_bf16, z1_bf16, dz1_bf16, dx, false, rows, H, p, (cudaStream_t)stream);
 }
 
-extern "C" size_t gsatb_gin_rows_stat_partials_elems(int H) { return (size_t)GSATB_NUM_SMS * RW2_ROW_WARPS * 2 * H; }
+extern "C" size_t gsatb_gin_rows_stat_partials_elems(int H) { return (size_t)GSATB_NUM_SMS * 2 * H; }
 
 extern "C" int gsatb_gin_rows_bwd2(const float* dh, const uint32_t* posmask, float drop_scale, const void* w2t_bf16_padded,
                                    const void* z1_bf16, const float* bn_scale, const float* bn_shift, const float* mean,
@@ -1079,13 +1092,11 @@ extern "C" int gsatb_gin_rows_bwd2(const float* dh, const uint32_t* posmask, flo
             return GSATB_ELAUNCH;
         attr_set = true;
     }
-    cudaMemsetAsync(stat_partials, 0, gsatb_gin_rows_stat_partials_elems(H) * sizeof(float), st);
     RowsBwd2Params p{posmask, drop_scale, (const uint16_t*)z1_bf16, bn_scale, bn_shift, mean, stat_partials};
-    const int max_grid = rows_env("GSATB_ROWS_GRID", GSATB_NUM_SMS, 1, GSATB_NUM_SMS);
-    const int grid = sh.num_tiles < max_grid ? sh.num_tiles : max_grid;
+    const int grid = rows_grid(rows);
     k_rows_bwd2<<<grid, RW_THREADS, L.total, st>>>(tw, tdh, td2, tg, sh, p);
     if (cudaPeekAtLastError() != cudaSuccess) return GSATB_ELAUNCH;
-    k_rows_bwd2_reduce<<<(2 * H + 127) / 128, 128, 0, st>>>(stat_partials, GSATB_NUM_SMS * RW2_ROW_WARPS, H, rstd, stats);
+    k_rows_bwd2_reduce<<<(2 * H + 63) / 64, 64, 0, st>>>(stat_partials, grid, H, rstd, stats);      // every CTA wrote its row
     GSATB_CHECK_LAUNCH();
     return GSATB_OK;
 }

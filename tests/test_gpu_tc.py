@@ -547,9 +547,11 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
             L.call(name, ptr(dh), None, ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
                    ptr(rstd), ptr(d2), ptr(g), None, ptr(part), ptr(stats), N, H, H, stream())
         else:
-            part = torch.empty(int(L.cdll.gsatb_gin_rows_stat_partials_elems(H)), device=dev)
+            n_part = int(L.cdll.gsatb_gin_rows_stat_partials_elems(H))
+            part = torch.full((n_part + 8192,), float('nan'), device=dev)       # guard band behind the declared workspace
             L.call(name, ptr(dh), ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
                    ptr(rstd), ptr(d2), ptr(g), ptr(part), ptr(stats), N, H, stream())
+            assert bool(torch.isnan(part[n_part:]).all()), 'the kernel wrote behind its partial-sum workspace'
         outs.append((d2, g, stats))
     (d2_o, g_o, st_o), (d2_n, g_n, st_n) = outs
     assert torch.equal(d2_n.view(torch.int16), d2_o.view(torch.int16))
