@@ -34,6 +34,10 @@ struct DwParams {
     int lda, ldb;        // tile-major operands: channel rows per 128-row block
     int n_chunk;         // B channels per slab: multiple of 64, <= 256
     int n_chunks;        // slabs per A block
+    int slabs;           // A blocks x n_chunks
+    int mpc;             // A blocks per CTA: 2 when no bias gradient is wanted and two accumulators fit in TMEM -- every B
+                         // tile then feeds two MMAs per fetch (the 4-block dW1 of the extractor was bound by L2 -> SM
+                         // traffic, 38 GB per launch at ~10 TB/s: 25 GB with pairs)
     int splits;
     int stages;
     float* ws;           // [splits][slabs][128][n_chunk + 16]
@@ -48,7 +52,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
 #endif
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = p.n_chunk * 128;
-    const int stage_bytes = DW_A_BYTES + b_bytes;
+    const int stage_bytes = p.mpc * DW_A_BYTES + b_bytes;
     uint8_t* ones = smem + (size_t)p.stages * stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(ones + DW_ONES_BYTES);
     uint64_t* full = bars;              // [stages <= 8]
@@ -57,8 +61,10 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int split = blockIdx.x, slab = blockIdx.y;
-    const int mb = slab / p.n_chunks, nc = slab % p.n_chunks;
+    const int split = blockIdx.x;
+    // CTA (split, y): mpc == 1: slab y = (A block y / n_chunks, B chunk y % n_chunks); mpc == 2 (n_chunks == 1): A blocks 2y, 2y + 1
+    const int mb = p.mpc == 2 ? 2 * (int)blockIdx.y : (int)blockIdx.y / p.n_chunks;
+    const int nc = p.mpc == 2 ? 0 : (int)blockIdx.y % p.n_chunks;
     const int64_t total_steps = (p.rows + DW_KSTEP - 1) / DW_KSTEP;
     // K-steps are dealt round-robin over the splits (split s takes steps s, s + splits, ...): at any moment the CTAs of a
     // slab stream ADJACENT 64-row slices of the operands, so a channel-major operand ([C, rows]: one 128-byte piece per
@@ -96,16 +102,20 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
                 const uint32_t s = it % p.stages, use = it / p.stages;
                 tc::mbar_wait(&empty[s], (use & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
-                uint8_t* sA = smem + (size_t)s * stage_bytes;
-                uint8_t* sB = sA + DW_A_BYTES;
+                uint8_t* sA0 = smem + (size_t)s * stage_bytes;
+                uint8_t* sB = sA0 + p.mpc * DW_A_BYTES;
                 const int r = (int)(st * DW_KSTEP);
-                if (p.a_cm == 2) {
-                    tc::tma_load_2d(sA, &tmap_a, &full[s], r & 127, (r >> 7) * p.lda + mb * 128);
-                } else if (p.a_cm) {
-                    tc::tma_load_2d(sA, &tmap_a, &full[s], r, mb * 128);                       // box {64 rows, 128 ch}
-                } else {
-                    tc::tma_load_2d(sA, &tmap_a, &full[s], mb * 128, r);                       // box {64 ch, 64 rows}
-                    tc::tma_load_2d(sA + 8192, &tmap_a, &full[s], mb * 128 + 64, r);
+                for (int ja = 0; ja < p.mpc; ++ja) {
+                    uint8_t* sA = sA0 + ja * DW_A_BYTES;
+                    const int mbj = mb + ja;
+                    if (p.a_cm == 2) {
+                        tc::tma_load_2d(sA, &tmap_a, &full[s], r & 127, (r >> 7) * p.lda + mbj * 128);
+                    } else if (p.a_cm) {
+                        tc::tma_load_2d(sA, &tmap_a, &full[s], r, mbj * 128);                   // box {64 rows, 128 ch}
+                    } else {
+                        tc::tma_load_2d(sA, &tmap_a, &full[s], mbj * 128, r);                   // box {64 ch, 64 rows}
+                        tc::tma_load_2d(sA + 8192, &tmap_a, &full[s], mbj * 128 + 64, r);
+                    }
                 }
                 if (p.b_cm == 2) {
                     for (int j = 0; j * 128 < p.n_chunk; ++j)
@@ -130,7 +140,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
                 tc::mbar_wait(&full[s], use & 1);
                 tc::tc_fence_after();
                 const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + DW_A_BYTES;
+                const uint32_t b_addr = a_addr + p.mpc * DW_A_BYTES;
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {          // 4 x (K = 16 rows)
                     const uint64_t a_desc = p.a_cm ? tc::make_desc_k_sw128(a_addr) + (uint64_t)(k4 * 2)
@@ -139,7 +149,13 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
                                                    : tc::make_desc_mn_sw128(b_addr + k4 * 2048, 8192);
                     const uint32_t accum = (it | (uint32_t)k4) != 0;
                     tc::mma_bf16_ss(tmem_base, a_desc, b_desc, idesc, accum);
-                    tc::mma_bf16_ss(tmem_base + p.n_chunk, a_desc, ones_desc + (uint64_t)(k4 * 2), idesc_b, accum);
+                    if (p.mpc == 2) {                     // second A block of the pair on the same B tile (no bias columns)
+                        const uint64_t a1_desc = p.a_cm ? tc::make_desc_k_sw128(a_addr + DW_A_BYTES) + (uint64_t)(k4 * 2)
+                                                        : tc::make_desc_mn_sw128(a_addr + DW_A_BYTES + k4 * 2048, 8192);
+                        tc::mma_bf16_ss(tmem_base + p.n_chunk, a1_desc, b_desc, idesc, accum);
+                    } else {
+                        tc::mma_bf16_ss(tmem_base + p.n_chunk, a_desc, ones_desc + (uint64_t)(k4 * 2), idesc_b, accum);
+                    }
                 }
                 tc::mma_commit(&empty[s]);
             }
@@ -148,25 +164,29 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUte
     } else if (warp >= 4) {
         const int q = warp - 4;
         const int TW = p.n_chunk + DW_BIAS_COLS;
-        float* out = p.ws + ((size_t)(split * gridDim.y + slab) * 128 + q * 32 + lane) * TW;
         const bool have = s1 > s0;
         if (have) {
             tc::mbar_wait(acc_full, 0);
             tc::tc_fence_after();
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c = 0; c < TW; c += 16) {
-            float v[16];
-            if (have) {
-                tc::tmem_ld_32x16(taddr + c, v);
-                tc::tmem_ld_wait();
-            } else {
+        for (int ja = 0; ja < p.mpc; ++ja) {
+            const int slab = (mb + ja) * p.n_chunks + nc;
+            float* out = p.ws + ((size_t)(split * p.slabs + slab) * 128 + q * 32 + lane) * TW;
+            // mpc == 2: accumulator ja sits at column ja * n_chunk and there are no bias columns (written as zeros)
+            const uint32_t taddr = tmem_base + (uint32_t)(ja * p.n_chunk) + ((uint32_t)(q * 32) << 16);
+            for (int c = 0; c < TW; c += 16) {
+                float v[16];
+                if (have && (p.mpc == 1 || c < p.n_chunk)) {
+                    tc::tmem_ld_32x16(taddr + c, v);
+                    tc::tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(out + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(out + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
     }
     tc::tc_fence_before();
@@ -193,11 +213,11 @@ __global__ void k_dw_reduce(const float* __restrict__ ws, int splits, int slabs,
 }
 
 struct DwPlan {
-    int n_chunk, n_chunks, m_blocks, slabs, splits, stages;
+    int n_chunk, n_chunks, m_blocks, slabs, splits, stages, mpc;
     size_t ws_bytes, smem;
 };
 
-inline DwPlan dw_plan(int64_t rows, int M, int N, int b_cm) {
+inline DwPlan dw_plan(int64_t rows, int M, int N, int b_cm, bool want_bias = true) {
     DwPlan d;
     const int unit = b_cm ? 128 : 64;          // B channels per TMA box
     const int npad = (N + unit - 1) / unit * unit;
@@ -205,12 +225,14 @@ inline DwPlan dw_plan(int64_t rows, int M, int N, int b_cm) {
     d.n_chunk = ((npad / unit + d.n_chunks - 1) / d.n_chunks) * unit;
     d.m_blocks = (M + 127) / 128;
     d.slabs = d.m_blocks * d.n_chunks;
+    // pairs of A blocks per CTA when nothing stands in the way: no bias columns wanted, one B chunk, two accumulators in TMEM
+    d.mpc = (!want_bias && d.n_chunks == 1 && d.m_blocks % 2 == 0 && 2 * d.n_chunk <= 512) ? 2 : 1;
     const int64_t steps = (rows + DW_KSTEP - 1) / DW_KSTEP;
-    int splits = GSATB_NUM_SMS / d.slabs;
+    int splits = GSATB_NUM_SMS / (d.slabs / d.mpc);
     if (splits < 1) splits = 1;
     if ((int64_t)splits > steps) splits = steps > 0 ? (int)steps : 1;
     d.splits = splits;
-    const int stage_bytes = DW_A_BYTES + d.n_chunk * 128;
+    const int stage_bytes = d.mpc * DW_A_BYTES + d.n_chunk * 128;
     int stages = (227 * 1024 - 1024 - DW_ONES_BYTES - 256) / stage_bytes;
     d.stages = stages > 8 ? 8 : stages;
     d.smem = (size_t)d.stages * stage_bytes + DW_ONES_BYTES + 256 + 1024;
@@ -248,8 +270,13 @@ inline int make_dw_tmap(CUtensorMap* tm, const void* x, int64_t rows, int C, int
 
 extern "C" size_t gsatb_tc_dw_workspace(int64_t rows, int M, int N) {
     if (rows < 0 || M <= 0 || N <= 0) return 0;
-    const size_t a = dw_plan(rows, M, N, 0).ws_bytes, b = dw_plan(rows, M, N, 1).ws_bytes;
-    return a > b ? a : b;
+    size_t w = 0;
+    for (int b_cm = 0; b_cm < 2; ++b_cm)
+        for (int bias = 0; bias < 2; ++bias) {
+            const size_t x = dw_plan(rows, M, N, b_cm, bias != 0).ws_bytes;
+            w = x > w ? x : w;
+        }
+    return w;
 }
 
 extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda, const void* b_bf16, int b_channel_major,
@@ -268,7 +295,7 @@ extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda,
     }
     if (!a_bf16 || !b_bf16 || !workspace) return GSATB_EINVAL;
     if (a_channel_major < 0 || a_channel_major > 2 || b_channel_major < 0 || b_channel_major > 2) return GSATB_EINVAL;
-    const DwPlan d = dw_plan(rows, M, N, b_channel_major ? 1 : 0);
+    const DwPlan d = dw_plan(rows, M, N, b_channel_major ? 1 : 0, db != nullptr);
     if (ws_bytes < d.ws_bytes) return GSATB_EWS_TOO_SMALL;
     if (d.stages < 2) return GSATB_ESHAPE;
     CUtensorMap ta, tb;
@@ -276,11 +303,11 @@ extern "C" int gsatb_tc_dw(const void* a_bf16, int a_channel_major, int64_t lda,
     if (rc != GSATB_OK) return rc;
     rc = make_dw_tmap(&tb, b_bf16, rows, N, ldb, b_channel_major);
     if (rc != GSATB_OK) return rc;
-    DwParams p{rows, M, N, a_channel_major, b_channel_major, (int)lda, (int)ldb, d.n_chunk, d.n_chunks, d.splits, d.stages,
-               (float*)workspace};
+    DwParams p{rows, M, N, a_channel_major, b_channel_major, (int)lda, (int)ldb, d.n_chunk, d.n_chunks, d.slabs, d.mpc, d.splits,
+               d.stages, (float*)workspace};
     if (cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return GSATB_ELAUNCH;
-    k_tc_dw<<<dim3(d.splits, d.slabs), DW_THREADS, d.smem, st>>>(ta, tb, p);
+    k_tc_dw<<<dim3(d.splits, d.slabs / d.mpc), DW_THREADS, d.smem, st>>>(ta, tb, p);
     GSATB_CHECK_LAUNCH();
     const int64_t total = (int64_t)M * (N + 1);
     int grid = (int)((total + 255) / 256);

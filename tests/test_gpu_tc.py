@@ -595,3 +595,23 @@ def test_gather_concat_bwd_bf16_equals_the_fp32_reduction_of_the_same_values(G, 
     src, dst = b.edge_index[0], b.edge_index[1]
     ref = torch.zeros(gi.N, H, device='cuda', dtype=torch.float64).index_add_(0, src, g32[:, :H].double()).index_add_(0, dst, g32[:, H:].double())
     assert torch.allclose(out16.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('M,N,rows,layouts', [(256, 192, 5000, (0, 0)), (512, 256, 9000, (0, 0)), (512, 256, 4096, (1, 0)),
+                                              (256, 64, 777, (0, 0)), (384, 256, 3000, (0, 0))])
+def test_weight_grad_pairs_of_a_blocks(G, M, N, rows, layouts):
+    """gsatb_tc_dw with two A blocks per CTA (no bias gradient wanted, an even number of 128-channel blocks, one B chunk:
+    the extractor's dW1, autograd of src/utils/get_model.py:57-68): same result as the one-block-per-CTA path that the
+    bias variant takes, and as the fp64 product of the bf16 operands."""
+    from dp_gsat_b200 import tc
+    torch.manual_seed(M + N)
+    a = torch.randn(rows, M, device='cuda').bfloat16()
+    b = torch.randn(rows, N, device='cuda').bfloat16()
+    a_op = a.t().contiguous() if layouts[0] else a
+    dW_pair, _ = tc.weight_grad(a_op, layouts[0], b, layouts[1], rows, M, N, want_bias=False)
+    dW_one, db = tc.weight_grad(a_op, layouts[0], b, layouts[1], rows, M, N, want_bias=True)
+    ref = a.double().t() @ b.double()
+    scale = float(ref.abs().max())
+    assert float((dW_pair.double() - ref).abs().max()) < 2e-5 * scale + 1e-3
+    assert float((dW_one.double() - ref).abs().max()) < 2e-5 * scale + 1e-3
+    assert torch.allclose(db.double(), a.double().sum(0), rtol=1e-4, atol=1e-2)
