@@ -508,12 +508,12 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
     inj = (torch.rand(N, H, device=dev) > 0.3).to(torch.uint8)
     for pdrop, mask in ((0.3, None), (0.5, None), (0.3, inj), (0.0, None)):
         pm_old = torch.zeros((N, H // 32), dtype=torch.int32, device=dev)
-        pm_new = torch.zeros_like(pm_old)
+        (pm_new, chk_pm), (a_new, chk_a), (h_new, chk_h) = (guarded((N, H // 32), torch.int32, 0x5A5A5A5A),
+                                                            guarded((N, H), torch.bfloat16, 7.0), guarded((N, H), torch.float32, float('nan')))
         h_old = tc.linear_bf16(a_old, w2p, b2, H, out_bf16=False, relu_out=True, pdrop=pdrop, drop_seed=5, drop_mask=mask, posmask=pm_old)
-        a_new = torch.zeros_like(z_old)
-        h_new = torch.full((N, H), float('nan'), device=dev)
         L.call('gsatb_gin_rows_lin2', ptr(z_old), ptr(scale), ptr(shift), ptr(w2p), ptr(b2), ptr(a_new), ptr(h_new), ptr(pm_new),
                ptr(mask), ctypes.c_uint64(5), ctypes.c_float(pdrop), N, H, stream())
+        chk_pm('posmask'), chk_a('a1'), chk_h('h')
         assert torch.equal(a_new.view(torch.int16), a_old.view(torch.int16))
         assert torch.equal(h_new != 0, h_old != 0)                     # same dropout decisions
         assert torch.allclose(h_new, h_old, rtol=1e-5, atol=1e-5)
@@ -527,10 +527,11 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
     # --- BatchNorm backward folded into the dX product of the first Linear
     g16 = torch.randn(N, H, device=dev).bfloat16()
     cA, cB, cC = torch.randn(H, device=dev), torch.randn(H, device=dev) * 0.1, torch.randn(H, device=dev) * 0.01
-    dz_old, dz_new = torch.empty_like(g16), torch.zeros_like(g16)
-    dx_old, dx_new = torch.empty((N, H), device=dev), torch.full((N, H), float('nan'), device=dev)
+    dz_old, dx_old = torch.empty_like(g16), torch.empty((N, H), device=dev)
+    (dz_new, chk_dz), (dx_new, chk_dx) = guarded((N, H), torch.bfloat16, 7.0), guarded((N, H), torch.float32, float('nan'))
     L.call('gsatb_tc_gin_bwd1', ptr(g16), ptr(z_old), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz_old), ptr(dx_old), N, H, H, stream())
     L.call('gsatb_gin_rows_bwd1', ptr(g16), ptr(z_old), ptr(cA), ptr(cB), ptr(cC), ptr(w1t), ptr(dz_new), ptr(dx_new), N, H, stream())
+    chk_dz('dz1'), chk_dx('dx')
     assert torch.equal(dz_new.view(torch.int16), dz_old.view(torch.int16))
     assert torch.allclose(dx_new, dx_old, rtol=1e-5, atol=1e-5)
     # --- ReLU / dropout backward folded into the dX product of the second Linear, BatchNorm-backward statistics
@@ -540,8 +541,8 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
     w2t = tc.prep_weight(w2, transpose=True)
     outs = []
     for name in ('gsatb_tc_gin_bwd2', 'gsatb_gin_rows_bwd2'):
-        d2, g = torch.zeros((N, H), dtype=torch.bfloat16, device=dev), torch.zeros((N, H), dtype=torch.bfloat16, device=dev)
-        stats = torch.empty(2 * H, device=dev)
+        (d2, chk_d2), (g, chk_g), (stats, chk_st) = (guarded((N, H), torch.bfloat16, 7.0), guarded((N, H), torch.bfloat16, 7.0),
+                                                     guarded((2 * H,), torch.float32, float('nan')))
         if name == 'gsatb_tc_gin_bwd2':
             part = torch.empty(int(L.cdll.gsatb_tc_stat_partials_elems(H)), device=dev)
             L.call(name, ptr(dh), None, ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
@@ -552,6 +553,7 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
             L.call(name, ptr(dh), ptr(pm), ctypes.c_float(1.43), ptr(w2t), ptr(z_old), ptr(scale), ptr(shift), ptr(mean),
                    ptr(rstd), ptr(d2), ptr(g), ptr(part), ptr(stats), N, H, stream())
             assert bool(torch.isnan(part[n_part:]).all()), 'the kernel wrote behind its partial-sum workspace'
+            chk_d2('d2'), chk_g('g'), chk_st('stats')
         outs.append((d2, g, stats))
     (d2_o, g_o, st_o), (d2_n, g_n, st_n) = outs
     assert torch.equal(d2_n.view(torch.int16), d2_o.view(torch.int16))
@@ -564,6 +566,23 @@ def test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, monkeyp
     xh = (z_old.double() - mean.double()) * rstd.double()
     assert torch.allclose(st_n[:H].double(), g64.sum(0), rtol=1e-4, atol=1e-2)
     assert torch.allclose(st_n[H:].double(), (g64 * xh).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def guarded(shape, dtype, fill, device='cuda', band=4096):
+    """A contiguous tensor of `shape` carved out of a larger buffer with sentinel bands on both sides, and a function that
+    asserts the bands are untouched (compute-sanitizer is not available on the GPU pool: out-of-bounds writes of a kernel
+    are looked for this way)."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    buf = torch.full((n + 2 * band,), fill, dtype=dtype, device=device)
+    view = buf[band:band + n].view(*shape)
+
+    def check(what=''):
+        lo, hi = buf[:band], buf[band + n:]
+        same = (lambda t: bool(torch.isnan(t).all())) if (dtype.is_floating_point and fill != fill) else (lambda t: bool((t == fill).all()))
+        assert same(lo) and same(hi), f'{what}: a kernel wrote outside its output tensor'
+    return view, check
 
 
 def tc_unpack_bits(words: torch.Tensor, H: int) -> torch.Tensor:
