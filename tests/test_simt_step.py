@@ -34,6 +34,14 @@ def _case(fn, **kw):
     return pytest.param(fn, kw, id=ident)
 
 
+def case_gin_rows_kernels(G, H, N, grid):
+    mp = pytest.MonkeyPatch()
+    try:
+        T.test_gin_rows_kernels_match_the_channel_owner_kernels(G, H, N, grid, mp)
+    finally:
+        mp.undo()
+
+
 CASES = [
     # K0: index / CSR / CSC / reverse map / flags, bit-exact
     *[_case(P.test_index_build_bit_exact, name=n) for n in ('ba2motifs', 'molhiv', 'mutag', 'shuffled', 'directed',
@@ -84,6 +92,14 @@ CASES = [
     _case(T.test_fused_extractor_fwd_bwd, case='mol_edge_H80_p03'),
     _case(T.test_fused_extractor_fwd_bwd, case='eval_mode'),
     _case(T.test_gin_mlp_fused_matches_torch, H=64),
+    _case(T.test_gin_mlp_fused_matches_torch, H=128),
+    # the row-owner node-MLP kernels (csrc/gin_rows.cu) against the channel-owner ones, many tiles per CTA included
+    _case(case_gin_rows_kernels, H=64, N=777, grid=148),
+    _case(case_gin_rows_kernels, H=128, N=777, grid=148),
+    _case(case_gin_rows_kernels, H=128, N=4096 + 40, grid=3),
+    _case(T.test_weight_grad_pairs_of_a_blocks, M=256, N=192, rows=5000, layouts=(0, 0)),
+    _case(T.test_weight_grad_pairs_of_a_blocks, M=512, N=256, rows=4096, layouts=(1, 0)),
+    _case(T.test_gather_concat_bwd_bf16_equals_the_fp32_reduction_of_the_same_values, H=64),
     _case(T.test_gsat_step_bf16_mode_tracks_oracle),
     _case(T.test_word_dropout_rate_and_scale, p=0.3),
     _case(T.test_bf16_mode_layer_by_layer_path, case='mutag_dual_big_graphs'),
